@@ -1,0 +1,35 @@
+"""FiniteVolumeSolver: flux plug-in + calcDeriv (hydro/solver/fvsolver.lua).
+
+Reference: fvsolver.lua:16-52 (class, createFlux), :57-198 (calcFlux kernel), :225-302 (calcDeriv =
+[calcLR] -> calcFlux -> calcDerivFromFlux).  Here calcDeriv, the RK stage combination, constrainU, the
+ghost fill and the CFL reduction are fused on the device (csrc/fv_stage.cuh); this class keeps the
+reference's constructor arguments (config.lua:8-690) and methods.
+"""
+from ..flux.roe import fluxes
+from .gridsolver import GridSolver
+
+
+class FiniteVolumeSolver(GridSolver):
+    name = "fvsolver"
+
+    def initObjs(self, args):
+        super().initObjs(args)
+        self.createFlux(args.get("flux", "roe"), args.get("fluxArgs"))
+        if not self.flux.usesFluxLimiter:
+            self.fluxLimiter = 0
+
+    def createFlux(self, fluxName, fluxArgs=None):
+        if fluxName not in fluxes:
+            raise NotImplementedError("flux %r is a 'next' row (SURVEY 8f2); only 'roe' is built" % (fluxName,))
+        self.flux = fluxes[fluxName](self, fluxArgs)
+
+    def createBackend(self, args):
+        backend = args.get("backend")
+        if backend is not None:
+            return backend(self)        # tests inject the CPU oracle here; the product never does
+        from ...backend import CudaBackend
+        return CudaBackend(self, device=args.get("device", 0), comm=args.get("comm"))
+
+    def calcDeriv(self, dt):
+        """fvsolver.lua:225-302: returns dU/dt (AoS, float64) of the current state.  Debug / test entry point."""
+        return self.backend.calc_deriv(dt)

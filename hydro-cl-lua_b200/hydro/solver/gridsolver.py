@@ -1,0 +1,136 @@
+"""GridSolver: structured grid, ghost cells, boundary methods (hydro/solver/gridsolver.lua).
+
+Reference: numGhost = 2 :41; gridSize += 2*numGhost, unused dims size 1 :94-95; mins/maxs default +-1 :75-76;
+grid_dx for all three axes :406-409; cell positions hydro/coord/coord.lua:1399-1458;
+boundaryMethods default 'freeflow' :121-135, classes :638-780; usePLM/slopeLimiter :105-120 (PLM requires
+fluxLimiter == 'donor cell', :119); calcExactError :1337-1366.
+"""
+import numpy as np
+
+from .. import app as hydro_app
+from .solverbase import SolverBase
+
+boundaryIds = {"periodic": 0, "mirror": 1, "freeflow": 2, "none": 3}
+xNames = ("x", "y", "z")
+minmaxs = ("min", "max")
+plmIds = {None: 0, False: 0, "plm cons": 1}
+
+
+class GridSolver(SolverBase):
+    name = "GridSolver"
+    numGhost = 2
+
+    def initMeshVars(self, args):
+        dim = self.dim
+        gs = args.get("gridSize", [256, 1, 1])
+        if isinstance(gs, (int, float)):
+            gs = [gs]
+        gs = list(gs) + [1] * (3 - len(gs))
+        self.sizeWithoutBorder = [int(gs[i]) if i < dim else 1 for i in range(3)]
+        g = self.numGhost
+        self.gridSize = [n + 2 * g if i < dim else 1 for i, n in enumerate(self.sizeWithoutBorder)]
+        self.numCells = self.gridSize[0] * self.gridSize[1] * self.gridSize[2]
+        self.stepsize = [1, self.gridSize[0], self.gridSize[0] * self.gridSize[1]]
+        self.mins = [float(v) for v in args.get("mins", (-1., -1., -1.))]
+        self.maxs = [float(v) for v in args.get("maxs", (1., 1., 1.))]
+
+    def initObjs(self, args):
+        super().initObjs(args)
+        # initCond-supplied domain overrides cfg (solverbase.lua:1546-1560)
+        if self.initCond.mins is not None and "mins" not in args:
+            self.mins = [float(v) for v in self.initCond.mins]
+        if self.initCond.maxs is not None and "maxs" not in args:
+            self.maxs = [float(v) for v in self.initCond.maxs]
+        self.initCondMins = [float(v) for v in args.get("initCondMins", self.mins)]
+        self.initCondMaxs = [float(v) for v in args.get("initCondMaxs", self.maxs)]
+        self.grid_dx = [(self.maxs[j] - self.mins[j]) / float(self.sizeWithoutBorder[j]) for j in range(3)]
+        self.mindx = min(self.grid_dx)
+        self.usePLM = args.get("usePLM") or None
+        if self.usePLM not in plmIds:
+            raise NotImplementedError("usePLM=%r: only 'plm cons' is in the hot-path scope so far" % (self.usePLM,))
+        self.slopeLimiter = hydro_app.limiterIndex(args.get("slopeLimiter", "minmod")) if self.usePLM else 0
+        if self.usePLM and self.fluxLimiter != 0:
+            # gridsolver.lua:119: "are you sure you want to use flux and slope limiters at the same time?"
+            raise ValueError("usePLM requires fluxLimiter='donor cell' (gridsolver.lua:119)")
+        # boundary: cfg.boundary table wins, else what the initCond sets, else freeflow
+        self.boundaryMethods = {}
+        bargs = args.get("boundary") or {}
+        for x in xNames:
+            for mm in minmaxs:
+                self.boundaryMethods[x + mm] = bargs.get(x + mm, "freeflow")
+        if self.initCond.boundary and not bargs:
+            self.setBoundaryMethods(self.initCond.boundary)
+
+    def setBoundaryMethods(self, name):
+        if isinstance(name, dict):
+            self.boundaryMethods.update(name)
+        else:
+            for k in self.boundaryMethods:
+                self.boundaryMethods[k] = name
+
+    def boundaryIdList(self):
+        out = []
+        for x in xNames:
+            for mm in minmaxs:
+                m = self.boundaryMethods[x + mm]
+                if m not in boundaryIds:
+                    raise NotImplementedError("boundary method %r is outside the hot-path scope" % (m,))
+                out.append(boundaryIds[m])
+        return out
+
+    def cellPositions(self):
+        """coord.lua:1421-1432: x = (i + .5 - g)/N * (max - min) + min on used axes, midpoint otherwise."""
+        g = self.numGhost
+        axes = []
+        for j in range(3):
+            if j < self.dim:
+                i = np.arange(self.gridSize[j], dtype=np.float64)
+                axes.append((i + .5 - g) / float(self.sizeWithoutBorder[j]) * (self.maxs[j] - self.mins[j]) + self.mins[j])
+            else:
+                axes.append(np.array([.5 * (self.maxs[j] + self.mins[j])]))
+        z, y, x = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
+        return x, y, z      # each [Sz, Sy, Sx]
+
+    def applyInitCond(self):
+        x, y, z = self.cellPositions()
+        W = self.initCond.prims(x, y, z, self)
+        U = self.eqn.consArray(W)                       # [Sz, Sy, Sx, numStates]
+        self.setState(U)
+
+    def setState(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64).reshape(self.numCells, self.eqn.numStates)
+        self.backend.set_state(U)
+
+    def getState(self):
+        """UBuf as float64 [Sz, Sy, Sx, numStates] (AoS cons_t order, ghost cells included)."""
+        U = self.backend.get_state()
+        return U.reshape(self.gridSize[2], self.gridSize[1], self.gridSize[0], self.eqn.numStates)
+
+    def interior(self, U=None):
+        U = self.getState() if U is None else U
+        g = self.numGhost
+        sl = [slice(g, -g) if j < self.dim else slice(None) for j in (2, 1, 0)]
+        return U[sl[0], sl[1], sl[2]]
+
+    def calcExactError(self, numStates=None):
+        """gridsolver.lua:1337-1366, including its loop bounds (imax = gridSize - 2*ghost - 1 on the ghost-inclusive
+        size, i.e. the last two interior cells per axis are skipped) and the division by the full interior volume."""
+        eqn = self.eqn
+        numStates = numStates or eqn.numIntStates
+        U = self.getState()
+        g = self.numGhost
+        x, y, z = self.cellPositions()
+
+        def rng(j):
+            if j >= self.dim:
+                return slice(0, 1)
+            return slice(g, self.gridSize[j] - 2 * g - 1 + 1)
+        sx, sy, sz = rng(0), rng(1), rng(2)
+        exact = self.initCond.exactSolution(self.t, x[sz, sy, sx], self)
+        err = 0.
+        for j in range(numStates):
+            err += float(np.sum(np.abs(U[sz, sy, sx, j] - exact[j])))
+        vol = 1
+        for n in self.sizeWithoutBorder:
+            vol *= n
+        return err / (numStates * vol)

@@ -1,0 +1,1222 @@
+// hydro_oracle.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// CPU restatement of hydro-cl-lua's explicit finite-volume update, used as the parity oracle
+// for the CUDA product in hydro-cl-lua_b200/ and as the "port" CPU baseline in bench.py.
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+// load this library.  The product never links, imports or calls it.
+//
+// PARITY PIN STATUS: the reference is LuaJIT + OpenCL-C templates whose third-party runtime
+// (lua-opencl, template, modules, struct, symmath, ...; distinfo:272-293) is not vendored and no
+// OpenCL device exists in the authoring container, so the reference itself cannot be executed
+// here.  The oracle is pinned against the only known-answer values the reference's tests hold
+// for this path: the n=1024 L1 errors in tests/test-order/schemes.lua:61-126 (see
+// tests/test_oracle_kat.py) and the analytic Sod / advect-wave solutions of hydro/init/euler.lua.
+// Symmath-emitted helpers (coordLenSq, cell_area, cell_volume) have unknown floating-point
+// association order: "parity unpinned" at the last-ulp level there.
+//
+// Every function cites the reference file:line it restates.  Structure deliberately follows the
+// reference (AoS cons_t records, one loop nest per OpenCL kernel, materialised ULR / flux / deriv
+// buffers, ~67 "launches" per RK4 step); the CUDA product is structured differently (SoA, fused).
+//
+// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp -shared -fPIC).
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <vector>
+#include <algorithm>
+
+extern "C" {
+// Plain-C descriptor shared with oracle/oracle.py (ctypes).  Field order is ABI.
+struct ho_desc {
+	int eqn;            // 0 = euler, 1 = mhd
+	int dim;            // 1..3
+	int n[3];           // interior cells per axis (unused axes = 1)
+	int real_bytes;     // 8 = double, 4 = float   (hydro/app.lua:892 'real' selection)
+	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91)
+	int slope_limiter;  // 0-based index into hydro/app.lua:614-635
+	int flux_limiter;   // 0-based index; 0 = 'donor cell' => useFluxLimiter=false (fvsolver.lua:61-63)
+	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none
+	int rk_order;       // 0 = forward Euler (int/fe.lua), else Butcher order (int/rk.lua)
+	double alphas[16];  // row-major [order][order] (int/all.lua)
+	double betas[16];
+	double mins[3], maxs[3];
+	double cfl;
+	double fixed_dt;
+	int use_fixed_dt;
+	double gamma;       // heatCapacityRatio
+	double rhoMin, PMin;   // euler.lua:193-197
+	double mu0_eff;     // solver->mu0 / unit_kg_m_per_C2 (mhd.lua:209-234, math.cl:270)
+	int nthreads;       // OpenMP threads (0 = default)
+};
+}
+
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace ho {
+
+// ---------------------------------------------------------------------------------------------
+// hydro/code/math.cl: real3 and helpers
+template<class real> struct real3_t {
+	real x, y, z;
+	real& s(int i) { return (&x)[i]; }
+	real const& s(int i) const { return (&x)[i]; }
+};
+
+// math.cl:175-181,221: real_add3(a,b,c) = a + (b + c)  -> real3_dot is right-nested
+template<class real> static inline real real3_dot(real3_t<real> a, real3_t<real> b) {
+	return a.x * b.x + (a.y * b.y + a.z * b.z);
+}
+template<class real> static inline real3_t<real> real3_real_mul(real3_t<real> a, real b) {
+	return real3_t<real>{a.x * b, a.y * b, a.z * b};
+}
+template<class real> static inline real3_t<real> real3_add(real3_t<real> a, real3_t<real> b) {
+	return real3_t<real>{a.x + b.x, a.y + b.y, a.z + b.z};
+}
+template<class real> static inline real3_t<real> real3_sub(real3_t<real> a, real3_t<real> b) {
+	return real3_t<real>{a.x - b.x, a.y - b.y, a.z - b.z};
+}
+// hydro/coord/coord.lua:720-727 coordLenSq = v^a v_a, identity metric; symmath emits the sum
+// in an order we cannot see (parity unpinned at the last ulp): left-associated here.
+template<class real> static inline real coordLenSq(real3_t<real> v) {
+	return v.x * v.x + v.y * v.y + v.z * v.z;
+}
+
+// OpenCL max/min on reals (not fmax/fmin)
+template<class real> static inline real clmax(real a, real b) { return a < b ? b : a; }
+template<class real> static inline real clmin(real a, real b) { return b < a ? b : a; }
+
+// hydro/coord/coord.lua:2357-2410 cartesian normal_t = {int side}
+struct normal_t { int side; };
+// normal_l<j><x_i>(n) = (n.side == (i-j)%3), i,j in 1..3 (Lua modulo is non-negative)
+static inline double nl(normal_t n, int j, int i) { return n.side == (((i - j) % 3) + 3) % 3 ? 1. : 0.; }
+template<class real> static inline real3_t<real> normal_vecDotNs(normal_t n, real3_t<real> v) {
+	return real3_t<real>{v.s(n.side), v.s((n.side + 1) % 3), v.s((n.side + 2) % 3)};
+}
+template<class real> static inline real3_t<real> normal_vecFromNs(normal_t n, real3_t<real> v) {
+	return real3_t<real>{v.s((3 - n.side) % 3), v.s((3 - n.side + 1) % 3), v.s((3 - n.side + 2) % 3)};
+}
+
+// ---------------------------------------------------------------------------------------------
+// hydro/app.lua:614-635 limiter table, literal expressions
+template<class real> static real limiter(int id, real r) {
+	switch (id) {
+	case 0: return 0.;                                             // donor cell
+	case 1: return 1.;                                             // Lax-Wendroff
+	case 2: return r;                                              // Beam-Warming
+	case 3: return real(.5) * (real(1.) + r);                      // Fromm
+	case 4: return clmax<real>(0., r) * (real(3.) * r + real(1.)) / ((r + real(1.)) * (r + real(1.)));  // CHARM
+	case 5: return clmax<real>(0., real(1.5) * (r + std::fabs(r)) / (r + real(2.)));  // HCUS
+	case 6: return clmax<real>(0., real(2.) * (r + std::fabs(r)) / (r + real(3.)));   // HQUICK
+	case 7: return clmax<real>(0., clmin<real>(real(2.) * r, clmin<real>((real(1.) + real(2.) * r) / real(3.), 2.)));  // Koren
+	case 8: return clmax<real>(0., clmin<real>(r, 1.));            // minmod
+	case 9: return clmax<real>(0., clmin<real>(r, 1.5));           // Oshker
+	case 10: return real(.5) * (r * r + r) / (r * r + r + real(1.));  // ospre
+	case 11: return clmax<real>(0., clmin<real>(real(2.) * r, clmin<real>(real(.25) + real(.75) * r, 4.)));  // smart
+	case 12: return clmax<real>(0., clmax<real>(clmin<real>(real(1.5) * r, 1.), clmin<real>(r, 1.5)));  // Sweby
+	case 13: return clmax<real>(0., clmin<real>(clmin<real>(real(2.) * r, real(.75) + real(.25) * r), clmin<real>(real(.25) + real(.75) * r, 2.)));  // UMIST
+	case 14: return (r * r + r) / (r * r + real(1.));              // van Albada 1
+	case 15: return real(2.) * r / (r * r + real(1.));             // van Albada 2
+	case 16: return clmax<real>(0., r) * real(2.) / (real(1.) + r);  // van Leer
+	case 17: return clmax<real>(0., clmin<real>(2., clmin<real>(real(.5) * (real(1.) + r), real(2.) * r)));  // monotized central
+	case 18: return clmax<real>(0., clmax<real>(clmin<real>(1., real(2.) * r), clmin<real>(2., r)));  // superbee
+	case 19: return real(.5) * (r + real(1.)) * clmin<real>(1., clmin<real>(real(4.) * r / (r + real(1.)), real(4.) / (r + real(1.))));  // Barth-Jespersen
+	}
+	return 0.;
+}
+
+// solver_t: hydro/solver/solverbase.lua:538-549, gridsolver.lua:68-73 + eqn guiVars
+template<class real> struct solver_t {
+	real3_t<real> mins, maxs;
+	real3_t<real> grid_dx;
+	int gridSize[3];
+	int stepsize[3];
+	int numGhost;
+	int dim;
+	real heatCapacityRatio, rhoMin, PMin;
+	real mu0_eff;
+};
+
+// =============================================================================================
+// Euler: hydro/eqn/euler.lua + euler.cl
+template<class real_> struct Euler {
+	typedef real_ real;
+	typedef real3_t<real> real3;
+	typedef solver_t<real> S;
+	enum { numStates = 6, numIntStates = 5, numWaves = 5 };   // euler.lua:13-14,166-171
+	static const bool roeUseFluxFromCons = true;               // eqn.lua:46
+	union cons_t { struct { real rho; real3 m; real ETotal; real ePot; }; real ptr[6]; };
+	struct prim_t { real rho; real3 v; real P; real ePot; };
+	struct eigen_t { real rho; real3 v; real hTotal; real Cs; real vSq; real3 vL; };  // euler.lua:298-307
+	struct waves_t { real ptr[5]; };
+
+	// euler.cl:60-66
+	static real calc_EKin_fromCons(S const& s, cons_t const& U) {
+		return U.rho < s.rhoMin ? real(0.) : (real(.5) * coordLenSq(U.m) / U.rho);
+	}
+	// euler.cl:76-83
+	static real calc_P(S const& s, cons_t const& U) {
+		return U.rho < s.rhoMin ? real(0.) : ((s.heatCapacityRatio - real(1.)) * (U.ETotal - calc_EKin_fromCons(s, U)));
+	}
+	// euler.cl:87-94
+	static real calc_Cs(S const& s, prim_t const& W) {
+		if (W.P <= s.PMin) return 0.;
+		if (W.rho < s.rhoMin) return std::numeric_limits<real>::infinity();
+		return std::sqrt(s.heatCapacityRatio * W.P / W.rho);
+	}
+	// euler.cl:98-112
+	static real calc_Cs_fromCons(S const& s, cons_t const& U) {
+		real const P = calc_P(s, U);
+		if (P <= s.PMin) return 0.;
+		else if (U.rho < s.rhoMin) return std::numeric_limits<real>::infinity();
+		return std::sqrt(s.heatCapacityRatio * P / U.rho);
+	}
+	// euler.cl:140-159 (the vacuum guard is dead code: unconditional overwrite :155-157)
+	static void primFromCons(prim_t& W, S const& s, cons_t const& U) {
+		W.rho = U.rho;
+		W.v = real3_real_mul(U.m, real(1.) / U.rho);   // calc_v, euler.cl:132-134
+		W.P = calc_P(s, U);
+		W.ePot = U.ePot;
+	}
+	// euler.cl:163-173 ; calc_ETotal = calc_EKin + calc_EInt (:68-74, :36-58)
+	static void consFromPrim(cons_t& U, S const& s, prim_t const& W) {
+		U.rho = W.rho;
+		U.m = real3_real_mul(W.v, W.rho);
+		U.ETotal = (W.rho * (real(.5) * coordLenSq(W.v))) + (W.P / (s.heatCapacityRatio - real(1.)));
+		U.ePot = W.ePot;
+	}
+	static real calc_hTotal(real rho, real P, real ETotal) { return (P + ETotal) / rho; }   // euler.cl:17-30
+	// euler.cl:273-291
+	static void fluxFromCons(cons_t& F, S const& s, cons_t const& U, normal_t n) {
+		prim_t W; primFromCons(W, s, U);
+		real const v_n = W.v.s(n.side);
+		F.rho = U.rho * v_n;
+		real3 const nu1{real(nl(n, 1, 1)), real(nl(n, 1, 2)), real(nl(n, 1, 3))};
+		F.m = real3_add(real3_real_mul(U.m, v_n), real3_real_mul(nu1, W.P));
+		real const HTotal = U.ETotal + W.P;
+		F.ETotal = HTotal * v_n;
+		F.ePot = 0;
+	}
+	// euler.cl:347-430
+	static void eigen_forInterface(eigen_t& r, S const& s, cons_t const& UL, cons_t const& UR, normal_t) {
+		real const rhoEpsilon = 1e-5;
+		real3 const zero{0, 0, 0};
+		if (UL.rho < rhoEpsilon && UR.rho < rhoEpsilon) {
+			r.rho = 0.; r.v = zero; r.vSq = 0.; r.vL = zero; r.hTotal = 0; r.Cs = 0;
+		} else if (UL.rho < rhoEpsilon) {
+			prim_t WR; primFromCons(WR, s, UR);
+			r.rho = UR.rho; r.v = WR.v; r.vL = WR.v; r.vSq = real3_dot(WR.v, r.vL);
+			r.hTotal = calc_hTotal(WR.rho, WR.P, UR.ETotal); r.Cs = calc_Cs(s, WR);
+		} else if (UR.rho < rhoEpsilon) {
+			prim_t WL; primFromCons(WL, s, UL);
+			r.rho = UL.rho; r.v = WL.v; r.vL = WL.v; r.vSq = real3_dot(WL.v, r.vL);
+			r.hTotal = calc_hTotal(WL.rho, WL.P, UL.ETotal); r.Cs = calc_Cs(s, WL);
+		} else {
+			prim_t WL; primFromCons(WL, s, UL);
+			real const sqrtRhoL = std::sqrt(WL.rho);
+			real3 const vLeft = WL.v;
+			real const hTotalL = calc_hTotal(WL.rho, WL.P, UL.ETotal);
+			prim_t WR; primFromCons(WR, s, UR);
+			real const sqrtRhoR = std::sqrt(WR.rho);
+			real3 const vR = WR.v;
+			real const hTotalR = calc_hTotal(WR.rho, WR.P, UR.ETotal);
+			real const invDenom = real(1.) / (sqrtRhoL + sqrtRhoR);
+			r.rho = sqrtRhoL * sqrtRhoR;
+			real3 const v = real3_add(real3_real_mul(vLeft, sqrtRhoL * invDenom), real3_real_mul(vR, sqrtRhoR * invDenom));
+			real const hTotal = invDenom * (sqrtRhoL * hTotalL + sqrtRhoR * hTotalR);
+			real3 const vLower = v;
+			real const vSq = real3_dot(v, vLower);
+			real const eKin = real(.5) * vSq;
+			real const h = hTotal - eKin;
+			if (h < rhoEpsilon) {
+				r.hTotal = eKin; r.Cs = 0.;
+			} else {
+				r.hTotal = hTotal;
+				real const CsSq = h < rhoEpsilon ? real(0.) : (s.heatCapacityRatio - real(1.)) * h;
+				r.Cs = std::sqrt(CsSq);
+			}
+			r.v = v; r.vSq = vSq; r.vL = vLower;
+		}
+	}
+	// euler.cl:434-489 (normal_len = 1)
+	static void eigen_leftTransform(waves_t& r, S const& s, eigen_t const& e, cons_t const& X, normal_t n) {
+		if (e.rho < s.rhoMin) {
+			for (int j = 0; j < 5; ++j) r.ptr[j] = X.ptr[j];
+		} else {
+			real3 const v_n = normal_vecDotNs(n, e.v);
+			real const nLen = 1., inv_nLen = real(1.) / nLen;
+			real const denom = real(2.) * e.Cs * e.Cs;
+			real const invDenom = real(1.) / denom;
+			real const gamma_1 = s.heatCapacityRatio - real(1.);
+			real const l1x = nl(n,1,1), l1y = nl(n,1,2), l1z = nl(n,1,3);
+			real const l2x = nl(n,2,1), l2y = nl(n,2,2), l2z = nl(n,2,3);
+			real const l3x = nl(n,3,1), l3y = nl(n,3,2), l3z = nl(n,3,3);
+			r.ptr[0] = (
+					X.ptr[0] * (real(.5) * gamma_1 * e.vSq + e.Cs * v_n.x * inv_nLen)
+					+ X.ptr[1] * (-gamma_1 * e.vL.x - e.Cs * l1x)
+					+ X.ptr[2] * (-gamma_1 * e.vL.y - e.Cs * l1y)
+					+ X.ptr[3] * (-gamma_1 * e.vL.z - e.Cs * l1z)
+					+ X.ptr[4] * gamma_1
+				) * invDenom;
+			r.ptr[1] = (
+					X.ptr[0] * (denom - gamma_1 * e.vSq)
+					+ X.ptr[1] * real(2.) * gamma_1 * e.vL.x
+					+ X.ptr[2] * real(2.) * gamma_1 * e.vL.y
+					+ X.ptr[3] * real(2.) * gamma_1 * e.vL.z
+					+ X.ptr[4] * real(-2.) * gamma_1
+				) * invDenom;
+			r.ptr[2] = X.ptr[0] * -v_n.y + X.ptr[1] * l2x + X.ptr[2] * l2y + X.ptr[3] * l2z;
+			r.ptr[3] = X.ptr[0] * -v_n.z + X.ptr[1] * l3x + X.ptr[2] * l3y + X.ptr[3] * l3z;
+			r.ptr[4] = (
+					X.ptr[0] * (real(.5) * gamma_1 * e.vSq - e.Cs * v_n.x * inv_nLen)
+					+ X.ptr[1] * (-gamma_1 * e.vL.x + e.Cs * l1x)
+					+ X.ptr[2] * (-gamma_1 * e.vL.y + e.Cs * l1y)
+					+ X.ptr[3] * (-gamma_1 * e.vL.z + e.Cs * l1z)
+					+ X.ptr[4] * gamma_1
+				) * invDenom;
+		}
+	}
+	// euler.cl:493-542
+	static void eigen_rightTransform(cons_t& r, S const& s, eigen_t const& e, waves_t const& X, normal_t n) {
+		if (e.rho < s.rhoMin) {
+			for (int j = 0; j < 5; ++j) r.ptr[j] = X.ptr[j];
+		} else {
+			real3 const v_n = normal_vecDotNs(n, e.v);
+			real const nLen = 1., inv_nLen = real(1.) / nLen;
+			real const u1x = nl(n,1,1), u1y = nl(n,1,2), u1z = nl(n,1,3);
+			real const u2x = nl(n,2,1), u2y = nl(n,2,2), u2z = nl(n,2,3);
+			real const u3x = nl(n,3,1), u3y = nl(n,3,2), u3z = nl(n,3,3);
+			r.ptr[0] = X.ptr[0] + X.ptr[1] + X.ptr[4];
+			r.ptr[1] = X.ptr[0] * (e.v.x - e.Cs * u1x) + X.ptr[1] * e.v.x + X.ptr[2] * u2x + X.ptr[3] * u3x + X.ptr[4] * (e.v.x + e.Cs * u1x);
+			r.ptr[2] = X.ptr[0] * (e.v.y - e.Cs * u1y) + X.ptr[1] * e.v.y + X.ptr[2] * u2y + X.ptr[3] * u3y + X.ptr[4] * (e.v.y + e.Cs * u1y);
+			r.ptr[3] = X.ptr[0] * (e.v.z - e.Cs * u1z) + X.ptr[1] * e.v.z + X.ptr[2] * u2z + X.ptr[3] * u3z + X.ptr[4] * (e.v.z + e.Cs * u1z);
+			r.ptr[4] = X.ptr[0] * (e.hTotal - e.Cs * v_n.x * inv_nLen)
+				+ X.ptr[1] * real(.5) * e.vSq
+				+ X.ptr[2] * v_n.y
+				+ X.ptr[3] * v_n.z
+				+ X.ptr[4] * (e.hTotal + e.Cs * v_n.x * inv_nLen);
+		}
+		r.ptr[5] = 0;
+	}
+	// euler.lua:309-325 eigenWaveCodePrefix / eigenWaveCode
+	static void eigenWaves(real* lambda, S const&, eigen_t const& e, normal_t n) {
+		real const Cs_nLen = real(1.) * e.Cs;
+		real const v_n = e.v.s(n.side);
+		lambda[0] = v_n - Cs_nLen;
+		lambda[1] = v_n; lambda[2] = v_n; lambda[3] = v_n;
+		lambda[4] = v_n + Cs_nLen;
+	}
+	// euler.cl:698-717
+	static void constrainU(S const& s, cons_t& U) {
+		if (U.rho < s.rhoMin) U.rho = s.rhoMin;
+		prim_t W; primFromCons(W, s, U);
+		if (W.P < s.PMin) W.P = s.PMin;
+		consFromPrim(U, s, W);
+	}
+	// calcDT.cl:38-73 with euler.lua:346-373 (consWaveCodeMinMaxAllSides[Prefix])
+	static void calcDTCell(real& dt, S const& s, cons_t const& U) {
+		real const Cs = calc_Cs_fromCons(s, U);
+		for (int side = 0; side < s.dim; ++side) {
+			real const dx = s.grid_dx.s(side);
+			if (dx > 0) {
+				real const Cs_nLen = Cs * real(1.);
+				real const v_n = U.rho < s.rhoMin ? real(0.) : U.m.s(side) / U.rho;
+				real const lambdaMin = v_n - Cs_nLen, lambdaMax = v_n + Cs_nLen;
+				real absLambdaMax = clmax<real>(std::fabs(lambdaMin), std::fabs(lambdaMax));
+				absLambdaMax = clmax<real>(real(1e-9), absLambdaMax);
+				dt = clmin<real>(dt, dx / absLambdaMax);
+			}
+		}
+	}
+	// gridsolver.lua:662-671,741 + eqn.lua:366-370: mirror negates m.side
+	static void mirrorReflect(cons_t& U, int side) { U.m.s(side) = real(-1.) * U.m.s(side); }
+};
+
+// =============================================================================================
+// ideal MHD (Stone et al 2008 / Athena eigensystem): hydro/eqn/mhd.lua + mhd.cl
+template<class real_> struct MHD {
+	typedef real_ real;
+	typedef real3_t<real> real3;
+	typedef solver_t<real> S;
+	enum { numStates = 10, numIntStates = 8, numWaves = 7 };   // mhd.lua:16-17,76-83
+	static const bool roeUseFluxFromCons = true;                // mhd.lua:19
+	union cons_t { struct { real rho; real3 m; real ETotal; real3 B; real psi; real ePot; }; real ptr[10]; };
+	struct prim_t { real rho; real3 v; real P; real3 B; real psi; real ePot; };
+	struct roe_t { real rho; real3 v; real hTotal; real3 B; real X, Y; };   // mhd.lua:27-34
+	struct eigen_t {   // mhd.lua:37-62
+		real rho; real3 v; real hTotal; real3 B; real X, Y;
+		real hHydro, aTildeSq, Cs, CAx, Cf, BStarPerpLen, betaY, betaZ, betaStarY, betaStarZ, betaStarSq;
+		real alphaF, alphaS, sqrtRho, sbx, Qf, Qs, Af, As;
+	};
+	struct waves_t { real ptr[7]; };
+
+	// mhd.cl:160-179
+	static void primFromCons(prim_t& W, S const& s, cons_t const& U) {
+		W.rho = U.rho;
+		W.v = real3_real_mul(U.m, real(1.) / U.rho);
+		W.B = U.B;
+		real const vSq = coordLenSq(W.v);
+		real const BSq = coordLenSq(W.B);
+		real const EKin = real(.5) * U.rho * vSq;
+		real const EMag = real(.5) * BSq / s.mu0_eff;
+		real const EInt = U.ETotal - EKin - EMag;
+		W.P = EInt * (s.heatCapacityRatio - real(1.));
+		W.P = clmax<real>(W.P, real(1e-7));
+		W.rho = clmax<real>(W.rho, real(1e-7));
+		W.psi = U.psi;
+		W.ePot = U.ePot;
+	}
+	// mhd.cl:184-201
+	static void consFromPrim(cons_t& U, S const& s, prim_t const& W) {
+		U.rho = W.rho;
+		U.m = real3_real_mul(W.v, W.rho);
+		U.B = W.B;
+		real const vSq = coordLenSq(W.v);
+		real const BSq = coordLenSq(W.B);
+		real const EKin = real(.5) * W.rho * vSq;
+		real const EMag = real(.5) * BSq / s.mu0_eff;
+		real const EInt = W.P / (s.heatCapacityRatio - real(1.));
+		U.ETotal = EInt + EKin + EMag;
+		U.psi = W.psi;
+		U.ePot = W.ePot;
+	}
+	// mhd.cl:296-340 (note: PMag omits mu0; swapped sqrt(rho) weights on B.y,B.z :335-336)
+	static void calcRoeValues(roe_t& r, S const& s, cons_t const& UL, cons_t const& UR, normal_t n) {
+		prim_t WL; primFromCons(WL, s, UL);
+		real const sqrtRhoL = std::sqrt(UL.rho);
+		real const PMagL = real(.5) * coordLenSq(UL.B);
+		real const hTotalL = (UL.ETotal + WL.P + PMagL) / UL.rho;
+		real3 const vL = normal_vecDotNs(n, WL.v);
+		real3 const BL = normal_vecDotNs(n, WL.B);
+		prim_t WR; primFromCons(WR, s, UR);
+		real const sqrtRhoR = std::sqrt(UR.rho);
+		real const PMagR = real(.5) * coordLenSq(UR.B);
+		real const hTotalR = (UR.ETotal + WR.P + PMagR) / UR.rho;
+		real3 const vR = normal_vecDotNs(n, WR.v);
+		real3 const BR = normal_vecDotNs(n, WR.B);
+		real const dby = BL.y - BR.y;
+		real const dbz = BL.z - BR.z;
+		real const invDenom = real(1) / (sqrtRhoL + sqrtRhoR);
+		r.rho = sqrtRhoL * sqrtRhoR;
+		r.v = real3_real_mul(real3_add(real3_real_mul(vL, sqrtRhoL), real3_real_mul(vR, sqrtRhoR)), invDenom);
+		r.hTotal = (sqrtRhoL * hTotalL + sqrtRhoR * hTotalR) * invDenom;
+		r.B.x = (sqrtRhoL * BL.x + sqrtRhoR * BR.x) * invDenom;
+		r.B.y = (sqrtRhoR * BL.y + sqrtRhoL * BR.y) * invDenom;
+		r.B.z = (sqrtRhoR * BL.z + sqrtRhoL * BR.z) * invDenom;
+		r.X = real(.5) * (dby * dby + dbz * dbz) * invDenom * invDenom;
+		r.Y = real(.5) * (UL.rho + UR.rho) / r.rho;
+	}
+	// mhd.cl:346-436
+	static void eigen_forRoeAvgs(eigen_t& e, S const& s, roe_t const& roe) {
+		real const gamma = s.heatCapacityRatio;
+		real const gamma_1 = gamma - real(1.);
+		real const gamma_2 = gamma - real(2.);
+		real const rho = roe.rho;
+		real3 const v = roe.v;
+		real const hTotal = roe.hTotal;
+		real3 const B = roe.B;
+		real const X = roe.X, Y = roe.Y;
+		real const _1_rho = real(1.) / rho;
+		real const vSq = coordLenSq(v);
+		real const BPerpSq = B.y * B.y + B.z * B.z;
+		real const BStarPerpSq = (gamma_1 - gamma_2 * Y) * BPerpSq;
+		real const CAxSq = B.x * B.x * _1_rho;
+		real const CASq = CAxSq + BPerpSq * _1_rho;
+		e.hHydro = hTotal - CASq;
+		e.aTildeSq = clmax<real>((gamma_1 * (e.hHydro - real(.5) * vSq) - gamma_2 * X), real(1e-20));
+		real const BStarPerpSq_rho = BStarPerpSq * _1_rho;
+		real const CATildeSq = CAxSq + BStarPerpSq_rho;
+		real const CStarSq = real(.5) * (CATildeSq + e.aTildeSq);
+		real const CA_a_TildeSqDiff = real(.5) * (CATildeSq - e.aTildeSq);
+		real const sqrtDiscr = std::sqrt(CA_a_TildeSqDiff * CA_a_TildeSqDiff + e.aTildeSq * BStarPerpSq_rho);
+		e.CAx = std::sqrt(CAxSq);
+		real const CfSq = CStarSq + sqrtDiscr;
+		e.Cf = std::sqrt(CfSq);
+		real const CsSq = e.aTildeSq * CAxSq / CfSq;
+		e.Cs = std::sqrt(CsSq);
+		real const BPerpLen = std::sqrt(BPerpSq);
+		e.BStarPerpLen = std::sqrt(BStarPerpSq);
+		if (BPerpLen == 0) { e.betaY = 1; e.betaZ = 0; }
+		else { e.betaY = B.y / BPerpLen; e.betaZ = B.z / BPerpLen; }
+		e.betaStarY = e.betaY / std::sqrt(gamma_1 - gamma_2 * Y);
+		e.betaStarZ = e.betaZ / std::sqrt(gamma_1 - gamma_2 * Y);
+		e.betaStarSq = e.betaStarY * e.betaStarY + e.betaStarZ * e.betaStarZ;
+		if (CfSq - CsSq == 0) { e.alphaF = 1; e.alphaS = 0; }
+		else if (e.aTildeSq - CsSq <= 0) { e.alphaF = 0; e.alphaS = 1; }
+		else if (CfSq - e.aTildeSq <= 0) { e.alphaF = 1; e.alphaS = 0; }
+		else {
+			e.alphaF = std::sqrt((e.aTildeSq - CsSq) / (CfSq - CsSq));
+			e.alphaS = std::sqrt((CfSq - e.aTildeSq) / (CfSq - CsSq));
+		}
+		e.sqrtRho = std::sqrt(rho);
+		real const _1_sqrtRho = real(1.) / e.sqrtRho;
+		e.sbx = B.x >= 0 ? real(1) : real(-1);
+		real const aTilde = std::sqrt(e.aTildeSq);
+		e.Qf = e.Cf * e.alphaF * e.sbx;
+		e.Qs = e.Cs * e.alphaS * e.sbx;
+		e.Af = aTilde * e.alphaF * _1_sqrtRho;
+		e.As = aTilde * e.alphaS * _1_sqrtRho;
+		e.rho = roe.rho; e.v = roe.v; e.hTotal = roe.hTotal; e.B = roe.B; e.X = roe.X; e.Y = roe.Y;
+	}
+	// mhd.cl:558-571
+	static void eigen_forInterface(eigen_t& e, S const& s, cons_t const& UL, cons_t const& UR, normal_t n) {
+		roe_t roe; calcRoeValues(roe, s, UL, UR, n);
+		eigen_forRoeAvgs(e, s, roe);
+	}
+	// mhd.cl:441-467
+	static void fluxFromCons(cons_t& F, S const& s, cons_t const& U, normal_t n) {
+		prim_t W; primFromCons(W, s, U);
+		real vj = W.v.s(n.side);
+		real Bj = W.B.s(n.side);
+		real BSq = coordLenSq(W.B);
+		real BDotV = real3_dot(W.B, W.v);
+		real PMag = real(.5) * BSq / s.mu0_eff;
+		real PTotal = W.P + PMag;
+		real HTotal = U.ETotal + PTotal;
+		F.rho = U.m.s(n.side);
+		F.m = real3_sub(real3_real_mul(U.m, vj), real3_real_mul(U.B, Bj / s.mu0_eff));
+		F.m.x += PTotal * real(nl(n, 1, 1));
+		F.m.y += PTotal * real(nl(n, 1, 2));
+		F.m.z += PTotal * real(nl(n, 1, 3));
+		F.B = real3_sub(real3_real_mul(U.B, vj), real3_real_mul(W.v, Bj));
+		F.ETotal = HTotal * vj - BDotV * Bj / s.mu0_eff;
+		F.psi = 0;
+		F.ePot = 0;
+	}
+	// mhd.cl:575-679
+	static void eigen_leftTransform(waves_t& r, S const& s, eigen_t const& e, cons_t const& U, normal_t n) {
+		real3 const Um = normal_vecDotNs(n, U.m);
+		real3 const UB = normal_vecDotNs(n, U.B);
+		real const gamma = s.heatCapacityRatio;
+		real const gamma_1 = gamma - real(1.);
+		real const gamma_2 = gamma - real(2.);
+		real const rho = e.rho; real3 const v = e.v; real3 const B = e.B; real const X = e.X;
+		real const Cs = e.Cs, Cf = e.Cf, BStarPerpLen = e.BStarPerpLen;
+		real const betaY = e.betaY, betaZ = e.betaZ, betaStarY = e.betaStarY, betaStarZ = e.betaStarZ, betaStarSq = e.betaStarSq;
+		real const alphaF = e.alphaF, alphaS = e.alphaS, sqrtRho = e.sqrtRho, sbx = e.sbx;
+		real const Qf = e.Qf, Qs = e.Qs, Af = e.Af, As = e.As;
+		real const vSq = coordLenSq(v);
+		real const norm = real(.5) / e.aTildeSq;
+		real const Cff = norm * alphaF * Cf;
+		real const Css = norm * alphaS * Cs;
+		real const Qf2 = Qf * norm;
+		real const Qs2 = Qs * norm;
+		real const AHatF = norm * Af * rho;
+		real const AHatS = norm * As * rho;
+		real const afpb = norm * Af * BStarPerpLen;
+		real const aspb = norm * As * BStarPerpLen;
+		real const norm2 = norm * gamma_1;
+		real const alphaF2 = alphaF * norm2;
+		real const alphaS2 = alphaS * norm2;
+		real const QStarY = betaStarY / betaStarSq;
+		real const QStarZ = betaStarZ / betaStarSq;
+		real const vqstr = (v.y * QStarY + v.z * QStarZ);
+		real norm3 = norm2 * real(2.);
+		real const l16 = AHatS * QStarY - alphaF2 * B.y;
+		real const l17 = AHatS * QStarZ - alphaF2 * B.z;
+		real const l21 = real(.5) * (v.y * betaZ - v.z * betaY);
+		real const l23 = real(.5) * betaZ;
+		real const l24 = real(.5) * betaY;
+		real const l26 = real(-.5) * sqrtRho * betaZ * sbx;
+		real const l27 = real(.5) * sqrtRho * betaY * sbx;
+		real const l36 = -AHatF * QStarY - alphaS2 * B.y;
+		real const l37 = -AHatF * QStarZ - alphaS2 * B.z;
+		r.ptr[0] =
+			  U.rho * (alphaF2 * (vSq - e.hHydro) + Cff * (Cf + v.x) - Qs2 * vqstr - aspb)
+			+ Um.x * (-alphaF2 * v.x - Cff)
+			+ Um.y * (-alphaF2 * v.y + Qs2 * QStarY)
+			+ Um.z * (-alphaF2 * v.z + Qs2 * QStarZ)
+			+ U.ETotal * alphaF2
+			+ UB.y * l16
+			+ UB.z * l17;
+		r.ptr[1] =
+			  U.rho * l21
+			+ Um.y * l23
+			+ Um.z * l24
+			+ UB.y * l26
+			+ UB.z * l27;
+		r.ptr[2] =
+			  U.rho * (alphaS2 * (vSq - e.hHydro) + Css * (Cs + v.x) + Qf2 * vqstr + afpb)
+			+ Um.x * (-alphaS2 * v.x - Css)
+			+ Um.y * (-alphaS2 * v.y - Qf2 * QStarY)
+			+ Um.z * (-alphaS2 * v.z - Qf2 * QStarZ)
+			+ U.ETotal * alphaS2
+			+ UB.y * l36
+			+ UB.z * l37;
+		r.ptr[3] =
+			  U.rho * (real(1.) - norm3 * (real(.5) * vSq - gamma_2 * X / gamma_1))
+			+ Um.x * norm3 * v.x
+			+ Um.y * norm3 * v.y
+			+ Um.z * norm3 * v.z
+			+ U.ETotal * -norm3
+			+ UB.y * norm3 * B.y
+			+ UB.z * norm3 * B.z;
+		r.ptr[4] =
+			  U.rho * (alphaS2 * (vSq - e.hHydro) + Css * (Cs - v.x) - Qf2 * vqstr + afpb)
+			+ Um.x * (-alphaS2 * v.x + Css)
+			+ Um.y * (-alphaS2 * v.y + Qf2 * QStarY)
+			+ Um.z * (-alphaS2 * v.z + Qf2 * QStarZ)
+			+ U.ETotal * alphaS2
+			+ UB.y * l36
+			+ UB.z * l37;
+		r.ptr[5] =
+			  U.rho * -l21
+			+ Um.y * -l23
+			+ Um.z * -l24
+			+ UB.y * l26
+			+ UB.z * l27;
+		r.ptr[6] =
+			  U.rho * (alphaF2 * (vSq - e.hHydro) + Cff * (Cf - v.x) + Qs2 * vqstr - aspb)
+			+ Um.x * (-alphaF2 * v.x + Cff)
+			+ Um.y * (-alphaF2 * v.y - Qs2 * QStarY)
+			+ Um.z * (-alphaF2 * v.z - Qs2 * QStarZ)
+			+ U.ETotal * alphaF2
+			+ UB.y * l16
+			+ UB.z * l17;
+	}
+	// mhd.cl:683-783
+	static void eigen_rightTransform(cons_t& r, S const& s, eigen_t const& e, waves_t const& in, normal_t n) {
+		real const gamma = s.heatCapacityRatio;
+		real const gamma_1 = gamma - real(1.);
+		real const gamma_2 = gamma - real(2.);
+		real3 const v = e.v; real const X = e.X;
+		real const Cs = e.Cs, Cf = e.Cf, BStarPerpLen = e.BStarPerpLen;
+		real const betaY = e.betaY, betaZ = e.betaZ, betaStarY = e.betaStarY, betaStarZ = e.betaStarZ, betaStarSq = e.betaStarSq;
+		real const alphaF = e.alphaF, alphaS = e.alphaS, sbx = e.sbx;
+		real const Qf = e.Qf, Qs = e.Qs, Af = e.Af, As = e.As;
+		real const vSq = coordLenSq(v);
+		real const vDotBeta = v.y * betaStarY + v.z * betaStarZ;
+		real const _1_sqrtRho = real(1.) / e.sqrtRho;
+		real const Afpbb = Af * BStarPerpLen * betaStarSq;
+		real const Aspbb = As * BStarPerpLen * betaStarSq;
+		real const lambdaFastMin = e.v.x - e.Cf;
+		real const lambdaSlowMin = e.v.x - e.Cs;
+		real const lambdaSlowMax = e.v.x + e.Cs;
+		real const lambdaFastMax = e.v.x + e.Cf;
+		real const qa3 = alphaF * v.y;
+		real const qb3 = alphaS * v.y;
+		real const qc3 = Qs * betaStarY;
+		real const qd3 = Qf * betaStarY;
+		real const qa4 = alphaF * v.z;
+		real const qb4 = alphaS * v.z;
+		real const qc4 = Qs * betaStarZ;
+		real const qd4 = Qf * betaStarZ;
+		real const r52 = -(v.y * betaZ - v.z * betaY);
+		real const r61 = As * betaStarY;
+		real const r62 = -betaZ * sbx * _1_sqrtRho;
+		real const r63 = -Af * betaStarY;
+		real const r71 = As * betaStarZ;
+		real const r72 = betaY * sbx * _1_sqrtRho;
+		real const r73 = -Af * betaStarZ;
+		r.rho =
+			  in.ptr[0] * alphaF
+			+ in.ptr[2] * alphaS
+			+ in.ptr[3]
+			+ in.ptr[4] * alphaS
+			+ in.ptr[6] * alphaF;
+		real3 resultm;
+		resultm.x =
+			  in.ptr[0] * alphaF * lambdaFastMin
+			+ in.ptr[2] * alphaS * lambdaSlowMin
+			+ in.ptr[3] * v.x
+			+ in.ptr[4] * alphaS * lambdaSlowMax
+			+ in.ptr[6] * alphaF * lambdaFastMax;
+		resultm.y =
+			  in.ptr[0] * (qa3 + qc3)
+			+ in.ptr[1] * -betaZ
+			+ in.ptr[2] * (qb3 - qd3)
+			+ in.ptr[3] * v.y
+			+ in.ptr[4] * (qb3 + qd3)
+			+ in.ptr[5] * betaZ
+			+ in.ptr[6] * (qa3 - qc3);
+		resultm.z =
+			  in.ptr[0] * (qa4 + qc4)
+			+ in.ptr[1] * betaY
+			+ in.ptr[2] * (qb4 - qd4)
+			+ in.ptr[3] * v.z
+			+ in.ptr[4] * (qb4 + qd4)
+			+ in.ptr[5] * -betaY
+			+ in.ptr[6] * (qa4 - qc4);
+		r.m = normal_vecFromNs(n, resultm);
+		r.ETotal =
+			  in.ptr[0] * (alphaF * (e.hHydro - v.x * Cf) + Qs * vDotBeta + Aspbb)
+			+ in.ptr[1] * r52
+			+ in.ptr[2] * (alphaS * (e.hHydro - v.x * Cs) - Qf * vDotBeta - Afpbb)
+			+ in.ptr[3] * (real(.5) * vSq + gamma_2 * X / gamma_1)
+			+ in.ptr[4] * (alphaS * (e.hHydro + v.x * Cs) + Qf * vDotBeta - Afpbb)
+			+ in.ptr[5] * -r52
+			+ in.ptr[6] * (alphaF * (e.hHydro + v.x * Cf) - Qs * vDotBeta + Aspbb);
+		real3 resultB;
+		resultB.x = 0;
+		resultB.y =
+			  in.ptr[0] * r61
+			+ in.ptr[1] * r62
+			+ in.ptr[2] * r63
+			+ in.ptr[4] * r63
+			+ in.ptr[5] * r62
+			+ in.ptr[6] * r61;
+		resultB.z =
+			  in.ptr[0] * r71
+			+ in.ptr[1] * r72
+			+ in.ptr[2] * r73
+			+ in.ptr[4] * r73
+			+ in.ptr[5] * r72
+			+ in.ptr[6] * r71;
+		r.B = normal_vecFromNs(n, resultB);
+		r.psi = 0;
+		// ePot is left untouched by the reference (fluxBuf is zero-initialised; only nI entries are consumed)
+		r.ePot = 0;
+	}
+	// mhd.lua:361-373
+	static void eigenWaves(real* lambda, S const&, eigen_t const& e, normal_t) {
+		lambda[0] = e.v.x - e.Cf;
+		lambda[1] = e.v.x - e.CAx;
+		lambda[2] = e.v.x - e.Cs;
+		lambda[3] = e.v.x;
+		lambda[4] = e.v.x + e.Cs;
+		lambda[5] = e.v.x + e.CAx;
+		lambda[6] = e.v.x + e.Cf;
+	}
+	// mhd.cl:915-931
+	static void constrainU(S const& s, cons_t& U) {
+		prim_t W; primFromCons(W, s, U);
+		W.rho = clmax<real>(W.rho, real(1e-7));
+		W.P = clmax<real>(W.P, real(1e-7));
+		consFromPrim(U, s, W);
+	}
+	// mhd.cl:473-554 (the live #else branch, bugs included: BStarPerpSq, aTildeSq, hTotal)
+	static void calcCellMinMaxEigenvalues(real& lmin, real& lmax, S const& s, cons_t const& U, normal_t n) {
+		prim_t W; primFromCons(W, s, U);
+		real const v_n = W.v.s(n.side);
+		real3 const B_n = normal_vecDotNs(n, W.B);
+		real const gamma = s.heatCapacityRatio;
+		real const gamma_1 = gamma - real(1.);
+		real const gamma_2 = gamma - real(2.);
+		real const vSq = coordLenSq(W.v);
+		real const BSq = coordLenSq(W.B);
+		real const hTotal = real(.5) * vSq + (W.P * gamma / gamma_1 + BSq) / W.rho;
+		real const _1_rho = real(1.) / W.rho;
+		real const BPerpSq = B_n.y * B_n.y + B_n.z * B_n.z;
+		real const BStarPerpSq = (gamma_1 - gamma_2) * BPerpSq;
+		real const CAxSq = B_n.x * B_n.x * _1_rho;
+		real const CASq = CAxSq + BPerpSq * _1_rho;
+		real const hHydro = hTotal - CASq;
+		real const aTildeSq = clmax<real>((gamma_1 * (hHydro - real(.5) * vSq) - gamma_2), real(1e-20));
+		real const BStarPerpSq_rho = BStarPerpSq * _1_rho;
+		real const CATildeSq = CAxSq + BStarPerpSq_rho;
+		real const CStarSq = real(.5) * (CATildeSq + aTildeSq);
+		real const CA_a_TildeSqDiff = real(.5) * (CATildeSq - aTildeSq);
+		real const sqrtDiscr = std::sqrt(CA_a_TildeSqDiff * CA_a_TildeSqDiff + aTildeSq * BStarPerpSq_rho);
+		real const CfSq = CStarSq + sqrtDiscr;
+		real const Cf = std::sqrt(CfSq);
+		lmin = v_n - Cf;
+		lmax = v_n + Cf;
+	}
+	// calcDT.cl:38-73 with mhd.lua:377-387
+	static void calcDTCell(real& dt, S const& s, cons_t const& U) {
+		for (int side = 0; side < s.dim; ++side) {
+			real const dx = s.grid_dx.s(side);
+			if (dx > 0) {
+				normal_t n{side};
+				real lambdaMin, lambdaMax;
+				calcCellMinMaxEigenvalues(lambdaMin, lambdaMax, s, U, n);
+				real absLambdaMax = clmax<real>(std::fabs(lambdaMin), std::fabs(lambdaMax));
+				absLambdaMax = clmax<real>(real(1e-9), absLambdaMax);
+				dt = clmin<real>(dt, dx / absLambdaMax);
+			}
+		}
+	}
+	static void mirrorReflect(cons_t& U, int side) {
+		U.m.s(side) = real(-1.) * U.m.s(side);
+		U.B.s(side) = real(-1.) * U.B.s(side);
+	}
+};
+
+// =============================================================================================
+struct SolverBase {
+	virtual ~SolverBase() {}
+	virtual void setState(const double* aos) = 0;
+	virtual void getState(double* aos) const = 0;
+	virtual void boundary() = 0;
+	virtual void constrainU() = 0;
+	virtual double calcDT() = 0;
+	virtual void update() = 0;
+	virtual void step(double dt) = 0;
+	virtual void calcDerivOut(double* aos, double dt) = 0;
+	virtual void roeFluxTest(const double* UL, const double* UR, int side, double* flux, double* lambdas, double* Lmat, double* Rmat) = 0;
+	virtual int numStates() const = 0;
+	virtual long numCells() const = 0;
+	double t = 0, dt = 0;
+};
+
+template<class Eqn> struct Solver : SolverBase {
+	typedef typename Eqn::real real;
+	typedef typename Eqn::cons_t cons_t;
+	typedef typename Eqn::eigen_t eigen_t;
+	typedef typename Eqn::waves_t waves_t;
+	enum { nS = Eqn::numStates, nI = Eqn::numIntStates, nW = Eqn::numWaves };
+	struct consLR_t { cons_t L, R; };   // gridsolver.lua:336-347
+
+	ho_desc d;
+	solver_t<real> solver;
+	int dim, g;
+	int S[3];
+	long ncells;
+	std::vector<cons_t> UBuf, fluxBuf;
+	std::vector<consLR_t> ULRBuf;
+	std::vector<cons_t> derivBufs[4];
+	std::vector<cons_t> UBufs[4];
+	std::vector<cons_t> feDeriv;
+	std::vector<real> reduceBuf;
+	bool useFluxLimiter;
+
+	Solver(ho_desc const& desc) : d(desc) {
+		dim = d.dim; g = 2;   // gridsolver.lua:41 numGhost = 2
+		for (int k = 0; k < 3; ++k) S[k] = k < dim ? d.n[k] + 2 * g : 1;   // gridsolver.lua:94-95
+		ncells = (long)S[0] * S[1] * S[2];
+		for (int k = 0; k < 3; ++k) {
+			solver.mins.s(k) = d.mins[k]; solver.maxs.s(k) = d.maxs[k];
+			// gridsolver.lua:406-409: dx for all three axes, computed in host double then cast
+			double dx = (d.maxs[k] - d.mins[k]) / double(k < dim ? d.n[k] : 1);
+			solver.grid_dx.s(k) = real(dx);
+			solver.gridSize[k] = S[k];
+		}
+		solver.stepsize[0] = 1; solver.stepsize[1] = S[0]; solver.stepsize[2] = S[0] * S[1];   // gridsolver.lua:377-380
+		solver.numGhost = g; solver.dim = dim;
+		solver.heatCapacityRatio = d.gamma; solver.rhoMin = d.rhoMin; solver.PMin = d.PMin; solver.mu0_eff = d.mu0_eff;
+		// fvsolver.lua:61-63 useFluxLimiter = fluxLimiter > 1 (1-based) and flux.usesFluxLimiter
+		useFluxLimiter = d.flux_limiter > 0;
+		cons_t zero; std::memset(&zero, 0, sizeof(zero));
+		UBuf.assign(ncells, zero);
+		fluxBuf.assign(ncells * dim, zero);
+		if (d.use_plm) ULRBuf.assign(ncells * dim, consLR_t{zero, zero});
+		reduceBuf.assign(ncells, 0);
+		if (d.rk_order == 0) feDeriv.assign(ncells, zero);
+		else {
+			// int/rk.lua:17-44: allocate only the snapshots / derivs some later stage needs
+			int order = d.rk_order;
+			for (int i = 0; i < order; ++i) {
+				bool needed = false;
+				for (int m = i; m < order; ++m) needed = needed || d.alphas[m * order + i] != 0;
+				if (needed) UBufs[i].assign(ncells, zero);
+				needed = false;
+				for (int m = i; m < order; ++m) needed = needed || d.betas[m * order + i] != 0;
+				if (needed) derivBufs[i].assign(ncells, zero);
+			}
+		}
+#ifdef _OPENMP
+		if (d.nthreads > 0) omp_set_num_threads(d.nthreads);
+#endif
+	}
+	int numStates() const override { return nS; }
+	long numCells() const override { return ncells; }
+	inline long INDEX(int i, int j, int k) const { return i + (long)S[0] * (j + (long)S[1] * k); }   // app.lua:976-984
+	// gridsolver.lua:280-283 OOB(lhs,rhs) over the used dims
+	inline bool OOB(int i, int j, int k, int l, int r) const {
+		if (i < l || i >= S[0] - r) return true;
+		if (dim >= 2 && (j < l || j >= S[1] - r)) return true;
+		if (dim >= 3 && (k < l || k >= S[2] - r)) return true;
+		return false;
+	}
+	void setState(const double* aos) override {
+		for (long c = 0; c < ncells; ++c) for (int j = 0; j < nS; ++j) UBuf[c].ptr[j] = real(aos[c * nS + j]);
+	}
+	void getState(double* aos) const override {
+		for (long c = 0; c < ncells; ++c) for (int j = 0; j < nS; ++j) aos[c * nS + j] = double(UBuf[c].ptr[j]);
+	}
+
+	// ---- boundary: gridsolver.lua:1070-1213 (kernel generator), :638-780 (methods), :1272-1320 (x, then y, then z)
+	void boundaryOnBuf(std::vector<cons_t>& buf) {
+		for (int side = 0; side < dim; ++side) {
+			int o1 = (side + 1) % 3, o2 = (side + 2) % 3;
+			if (side == 1) { o1 = 0; o2 = 2; }
+			if (side == 2) { o1 = 0; o2 = 1; }
+			int const Sd = S[side];
+			int const N = Sd - 2 * g;
+			#pragma omp parallel for collapse(2)
+			for (int b = 0; b < S[o2]; ++b) for (int a = 0; a < S[o1]; ++a) {
+				auto idx = [&](int jj) -> long {
+					int v[3]; v[side] = jj; v[o1] = a; v[o2] = b;
+					return INDEX(v[0], v[1], v[2]);
+				};
+				for (int j = 0; j < g; ++j) {
+					for (int mm = 0; mm < 2; ++mm) {   // min then max
+						int method = d.bc[2 * side + mm];
+						long dst, src;
+						switch (method) {
+						case 0:   // periodic :638-651
+							if (mm == 0) { dst = idx(j); src = idx(g + (j - g + 2 * N) % N); }
+							else { dst = idx(Sd - 1 - j); src = idx(g + (g - 1 - j) % N); }
+							buf[dst] = buf[src];
+							break;
+						case 1:   // mirror :654-744
+							if (mm == 0) { dst = idx(j); src = idx(2 * g - 1 - j); }
+							else { dst = idx(Sd - g + j); src = idx(Sd - g - 1 - j); }
+							buf[dst] = buf[src];
+							Eqn::mirrorReflect(buf[dst], side);
+							break;
+						case 2:   // freeflow :766-780
+							if (mm == 0) { dst = idx(j); src = idx(g); }
+							else { dst = idx(Sd - g + j); src = idx(Sd - g - 1); }
+							buf[dst] = buf[src];
+							break;
+						default: break;   // 'none' :618-621
+						}
+					}
+				}
+			}
+		}
+	}
+	void boundary() override { boundaryOnBuf(UBuf); }
+
+	// ---- constrainU: solverbase.lua:2116-2127 = kernel on all cells (SETBOUNDS(0,0)) then boundary()
+	void constrainU() override {
+		#pragma omp parallel for
+		for (long c = 0; c < ncells; ++c) Eqn::constrainU(solver, UBuf[c]);
+		boundary();
+	}
+
+	// ---- calcLR: plm.cl:976-997 kernel, 'plm cons' :32-91
+	void calcLR() {
+		int const sl = d.slope_limiter;
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, 1, 1)) continue;
+			long index = INDEX(i, j, k);
+			cons_t const& U = UBuf[index];
+			for (int side = 0; side < dim; ++side) {
+				consLR_t& result = ULRBuf[side + dim * index];
+				cons_t const& UL = UBuf[index - solver.stepsize[side]];
+				cons_t const& UR = UBuf[index + solver.stepsize[side]];
+				result.L = U; result.R = U;
+				for (int q = 0; q < nI; ++q) {
+					real const dUR = UR.ptr[q] - U.ptr[q];
+					real const dUL = U.ptr[q] - UL.ptr[q];
+					real sigma;
+					real const dUC = real(.5) * (dUR - dUL);
+					if (dUC >= 0) {
+						real const r = dUR == 0 ? real(0) : (dUL / dUR);
+						real const phi = limiter<real>(sl, r);
+						sigma = phi * dUR;
+					} else {
+						real const r = dUL == 0 ? real(0) : (dUR / dUL);
+						real const phi = limiter<real>(sl, r);
+						sigma = phi * dUL;
+					}
+					result.R.ptr[q] += real(.5) * sigma;
+					result.L.ptr[q] -= real(.5) * sigma;
+				}
+			}
+		}
+	}
+
+	// ---- calcFluxForInterface, Roe: hydro/flux/roe.cl:17-163
+	void roeFlux(cons_t& resultFlux, cons_t const& UL, cons_t const& UR, normal_t n,
+		real dt_dx, cons_t const* UL_L, cons_t const* UR_L, cons_t const* UL_R, cons_t const* UR_R) const
+	{
+		eigen_t eig;
+		Eqn::eigen_forInterface(eig, solver, UL, UR, n);
+		real lambdas[nW];
+		Eqn::eigenWaves(lambdas, solver, eig, n);
+		waves_t fluxEig;
+		if (!Eqn::roeUseFluxFromCons) {
+			cons_t UAvg; std::memset(&UAvg, 0, sizeof(UAvg));
+			for (int j = 0; j < nI; ++j) UAvg.ptr[j] = real(.5) * (UL.ptr[j] + UR.ptr[j]);
+			Eqn::eigen_leftTransform(fluxEig, solver, eig, UAvg, n);
+		}
+		cons_t deltaU, deltaUL, deltaUR;
+		for (int j = 0; j < nS; ++j) {
+			deltaU.ptr[j] = UR.ptr[j] - UL.ptr[j];
+			if (useFluxLimiter) {
+				deltaUL.ptr[j] = UR_L->ptr[j] - UL_L->ptr[j];
+				deltaUR.ptr[j] = UR_R->ptr[j] - UL_R->ptr[j];
+			}
+		}
+		waves_t deltaUEig;
+		Eqn::eigen_leftTransform(deltaUEig, solver, eig, deltaU, n);
+		waves_t deltaUEigL, deltaUEigR;
+		if (useFluxLimiter) {
+			eigen_t eigL; Eqn::eigen_forInterface(eigL, solver, *UL_L, *UR_L, n);
+			eigen_t eigR; Eqn::eigen_forInterface(eigR, solver, *UL_R, *UR_R, n);
+			Eqn::eigen_leftTransform(deltaUEigL, solver, eigL, deltaUL, n);
+			Eqn::eigen_leftTransform(deltaUEigR, solver, eigR, deltaUR, n);
+		}
+		for (int j = 0; j < nW; ++j) {
+			real const lambda = lambdas[j];
+			if (!Eqn::roeUseFluxFromCons) fluxEig.ptr[j] *= lambda;
+			else fluxEig.ptr[j] = 0.;
+			real sgnLambda = lambda >= 0 ? real(1) : real(-1);
+			real phi = 0;
+			if (useFluxLimiter) {
+				real rEig;
+				if (deltaUEig.ptr[j] == 0) rEig = 0;
+				else if (lambda >= 0) rEig = deltaUEigL.ptr[j] / deltaUEig.ptr[j];
+				else rEig = deltaUEigR.ptr[j] / deltaUEig.ptr[j];
+				phi = limiter<real>(d.flux_limiter, rEig);
+				fluxEig.ptr[j] -= real(.5) * lambda * deltaUEig.ptr[j] * (sgnLambda + phi * (lambda * dt_dx - sgnLambda));
+			} else {
+				fluxEig.ptr[j] -= real(.5) * lambda * deltaUEig.ptr[j] * (sgnLambda);
+			}
+		}
+		Eqn::eigen_rightTransform(resultFlux, solver, eig, fluxEig, n);
+		if (Eqn::roeUseFluxFromCons) {
+			cons_t FL; Eqn::fluxFromCons(FL, solver, UL, n);
+			cons_t FR; Eqn::fluxFromCons(FR, solver, UR, n);
+			for (int j = 0; j < nI; ++j) resultFlux.ptr[j] += real(.5) * (FL.ptr[j] + FR.ptr[j]);
+		}
+	}
+
+	// cell_area<side>: symmath product of the other axes' grid_dx (coord.lua:990-1015); 1 for dim==1
+	real cellArea(int side) const {
+		real area = 1.;
+		for (int i = 0; i < dim; ++i) if (i != side) area = area * solver.grid_dx.s(i);
+		return area;
+	}
+
+	// ---- calcFlux kernel: fvsolver.lua:57-198
+	void calcFlux(real dt) {
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, g, g - 1)) continue;
+			long index = INDEX(i, j, k);
+			long const indexR = index;
+			for (int side = 0; side < dim; ++side) {
+				real const dx = solver.grid_dx.s(side);
+				long const indexL = index - solver.stepsize[side];
+				cons_t& flux = fluxBuf[side + dim * index];
+				real area = cellArea(side);
+				if (area <= real(1e-7)) {
+					for (int q = 0; q < nS; ++q) flux.ptr[q] = 0;
+				} else {
+					normal_t n{side};
+					cons_t const* UL; cons_t const* UR;
+					if (d.use_plm) {   // gridsolver.lua:486-496
+						UL = &ULRBuf[side + dim * indexL].R;
+						UR = &ULRBuf[side + dim * indexR].L;
+					} else {
+						UL = &UBuf[indexL]; UR = &UBuf[indexR];
+					}
+					if (useFluxLimiter) {
+						real const dt_dx = dt / dx;   // fvsolver.lua:135
+						long const indexR2 = indexR + solver.stepsize[side];
+						long const indexL2 = indexL - solver.stepsize[side];
+						cons_t const *UL_L, *UR_L, *UL_R, *UR_R;
+						if (d.use_plm) {
+							UL_L = &ULRBuf[side + dim * indexL2].R; UR_L = &ULRBuf[side + dim * indexL].L;
+							UL_R = &ULRBuf[side + dim * indexR].R; UR_R = &ULRBuf[side + dim * indexR2].L;
+						} else {
+							UL_L = &UBuf[indexL2]; UR_L = &UBuf[indexL];
+							UL_R = &UBuf[indexR]; UR_R = &UBuf[indexR2];
+						}
+						roeFlux(flux, *UL, *UR, n, dt_dx, UL_L, UR_L, UL_R, UR_R);
+					} else {
+						roeFlux(flux, *UL, *UR, n, 0, nullptr, nullptr, nullptr, nullptr);
+					}
+				}
+			}
+		}
+	}
+
+	// ---- calcDerivFromFlux: fvsolver.cl:6-125 (cartesian)
+	void calcDerivFromFlux(std::vector<cons_t>& derivBuf) {
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, g, g)) continue;
+			long index = INDEX(i, j, k);
+			cons_t& deriv = derivBuf[index];
+			real volume = 1.;
+			for (int q = 0; q < dim; ++q) volume = volume * solver.grid_dx.s(q);
+			for (int side = 0; side < dim; ++side) {
+				long const indexIntL = side + dim * index;
+				cons_t const& fluxL = fluxBuf[indexIntL];
+				long const indexIntR = indexIntL + dim * solver.stepsize[side];
+				cons_t const& fluxR = fluxBuf[indexIntR];
+				real areaL = cellArea(side);
+				real areaR = areaL;
+				if (volume > real(1e-7)) {
+					real const invVolume = real(1.) / volume;
+					if (areaL <= real(1e-7)) areaL = 0.;
+					if (areaR <= real(1e-7)) areaR = 0.;
+					areaL *= invVolume;
+					areaR *= invVolume;
+					for (int q = 0; q < nI; ++q)
+						deriv.ptr[q] -= fluxR.ptr[q] * areaR - fluxL.ptr[q] * areaL;
+				}
+			}
+		}
+	}
+
+	// ---- FiniteVolumeSolver:calcDeriv: fvsolver.lua:225-302 (+ addSource: none for euler / cartesian mhd)
+	void calcDeriv(std::vector<cons_t>& derivBuf, real dt) {
+		if (d.use_plm) calcLR();
+		calcFlux(dt);
+		calcDerivFromFlux(derivBuf);
+	}
+	void calcDerivOut(double* aos, double dt_) override {
+		std::vector<cons_t> deriv(ncells);
+		std::memset(deriv.data(), 0, sizeof(cons_t) * ncells);
+		calcDeriv(deriv, real(dt_));
+		for (long c = 0; c < ncells; ++c) for (int j = 0; j < nS; ++j) aos[c * nS + j] = double(deriv[c].ptr[j]);
+	}
+
+	// ---- calcDT: eqn.lua:1187-1224 + solverbase.lua:3004-3023 (reduceMin over all cells)
+	double calcDT() override {
+		if (d.use_fixed_dt) return d.fixed_dt;
+		real const inf = std::numeric_limits<real>::infinity();
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			long index = INDEX(i, j, k);
+			reduceBuf[index] = inf;
+			if (OOB(i, j, k, g, g)) continue;
+			real dtc = inf;
+			Eqn::calcDTCell(dtc, solver, UBuf[index]);
+			reduceBuf[index] = dtc;
+		}
+		real m = inf;
+		for (long c = 0; c < ncells; ++c) m = reduceBuf[c] < m ? reduceBuf[c] : m;
+		return d.cfl * double(m);   // dt = cfl * fromreal(reduceMin()) in host double
+	}
+
+	// solverbase.lua:1216-1228 multAddInto: a += b*c (interior, nI)
+	void multAddInto(std::vector<cons_t>& a, std::vector<cons_t> const& b, real c) {
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, g, g)) continue;
+			long index = INDEX(i, j, k);
+			for (int q = 0; q < nI; ++q) a[index].ptr[q] += b[index].ptr[q] * c;
+		}
+	}
+	// solverbase.lua:1230-1248 multAdd: a = b + c*d (interior, nI)
+	void multAdd(std::vector<cons_t>& a, std::vector<cons_t> const& b, std::vector<cons_t> const& c, real dd) {
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, g, g)) continue;
+			long index = INDEX(i, j, k);
+			for (int q = 0; q < nI; ++q) a[index].ptr[q] = b[index].ptr[q] + c[index].ptr[q] * dd;
+		}
+	}
+	static void clearBuffer(std::vector<cons_t>& b) { std::memset(b.data(), 0, sizeof(cons_t) * b.size()); }   // int/int.lua:6-8
+
+	// ---- SolverBase:step: solverbase.lua:3193-3238 ; integrators int/fe.lua:33-49, int/rk.lua:47-167
+	void step(double dt_) override {
+		real const dtArg = real(dt_);
+		if (d.rk_order == 0) {
+			clearBuffer(feDeriv);
+			calcDeriv(feDeriv, dtArg);
+			multAddInto(UBuf, feDeriv, real(dt_));
+			boundary();
+			constrainU();
+			return;
+		}
+		int const order = d.rk_order;
+		auto alpha = [&](int i, int k) { return d.alphas[i * order + k]; };
+		auto beta = [&](int i, int k) { return d.betas[i * order + k]; };
+		{
+			bool needed = false;
+			for (int m = 0; m < order; ++m) needed = needed || alpha(m, 0) != 0;
+			if (needed) UBufs[0] = UBuf;
+			needed = false;
+			for (int m = 0; m < order; ++m) needed = needed || beta(m, 0) != 0;
+			if (needed) { clearBuffer(derivBufs[0]); calcDeriv(derivBufs[0], dtArg); }
+		}
+		for (int i = 1; i <= order; ++i) {   // Lua i = 2..order+1
+			clearBuffer(UBuf);
+			for (int k = 0; k < i; ++k)
+				if (alpha(i - 1, k) != 0) multAdd(UBuf, UBuf, UBufs[k], real(alpha(i - 1, k)));
+			for (int k = 0; k < i; ++k)
+				if (beta(i - 1, k) != 0) multAdd(UBuf, UBuf, derivBufs[k], real(beta(i - 1, k) * dt_));
+			boundary();
+			constrainU();
+			if (i < order) {
+				bool needed = false;
+				for (int m = i; m < order; ++m) needed = needed || alpha(m, i) != 0;
+				if (needed) UBufs[i] = UBuf;
+				needed = false;
+				for (int m = i; m < order; ++m) needed = needed || beta(m, i) != 0;
+				if (needed) { clearBuffer(derivBufs[i]); calcDeriv(derivBufs[i], dtArg); }
+			}
+		}
+	}
+
+	// ---- SolverBase:update: solverbase.lua:3026-3190 (ops list empty: parity contract)
+	void update() override {
+		double dt_ = calcDT();
+		step(dt_);
+		t = t + dt_;
+		dt = dt_;
+		boundary();
+	}
+
+	// unit-test hook: one Roe interface flux (no flux limiter) + wave speeds + L and R matrices
+	// (the "ortho error"/"flux error" identities of fvsolver.lua:396-527)
+	void roeFluxTest(const double* UL_, const double* UR_, int side, double* flux, double* lambdas_, double* Lmat, double* Rmat) override {
+		cons_t UL, UR, F;
+		for (int j = 0; j < nS; ++j) { UL.ptr[j] = real(UL_[j]); UR.ptr[j] = real(UR_[j]); F.ptr[j] = 0; }
+		normal_t n{side};
+		bool save = useFluxLimiter; useFluxLimiter = false;
+		roeFlux(F, UL, UR, n, 0, nullptr, nullptr, nullptr, nullptr);
+		useFluxLimiter = save;
+		for (int j = 0; j < nS; ++j) flux[j] = double(F.ptr[j]);
+		eigen_t eig; Eqn::eigen_forInterface(eig, solver, UL, UR, n);
+		real lam[nW]; Eqn::eigenWaves(lam, solver, eig, n);
+		for (int j = 0; j < nW; ++j) lambdas_[j] = double(lam[j]);
+		for (int c = 0; c < nI; ++c) {   // L[:,c] = leftTransform(e_c)
+			cons_t e; std::memset(&e, 0, sizeof(e)); e.ptr[c] = 1;
+			waves_t w; Eqn::eigen_leftTransform(w, solver, eig, e, n);
+			for (int r = 0; r < nW; ++r) Lmat[r * nI + c] = double(w.ptr[r]);
+		}
+		for (int c = 0; c < nW; ++c) {   // R[:,c] = rightTransform(e_c)
+			waves_t w; for (int r = 0; r < nW; ++r) w.ptr[r] = 0; w.ptr[c] = 1;
+			cons_t e; std::memset(&e, 0, sizeof(e)); Eqn::eigen_rightTransform(e, solver, eig, w, n);
+			for (int r = 0; r < nI; ++r) Rmat[r * nW + c] = double(e.ptr[r]);
+		}
+	}
+};
+
+}   // namespace ho
+
+extern "C" {
+
+void* ho_create(const ho_desc* d) {
+	using namespace ho;
+	if (d->real_bytes == 8) {
+		if (d->eqn == 0) return static_cast<SolverBase*>(new Solver<Euler<double>>(*d));
+		if (d->eqn == 1) return static_cast<SolverBase*>(new Solver<MHD<double>>(*d));
+	} else if (d->real_bytes == 4) {
+		if (d->eqn == 0) return static_cast<SolverBase*>(new Solver<Euler<float>>(*d));
+		if (d->eqn == 1) return static_cast<SolverBase*>(new Solver<MHD<float>>(*d));
+	}
+	return nullptr;
+}
+void ho_destroy(void* h) { delete static_cast<ho::SolverBase*>(h); }
+int ho_num_states(void* h) { return static_cast<ho::SolverBase*>(h)->numStates(); }
+long ho_num_cells(void* h) { return static_cast<ho::SolverBase*>(h)->numCells(); }
+void ho_set_state(void* h, const double* aos) { static_cast<ho::SolverBase*>(h)->setState(aos); }
+void ho_get_state(void* h, double* aos) { static_cast<ho::SolverBase*>(h)->getState(aos); }
+void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }
+void ho_constrainU(void* h) { static_cast<ho::SolverBase*>(h)->constrainU(); }
+double ho_calc_dt(void* h) { return static_cast<ho::SolverBase*>(h)->calcDT(); }
+void ho_update(void* h, int nsteps) { auto* s = static_cast<ho::SolverBase*>(h); for (int i = 0; i < nsteps; ++i) s->update(); }
+void ho_step(void* h, double dt) { static_cast<ho::SolverBase*>(h)->step(dt); }
+double ho_get_t(void* h) { return static_cast<ho::SolverBase*>(h)->t; }
+double ho_get_dt(void* h) { return static_cast<ho::SolverBase*>(h)->dt; }
+void ho_set_t(void* h, double t) { static_cast<ho::SolverBase*>(h)->t = t; }
+void ho_calc_deriv(void* h, double* aos, double dt) { static_cast<ho::SolverBase*>(h)->calcDerivOut(aos, dt); }
+void ho_roe_flux_test(void* h, const double* UL, const double* UR, int side, double* flux, double* lambdas, double* Lmat, double* Rmat) {
+	static_cast<ho::SolverBase*>(h)->roeFluxTest(UL, UR, side, flux, lambdas, Lmat, Rmat);
+}
+double ho_limiter(int id, double r) { return ho::limiter<double>(id, r); }
+int ho_max_threads() {
+#ifdef _OPENMP
+	return omp_get_max_threads();
+#else
+	return 1;
+#endif
+}
+
+}   // extern "C"

@@ -1,0 +1,184 @@
+"""ctypes loader for the CPU parity oracle (oracle/hydro_oracle.cpp).  TEST INFRASTRUCTURE ONLY.
+
+May be imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs.
+The product package (hydro-cl-lua_b200/) never imports this module.
+
+``OracleBackend`` implements the same backend interface the host-side solver mirror uses
+(set_state/get_state/boundary/constrainU/calc_dt/step/update), so a parity test reads:
+
+    ref = FiniteVolumeSolver(dict(cfg, backend=OracleBackend))     # CPU restatement of the reference
+    gpu = FiniteVolumeSolver(cfg)                                  # CUDA product through the C-ABI
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_here = os.path.dirname(os.path.abspath(__file__))
+
+
+class ho_desc(C.Structure):
+    _fields_ = [
+        ("eqn", C.c_int), ("dim", C.c_int), ("n", C.c_int * 3), ("real_bytes", C.c_int),
+        ("use_plm", C.c_int), ("slope_limiter", C.c_int), ("flux_limiter", C.c_int),
+        ("bc", C.c_int * 6), ("rk_order", C.c_int),
+        ("alphas", C.c_double * 16), ("betas", C.c_double * 16),
+        ("mins", C.c_double * 3), ("maxs", C.c_double * 3),
+        ("cfl", C.c_double), ("fixed_dt", C.c_double), ("use_fixed_dt", C.c_int),
+        ("gamma", C.c_double), ("rhoMin", C.c_double), ("PMin", C.c_double), ("mu0_eff", C.c_double),
+        ("nthreads", C.c_int),
+    ]
+
+
+def build(force=False):
+    """Compile the oracle with oracle/Makefile (g++, a few seconds)."""
+    so = os.path.join(_here, "libhydro_oracle.so")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(_here, "hydro_oracle.cpp")):
+        subprocess.check_call(["make", "-C", _here, "-j2"], stdout=subprocess.DEVNULL)
+    return so
+
+
+_libs = {}
+
+
+def lib(fma=False):
+    key = bool(fma)
+    if key not in _libs:
+        build()
+        L = C.CDLL(os.path.join(_here, "libhydro_oracle_fma.so" if fma else "libhydro_oracle.so"))
+        L.ho_create.restype = C.c_void_p
+        L.ho_create.argtypes = [C.POINTER(ho_desc)]
+        for name in ("ho_destroy", "ho_boundary", "ho_constrainU"):
+            getattr(L, name).argtypes = [C.c_void_p]
+            getattr(L, name).restype = None
+        L.ho_num_states.argtypes = [C.c_void_p]
+        L.ho_num_cells.argtypes = [C.c_void_p]
+        L.ho_num_cells.restype = C.c_long
+        L.ho_set_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ho_get_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ho_calc_dt.argtypes = [C.c_void_p]
+        L.ho_calc_dt.restype = C.c_double
+        L.ho_update.argtypes = [C.c_void_p, C.c_int]
+        L.ho_step.argtypes = [C.c_void_p, C.c_double]
+        L.ho_get_t.argtypes = [C.c_void_p]
+        L.ho_get_t.restype = C.c_double
+        L.ho_get_dt.argtypes = [C.c_void_p]
+        L.ho_get_dt.restype = C.c_double
+        L.ho_set_t.argtypes = [C.c_void_p, C.c_double]
+        L.ho_calc_deriv.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
+        L.ho_roe_flux_test.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.ho_limiter.argtypes = [C.c_int, C.c_double]
+        L.ho_limiter.restype = C.c_double
+        L.ho_max_threads.restype = C.c_int
+        _libs[key] = L
+    return _libs[key]
+
+
+def desc_from_solver(solver, nthreads=0):
+    d = ho_desc()
+    d.eqn = solver.eqn.eqnId
+    d.dim = solver.dim
+    for i in range(3):
+        d.n[i] = solver.sizeWithoutBorder[i]
+        d.mins[i] = solver.mins[i]
+        d.maxs[i] = solver.maxs[i]
+    d.real_bytes = solver.real_bytes
+    d.use_plm = 1 if solver.usePLM else 0
+    d.slope_limiter = solver.slopeLimiter
+    d.flux_limiter = solver.fluxLimiter
+    for i, b in enumerate(solver.boundaryIdList()):
+        d.bc[i] = b
+    d.rk_order = solver.rkOrder
+    for i in range(16):
+        d.alphas[i] = solver.alphas[i]
+        d.betas[i] = solver.betas[i]
+    d.cfl = solver.cfl
+    d.fixed_dt = solver.fixedDT if solver.useFixedDT else 0.
+    d.use_fixed_dt = 1 if solver.useFixedDT else 0
+    v = solver.eqn.vars
+    d.gamma = v["heatCapacityRatio"]
+    d.rhoMin = v.get("rhoMin", 1e-7)
+    d.PMin = v.get("PMin", 1e-7)
+    d.mu0_eff = getattr(solver.eqn, "mu0_eff", 1.)
+    d.nthreads = nthreads
+    return d
+
+
+class OracleBackend:
+    """Backend interface of hydro/solver/solverbase.py, served by the CPU oracle."""
+    fma = False
+    nthreads = 0
+
+    def __init__(self, solver):
+        self.solver = solver
+        self.L = lib(self.fma)
+        self.desc = desc_from_solver(solver, self.nthreads)
+        self.h = self.L.ho_create(C.byref(self.desc))
+        if not self.h:
+            raise RuntimeError("oracle: unsupported configuration")
+        self.nS = self.L.ho_num_states(self.h)
+        self.ncells = self.L.ho_num_cells(self.h)
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.L.ho_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    def set_state(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        assert U.size == self.ncells * self.nS
+        self.L.ho_set_state(self.h, U.ctypes.data)
+
+    def get_state(self):
+        U = np.empty((self.ncells, self.nS), dtype=np.float64)
+        self.L.ho_get_state(self.h, U.ctypes.data)
+        return U
+
+    def boundary(self):
+        self.L.ho_boundary(self.h)
+
+    def constrainU(self):
+        self.L.ho_constrainU(self.h)
+
+    def calc_dt(self):
+        return self.L.ho_calc_dt(self.h)
+
+    def step(self, dt):
+        self.L.ho_step(self.h, dt)
+
+    def update(self, nsteps=1):
+        self.L.ho_update(self.h, nsteps)
+        return self.L.ho_get_t(self.h), self.L.ho_get_dt(self.h)
+
+    def set_t(self, t):
+        self.L.ho_set_t(self.h, t)
+
+    def calc_deriv(self, dt):
+        D = np.empty((self.ncells, self.nS), dtype=np.float64)
+        self.L.ho_calc_deriv(self.h, D.ctypes.data, dt)
+        return D
+
+    def roe_flux_test(self, UL, UR, side):
+        nI, nW = self.solver.eqn.numIntStates, self.solver.eqn.numWaves
+        UL = np.ascontiguousarray(UL, dtype=np.float64)
+        UR = np.ascontiguousarray(UR, dtype=np.float64)
+        flux = np.zeros(self.nS)
+        lam = np.zeros(nW)
+        Lm = np.zeros((nW, nI))
+        Rm = np.zeros((nI, nW))
+        self.L.ho_roe_flux_test(self.h, UL.ctypes.data, UR.ctypes.data, side, flux.ctypes.data, lam.ctypes.data,
+                                Lm.ctypes.data, Rm.ctypes.data)
+        return flux, lam, Lm, Rm
+
+
+class OracleBackendFMA(OracleBackend):
+    """Same restatement compiled with -ffp-contract=fast (OpenCL's FP_CONTRACT default is ON)."""
+    fma = True
+
+
+def OracleBackendThreads(n):
+    return type("OracleBackendT%d" % n, (OracleBackend,), {"nthreads": n})
