@@ -1,0 +1,197 @@
+// hb_eqn_euler.cuh -- compressible Euler device functions for the fused finite-volume stage kernel.
+//
+// This is the equation plug-in contract of the reference (hydro/eqn/eqn.lua:382-419) for `euler`:
+//   primFromCons        hydro/eqn/euler.cl:140-159   (vacuum guard there is dead code: unconditional overwrite :155-157)
+//   consFromPrim        hydro/eqn/euler.cl:163-173
+//   fluxFromCons        hydro/eqn/euler.cl:273-291
+//   eigen_forInterface  hydro/eqn/euler.cl:347-430   (Roe average; literal rhoEpsilon = 1e-5 vacuum branches)
+//   eigen_leftTransform hydro/eqn/euler.cl:434-489
+//   eigen_rightTransform hydro/eqn/euler.cl:493-542
+//   wave speeds         hydro/eqn/euler.lua:309-325  (v_n - Cs, v_n x3, v_n + Cs)
+//   calcDTCell          hydro/eqn/cl/calcDT.cl:38-73 + hydro/eqn/euler.lua:346-373
+//   constrainU          hydro/eqn/euler.cl:698-717
+// State: integrated variables only, U[0..4] = rho, m.x, m.y, m.z, ETotal (ePot, the 6th cons_t field, is
+// never read by the flux and is carried untouched in HBM).  The interface normal is a template parameter
+// (Cartesian: normal_t = {side}), so the normal_l/u selectors (hydro/coord/coord.lua:2379-2386) resolve at
+// compile time and the `x * 0` terms they would produce are simply not emitted (adding an exact zero is a
+// no-op in IEEE arithmetic, so results are unchanged).
+#pragma once
+#include "hb_math.cuh"
+
+namespace hb {
+
+template<class real_> struct Euler {
+	typedef real_ real;
+	static constexpr int eqnId = 0;
+	static constexpr int nS = 6, nI = 5, nW = 5;
+	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/eqn.lua:46
+	struct Params { real gamma, rhoMin, PMin; };
+	static HB_HD Params makeParams(const double* p) { return Params{real(p[0]), real(p[1]), real(p[2])}; }
+
+	struct Prim { real rho, v[3], P; };
+	struct Eig { real rho, v[3], hTotal, Cs, vSq; };   // vL == v for the identity metric
+
+	// euler.cl:60-66, :76-83
+	static HB_HD real calc_P(Params const& s, real const (&U)[nI]) {
+		if (U[0] < s.rhoMin) return real(0.);
+		real const EKin = real(.5) * lenSq3(U[1], U[2], U[3]) / U[0];
+		return (s.gamma - real(1.)) * (U[4] - EKin);
+	}
+	static HB_HD void primFromCons(Prim& W, Params const& s, real const (&U)[nI]) {
+		W.rho = U[0];
+		real const invRho = real(1.) / U[0];
+		W.v[0] = U[1] * invRho; W.v[1] = U[2] * invRho; W.v[2] = U[3] * invRho;
+		W.P = calc_P(s, U);
+	}
+	static HB_HD void consFromPrim(real (&U)[nI], Params const& s, Prim const& W) {
+		U[0] = W.rho;
+		U[1] = W.v[0] * W.rho; U[2] = W.v[1] * W.rho; U[3] = W.v[2] * W.rho;
+		U[4] = (W.rho * (real(.5) * lenSq3(W.v[0], W.v[1], W.v[2]))) + (W.P / (s.gamma - real(1.)));
+	}
+	// euler.cl:87-94
+	static HB_HD real calc_Cs(Params const& s, Prim const& W) {
+		if (W.P <= s.PMin) return real(0.);
+		if (W.rho < s.rhoMin) return inf_of<real>::v();
+		return rsqrt_ieee(s.gamma * W.P / W.rho);
+	}
+
+	template<int SIDE> static HB_HD void fluxFromCons(real (&F)[nI], Params const& s, real const (&U)[nI]) {
+		Prim W; primFromCons(W, s, U);
+		real const v_n = W.v[SIDE];
+		F[0] = U[0] * v_n;
+		F[1] = U[1] * v_n; F[2] = U[2] * v_n; F[3] = U[3] * v_n;
+		F[1 + SIDE] = F[1 + SIDE] + W.P;
+		real const HTotal = U[4] + W.P;
+		F[4] = HTotal * v_n;
+	}
+
+	static HB_HD void eigFromPrim(Eig& r, Params const& s, Prim const& W, real ETotal) {
+		r.rho = W.rho;
+		r.v[0] = W.v[0]; r.v[1] = W.v[1]; r.v[2] = W.v[2];
+		r.vSq = dot3(W.v[0], W.v[1], W.v[2], W.v[0], W.v[1], W.v[2]);
+		r.hTotal = (W.P + ETotal) / W.rho;
+		r.Cs = calc_Cs(s, W);
+	}
+
+	template<int SIDE> static HB_HD void eigen_forInterface(Eig& r, Params const& s, real const (&UL)[nI], real const (&UR)[nI]) {
+		real const rhoEpsilon = real(1e-5);
+		if (UL[0] < rhoEpsilon && UR[0] < rhoEpsilon) {
+			r.rho = 0; r.v[0] = r.v[1] = r.v[2] = 0; r.vSq = 0; r.hTotal = 0; r.Cs = 0;
+		} else if (UL[0] < rhoEpsilon) {
+			Prim WR; primFromCons(WR, s, UR);
+			eigFromPrim(r, s, WR, UR[4]);
+		} else if (UR[0] < rhoEpsilon) {
+			Prim WL; primFromCons(WL, s, UL);
+			eigFromPrim(r, s, WL, UL[4]);
+		} else {
+			Prim WL; primFromCons(WL, s, UL);
+			real const sqrtRhoL = rsqrt_ieee(WL.rho);
+			real const hTotalL = (WL.P + UL[4]) / WL.rho;
+			Prim WR; primFromCons(WR, s, UR);
+			real const sqrtRhoR = rsqrt_ieee(WR.rho);
+			real const hTotalR = (WR.P + UR[4]) / WR.rho;
+			real const invDenom = real(1.) / (sqrtRhoL + sqrtRhoR);
+			r.rho = sqrtRhoL * sqrtRhoR;
+			real const wL = sqrtRhoL * invDenom, wR = sqrtRhoR * invDenom;
+			r.v[0] = WL.v[0] * wL + WR.v[0] * wR;
+			r.v[1] = WL.v[1] * wL + WR.v[1] * wR;
+			r.v[2] = WL.v[2] * wL + WR.v[2] * wR;
+			real const hTotal = invDenom * (sqrtRhoL * hTotalL + sqrtRhoR * hTotalR);
+			real const vSq = dot3(r.v[0], r.v[1], r.v[2], r.v[0], r.v[1], r.v[2]);
+			real const eKin = real(.5) * vSq;
+			real const h = hTotal - eKin;
+			if (h < rhoEpsilon) {
+				r.hTotal = eKin; r.Cs = 0;
+			} else {
+				r.hTotal = hTotal;
+				r.Cs = rsqrt_ieee((s.gamma - real(1.)) * h);
+			}
+			r.vSq = vSq;
+		}
+	}
+
+	template<int SIDE> static HB_HD void waves(real (&lam)[nW], Params const&, Eig const& e) {
+		real const v_n = e.v[SIDE];
+		lam[0] = v_n - e.Cs;
+		lam[1] = v_n; lam[2] = v_n; lam[3] = v_n;
+		lam[4] = v_n + e.Cs;
+	}
+
+	template<int SIDE> static HB_HD void leftTransform(real (&r)[nW], Params const& s, Eig const& e, real const (&X)[nI]) {
+		if (e.rho < s.rhoMin) {
+			for (int j = 0; j < 5; ++j) r[j] = X[j];
+			return;
+		}
+		real vn[3]; rot<SIDE>::fwd(e.v, vn);
+		real const denom = real(2.) * e.Cs * e.Cs;
+		real const invDenom = real(1.) / denom;
+		real const gamma_1 = s.gamma - real(1.);
+		// c[q] = -gamma_1 * v_q -/+ Cs * l1_q
+		real cm[3], cp[3];
+		for (int q = 0; q < 3; ++q) { cm[q] = -gamma_1 * e.v[q]; cp[q] = cm[q]; }
+		cm[SIDE] = cm[SIDE] - e.Cs;
+		cp[SIDE] = cp[SIDE] + e.Cs;
+		real const hk = real(.5) * gamma_1 * e.vSq;
+		real const cv = e.Cs * vn[0];
+		r[0] = (X[0] * (hk + cv) + X[1] * cm[0] + X[2] * cm[1] + X[3] * cm[2] + X[4] * gamma_1) * invDenom;
+		r[1] = (X[0] * (denom - gamma_1 * e.vSq)
+				+ X[1] * real(2.) * gamma_1 * e.v[0]
+				+ X[2] * real(2.) * gamma_1 * e.v[1]
+				+ X[3] * real(2.) * gamma_1 * e.v[2]
+				+ X[4] * real(-2.) * gamma_1) * invDenom;
+		r[2] = X[0] * -vn[1] + X[1 + (SIDE + 1) % 3];
+		r[3] = X[0] * -vn[2] + X[1 + (SIDE + 2) % 3];
+		r[4] = (X[0] * (hk - cv) + X[1] * cp[0] + X[2] * cp[1] + X[3] * cp[2] + X[4] * gamma_1) * invDenom;
+	}
+
+	template<int SIDE> static HB_HD void rightTransform(real (&r)[nI], Params const& s, Eig const& e, real const (&X)[nW]) {
+		if (e.rho < s.rhoMin) {
+			for (int j = 0; j < 5; ++j) r[j] = X[j];
+			return;
+		}
+		real vn[3]; rot<SIDE>::fwd(e.v, vn);
+		r[0] = X[0] + X[1] + X[4];
+		constexpr int q0 = SIDE, q1 = (SIDE + 1) % 3, q2 = (SIDE + 2) % 3;
+		r[1 + q0] = X[0] * (e.v[q0] - e.Cs) + X[1] * e.v[q0] + X[4] * (e.v[q0] + e.Cs);
+		r[1 + q1] = X[0] * e.v[q1] + X[1] * e.v[q1] + X[2] + X[4] * e.v[q1];
+		r[1 + q2] = X[0] * e.v[q2] + X[1] * e.v[q2] + X[3] + X[4] * e.v[q2];
+		real const cv = e.Cs * vn[0];
+		r[4] = X[0] * (e.hTotal - cv)
+			+ X[1] * real(.5) * e.vSq
+			+ X[2] * vn[1]
+			+ X[3] * vn[2]
+			+ X[4] * (e.hTotal + cv);
+	}
+
+	static HB_HD void constrainU(Params const& s, real (&U)[nI]) {
+		if (U[0] < s.rhoMin) U[0] = s.rhoMin;
+		Prim W; primFromCons(W, s, U);
+		if (W.P < s.PMin) W.P = s.PMin;
+		consFromPrim(U, s, W);
+	}
+
+	// euler.cl:98-112 calc_Cs_fromCons; calcDT.cl:38-73
+	static HB_HD real calcDTCell(Params const& s, real const (&U)[nI], real const (&dx)[3], int dim) {
+		real Cs;
+		real const P = calc_P(s, U);
+		if (P <= s.PMin) Cs = real(0.);
+		else if (U[0] < s.rhoMin) Cs = inf_of<real>::v();
+		else Cs = rsqrt_ieee(s.gamma * P / U[0]);
+		real dt = inf_of<real>::v();
+		for (int side = 0; side < dim; ++side) {
+			if (dx[side] > 0) {
+				real const v_n = U[0] < s.rhoMin ? real(0.) : U[1 + side] / U[0];
+				real const lambdaMin = v_n - Cs, lambdaMax = v_n + Cs;
+				real absLambdaMax = rmax<real>(rabs(lambdaMin), rabs(lambdaMax));
+				absLambdaMax = rmax<real>(real(1e-9), absLambdaMax);
+				dt = rmin<real>(dt, dx[side] / absLambdaMax);
+			}
+		}
+		return dt;
+	}
+
+	// mirror boundary: negate m.side (hydro/solver/gridsolver.lua:662-671,741; eqn.lua:366-370)
+	static HB_HD bool mirrorFlips(int var, int side) { return var == 1 + side; }
+};
+
+}   // namespace hb

@@ -1,0 +1,628 @@
+// hb_fv.cu -- host side of the fused finite-volume path of the C ABI (hb_fv_* in include/hydrob200.h).
+//
+// What the reference's LuaJIT host does per solver:update() (hydro/solver/solverbase.lua:3026-3238,
+// hydro/int/rk.lua:47-167, hydro/int/fe.lua:33-49) is turned into a static per-stage plan at creation time:
+//   stage i (0-based) reads U^i with its ghosts, forms L^i = dU/dt(U^i) on chip, and writes
+//       U^{i+1} = sum_{k<=i} alpha[i][k] U^k + dt sum_{k<=i} beta[i][k] L^k      (alpha terms first, k ascending)
+//   already constrained (constrainU), followed by one ghost fill; L^i goes to HBM only if a later stage needs it;
+//   the last stage also produces the CFL minimum for the next step.  dt and t live on the device
+//   (`ctl`), so a whole update is one stream-ordered sequence without host read-back; it can be replayed as a CUDA graph.
+// Slab decomposition (one process per GPU): the slowest used axis is split; after each ghost fill the two
+// boundary plane pairs are exchanged with ncclSend/ncclRecv and dt is min-allreduced (choppedup.lua:193-233,344-409).
+#include "hb_core.h"
+#include "hb_fv_ops.h"
+#include <dlfcn.h>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <set>
+#include <sstream>
+
+namespace hb {
+
+// Step bookkeeping on the device (solverbase.lua:3160-3173): dt = fixedDT | cfl * min ; t += dt.
+// Runs at the top of every update so that a whole update is one stream-ordered (graph-capturable) sequence
+// with no host read-back.  `ctl` = { t, dt, cfl, fixedDT(<0: adaptive) }.
+__global__ void begin_step(double* ctl, unsigned long long* dtMinBits)
+{
+	double dt;
+	if (ctl[3] >= 0) dt = ctl[3];
+	else dt = ctl[2] * __longlong_as_double((long long)*dtMinBits);
+	ctl[1] = dt;
+	ctl[0] = ctl[0] + dt;
+	*dtMinBits = dtBits(HUGE_VAL);
+}
+
+
+__global__ void set_step(double* ctl, unsigned long long* dtMinBits, double dt) {
+	ctl[1] = dt;
+	*dtMinBits = dtBits(HUGE_VAL);
+}
+__global__ void reset_dtmin(unsigned long long* dtMinBits) { *dtMinBits = dtBits(HUGE_VAL); }
+
+// ---- NCCL, bound at run time (the library is the one the host process already loaded, e.g. torch's)
+struct Nccl {
+	typedef struct ncclComm* comm_t;
+	struct uid { char internal[128]; };
+	int (*GetUniqueId)(uid*) = nullptr;
+	int (*CommInitRank)(comm_t*, int, uid, int) = nullptr;
+	int (*CommDestroy)(comm_t) = nullptr;
+	int (*Send)(const void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, comm_t, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+	bool ok = false;
+	std::string why;
+	static Nccl& get() {
+		static Nccl n;
+		static bool tried = false;
+		if (!tried) {
+			tried = true;
+			void* h = nullptr;
+			const char* names[] = {"libnccl.so.2", "libnccl.so"};
+			for (const char* nm : names) { h = dlopen(nm, RTLD_NOW | RTLD_GLOBAL); if (h) break; }
+			if (!h) { n.why = std::string("cannot load libnccl: ") + dlerror(); return n; }
+#define HB_SYM(field, name) *(void**)(&n.field) = dlsym(h, name); if (!n.field) { n.why = std::string("libnccl lacks ") + name; return n; }
+			HB_SYM(GetUniqueId, "ncclGetUniqueId") HB_SYM(CommInitRank, "ncclCommInitRank") HB_SYM(CommDestroy, "ncclCommDestroy")
+			HB_SYM(Send, "ncclSend") HB_SYM(Recv, "ncclRecv") HB_SYM(AllReduce, "ncclAllReduce")
+			HB_SYM(GroupStart, "ncclGroupStart") HB_SYM(GroupEnd, "ncclGroupEnd") HB_SYM(GetErrorString, "ncclGetErrorString")
+#undef HB_SYM
+			n.ok = true;
+		}
+		return n;
+	}
+};
+enum { kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclMin = 3 };
+#define HB_NCCL(expr) do { int r_ = (expr); if (r_ != 0) return setError(HB_ERR_CUDA, std::string(#expr) + ": " + Nccl::get().GetErrorString(r_)); } while (0)
+
+struct Term { int k; double coef; };
+struct StagePlan {
+	int uIn, uOut;                 // physical U buffers
+	int lOut;                      // physical L buffer or -1
+	std::vector<Term> alpha;       // k = physical U buffer
+	std::vector<Term> beta;        // k = physical L buffer
+	double betaSelf; bool computeL; bool last;
+	int readsU, readsL;            // words per cell (x nI) for hb_fv_describe
+};
+
+// Static plan of one update for a Butcher tableau (hydro/int/rk.lua:17-44 decides the same "needed later" sets).
+static void buildPlan(int order, const double* A, const double* B, std::vector<StagePlan>& plan, int& nU, int& nL) {
+	int const n = order < 1 ? 1 : order;
+	auto a = [&](int i, int k) { return order < 1 ? 1. : A[i * order + k]; };
+	auto b = [&](int i, int k) { return order < 1 ? 1. : B[i * order + k]; };
+	std::vector<int> uPhys(n + 1, -1), lPhys(n, -1);
+	std::set<int> liveU, liveL;
+	uPhys[0] = 0; liveU.insert(0);
+	nU = 1; nL = 0;
+	plan.clear();
+	for (int i = 0; i < n; ++i) {
+		StagePlan s;
+		s.last = i == n - 1;
+		s.uIn = uPhys[i];
+		int out;
+		if (s.last && n >= 2) out = 0;                // in place over U^0 (only read pointwise by its own cell's thread)
+		else { out = 0; while (liveU.count(out)) ++out; }
+		uPhys[i + 1] = out; liveU.insert(out);
+		if (out + 1 > nU) nU = out + 1;
+		bool neededLater = false;
+		for (int m = i + 1; m < n; ++m) neededLater = neededLater || b(m, i) != 0;
+		s.betaSelf = b(i, i);
+		s.computeL = s.betaSelf != 0 || neededLater;
+		s.lOut = -1;
+		if (neededLater) {
+			int l = 0; while (liveL.count(l)) ++l;
+			lPhys[i] = l; liveL.insert(l); s.lOut = l;
+			if (l + 1 > nL) nL = l + 1;
+		}
+		for (int k = 0; k <= i; ++k) if (a(i, k) != 0) s.alpha.push_back(Term{uPhys[k], a(i, k)});
+		for (int k = 0; k < i; ++k) if (b(i, k) != 0) s.beta.push_back(Term{lPhys[k], b(i, k)});
+		s.readsU = 1; s.readsL = (int)s.beta.size();
+		for (auto& t : s.alpha) if (t.k != s.uIn) s.readsU++;
+		plan.push_back(s);
+		// release what no later stage reads (U^0 is kept: the last stage writes the new state there)
+		for (int k = 1; k <= i; ++k) {
+			bool later = false;
+			for (int m = i + 1; m < n; ++m) later = later || a(m, k) != 0;
+			if (!later && uPhys[k] > 0 && uPhys[k] != uPhys[i + 1]) liveU.erase(uPhys[k]);
+		}
+		for (int k = 0; k <= i; ++k) {
+			bool later = false;
+			for (int m = i + 1; m < n; ++m) later = later || b(m, k) != 0;
+			if (!later && lPhys[k] >= 0) liveL.erase(lPhys[k]);
+		}
+	}
+}
+
+struct FvBase {
+	virtual ~FvBase() {}
+	virtual int init() = 0;
+	virtual int setState(const double* aos) = 0;
+	virtual int getState(double* aos) = 0;
+	virtual int stateDevPtr(void** p, long long* sy, long long* sz, long long* sv) = 0;
+	virtual int boundary() = 0;
+	virtual int constrainU() = 0;
+	virtual int calcDT(double* out) = 0;
+	virtual int step(double dt) = 0;
+	virtual int update(int nsteps) = 0;
+	virtual int getTime(double* t, double* dt) = 0;
+	virtual int setTime(double t) = 0;
+	virtual int calcDeriv(double dt, double* aos) = 0;
+	virtual int describe(char* out, size_t cap) = 0;
+	virtual int commInit(int nranks, int rank, const char* id) = 0;
+	virtual int commDestroy() = 0;
+	int nS = 0, nI = 0, nW = 0;
+	long long cells = 0;
+	long long launches = 0;
+};
+
+template<class real> struct Fv : FvBase {
+	hb_ctx* ctx;
+	hb_fv_desc d;
+	const FvOps<real>* ops;
+	GridP<real> grid;
+	BcP bc;
+	std::vector<real*> upool, lpool;
+	real* scratchL = nullptr;
+	double* stagingAos = nullptr;
+	double* ctl = nullptr;                 // device: t, dt, cfl, fixedDT(<0 adaptive)
+	unsigned long long* dtMinBits = nullptr;
+	std::vector<StagePlan> plan;
+	int nU = 0, nL = 0;
+	bool dtValid = false, rkZeroed = false;
+	int nonIntSync = 0;
+	cudaGraphExec_t graphExec = nullptr;
+	long long graphLaunches = 0;
+	// slab decomposition
+	Nccl::comm_t comm = nullptr;
+	int nranks = 1, rank = 0;
+	int axis;
+
+	Fv(hb_ctx* c, const hb_fv_desc& desc, const FvOps<real>* o) : ctx(c), d(desc), ops(o) {
+		nS = o->nS; nI = o->nI; nW = o->nW;
+		axis = d.dim - 1;
+	}
+	~Fv() override {
+		useDevice(ctx);
+		cudaStreamSynchronize(ctx->stream);
+		if (graphExec) cudaGraphExecDestroy(graphExec);
+		for (auto p : upool) cudaFree(p);
+		for (auto p : lpool) cudaFree(p);
+		if (scratchL) cudaFree(scratchL);
+		if (stagingAos) cudaFree(stagingAos);
+		if (ctl) cudaFree(ctl);
+		if (dtMinBits) cudaFree(dtMinBits);
+		if (comm) Nccl::get().CommDestroy(comm);
+	}
+	cudaStream_t st() const { return ctx->stream; }
+	size_t uBytes() const { return sizeof(real) * (size_t)nS * (size_t)cells; }
+	size_t lBytes() const { return sizeof(real) * (size_t)nI * (size_t)cells; }
+
+	int init() override {
+		useDevice(ctx);
+		grid.dim = d.dim;
+		for (int k = 0; k < 3; ++k) {
+			grid.N[k] = k < d.dim ? d.n[k] : 1;
+			grid.S[k] = k < d.dim ? d.n[k] + 2 * HB_G : 1;
+			int const gn = k < d.dim ? d.global_n[k] : 1;
+			double const dx = (d.maxs[k] - d.mins[k]) / double(gn);     // gridsolver.lua:406-409, host double then cast
+			grid.dx[k] = real(dx);
+		}
+		grid.strideY = grid.S[0];
+		grid.strideZ = (long long)grid.S[0] * grid.S[1];
+		cells = (long long)grid.S[0] * grid.S[1] * grid.S[2];
+		grid.strideV = cells;
+		// fvsolver.cl:34-41,97-102: volume = prod dx (used axes), area_s = prod_{i != s} dx_i, scaled by 1/volume, in `real`
+		real volume = 1;
+		for (int k = 0; k < d.dim; ++k) volume = volume * grid.dx[k];
+		grid.volOn = volume > real(1e-7);
+		for (int s = 0; s < 3; ++s) {
+			real area = 1;
+			for (int k = 0; k < d.dim; ++k) if (k != s) area = area * grid.dx[k];
+			grid.fluxOn[s] = s < d.dim && !(area <= real(1e-7));
+			real a = area;
+			if (a <= real(1e-7)) a = 0;
+			grid.aov[s] = grid.volOn ? a * (real(1.) / volume) : real(0);
+		}
+		for (int k = 0; k < 6; ++k) bc.bc[k] = d.bc[k];
+		buildPlan(d.rk_order, d.alphas, d.betas, plan, nU, nL);
+		for (auto& s : plan) {
+			if ((int)s.alpha.size() > HB_MAX_TERMS || (int)s.beta.size() > HB_MAX_TERMS)
+				return setError(HB_ERR_INVALID, "hb_fv_create: tableau row has more than 4 alpha or beta terms");
+		}
+		if (nU < 2 && d.rk_order < 2) nU = 2;
+		for (int k = 0; k < nU; ++k) {
+			real* p = nullptr;
+			HB_CUDA(cudaMalloc(&p, uBytes()));
+			upool.push_back(p);
+			HB_CUDA(cudaMemsetAsync(p, 0, uBytes(), st()));
+		}
+		for (int k = 0; k < nL; ++k) {
+			real* p = nullptr;
+			HB_CUDA(cudaMalloc(&p, lBytes()));
+			lpool.push_back(p);
+			HB_CUDA(cudaMemsetAsync(p, 0, lBytes(), st()));
+		}
+		HB_CUDA(cudaMalloc(&ctl, 4 * sizeof(double)));
+		HB_CUDA(cudaMalloc(&dtMinBits, sizeof(unsigned long long)));
+		double h[4] = {0., 0., d.cfl, d.use_fixed_dt ? d.fixed_dt : -1.};
+		HB_CUDA(cudaMemcpyAsync(ctl, h, sizeof(h), cudaMemcpyHostToDevice, st()));
+		reset_dtmin<<<1, 1, 0, st()>>>(dtMinBits);
+		HB_CUDA(cudaGetLastError());
+		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
+	}
+
+	int ensureStaging() {
+		if (!stagingAos) HB_CUDA(cudaMalloc(&stagingAos, sizeof(double) * (size_t)nS * (size_t)cells));
+		return HB_OK;
+	}
+	void invalidateGraph() {
+		if (graphExec) { cudaStreamSynchronize(st()); cudaGraphExecDestroy(graphExec); graphExec = nullptr; }
+	}
+
+	int setState(const double* aos) override {
+		if (!aos) return setError(HB_ERR_INVALID, "hb_fv_set_state: null pointer");
+		useDevice(ctx);
+		if (int r = ensureStaging()) return r;
+		size_t const n = (size_t)nS * (size_t)cells;
+		HB_CUDA(cudaMemcpyAsync(stagingAos, aos, sizeof(double) * n, cudaMemcpyHostToDevice, st()));
+		aos_to_soa<real><<<(unsigned)((n + 255) / 256), 256, 0, st()>>>(grid, nS, stagingAos, upool[0]);
+		HB_CUDA(cudaGetLastError());
+		launches++;
+		dtValid = false; rkZeroed = false; nonIntSync = 2;
+		return HB_OK;
+	}
+	int getState(double* aos) override {
+		if (!aos) return setError(HB_ERR_INVALID, "hb_fv_get_state: null pointer");
+		useDevice(ctx);
+		if (int r = ensureStaging()) return r;
+		size_t const n = (size_t)nS * (size_t)cells;
+		soa_to_aos<real><<<(unsigned)((n + 255) / 256), 256, 0, st()>>>(grid, nS, upool[0], stagingAos);
+		HB_CUDA(cudaGetLastError());
+		launches++;
+		HB_CUDA(cudaMemcpyAsync(aos, stagingAos, sizeof(double) * n, cudaMemcpyDeviceToHost, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
+	}
+	int stateDevPtr(void** p, long long* sy, long long* sz, long long* sv) override {
+		if (p) *p = upool[0];
+		if (sy) *sy = grid.strideY;
+		if (sz) *sz = grid.strideZ;
+		if (sv) *sv = grid.strideV;
+		return HB_OK;
+	}
+
+	// ghost planes of the decomposed axis: 2 planes x (everything faster) are contiguous per variable
+	int exchange(real* U, int nVars) {
+		if (!comm) return HB_OK;
+		Nccl& N = Nccl::get();
+		long long const strideA = axis == 0 ? 1 : (axis == 1 ? grid.strideY : grid.strideZ);
+		size_t const chunk = (size_t)(HB_G * strideA);
+		int const S = grid.S[axis];
+		bool const periodic = d.bc[2 * axis] == HB_BC_PERIODIC && d.bc[2 * axis + 1] == HB_BC_PERIODIC;
+		int lo = rank - 1, hi = rank + 1;
+		if (lo < 0) lo = periodic ? nranks - 1 : -1;
+		if (hi >= nranks) hi = periodic ? 0 : -1;
+		int const dtype = sizeof(real) == 8 ? kNcclFloat64 : kNcclFloat32;
+		HB_NCCL(N.GroupStart());
+		for (int q = 0; q < nVars; ++q) {
+			real* base = U + (size_t)q * grid.strideV;
+			if (lo >= 0) {
+				HB_NCCL(N.Send(base + (size_t)HB_G * strideA, chunk, dtype, lo, comm, st()));
+				HB_NCCL(N.Recv(base, chunk, dtype, lo, comm, st()));
+			}
+			if (hi >= 0) {
+				HB_NCCL(N.Send(base + (size_t)(S - 2 * HB_G) * strideA, chunk, dtype, hi, comm, st()));
+				HB_NCCL(N.Recv(base + (size_t)(S - HB_G) * strideA, chunk, dtype, hi, comm, st()));
+			}
+		}
+		HB_NCCL(N.GroupEnd());
+		return HB_OK;
+	}
+	int reduceDtMin() {
+		if (!comm) return HB_OK;
+		// positive doubles order like their bit patterns, so the scalar can be min-reduced as a double
+		HB_NCCL(Nccl::get().AllReduce(dtMinBits, dtMinBits, 1, kNcclFloat64, kNcclMin, comm, st()));
+		return HB_OK;
+	}
+
+	int fillGhosts(real* U, int nVars) {
+		HB_CUDA(ops->ghosts(grid, bc, U, nVars, st()));
+		launches++;
+		return exchange(U, nVars);
+	}
+	int boundary() override {
+		useDevice(ctx);
+		return fillGhosts(upool[0], nS);
+	}
+	int constrainU() override {
+		useDevice(ctx);
+		HB_CUDA(ops->constrainAll(grid, d.eqn_params, upool[0], st()));
+		launches++;
+		dtValid = false;
+		return fillGhosts(upool[0], nS);
+	}
+	int launchCalcDT() {
+		reset_dtmin<<<1, 1, 0, st()>>>(dtMinBits);
+		HB_CUDA(cudaGetLastError());
+		HB_CUDA(ops->calcDT(grid, d.eqn_params, upool[0], dtMinBits, st()));
+		launches += 2;
+		if (int r = reduceDtMin()) return r;
+		dtValid = true;
+		return HB_OK;
+	}
+	int calcDT(double* out) override {
+		if (!out) return setError(HB_ERR_INVALID, "hb_fv_calc_dt: null pointer");
+		if (d.use_fixed_dt) { *out = d.fixed_dt; return HB_OK; }   // solverbase.lua:3007-3008
+		useDevice(ctx);
+		if (!dtValid) if (int r = launchCalcDT()) return r;
+		unsigned long long bits;
+		HB_CUDA(cudaMemcpyAsync(&bits, dtMinBits, 8, cudaMemcpyDeviceToHost, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		double m; memcpy(&m, &bits, 8);
+		*out = d.cfl * m;                                           // solverbase.lua:3016
+		return HB_OK;
+	}
+
+	void fillStageP(StageP<real>& sp, StagePlan const& s, bool wantDtMin) {
+		memset(&sp, 0, sizeof(sp));
+		sp.Uin = upool[s.uIn];
+		sp.Uout = upool[s.uOut];
+		sp.Lout = s.lOut >= 0 ? lpool[s.lOut] : nullptr;
+		sp.nA = (int)s.alpha.size();
+		for (int k = 0; k < sp.nA; ++k) { sp.aPtr[k] = upool[s.alpha[k].k]; sp.aCoef[k] = s.alpha[k].coef; }
+		sp.nB = (int)s.beta.size();
+		for (int k = 0; k < sp.nB; ++k) { sp.bPtr[k] = lpool[s.beta[k].k]; sp.bCoef[k] = s.beta[k].coef; }
+		sp.betaSelf = s.betaSelf;
+		sp.computeL = s.computeL ? 1 : 0;
+		sp.dt = ctl + 1;
+		sp.dtMinBits = wantDtMin ? dtMinBits : nullptr;
+		sp.slopeLimiter = d.slope_limiter;
+		sp.fluxLimiter = d.flux_limiter;
+	}
+
+	// integrator:integrate(dt, calcDeriv) + boundary/constrainU after every stage (rk.lua:91-165, fe.lua:33-49)
+	int runStages() {
+		bool const rk = d.rk_order >= 1;
+		if (rk && !rkZeroed && nS > nI) {
+			// rk.lua:94 clears UBuf (all fields, ghosts too); multAdd restores only the integrated fields (App. C #3)
+			HB_CUDA(cudaMemsetAsync(upool[0] + (size_t)nI * cells, 0, sizeof(real) * (size_t)(nS - nI) * cells, st()));
+			for (int k = 1; k < nU; ++k)
+				HB_CUDA(cudaMemsetAsync(upool[k] + (size_t)nI * cells, 0, sizeof(real) * (size_t)(nS - nI) * cells, st()));
+			rkZeroed = true;
+		}
+		if (!rk && nonIntSync > 0 && nS > nI) {
+			// forward Euler keeps the non-integrated fields; carry them into the ping-pong partner
+			HB_CUDA(cudaMemcpyAsync(upool[1] + (size_t)nI * cells, upool[0] + (size_t)nI * cells,
+				sizeof(real) * (size_t)(nS - nI) * cells, cudaMemcpyDeviceToDevice, st()));
+			nonIntSync--;
+		}
+		bool const plm = d.use_plm != 0;
+		bool const flim = !plm && d.flux_limiter > 0;
+		for (auto& s : plan) {
+			StageP<real> sp;
+			fillStageP(sp, s, s.last);
+			HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
+			launches++;
+			if (int r = fillGhosts(upool[s.uOut], rk ? nI : nS)) return r;
+		}
+		if (int r = reduceDtMin()) return r;
+		if (plan.back().uOut != 0) std::swap(upool[0], upool[plan.back().uOut]);   // order <= 1: ping-pong
+		dtValid = true;
+		return HB_OK;
+	}
+
+	int step(double dt) override {
+		useDevice(ctx);
+		set_step<<<1, 1, 0, st()>>>(ctl, dtMinBits, dt);
+		HB_CUDA(cudaGetLastError());
+		launches++;
+		return runStages();
+	}
+
+	int oneUpdate() {
+		begin_step<<<1, 1, 0, st()>>>(ctl, dtMinBits);
+		HB_CUDA(cudaGetLastError());
+		launches++;
+		return runStages();
+	}
+
+	int update(int nsteps) override {
+		useDevice(ctx);
+		if (nsteps <= 0) return HB_OK;
+		if (!d.use_fixed_dt && !dtValid) if (int r = launchCalcDT()) return r;
+		bool const graphable = d.use_graph && d.rk_order >= 2;
+		int done = 0;
+		if (graphable) {
+			if (d.rk_order >= 1 && !rkZeroed) { if (int r = oneUpdate()) return r; done = 1; }   // one-off memsets stay outside the graph
+			if (done < nsteps && !graphExec) {
+				long long const before = launches;
+				cudaGraph_t graph = nullptr;
+				HB_CUDA(cudaStreamBeginCapture(st(), cudaStreamCaptureModeThreadLocal));
+				int r = oneUpdate();
+				cudaError_t e = cudaStreamEndCapture(st(), &graph);
+				if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+				if (e != cudaSuccess) return cudaFail(e, "cudaStreamEndCapture");
+				graphLaunches = launches - before;
+				launches = before;
+				e = cudaGraphInstantiate(&graphExec, graph, 0);
+				cudaGraphDestroy(graph);
+				if (e != cudaSuccess) return cudaFail(e, "cudaGraphInstantiate");
+			}
+			for (; done < nsteps; ++done) {
+				HB_CUDA(cudaGraphLaunch(graphExec, st()));
+				launches += graphLaunches;
+			}
+			return HB_OK;
+		}
+		for (; done < nsteps; ++done) if (int r = oneUpdate()) return r;
+		return HB_OK;
+	}
+
+	int getTime(double* t, double* dt) override {
+		useDevice(ctx);
+		double h[2];
+		HB_CUDA(cudaMemcpyAsync(h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		if (t) *t = h[0];
+		if (dt) *dt = h[1];
+		return HB_OK;
+	}
+	int setTime(double t) override {
+		useDevice(ctx);
+		HB_CUDA(cudaMemcpyAsync(ctl, &t, sizeof(double), cudaMemcpyHostToDevice, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
+	}
+
+	int calcDeriv(double dt, double* aos) override {
+		if (!aos) return setError(HB_ERR_INVALID, "hb_fv_calc_deriv: null pointer");
+		useDevice(ctx);
+		if (int r = ensureStaging()) return r;
+		if (!scratchL) HB_CUDA(cudaMalloc(&scratchL, uBytes()));
+		HB_CUDA(cudaMemsetAsync(scratchL, 0, uBytes(), st()));
+		// keep the device dt of a running simulation intact: use a private dt slot (ctl+1 is restored below)
+		double saved[2];
+		HB_CUDA(cudaMemcpyAsync(saved, ctl, sizeof(saved), cudaMemcpyDeviceToHost, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		HB_CUDA(cudaMemcpyAsync(ctl + 1, &dt, sizeof(double), cudaMemcpyHostToDevice, st()));
+		StageP<real> sp;
+		memset(&sp, 0, sizeof(sp));
+		sp.Uin = upool[0]; sp.Uout = nullptr; sp.Lout = scratchL;
+		sp.computeL = 1; sp.dt = ctl + 1;
+		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter;
+		bool const plm = d.use_plm != 0;
+		HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
+		launches++;
+		HB_CUDA(cudaMemcpyAsync(ctl + 1, &saved[1], sizeof(double), cudaMemcpyHostToDevice, st()));
+		size_t const n = (size_t)nS * (size_t)cells;
+		soa_to_aos<real><<<(unsigned)((n + 255) / 256), 256, 0, st()>>>(grid, nS, scratchL, stagingAos);
+		HB_CUDA(cudaGetLastError());
+		launches++;
+		HB_CUDA(cudaMemcpyAsync(aos, stagingAos, sizeof(double) * n, cudaMemcpyDeviceToHost, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
+	}
+
+	int describe(char* out, size_t cap) override {
+		std::ostringstream o;
+		int ti[5];
+		bool const plm = d.use_plm != 0;
+		ops->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
+		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
+		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
+		  << " Ubufs=" << nU << " Lbufs=" << nL << "\n";
+		int words = 0;
+		for (size_t i = 0; i < plan.size(); ++i) {
+			auto& s = plan[i];
+			int const w = s.readsU + s.readsL + 1 + (s.lOut >= 0 ? 1 : 0);
+			words += w;
+			o << "stage " << i << ": in=U" << s.uIn << " out=U" << s.uOut << " storeL=" << s.lOut << " alpha=" << s.alpha.size()
+			  << " beta=" << s.beta.size() << " betaSelf=" << s.betaSelf << " words=" << w << "\n";
+		}
+		o << "words_per_cell_update=" << words << " (x nI=" << nI << " x " << sizeof(real) << " B)\n";
+		snprintf(out, cap, "%s", o.str().c_str());
+		return HB_OK;
+	}
+
+	int commInit(int nr, int rk_, const char* id) override {
+		useDevice(ctx);
+		Nccl& N = Nccl::get();
+		if (!N.ok) return setError(HB_ERR_CUDA, "hb_fv_comm_init: " + N.why);
+		if (nr < 1 || rk_ < 0 || rk_ >= nr || !id) return setError(HB_ERR_INVALID, "hb_fv_comm_init: bad arguments");
+		if (comm) return setError(HB_ERR_INVALID, "hb_fv_comm_init: already initialised");
+		nranks = nr; rank = rk_;
+		if (nr == 1) return HB_OK;
+		Nccl::uid u; memcpy(u.internal, id, 128);
+		HB_NCCL(N.CommInitRank(&comm, nr, u, rk_));
+		// faces owned by a neighbouring slab are filled by exchange(), not by the local boundary kernel
+		bool const periodic = d.bc[2 * axis] == HB_BC_PERIODIC && d.bc[2 * axis + 1] == HB_BC_PERIODIC;
+		if (rank > 0 || periodic) bc.bc[2 * axis] = HB_BC_NONE;
+		if (rank < nr - 1 || periodic) bc.bc[2 * axis + 1] = HB_BC_NONE;
+		invalidateGraph();
+		dtValid = false;
+		return HB_OK;
+	}
+	int commDestroy() override {
+		if (comm) { useDevice(ctx); cudaStreamSynchronize(st()); Nccl::get().CommDestroy(comm); comm = nullptr; }
+		return HB_OK;
+	}
+};
+
+}   // namespace hb
+
+struct hb_fv { hb::FvBase* impl; };
+
+using namespace hb;
+
+extern "C" {
+
+int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
+	if (!ctx || !d || !out) return setError(HB_ERR_INVALID, "hb_fv_create: null argument");
+	*out = nullptr;
+	if (d->dim < 1 || d->dim > 3) return setError(HB_ERR_INVALID, "hb_fv_create: dim must be 1..3");
+	for (int k = 0; k < d->dim; ++k) {
+		if (d->n[k] < 1 || d->global_n[k] < d->n[k]) return setError(HB_ERR_INVALID, "hb_fv_create: bad grid size");
+		for (int m = 0; m < 2; ++m) if (d->bc[2 * k + m] < 0 || d->bc[2 * k + m] > 3) return setError(HB_ERR_INVALID, "hb_fv_create: unknown boundary method");
+	}
+	if (d->rk_order < 0 || d->rk_order > 4) return setError(HB_ERR_INVALID, "hb_fv_create: rk_order must be 0..4");
+	if (d->use_plm < 0 || d->use_plm > 1) return setError(HB_ERR_INVALID, "hb_fv_create: only usePLM none / 'plm cons' are built");
+	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");
+	if (d->use_plm && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM requires fluxLimiter 'donor cell' (gridsolver.lua:119)");
+	FvBase* impl = nullptr;
+	bool const strict = d->strict_fp != 0;
+	if (ctx->real_bytes == 8) {
+		const FvOps<double>* o = nullptr;
+		if (d->eqn == HB_EQN_EULER) o = strict ? ops_euler_f64_strict() : ops_euler_f64_fast();
+		else if (d->eqn == HB_EQN_MHD) o = strict ? ops_mhd_f64_strict() : ops_mhd_f64_fast();
+		if (o) impl = new Fv<double>(ctx, *d, o);
+	} else {
+		const FvOps<float>* o = nullptr;
+		if (d->eqn == HB_EQN_EULER) o = strict ? ops_euler_f32_strict() : ops_euler_f32_fast();
+		else if (d->eqn == HB_EQN_MHD) o = strict ? ops_mhd_f32_strict() : ops_mhd_f32_fast();
+		if (o) impl = new Fv<float>(ctx, *d, o);
+	}
+	if (!impl) return setError(HB_ERR_INVALID, "hb_fv_create: unknown equation id");
+	if (int r = impl->init()) { delete impl; return r; }
+	*out = new hb_fv{impl};
+	return HB_OK;
+}
+int hb_fv_destroy(hb_fv* fv) { if (fv) { delete fv->impl; delete fv; } return HB_OK; }
+#define HB_FV(fv) if (!(fv)) return setError(HB_ERR_INVALID, "null hb_fv handle")
+int hb_fv_num_states(hb_fv* fv, int* ns, int* ni, int* nw) { HB_FV(fv); if (ns) *ns = fv->impl->nS; if (ni) *ni = fv->impl->nI; if (nw) *nw = fv->impl->nW; return HB_OK; }
+long long hb_fv_num_cells(hb_fv* fv) { return fv ? fv->impl->cells : 0; }
+int hb_fv_set_state(hb_fv* fv, const double* aos) { HB_FV(fv); return fv->impl->setState(aos); }
+int hb_fv_get_state(hb_fv* fv, double* aos) { HB_FV(fv); return fv->impl->getState(aos); }
+int hb_fv_state_devptr(hb_fv* fv, void** p, long long* sy, long long* sz, long long* sv) { HB_FV(fv); return fv->impl->stateDevPtr(p, sy, sz, sv); }
+int hb_fv_boundary(hb_fv* fv) { HB_FV(fv); return fv->impl->boundary(); }
+int hb_fv_constrainU(hb_fv* fv) { HB_FV(fv); return fv->impl->constrainU(); }
+int hb_fv_calc_dt(hb_fv* fv, double* dt) { HB_FV(fv); return fv->impl->calcDT(dt); }
+int hb_fv_step(hb_fv* fv, double dt) { HB_FV(fv); return fv->impl->step(dt); }
+int hb_fv_update(hb_fv* fv, int nsteps) { HB_FV(fv); return fv->impl->update(nsteps); }
+int hb_fv_get_time(hb_fv* fv, double* t, double* dt) { HB_FV(fv); return fv->impl->getTime(t, dt); }
+int hb_fv_set_time(hb_fv* fv, double t) { HB_FV(fv); return fv->impl->setTime(t); }
+int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos) { HB_FV(fv); return fv->impl->calcDeriv(dt, aos); }
+int hb_fv_launch_count(hb_fv* fv, long long* n) { HB_FV(fv); if (n) *n = fv->impl->launches; return HB_OK; }
+int hb_fv_describe(hb_fv* fv, char* out, size_t cap) { HB_FV(fv); if (!out || !cap) return setError(HB_ERR_INVALID, "hb_fv_describe: bad buffer"); return fv->impl->describe(out, cap); }
+int hb_ghost_source(int j, int S, int bcMin, int bcMax, int* flip, int* skip) {
+	bool f, s;
+	int const r = ghostSource(j, S, bcMin, bcMax, f, s);
+	if (flip) *flip = f; if (skip) *skip = s;
+	return r;
+}
+int hb_comm_unique_id(char* out128) {
+	if (!out128) return setError(HB_ERR_INVALID, "hb_comm_unique_id: null pointer");
+	Nccl& N = Nccl::get();
+	if (!N.ok) return setError(HB_ERR_CUDA, "hb_comm_unique_id: " + N.why);
+	Nccl::uid u;
+	HB_NCCL(N.GetUniqueId(&u));
+	memcpy(out128, u.internal, 128);
+	return HB_OK;
+}
+int hb_fv_comm_init(hb_fv* fv, int nranks, int rank, const char* id) { HB_FV(fv); return fv->impl->commInit(nranks, rank, id); }
+int hb_fv_comm_destroy(hb_fv* fv) { HB_FV(fv); return fv->impl->commDestroy(); }
+
+}   // extern "C"

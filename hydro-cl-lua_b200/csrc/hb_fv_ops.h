@@ -1,0 +1,30 @@
+// hb_fv_ops.h -- table of launchers one (equation, real, fp-mode) translation unit exports to the host API.
+// The kernels are compiled once per table (hb_fv_inst.cu with -DHB_EQN/-DHB_REAL/-DHB_STRICT):
+//   fast   : nvcc default floating point (FMA contraction on) -- the production kernels
+//   strict : -fmad=false -- same source, no contraction; bit-comparable with the non-contracted CPU oracle
+#pragma once
+#include <cuda_runtime.h>
+#include "hb_fv_kernels.cuh"
+
+namespace hb {
+
+template<class real> struct FvOps {
+	int eqnId, nS, nI, nW;
+	cudaError_t (*stage)(int dim, bool plm, bool flim, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st);
+	cudaError_t (*ghosts)(GridP<real> const& g, BcP const& bc, real* U, int nVars, cudaStream_t st);
+	cudaError_t (*calcDT)(GridP<real> const& g, const double* eqnParams, const real* U, unsigned long long* dtMinBits, cudaStream_t st);
+	cudaError_t (*constrainAll)(GridP<real> const& g, const double* eqnParams, real* U, cudaStream_t st);
+	void (*tileInfo)(int dim, bool plm, bool flim, int out[5]);   // TX, TY, TZ, NT, dynamic smem bytes
+};
+
+// exported by hb_fv_inst.cu instantiations
+const FvOps<double>* ops_euler_f64_fast();
+const FvOps<double>* ops_euler_f64_strict();
+const FvOps<float>* ops_euler_f32_fast();
+const FvOps<float>* ops_euler_f32_strict();
+const FvOps<double>* ops_mhd_f64_fast();
+const FvOps<double>* ops_mhd_f64_strict();
+const FvOps<float>* ops_mhd_f32_fast();
+const FvOps<float>* ops_mhd_f32_strict();
+
+}   // namespace hb

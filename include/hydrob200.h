@@ -1,0 +1,156 @@
+/* hydrob200.h -- C ABI of libhydrob200.so: the drop-in boundary between hydro-cl-lua's LuaJIT host side and the
+ * B200 (sm_100a CUDA) backend.
+ *
+ * The reference reaches its device only through lua-opencl's `cl.obj.*` objects.  Each group
+ * below names the reference call sites it replaces (file:line into the reference tree).  A LuaJIT binding
+ * `ffi.cdef`s this header verbatim (INTEGRATION.md shows it); the Python host mirror in hydro-cl-lua_b200/
+ * binds it through ctypes.  No C++ or torch types cross this boundary: plain pointers, sizes and PODs.
+ *
+ * Conventions: every function returns 0 on success and a non-zero code on failure; hb_last_error() returns the
+ * message of the calling thread's last failure.  Objects are opaque handles.  A context owns one CUDA stream (the
+ * analogue of the reference's single in-order command queue, hydro/solver/solverbase.lua:532-533); all work of a
+ * context is stream-ordered and asynchronous unless stated.  Thread-compatible, not thread-safe: one host
+ * thread per context, as in the reference (single LuaJIT thread).
+ * There is no CPU fallback: without a CUDA device every device entry point fails with HB_ERR_NO_DEVICE.
+ */
+#ifndef HYDROB200_H
+#define HYDROB200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HB_OK 0
+#define HB_ERR_INVALID 1      /* bad argument / unsupported configuration */
+#define HB_ERR_NO_DEVICE 2    /* no CUDA device or driver */
+#define HB_ERR_CUDA 3         /* CUDA runtime / driver / NVRTC / NCCL failure (see hb_last_error) */
+#define HB_ERR_COMPILE 4      /* NVRTC compilation failed: log returned by hb_module_compile */
+
+typedef struct hb_ctx hb_ctx;
+typedef struct hb_buf hb_buf;
+typedef struct hb_module hb_module;
+typedef struct hb_kernel hb_kernel;
+typedef struct hb_fv hb_fv;
+
+const char* hb_last_error(void);
+int hb_version(void);
+
+/* ---- environment: replaces CLEnv{precision, cpu, ...} -> env.real, env.devices, env.cmds
+ *      (hydro/app.lua:891-929; CL_DEVICE_MAX_WORK_GROUP_SIZE use at hydro/solver/solverbase.lua:765) */
+int hb_device_count(int* count);
+int hb_ctx_create(int device, int real_bytes /* 8 = double, 4 = float (hydro/app.lua:892) */, hb_ctx** out);
+int hb_ctx_destroy(hb_ctx* ctx);
+int hb_ctx_real_bytes(hb_ctx* ctx);
+int hb_device_name(hb_ctx* ctx, char* out, size_t cap);
+int hb_device_max_threads(hb_ctx* ctx, int* out);
+int hb_device_sm_count(hb_ctx* ctx, int* out);
+int hb_sync(hb_ctx* ctx);                                   /* cmds:finish(), hydro/solver/solverbase.lua:2096,2133 */
+void* hb_ctx_stream(hb_ctx* ctx);                           /* the cudaStream_t, for event timing by the caller */
+/* device-side timing on the context's stream (CUDA events) */
+int hb_timer_start(hb_ctx* ctx);
+int hb_timer_stop(hb_ctx* ctx, float* ms_out);              /* synchronises the stop event */
+/* pinned host memory for hb_buf_write / hb_buf_read / hb_fv_set_state / hb_fv_get_state sources */
+int hb_host_alloc(size_t bytes, void** out);
+int hb_host_free(void* p);
+
+/* ---- buffers: replaces CLBuffer{env,name,type,count}:fromCPU/toCPU/fill, ctx:buffer{rw,size}, enqueueCopyBuffer,
+ *      clEnqueueCopyBufferRect (hydro/solver/solverbase.lua:1077-1095,1132,1417-1428; hydro/int/rk.lua:25,33,63;
+ *      hydro/int/int.lua:6-8; hydro/solver/choppedup.lua:199-231) */
+int hb_buf_alloc(hb_ctx* ctx, size_t bytes, hb_buf** out);
+int hb_buf_free(hb_buf* buf);
+size_t hb_buf_size(hb_buf* buf);
+void* hb_buf_devptr(hb_buf* buf);
+int hb_buf_write(hb_buf* buf, const void* host, size_t offset, size_t bytes);        /* fromCPU; async w.r.t. pinned host memory */
+int hb_buf_read(hb_buf* buf, void* host, size_t offset, size_t bytes);               /* toCPU; blocking */
+int hb_buf_fill(hb_buf* buf, const void* pattern, size_t pattern_bytes, size_t offset, size_t bytes);
+int hb_buf_copy(hb_buf* dst, size_t dst_offset, hb_buf* src, size_t src_offset, size_t bytes);
+/* origins/region in (bytes along x, rows, slices); pitches in bytes -- same meaning as clEnqueueCopyBufferRect */
+int hb_buf_copy_rect(hb_buf* dst, hb_buf* src, const size_t src_origin[3], const size_t dst_origin[3], const size_t region[3],
+	size_t src_row_pitch, size_t src_slice_pitch, size_t dst_row_pitch, size_t dst_slice_pitch);
+
+/* ---- programs and kernels: replaces Program{name,code}:compile{buildOptions} + binary cache, program:kernel(name,...),
+ *      k.obj:setArg(i,x), k(...) / cmds:enqueueNDRangeKernel{kernel,globalSize,localSize}
+ *      (hydro/solver/solverbase.lua:558-713,1328-1345,1696-1699; hydro/solver/fvsolver.lua:216-221;
+ *       hydro/solver/gridsolver.lua:1206-1209,1277-1309).  Source is CUDA C++ compiled by NVRTC for sm_100a. */
+int hb_module_compile(hb_ctx* ctx, const char* cuda_src, const char* name, const char* const* opts, int nopts,
+	hb_module** out, char* log, size_t log_cap);
+int hb_module_free(hb_module* m);
+int hb_kernel_get(hb_module* m, const char* name, hb_kernel** out);
+int hb_kernel_set_arg(hb_kernel* k, int index, const void* value, size_t bytes);     /* by-value argument */
+int hb_kernel_set_arg_buf(hb_kernel* k, int index, hb_buf* buf);                     /* device pointer argument */
+int hb_kernel_launch(hb_kernel* k, const size_t global_size[3], const size_t local_size[3], size_t shared_bytes);
+
+/* ---- reductions: replaces env:reduce{count,op,buffer,...}() -> host scalar
+ *      (hydro/solver/solverbase.lua:1350-1376, used at :3016) */
+#define HB_REDUCE_MIN 0
+#define HB_REDUCE_MAX 1
+#define HB_REDUCE_SUM 2
+int hb_reduce(hb_ctx* ctx, hb_buf* buf, size_t count, int op, double* host_out);     /* elements are the ctx's `real` */
+
+/* ---- the fused finite-volume path (no single reference analogue: it is what FiniteVolumeSolver:calcDeriv,
+ *      integrator:integrate, SolverBase:calcDT/step/update/boundary/constrainU enqueue together;
+ *      hydro/solver/fvsolver.lua:225-302, hydro/int/fe.lua:33-49, hydro/int/rk.lua:47-167,
+ *      hydro/solver/solverbase.lua:2116-2127,3004-3023,3026-3238, hydro/solver/gridsolver.lua:1272-1320) */
+#define HB_EQN_EULER 0        /* hydro/eqn/euler.lua: eqn_params = { heatCapacityRatio, rhoMin, PMin } */
+#define HB_EQN_MHD 1          /* hydro/eqn/mhd.lua:   eqn_params = { heatCapacityRatio, mu0 / unit_kg_m_per_C2 } */
+#define HB_BC_PERIODIC 0      /* hydro/solver/gridsolver.lua:638-651 */
+#define HB_BC_MIRROR 1        /* :654-744 */
+#define HB_BC_FREEFLOW 2      /* :766-780 */
+#define HB_BC_NONE 3          /* :618-621; also: face owned by a neighbouring slab (hb_fv_exchange fills it) */
+
+typedef struct hb_fv_desc {
+	int eqn;                  /* HB_EQN_* */
+	int dim;                  /* 1..3 */
+	int n[3];                 /* interior cells of THIS rank's slab per axis (1 on unused axes) */
+	int global_n[3];          /* interior cells of the whole grid (== n without decomposition); defines grid_dx */
+	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91) */
+	int slope_limiter;        /* 0-based index into hydro/app.lua:614-635 */
+	int flux_limiter;         /* 0-based; 0 = 'donor cell' = no flux limiter (hydro/solver/fvsolver.lua:61-63) */
+	int bc[6];                /* xmin,xmax,ymin,ymax,zmin,zmax: HB_BC_* */
+	int rk_order;             /* 0 = forward Euler (hydro/int/fe.lua), else Butcher order (hydro/int/rk.lua) */
+	double alphas[16];        /* row-major [order][order], hydro/int/all.lua */
+	double betas[16];
+	double mins[3], maxs[3];  /* whole-grid domain (solver_t mins/maxs) */
+	double cfl;               /* hydro/solver/solverbase.lua:806, config.lua:37 */
+	double fixed_dt;          /* used when use_fixed_dt (hydro/solver/solverbase.lua:3007-3008) */
+	int use_fixed_dt;
+	double eqn_params[16];
+	int strict_fp;            /* 1: kernels built with -fmad=false (no FMA contraction); 0: production kernels */
+	int use_graph;            /* 1: replay each update() as a captured CUDA graph */
+} hb_fv_desc;
+
+int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* desc, hb_fv** out);
+int hb_fv_destroy(hb_fv* fv);
+int hb_fv_num_states(hb_fv* fv, int* num_states, int* num_int_states, int* num_waves);
+long long hb_fv_num_cells(hb_fv* fv);                        /* ghost-inclusive cell count of this rank's slab */
+/* state exchange in the reference's layout: AoS cons_t records of doubles, INDEX order (hydro/app.lua:976-984),
+ * ghost cells included; converted to/from the SoA `real` device layout on the device */
+int hb_fv_set_state(hb_fv* fv, const double* aos_host);
+int hb_fv_get_state(hb_fv* fv, double* aos_host);           /* blocking */
+int hb_fv_state_devptr(hb_fv* fv, void** soa_dev, long long* stride_y, long long* stride_z, long long* stride_var);
+int hb_fv_boundary(hb_fv* fv);                               /* solver:boundary(), gridsolver.lua:1316 */
+int hb_fv_constrainU(hb_fv* fv);                             /* solver:constrainU() = kernel + boundary(), solverbase.lua:2116-2127 */
+int hb_fv_calc_dt(hb_fv* fv, double* dt_out);                /* solver:calcDT(), solverbase.lua:3004-3023 (blocking) */
+int hb_fv_step(hb_fv* fv, double dt);                        /* solver:step(dt), solverbase.lua:3193-3238 */
+int hb_fv_update(hb_fv* fv, int nsteps);                     /* nsteps x solver:update(); dt stays on the device */
+int hb_fv_get_time(hb_fv* fv, double* t_out, double* last_dt_out);   /* blocking read of t and the last dt */
+int hb_fv_set_time(hb_fv* fv, double t);
+int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos_host_out);    /* FiniteVolumeSolver:calcDeriv into a zeroed deriv buffer (blocking) */
+int hb_fv_launch_count(hb_fv* fv, long long* kernel_launches);       /* kernels this object has launched so far */
+int hb_fv_describe(hb_fv* fv, char* out, size_t cap);        /* text: tile shape, smem, per-stage plan (reads / writes per cell) */
+/* host-side helper exported for tests: source index of ghost index j on an axis of ghost-inclusive size S */
+int hb_ghost_source(int j, int S, int bc_min, int bc_max, int* flip_out, int* skip_out);
+
+/* ---- multi-GPU: slab decomposition along the slowest used axis, one process per GPU.  Replaces
+ *      hydro/solver/choppedup.lua:193-233,344-409 (rect copies once per step + host min of dt) by a per-stage
+ *      ghost-plane exchange and a min-allreduce of dt, both over NCCL (NVLink 5 / NVSwitch). */
+int hb_comm_unique_id(char* out128);                         /* ncclGetUniqueId; broadcast by the caller (e.g. torch.distributed) */
+int hb_fv_comm_init(hb_fv* fv, int nranks, int rank, const char* id128);
+int hb_fv_comm_destroy(hb_fv* fv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HYDROB200_H */

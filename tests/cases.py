@@ -1,0 +1,40 @@
+"""Shared parity cases: reduced-size versions of the BASELINE.json configs, sized so the CPU oracle
+finishes each in seconds.  Grid sizes are deliberately not multiples of the CUDA tile shapes."""
+
+CASES = {
+    # C1: 1D Sod, Euler, Roe + superbee flux limiter, forward Euler, 256 cells (the reference's CPU-runnable config)
+    "C1_sod_fe_superbee": (dict(eqn="euler", dim=1, gridSize=[256], initCond="Sod", fluxLimiter="superbee",
+                                integrator="forward Euler", cfl=.3), 100),
+    "C1_sod_fe_donor": (dict(eqn="euler", dim=1, gridSize=[300], initCond="Sod", fluxLimiter="donor cell",
+                             integrator="forward Euler", cfl=.3), 50),
+    "C1_sod_rk4_plm_mirror": (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm cons", slopeLimiter="minmod",
+                                   integrator="Runge-Kutta 4", cfl=.3, boundary=dict(xmin="mirror", xmax="mirror")), 40),
+    # C2: 2D Kelvin-Helmholtz, Euler, Roe + PLM, RK4-TVD, periodic
+    "C2_kh_rk4tvd_minmod": (dict(eqn="euler", dim=2, gridSize=[80, 56], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                                 slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 20),
+    "C2_kh_rk4tvd_superbee": (dict(eqn="euler", dim=2, gridSize=[72, 40], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                                   slopeLimiter="superbee", integrator="Runge-Kutta 4, TVD", cfl=.15), 20),
+    "C2_sod2d_mirror_fluxlim": (dict(eqn="euler", dim=2, gridSize=[48, 36], initCond="Sod", fluxLimiter="superbee",
+                                     integrator="Runge-Kutta 2, TVD", cfl=.15,
+                                     boundary=dict(xmin="mirror", xmax="mirror", ymin="mirror", ymax="mirror")), 20),
+    # C3: 2D Orszag-Tang, ideal MHD, Roe + PLM, RK3-TVD, periodic
+    "C3_ot_rk3tvd": (dict(eqn="mhd", dim=2, gridSize=[72, 44], initCond="Orszag-Tang", usePLM="plm cons",
+                          slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15), 20),
+    "C3_briowu_1d_fluxlim": (dict(eqn="mhd", dim=1, gridSize=[256], initCond="Brio-Wu", fluxLimiter="superbee",
+                                  integrator="forward Euler", cfl=.3), 50),
+    # C4: 3D spherical blast, Euler, Roe + PLM, RK4, freeflow, domain +-2
+    "C4_sphere_rk4": (dict(eqn="euler", dim=3, gridSize=[40, 20, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                           usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 10),
+    "C4_sphere_rk4_mirror_periodic": (dict(eqn="euler", dim=3, gridSize=[24, 18, 10], mins=[-2, -2, -2], maxs=[2, 2, 2],
+                                           initCond="sphere", usePLM="plm cons", slopeLimiter="minmod",
+                                           integrator="Runge-Kutta 4", cfl=.1,
+                                           boundary=dict(xmin="mirror", xmax="mirror", ymin="periodic", ymax="periodic",
+                                                         zmin="freeflow", zmax="mirror")), 6),
+    "C4_mhd3d_rk3": (dict(eqn="mhd", dim=3, gridSize=[20, 12, 10], initCond="Orszag-Tang", usePLM="plm cons",
+                          slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]), 5),
+    # the volume > 1e-7 guard (fvsolver.cl:97): 512^3 on [-1,1]^3 would freeze; here a small grid on a tiny domain
+    "frozen_volume_guard": (dict(eqn="euler", dim=3, gridSize=[12, 10, 8], mins=[-.01] * 3, maxs=[.01] * 3, initCond="sphere",
+                                 usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 2),
+}
+
+FLOAT_CASES = ["C2_kh_rk4tvd_minmod", "C4_sphere_rk4", "C3_ot_rk3tvd", "C1_sod_fe_superbee"]
