@@ -105,7 +105,7 @@ static void buildPlan(int order, const double* A, const double* B, std::vector<S
 		int out;
 		if (s.last && n >= 2) out = 0;                // in place over U^0 (only read pointwise by its own cell's thread)
 		else { out = 0; while (liveU.count(out)) ++out; }
-		uPhys[i + 1] = out; liveU.insert(out);
+		uPhys[i + 1] = out; liveU.insert(out); s.uOut = out;
 		if (out + 1 > nU) nU = out + 1;
 		bool neededLater = false;
 		for (int m = i + 1; m < n; ++m) neededLater = neededLater || b(m, i) != 0;
@@ -612,6 +612,30 @@ int hb_ghost_source(int j, int S, int bcMin, int bcMax, int* flip, int* skip) {
 	int const r = ghostSource(j, S, bcMin, bcMax, f, s);
 	if (flip) *flip = f; if (skip) *skip = s;
 	return r;
+}
+// unit-test hook (not used by the product path): evaluate one device function per item on the GPU
+int hb_debug_eval(hb_ctx* ctx, int eqn, int strict, int kind, int side, int n, const double* params, const double* aux4,
+	const double* in, size_t inCount, double* out, size_t outCount)
+{
+	if (!ctx || !params || !aux4 || !in || !out || n <= 0) return setError(HB_ERR_INVALID, "hb_debug_eval: bad argument");
+	useDevice(ctx);
+	double *dIn = nullptr, *dOut = nullptr, *dAux = nullptr;
+	HB_CUDA(cudaMalloc(&dIn, inCount * 8)); HB_CUDA(cudaMalloc(&dOut, outCount * 8)); HB_CUDA(cudaMalloc(&dAux, 4 * 8));
+	HB_CUDA(cudaMemcpy(dIn, in, inCount * 8, cudaMemcpyHostToDevice));
+	HB_CUDA(cudaMemcpy(dAux, aux4, 4 * 8, cudaMemcpyHostToDevice));
+	cudaError_t e = cudaErrorInvalidValue;
+	if (ctx->real_bytes == 8) {
+		const FvOps<double>* o = eqn == HB_EQN_EULER ? (strict ? ops_euler_f64_strict() : ops_euler_f64_fast()) : (strict ? ops_mhd_f64_strict() : ops_mhd_f64_fast());
+		e = o->debugEval(kind, side, n, params, dAux, dIn, dOut, ctx->stream);
+	} else {
+		const FvOps<float>* o = eqn == HB_EQN_EULER ? (strict ? ops_euler_f32_strict() : ops_euler_f32_fast()) : (strict ? ops_mhd_f32_strict() : ops_mhd_f32_fast());
+		e = o->debugEval(kind, side, n, params, dAux, dIn, dOut, ctx->stream);
+	}
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpy(out, dOut, outCount * 8, cudaMemcpyDeviceToHost);
+	cudaFree(dIn); cudaFree(dOut); cudaFree(dAux);
+	if (e != cudaSuccess) return cudaFail(e, "hb_debug_eval");
+	return HB_OK;
 }
 int hb_comm_unique_id(char* out128) {
 	if (!out128) return setError(HB_ERR_INVALID, "hb_comm_unique_id: null pointer");

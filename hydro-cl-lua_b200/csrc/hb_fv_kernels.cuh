@@ -122,6 +122,7 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 		}
 		__syncthreads();
 	}
+	if (!PLM && SIDE > 0) __syncthreads();   // phase C of the previous side still reads FX
 	// ---- B: Roe flux at interfaces f = 0 .. TS (low face of cell f)
 	for (int w = tid; w < (TS + 1) * P; w += T::NT) {
 		int f, p, i, j, k;
@@ -179,7 +180,9 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 	}
 }
 
-template<class Eqn, int DIM, bool PLM, bool FLIM, class T>
+// MODE (0 = production, 1 = strict -fmad=false build) only makes the two builds' kernels distinct symbols: the
+// translation units are linked into one library and must not share host stubs.
+template<class Eqn, int DIM, bool PLM, bool FLIM, class T, int MODE>
 __global__ void __launch_bounds__(T::NT)
 fv_stage(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep)
 {
@@ -316,7 +319,7 @@ HB_HD int ghostSource(int j, int S, int bcMin, int bcMax, bool& flip, bool& skip
 }
 
 // Enumerates the ghost cells: z slabs (whole planes), then y slabs of the remaining planes, then x slabs.
-template<class Eqn>
+template<class Eqn, int MODE>
 __global__ void fill_ghosts(GridP<typename Eqn::real> const g, BcP const bc, typename Eqn::real* __restrict__ U, int nVars)
 {
 	typedef typename Eqn::real real;
@@ -362,7 +365,7 @@ __global__ void fill_ghosts(GridP<typename Eqn::real> const g, BcP const bc, typ
 // ---------------------------------------------------------------------------------------------------
 // Stand-alone kernels: calcDT (eqn.lua:1187-1224 + reduceMin, solverbase.lua:1350-1358, 3004-3023),
 // constrainU on every cell (solverbase.lua:2116-2127), AoS <-> SoA conversion at the API boundary.
-template<class Eqn>
+template<class Eqn, int MODE>
 __global__ void calc_dt(GridP<typename Eqn::real> const g, typename Eqn::Params const ep,
 	typename Eqn::real const* __restrict__ U, unsigned long long* dtMinBits)
 {
@@ -391,7 +394,7 @@ __global__ void calc_dt(GridP<typename Eqn::real> const g, typename Eqn::Params 
 	}
 }
 
-template<class Eqn>
+template<class Eqn, int MODE>
 __global__ void constrain_all(GridP<typename Eqn::real> const g, typename Eqn::Params const ep, typename Eqn::real* __restrict__ U)
 {
 	typedef typename Eqn::real real;

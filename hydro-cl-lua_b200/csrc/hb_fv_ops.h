@@ -15,6 +15,8 @@ template<class real> struct FvOps {
 	cudaError_t (*calcDT)(GridP<real> const& g, const double* eqnParams, const real* U, unsigned long long* dtMinBits, cudaStream_t st);
 	cudaError_t (*constrainAll)(GridP<real> const& g, const double* eqnParams, real* U, cudaStream_t st);
 	void (*tileInfo)(int dim, bool plm, bool flim, int out[5]);   // TX, TY, TZ, NT, dynamic smem bytes
+	// unit-test hook: evaluates one device function per item on the GPU (device pointers; doubles in and out)
+	cudaError_t (*debugEval)(int kind, int side, int n, const double* eqnParams, const double* aux, const double* in, double* out, cudaStream_t st);
 };
 
 // exported by hb_fv_inst.cu instantiations

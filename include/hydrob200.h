@@ -140,6 +140,10 @@ int hb_fv_set_time(hb_fv* fv, double t);
 int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos_host_out);    /* FiniteVolumeSolver:calcDeriv into a zeroed deriv buffer (blocking) */
 int hb_fv_launch_count(hb_fv* fv, long long* kernel_launches);       /* kernels this object has launched so far */
 int hb_fv_describe(hb_fv* fv, char* out, size_t cap);        /* text: tile shape, smem, per-stage plan (reads / writes per cell) */
+/* unit-test hook: evaluate one device function per item on the GPU (kind 0 Roe flux, 1 constrainU, 2 calcDTCell,
+ * 3 PLM half slope, 4 Roe flux with flux limiter); host pointers of doubles; strict selects the -fmad=false build */
+int hb_debug_eval(hb_ctx* ctx, int eqn, int strict, int kind, int side, int n, const double* params, const double* aux4,
+	const double* in, size_t in_count, double* out, size_t out_count);
 /* host-side helper exported for tests: source index of ghost index j on an axis of ghost-inclusive size S */
 int hb_ghost_source(int j, int S, int bc_min, int bc_max, int* flip_out, int* skip_out);
 

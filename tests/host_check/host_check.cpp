@@ -1,0 +1,61 @@
+// host_check.cpp -- TEST INFRASTRUCTURE.  Compiles the product's per-interface / per-cell device functions
+// (hydro-cl-lua_b200/csrc/hb_*.cuh, which are __host__ __device__) with g++ -ffp-contract=off so that the CPU test
+// suite can compare them with the oracle without a GPU.  Nothing in the product links or loads this library.
+#include "../../hydro-cl-lua_b200/csrc/hb_roe.cuh"
+#include "../../hydro-cl-lua_b200/csrc/hb_eqn_euler.cuh"
+#include "../../hydro-cl-lua_b200/csrc/hb_eqn_mhd.cuh"
+
+using namespace hb;
+
+template<class Eqn> static void roe(int side, const double* params, const double* UL_, const double* UR_, double* F_) {
+	typedef typename Eqn::real real;
+	typename Eqn::Params p = Eqn::makeParams(params);
+	real UL[Eqn::nI], UR[Eqn::nI], F[Eqn::nI];
+	for (int q = 0; q < Eqn::nI; ++q) { UL[q] = real(UL_[q]); UR[q] = real(UR_[q]); }
+	if (side == 0) roeFlux<Eqn, 0>(F, p, UL, UR);
+	else if (side == 1) roeFlux<Eqn, 1>(F, p, UL, UR);
+	else roeFlux<Eqn, 2>(F, p, UL, UR);
+	for (int q = 0; q < Eqn::nI; ++q) F_[q] = double(F[q]);
+}
+template<class Eqn> static void roeLim(int side, const double* params, int lim, double dt_dx, const double* U4, double* F_) {
+	typedef typename Eqn::real real;
+	typename Eqn::Params p = Eqn::makeParams(params);
+	real U[4][Eqn::nI], F[Eqn::nI];
+	for (int c = 0; c < 4; ++c) for (int q = 0; q < Eqn::nI; ++q) U[c][q] = real(U4[c * Eqn::nI + q]);
+	if (side == 0) roeFluxLimited<Eqn, 0>(F, p, lim, real(dt_dx), U[0], U[1], U[2], U[3]);
+	else if (side == 1) roeFluxLimited<Eqn, 1>(F, p, lim, real(dt_dx), U[0], U[1], U[2], U[3]);
+	else roeFluxLimited<Eqn, 2>(F, p, lim, real(dt_dx), U[0], U[1], U[2], U[3]);
+	for (int q = 0; q < Eqn::nI; ++q) F_[q] = double(F[q]);
+}
+template<class Eqn> static void constrain(const double* params, double* U_) {
+	typedef typename Eqn::real real;
+	typename Eqn::Params p = Eqn::makeParams(params);
+	real U[Eqn::nI];
+	for (int q = 0; q < Eqn::nI; ++q) U[q] = real(U_[q]);
+	Eqn::constrainU(p, U);
+	for (int q = 0; q < Eqn::nI; ++q) U_[q] = double(U[q]);
+}
+template<class Eqn> static double dtCell(const double* params, const double* U_, const double* dx_, int dim) {
+	typedef typename Eqn::real real;
+	typename Eqn::Params p = Eqn::makeParams(params);
+	real U[Eqn::nI]; real dx[3] = {real(dx_[0]), real(dx_[1]), real(dx_[2])};
+	for (int q = 0; q < Eqn::nI; ++q) U[q] = real(U_[q]);
+	return double(Eqn::calcDTCell(p, U, dx, dim));
+}
+
+#define DISPATCH(call) \
+	if (eqn == 0 && rb == 8) { typedef Euler<double> E; call; } \
+	else if (eqn == 0) { typedef Euler<float> E; call; } \
+	else if (rb == 8) { typedef MHD<double> E; call; } \
+	else { typedef MHD<float> E; call; }
+
+extern "C" {
+void hc_roe_flux(int eqn, int rb, int side, const double* params, const double* UL, const double* UR, double* F) { DISPATCH(roe<E>(side, params, UL, UR, F)) }
+void hc_roe_flux_limited(int eqn, int rb, int side, const double* params, int lim, double dt_dx, const double* U4, double* F) { DISPATCH(roeLim<E>(side, params, lim, dt_dx, U4, F)) }
+void hc_constrainU(int eqn, int rb, const double* params, double* U) { DISPATCH(constrain<E>(params, U)) }
+double hc_calc_dt_cell(int eqn, int rb, const double* params, const double* U, const double* dx, int dim) { double r = 0; DISPATCH(r = dtCell<E>(params, U, dx, dim)) return r; }
+double hc_plm_half_slope(int rb, int lim, double UL, double U, double UR) {
+	return rb == 8 ? plmHalfSlope<double>(lim, UL, U, UR) : double(plmHalfSlope<float>(lim, float(UL), float(U), float(UR)));
+}
+double hc_limiter(int id, double r) { return limiter<double>(id, r); }
+}

@@ -33,6 +33,19 @@ def rel_linf(a, b):
     return max(out), out
 
 
+def rel_linf_grouped(a, b):
+    """Relative L-infinity with the components of a vector field (m, B) sharing one scale: a velocity component that
+    is physically ~0 (KH: m.y ~ 1e-2 of m.x) is measured against the size of the vector, not against itself."""
+    nv = a.shape[-1]
+    groups = [[0], [1, 2, 3], [4]] + ([[5, 6, 7], [8], [9]] if nv == 10 else [[5]])
+    out = []
+    for g in groups:
+        scale = np.abs(b[..., g]).max()
+        err = np.abs(a[..., g] - b[..., g]).max()
+        out.append(err / scale if scale > 0 else err)
+    return max(out), out
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_strict_bitexact_double(hydrob200, oracle, name):
     cfg, n = CASES[name]
@@ -63,7 +76,7 @@ def test_float(hydrob200, oracle, name):
     assert tgot == tref
     assert np.array_equal(got, ref)
     got, tgot, _ = run(hydrob200, cfg, n)
-    err, per = rel_linf(got, ref)
+    err, per = rel_linf_grouped(got, ref)
     assert err <= TOL_FLOAT, per
 
 
