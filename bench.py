@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py -- cell-updates/s of the explicit finite-volume update (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4|C2|C3]
+
+Workload (default C4, the config BASELINE.json quotes "at 1/2/4/8 B200" on): 3-D Euler spherical blast, Roe + PLM
+('plm cons', minmod) + classic RK4, double precision, freeflow boundaries, 512^3 interior cells PER GPU (weak
+scaling: the grid is 512 x 512 x 512*N, slab-decomposed along z, ghost planes exchanged every RK stage over NCCL, dt
+min-allreduced).  One "step" = one solver:update() = 4 fused stage kernels + 4 ghost fills + bookkeeping, dt device-resident.
+Synthetic inputs: the 'sphere' initial condition of hydro/init/euler.lua:1274-1296 evaluated on the host.
+
+The JSON line carries: value (resident-state throughput, all ranks), e2e (same metric through the C-ABI with HOST
+buffers: pinned host -> device state upload, one update, device -> host download, every step), roofline of the fused
+stage kernel (algorithmic bytes per launch / live CUDA-event duration, against MEASURED_PEAKS.json), cpu_baseline (the
+oracle -- a CPU restatement of the reference's kernels, NOT the reference binary -- on a bounded sample), clocks, gpu_launches.
+
+--impl reference times that CPU restatement with all host threads on a bounded sample of the same workload (the reference
+itself is LuaJIT + OpenCL with un-vendored dependencies and cannot run here or on the GPU box: DESIGN.md).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT,):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np  # noqa: E402
+
+# algorithmic HBM bytes per cell-update: words x nI x sizeof(double)
+WORKLOADS = {
+    "C4": dict(name="3D Euler spherical blast, Roe+PLM(minmod)+RK4, double, freeflow, 512^3 per GPU (z slabs)",
+               cfg=dict(eqn="euler", dim=3, gridSize=[512, 512, 512], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                        usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1),
+               words=16, nI=5, stages=4, cpu_sample=[128, 128, 128]),
+    "C2": dict(name="2D Euler Kelvin-Helmholtz, Roe+PLM(minmod)+RK4-TVD, double, periodic, 2048^2 per GPU (y slabs)",
+               cfg=dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                        slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15),
+               words=21, nI=5, stages=4, cpu_sample=[1024, 1024]),
+    "C3": dict(name="2D ideal-MHD Orszag-Tang, Roe+PLM(minmod)+RK3-TVD, double, periodic, 4096^2 per GPU (y slabs)",
+               cfg=dict(eqn="mhd", dim=2, gridSize=[4096, 4096], initCond="Orszag-Tang", usePLM="plm cons",
+                        slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15),
+               words=8, nI=8, stages=3, cpu_sample=[1024, 1024]),
+}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f)["hbm_gbs"], "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650., "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(.2)
+
+    def summary(self):
+        sm = [float(s[1]) for s in self.samples if len(s) > 8 and s[1].replace(".", "").isdigit()]
+        mx = [float(s[2]) for s in self.samples if len(s) > 8 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            if len(s) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def cpu_oracle_rate(w, nthreads, steps, warmup=1):
+    """cell-updates/s of the CPU restatement (oracle) on a bounded sample of the workload.  Test/baseline infrastructure:
+    the one place besides tests/ and smoke() that executes oracle/."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hydrob200
+    import oracle
+    cfg = dict(w["cfg"], gridSize=w["cpu_sample"], backend=oracle.OracleBackendThreads(nthreads))
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    cells = int(np.prod(w["cpu_sample"]))
+    for _ in range(warmup):
+        S.update()
+    per = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        S.update()
+        per.append(time.perf_counter() - t0)
+    total = sum(per)
+    return cells * steps / total, total / steps, cells
+
+
+def run_reference(args, w):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    cores = oracle.lib().ho_max_threads()
+    rate, sec, cells = cpu_oracle_rate(w, cores, args.steps, max(1, min(args.warmup, 2)))
+    sample = "one update of the %s workload on a %s interior sample per step (CPU restatement of the reference kernels, OpenMP)" % (
+        args.workload, "x".join(map(str, w["cpu_sample"])))
+    line = {
+        "impl": "reference", "metric": "cell-updates/sec", "value": rate, "unit": "cell-updates/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "sample": "x".join(map(str, w["cpu_sample"]))},
+        "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C4", choices=list(WORKLOADS))
+    ap.add_argument("--grid", default=None, help="override the per-GPU interior grid, e.g. 256,256,256")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = dict(WORKLOADS[args.workload])
+    if args.impl == "reference":
+        return run_reference(args, w)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import hydrob200
+    from importlib import import_module
+    hb = import_module("hydro-cl-lua_b200._lib")
+    SlabComm = import_module("hydro-cl-lua_b200.hydro.solver.choppedup").SlabComm
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", str(rank)))
+    if world != args.gpus and world != 1:
+        raise SystemExit("WORLD_SIZE (%d) != --gpus (%d)" % (world, args.gpus))
+    dist = None
+    comm = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+        comm = SlabComm(world, rank, dist)
+
+    cfg = dict(w["cfg"])
+    if args.grid:
+        cfg["gridSize"] = [int(x) for x in args.grid.split(",")]
+    perGpu = list(cfg["gridSize"])
+    ax = cfg["dim"] - 1
+    if world > 1:                     # weak scaling: per-GPU slab fixed, the grid grows along the decomposed axis
+        cfg["gridSize"] = list(perGpu)
+        cfg["gridSize"][ax] = perGpu[ax] * world
+        span = cfg.get("maxs", [1.] * 3)[ax] - cfg.get("mins", [-1.] * 3)[ax]
+        mins = list(cfg.get("mins", [-1.] * 3)); maxs = list(cfg.get("maxs", [1.] * 3))
+        maxs[ax] = mins[ax] + span * world       # same dx as the 1-GPU grid
+        cfg["mins"], cfg["maxs"] = mins, maxs
+    S = hydrob200.FiniteVolumeSolver(dict(cfg, device=local, comm=comm, use_graph=True))
+    B = S.backend
+    L = B.L
+    ctx = B.ctx
+    cellsLocal = int(np.prod(perGpu))
+    cellsAll = cellsLocal * world
+
+    def barrier():
+        ctx.sync()
+        if dist is not None:
+            dist.barrier()
+        ctx.sync()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        import torch
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    # ---- resident-state throughput: W warm-up updates, then exactly K timed updates (CUDA events on the library's stream)
+    hb.check(L.hb_fv_update(B.h, args.warmup))
+    n0 = B.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ctx.timerStart()
+    hb.check(L.hb_fv_update(B.h, args.steps))
+    ms = ctx.timerStop()
+    barrier()
+    sampler.stop_flag = True
+    ms = max_over_ranks(ms)
+    launches = B.launch_count() - n0
+    value = cellsAll * args.steps / (ms * 1e-3)
+    t_sim, dt_sim = B.get_time()
+    finite = bool(np.isfinite(t_sim) and np.isfinite(dt_sim) and dt_sim > 0)
+
+    # ---- the dominant kernel (fused stage kernel), timed live per launch with CUDA events (eager launches)
+    hb.check(L.hb_fv_profile(B.h, 1))
+    hb.check(L.hb_fv_update(B.h, max(2, min(args.steps, 5))))
+    sms, sn = C.c_double(), C.c_longlong()
+    hb.check(L.hb_fv_profile_read(B.h, C.byref(sms), C.byref(sn)))
+    hb.check(L.hb_fv_profile(B.h, 0))
+    stage_ms = sms.value / max(1, sn.value)
+    bytes_per_launch = w["words"] * w["nI"] * 8 / w["stages"] * cellsLocal
+    peak, peak_src = peaks()
+    achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "fv_stage", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "stage_kernel_ms": stage_ms,
+                "stage_share_of_step": stage_ms * w["stages"] / (ms / args.steps),
+                "algorithmic_bytes_per_cell_update": w["words"] * w["nI"] * 8}
+
+    # ---- end to end through the C-ABI with HOST buffers: upload state (pinned host, AoS doubles) -> update -> download
+    nS = B.nS
+    nbytes = int(B.ncells) * nS * 8
+    hp = C.c_void_p()
+    hb.check(L.hb_host_alloc(nbytes, C.byref(hp)))
+    hb.check(L.hb_fv_get_state(B.h, hp))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        hb.check(L.hb_fv_set_state(B.h, hp))
+        hb.check(L.hb_fv_update(B.h, 1))
+        hb.check(L.hb_fv_get_state(B.h, hp))
+    ctx.sync()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    hb.check(L.hb_host_free(hp))
+    e2e = {"value": cellsAll * args.e2e_steps / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+           "steps": args.e2e_steps, "ms_per_step": e2e_s / args.e2e_steps * 1e3}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        cores = oracle.lib().ho_max_threads()
+        rate, sec, cells = cpu_oracle_rate(w, cores, 4)
+        cpu = {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
+               "sample": "4 updates of the same workload on a %s interior sample (CPU restatement of the reference kernels, OpenMP, %d threads)" % (
+                   "x".join(map(str, w["cpu_sample"])), cores)}
+
+    if rank == 0:
+        line = {
+            "metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"] if not args.grid else w["name"] + " [grid override %s]" % args.grid,
+                       "per_gpu_grid": perGpu, "global_grid": cfg["gridSize"], "parallelism": "slab-z x%d" % world,
+                       "l2": "state arrays (%.1f GB per buffer) exceed the 126 MB L2; no flush needed" % (B.ncells * nS * 8 / 1e9),
+                       "timing": "CUDA events on the library stream, max over ranks", "finite": finite, "t": t_sim, "dt": dt_sim},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,8 +95,7 @@ class CudaBackend:
         strict = args.get("strict_fp", self.strict_fp)
         graph = args.get("use_graph", self.use_graph)
         self.comm = comm
-        local_n = comm.localSize(solver) if comm is not None else None
-        self.desc = desc_from_solver(solver, strict, graph, local_n)
+        self.desc = desc_from_solver(solver, strict, graph, solver.localSizeWithoutBorder)
         self.h = hb.P()
         hb.check(self.L.hb_fv_create(self.ctx.h, C.byref(self.desc), C.byref(self.h)))
         ns, ni, nw = C.c_int(), C.c_int(), C.c_int()
@@ -120,8 +119,6 @@ class CudaBackend:
     # ---- backend interface (same as oracle.OracleBackend)
     def set_state(self, U):
         U = np.ascontiguousarray(U, dtype=np.float64)
-        if self.comm is not None:
-            U = self.comm.scatterState(self.solver, U, self.nS)
         assert U.size == self.ncells * self.nS, (U.size, self.ncells, self.nS)
         hb.check(self.L.hb_fv_set_state(self.h, U.ctypes.data))
         self.ctx.sync()
@@ -129,8 +126,6 @@ class CudaBackend:
     def get_state(self):
         U = np.empty((self.ncells, self.nS), dtype=np.float64)
         hb.check(self.L.hb_fv_get_state(self.h, U.ctypes.data))
-        if self.comm is not None:
-            U = self.comm.gatherState(self.solver, U, self.nS)
         return U
 
     def boundary(self):

@@ -151,6 +151,8 @@ struct FvBase {
 	virtual int setTime(double t) = 0;
 	virtual int calcDeriv(double dt, double* aos) = 0;
 	virtual int describe(char* out, size_t cap) = 0;
+	virtual int profile(int enable) = 0;
+	virtual int profileRead(double* ms, long long* n) = 0;
 	virtual int commInit(int nranks, int rank, const char* id) = 0;
 	virtual int commDestroy() = 0;
 	int nS = 0, nI = 0, nW = 0;
@@ -175,6 +177,10 @@ template<class real> struct Fv : FvBase {
 	int nonIntSync = 0;
 	cudaGraphExec_t graphExec = nullptr;
 	long long graphLaunches = 0;
+	// optional per-launch timing of the stage kernel (CUDA events on the launching stream; eager mode only)
+	bool profiling = false;
+	std::vector<std::pair<cudaEvent_t, cudaEvent_t>> profEvents;
+	size_t profUsed = 0;
 	// slab decomposition
 	Nccl::comm_t comm = nullptr;
 	int nranks = 1, rank = 0;
@@ -188,6 +194,7 @@ template<class real> struct Fv : FvBase {
 		useDevice(ctx);
 		cudaStreamSynchronize(ctx->stream);
 		if (graphExec) cudaGraphExecDestroy(graphExec);
+		for (auto& e : profEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
 		for (auto p : upool) cudaFree(p);
 		for (auto p : lpool) cudaFree(p);
 		if (scratchL) cudaFree(scratchL);
@@ -405,7 +412,18 @@ template<class real> struct Fv : FvBase {
 		for (auto& s : plan) {
 			StageP<real> sp;
 			fillStageP(sp, s, s.last);
+			cudaEvent_t e0 = nullptr, e1 = nullptr;
+			if (profiling) {
+				if (profUsed == profEvents.size()) {
+					cudaEvent_t a, b;
+					HB_CUDA(cudaEventCreate(&a)); HB_CUDA(cudaEventCreate(&b));
+					profEvents.push_back(std::make_pair(a, b));
+				}
+				e0 = profEvents[profUsed].first; e1 = profEvents[profUsed].second; profUsed++;
+				HB_CUDA(cudaEventRecord(e0, st()));
+			}
 			HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
+			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches++;
 			if (int r = fillGhosts(upool[s.uOut], rk ? nI : nS)) return r;
 		}
@@ -434,7 +452,7 @@ template<class real> struct Fv : FvBase {
 		useDevice(ctx);
 		if (nsteps <= 0) return HB_OK;
 		if (!d.use_fixed_dt && !dtValid) if (int r = launchCalcDT()) return r;
-		bool const graphable = d.use_graph && d.rk_order >= 2;
+		bool const graphable = d.use_graph && d.rk_order >= 2 && !profiling;
 		int done = 0;
 		if (graphable) {
 			if (d.rk_order >= 1 && !rkZeroed) { if (int r = oneUpdate()) return r; done = 1; }   // one-off memsets stay outside the graph
@@ -528,6 +546,26 @@ template<class real> struct Fv : FvBase {
 		return HB_OK;
 	}
 
+	int profile(int enable) override {
+		useDevice(ctx);
+		HB_CUDA(cudaStreamSynchronize(st()));
+		profiling = enable != 0;
+		profUsed = 0;
+		return HB_OK;
+	}
+	int profileRead(double* ms, long long* n) override {
+		useDevice(ctx);
+		HB_CUDA(cudaStreamSynchronize(st()));
+		double total = 0;
+		for (size_t i = 0; i < profUsed; ++i) {
+			float t = 0;
+			HB_CUDA(cudaEventElapsedTime(&t, profEvents[i].first, profEvents[i].second));
+			total += t;
+		}
+		if (ms) *ms = total;
+		if (n) *n = (long long)profUsed;
+		return HB_OK;
+	}
 	int commInit(int nr, int rk_, const char* id) override {
 		useDevice(ctx);
 		Nccl& N = Nccl::get();
@@ -607,6 +645,8 @@ int hb_fv_set_time(hb_fv* fv, double t) { HB_FV(fv); return fv->impl->setTime(t)
 int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos) { HB_FV(fv); return fv->impl->calcDeriv(dt, aos); }
 int hb_fv_launch_count(hb_fv* fv, long long* n) { HB_FV(fv); if (n) *n = fv->impl->launches; return HB_OK; }
 int hb_fv_describe(hb_fv* fv, char* out, size_t cap) { HB_FV(fv); if (!out || !cap) return setError(HB_ERR_INVALID, "hb_fv_describe: bad buffer"); return fv->impl->describe(out, cap); }
+int hb_fv_profile(hb_fv* fv, int enable) { HB_FV(fv); return fv->impl->profile(enable); }
+int hb_fv_profile_read(hb_fv* fv, double* ms, long long* n) { HB_FV(fv); return fv->impl->profileRead(ms, n); }
 int hb_ghost_source(int j, int S, int bcMin, int bcMax, int* flip, int* skip) {
 	bool f, s;
 	int const r = ghostSource(j, S, bcMin, bcMax, f, s);

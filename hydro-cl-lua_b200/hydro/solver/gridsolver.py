@@ -33,6 +33,14 @@ class GridSolver(SolverBase):
         self.stepsize = [1, self.gridSize[0], self.gridSize[0] * self.gridSize[1]]
         self.mins = [float(v) for v in args.get("mins", (-1., -1., -1.))]
         self.maxs = [float(v) for v in args.get("maxs", (1., 1., 1.))]
+        # slab decomposition (hydro/solver/choppedup.py): this process owns localSizeWithoutBorder cells at localOffset
+        self.comm = args.get("comm")
+        if self.comm is not None:
+            self.localSizeWithoutBorder, self.localOffset = self.comm.split(self.sizeWithoutBorder, dim)
+        else:
+            self.localSizeWithoutBorder, self.localOffset = list(self.sizeWithoutBorder), [0, 0, 0]
+        self.localGridSize = [n + 2 * g if i < dim else 1 for i, n in enumerate(self.localSizeWithoutBorder)]
+        self.localNumCells = self.localGridSize[0] * self.localGridSize[1] * self.localGridSize[2]
 
     def initObjs(self, args):
         super().initObjs(args)
@@ -79,12 +87,13 @@ class GridSolver(SolverBase):
         return out
 
     def cellPositions(self):
-        """coord.lua:1421-1432: x = (i + .5 - g)/N * (max - min) + min on used axes, midpoint otherwise."""
+        """coord.lua:1421-1432: x = (i + .5 - g)/N * (max - min) + min on used axes, midpoint otherwise.
+        With a slab decomposition these are the positions of this rank's (ghost-inclusive) slab."""
         g = self.numGhost
         axes = []
         for j in range(3):
             if j < self.dim:
-                i = np.arange(self.gridSize[j], dtype=np.float64)
+                i = np.arange(self.localGridSize[j], dtype=np.float64) + float(self.localOffset[j])
                 axes.append((i + .5 - g) / float(self.sizeWithoutBorder[j]) * (self.maxs[j] - self.mins[j]) + self.mins[j])
             else:
                 axes.append(np.array([.5 * (self.maxs[j] + self.mins[j])]))
@@ -98,13 +107,18 @@ class GridSolver(SolverBase):
         self.setState(U)
 
     def setState(self, U):
-        U = np.ascontiguousarray(U, dtype=np.float64).reshape(self.numCells, self.eqn.numStates)
+        U = np.ascontiguousarray(U, dtype=np.float64).reshape(self.localNumCells, self.eqn.numStates)
         self.backend.set_state(U)
 
     def getState(self):
-        """UBuf as float64 [Sz, Sy, Sx, numStates] (AoS cons_t order, ghost cells included)."""
+        """UBuf as float64 [Sz, Sy, Sx, numStates] (AoS cons_t order, ghost cells included); this rank's slab."""
         U = self.backend.get_state()
-        return U.reshape(self.gridSize[2], self.gridSize[1], self.gridSize[0], self.eqn.numStates)
+        return U.reshape(self.localGridSize[2], self.localGridSize[1], self.localGridSize[0], self.eqn.numStates)
+
+    def getGlobalInterior(self):
+        """Interior of the whole grid, gathered from every rank's slab (tests of the decomposed path)."""
+        Ui = self.interior()
+        return self.comm.gatherInterior(Ui, self.dim) if self.comm is not None else Ui
 
     def interior(self, U=None):
         U = self.getState() if U is None else U

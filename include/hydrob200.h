@@ -139,7 +139,11 @@ int hb_fv_get_time(hb_fv* fv, double* t_out, double* last_dt_out);   /* blocking
 int hb_fv_set_time(hb_fv* fv, double t);
 int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos_host_out);    /* FiniteVolumeSolver:calcDeriv into a zeroed deriv buffer (blocking) */
 int hb_fv_launch_count(hb_fv* fv, long long* kernel_launches);       /* kernels this object has launched so far */
-int hb_fv_describe(hb_fv* fv, char* out, size_t cap);        /* text: tile shape, smem, per-stage plan (reads / writes per cell) */
+int hb_fv_describe(hb_fv* fv, char* out, size_t cap);
+/* per-launch device timing of the fused stage kernel (CUDA events on the context's stream; disables graph replay
+ * while enabled): total milliseconds and number of stage launches since hb_fv_profile(fv, 1) */
+int hb_fv_profile(hb_fv* fv, int enable);
+int hb_fv_profile_read(hb_fv* fv, double* stage_ms_total, long long* stage_launches);        /* text: tile shape, smem, per-stage plan (reads / writes per cell) */
 /* unit-test hook: evaluate one device function per item on the GPU (kind 0 Roe flux, 1 constrainU, 2 calcDTCell,
  * 3 PLM half slope, 4 Roe flux with flux limiter); host pointers of doubles; strict selects the -fmad=false build */
 int hb_debug_eval(hb_ctx* ctx, int eqn, int strict, int kind, int side, int n, const double* params, const double* aux4,

@@ -51,6 +51,7 @@ struct ho_desc {
 	double rhoMin, PMin;   // euler.lua:193-197
 	double mu0_eff;     // solver->mu0 / unit_kg_m_per_C2 (mhd.lua:209-234, math.cl:270)
 	int nthreads;       // OpenMP threads (0 = default)
+	int global_n[3];    // 0 = same as n; otherwise the whole grid's interior size (this object is one slab of it): defines grid_dx
 };
 }
 
@@ -782,7 +783,7 @@ template<class Eqn> struct Solver : SolverBase {
 		for (int k = 0; k < 3; ++k) {
 			solver.mins.s(k) = d.mins[k]; solver.maxs.s(k) = d.maxs[k];
 			// gridsolver.lua:406-409: dx for all three axes, computed in host double then cast
-			double dx = (d.maxs[k] - d.mins[k]) / double(k < dim ? d.n[k] : 1);
+			double dx = (d.maxs[k] - d.mins[k]) / double(k < dim ? (d.global_n[k] > 0 ? d.global_n[k] : d.n[k]) : 1);
 			solver.grid_dx.s(k) = real(dx);
 			solver.gridSize[k] = S[k];
 		}

@@ -27,7 +27,7 @@ class ho_desc(C.Structure):
         ("mins", C.c_double * 3), ("maxs", C.c_double * 3),
         ("cfl", C.c_double), ("fixed_dt", C.c_double), ("use_fixed_dt", C.c_int),
         ("gamma", C.c_double), ("rhoMin", C.c_double), ("PMin", C.c_double), ("mu0_eff", C.c_double),
-        ("nthreads", C.c_int),
+        ("nthreads", C.c_int), ("global_n", C.c_int * 3),
     ]
 
 
@@ -80,14 +80,18 @@ def desc_from_solver(solver, nthreads=0):
     d.eqn = solver.eqn.eqnId
     d.dim = solver.dim
     for i in range(3):
-        d.n[i] = solver.sizeWithoutBorder[i]
+        d.n[i] = solver.localSizeWithoutBorder[i]
+        d.global_n[i] = solver.sizeWithoutBorder[i]
         d.mins[i] = solver.mins[i]
         d.maxs[i] = solver.maxs[i]
     d.real_bytes = solver.real_bytes
     d.use_plm = 1 if solver.usePLM else 0
     d.slope_limiter = solver.slopeLimiter
     d.flux_limiter = solver.fluxLimiter
-    for i, b in enumerate(solver.boundaryIdList()):
+    bcs = solver.boundaryIdList()
+    if getattr(solver, "comm", None) is not None:
+        bcs = solver.comm.localBoundaryIds(bcs, solver.dim)     # faces owned by a neighbouring slab: 'none'
+    for i, b in enumerate(bcs):
         d.bc[i] = b
     d.rk_order = solver.rkOrder
     for i in range(16):

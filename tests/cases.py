@@ -25,7 +25,7 @@ CASES = {
     # C4: 3D spherical blast, Euler, Roe + PLM, RK4, freeflow, domain +-2
     "C4_sphere_rk4": (dict(eqn="euler", dim=3, gridSize=[40, 20, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
                            usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 10),
-    "C4_sphere_rk4_mirror_periodic": (dict(eqn="euler", dim=3, gridSize=[24, 18, 10], mins=[-2, -2, -2], maxs=[2, 2, 2],
+    "C4_sphere_rk4_mirror_periodic": (dict(eqn="euler", dim=3, gridSize=[24, 18, 12], mins=[-2, -2, -2], maxs=[2, 2, 2],
                                            initCond="sphere", usePLM="plm cons", slopeLimiter="minmod",
                                            integrator="Runge-Kutta 4", cfl=.1,
                                            boundary=dict(xmin="mirror", xmax="mirror", ymin="periodic", ymax="periodic",
@@ -36,5 +36,13 @@ CASES = {
     "frozen_volume_guard": (dict(eqn="euler", dim=3, gridSize=[12, 10, 8], mins=[-.01] * 3, maxs=[.01] * 3, initCond="sphere",
                                  usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 2),
 }
+
+# forward-Euler cases for the host-side (gloo) decomposition test; axis sizes divisible by 2 ranks
+CASES["slab_fe_2d_periodic"] = (dict(eqn="euler", dim=2, gridSize=[24, 16], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                                     slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 6)
+CASES["slab_fe_3d_mixed"] = (dict(eqn="mhd", dim=3, gridSize=[10, 8, 12], initCond="Orszag-Tang", fluxLimiter="superbee",
+                                  integrator="forward Euler", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2],
+                                  boundary=dict(xmin="periodic", xmax="periodic", ymin="mirror", ymax="mirror",
+                                                zmin="freeflow", zmax="mirror")), 6)
 
 FLOAT_CASES = ["C2_kh_rk4tvd_minmod", "C4_sphere_rk4", "C3_ot_rk3tvd", "C1_sod_fe_superbee"]

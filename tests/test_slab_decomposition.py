@@ -1,0 +1,81 @@
+"""Slab decomposition (hydro/solver/choppedup.py): a run split over 2 ranks must equal the single-domain run exactly.
+
+CPU: world_size-2 gloo, oracle backend per slab, ghost planes exchanged by SlabComm.exchangeHost (host-side logic).
+GPU (needs >= 2 devices): CUDA backend per slab, exchange by ncclSend/ncclRecv inside libhydrob200, dt by ncclAllReduce(min)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def launch(mode, case, nsteps, out, world=2):
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "slab_worker.py"), mode, case, str(nsteps), out], env=env))
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+
+
+def single(hydrob200, case, nsteps, **kw):
+    from cases import CASES
+    cfg, _ = CASES[case]
+    S = hydrob200.FiniteVolumeSolver(dict(cfg, **kw))
+    for _ in range(nsteps):
+        S.update()
+    return S.interior(), S.t
+
+
+def test_slab_geometry(hydrob200):
+    from importlib import import_module
+    SlabComm = import_module("hydro-cl-lua_b200.hydro.solver.choppedup").SlabComm
+    c = SlabComm(4, 1)
+    assert c.split([16, 12, 8], 3) == ([16, 12, 2], [0, 0, 2])
+    assert c.split([16, 12, 1], 2) == ([16, 3, 1], [0, 3, 0])
+    assert c.neighbours(False) == (0, 2) and SlabComm(4, 0).neighbours(False) == (None, 1)
+    assert SlabComm(4, 0).neighbours(True) == (3, 1) and SlabComm(4, 3).neighbours(True) == (2, 0)
+    assert SlabComm(4, 0).localBoundaryIds([2, 2, 1, 1, 0, 0], 3) == [2, 2, 1, 1, 3, 3]       # periodic: both faces exchanged
+    assert SlabComm(4, 0).localBoundaryIds([2, 2, 1, 1, 2, 1], 3) == [2, 2, 1, 1, 2, 3]       # physical low face kept
+    assert SlabComm(4, 3).localBoundaryIds([2, 2, 1, 1, 2, 1], 3) == [2, 2, 1, 1, 3, 1]
+    with pytest.raises(ValueError):
+        c.split([16, 12, 6], 3)
+
+
+@pytest.mark.parametrize("case", ["slab_fe_2d_periodic", "slab_fe_3d_mixed"])
+def test_cpu_gloo_two_ranks_equal_single(hydrob200, oracle, tmp_path, case):
+    out = str(tmp_path / "dec")
+    launch("cpu", case, 6, out)
+    got = np.load(out + ".npy")
+    ref, tref = single(hydrob200, case, 6, backend=oracle.OracleBackend)
+    assert np.load(out + ".t.npy")[0] == tref
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,mode", [("C4_sphere_rk4", "gpu_strict"), ("C2_kh_rk4tvd_minmod", "gpu"), ("C3_ot_rk3tvd", "gpu"),
+                                       ("C4_sphere_rk4_mirror_periodic", "gpu")])
+def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    out = str(tmp_path / "dec")
+    launch(mode, case, 5, out)
+    got = np.load(out + ".npy")
+    ref, tref = single(hydrob200, case, 5, strict_fp=(mode == "gpu_strict"), use_graph=False)
+    assert np.load(out + ".t.npy")[0] == tref
+    assert np.array_equal(got, ref)
