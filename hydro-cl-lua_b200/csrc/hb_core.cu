@@ -17,6 +17,17 @@ int cudaFail(cudaError_t e, const char* what) {
 	return setError(code, std::string(what) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")");
 }
 bool useDevice(hb_ctx* ctx) { return cudaSetDevice(ctx->device) == cudaSuccess; }
+void ctxRetain(hb_ctx* c) { if (c) c->refs++; }
+void ctxRelease(hb_ctx* c) {
+	if (!c || --c->refs > 0) return;
+	useDevice(c);
+	cudaStreamSynchronize(c->stream);
+	if (c->reduceScratch) cudaFree(c->reduceScratch);
+	if (c->ev0) cudaEventDestroy(c->ev0);
+	if (c->ev1) cudaEventDestroy(c->ev1);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+}
 
 // element-generic grid-stride reduction into a double scalar (ordered-bits atomics for min/max, atomicAdd for sum)
 template<class real, int OP>
@@ -98,11 +109,7 @@ int hb_ctx_destroy(hb_ctx* c) {
 	if (!c) return HB_OK;
 	useDevice(c);
 	cudaStreamSynchronize(c->stream);
-	if (c->reduceScratch) cudaFree(c->reduceScratch);
-	if (c->ev0) cudaEventDestroy(c->ev0);
-	if (c->ev1) cudaEventDestroy(c->ev1);
-	if (c->stream) cudaStreamDestroy(c->stream);
-	delete c;
+	hb::ctxRelease(c);
 	return HB_OK;
 }
 
@@ -167,6 +174,7 @@ int hb_buf_alloc(hb_ctx* c, size_t bytes, hb_buf** out) {
 	HB_CUDA(cudaMalloc(&d, bytes ? bytes : 1));
 	hb_buf* b = new hb_buf();
 	b->ctx = c; b->d = d; b->bytes = bytes;
+	hb::ctxRetain(c);
 	*out = b;
 	return HB_OK;
 }
@@ -175,6 +183,7 @@ int hb_buf_free(hb_buf* b) {
 	useDevice(b->ctx);
 	cudaStreamSynchronize(b->ctx->stream);
 	cudaFree(b->d);
+	hb::ctxRelease(b->ctx);
 	delete b;
 	return HB_OK;
 }

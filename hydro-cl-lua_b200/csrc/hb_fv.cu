@@ -189,6 +189,7 @@ template<class real> struct Fv : FvBase {
 	Fv(hb_ctx* c, const hb_fv_desc& desc, const FvOps<real>* o) : ctx(c), d(desc), ops(o) {
 		nS = o->nS; nI = o->nI; nW = o->nW;
 		axis = d.dim - 1;
+		ctxRetain(ctx);
 	}
 	~Fv() override {
 		useDevice(ctx);
@@ -202,6 +203,7 @@ template<class real> struct Fv : FvBase {
 		if (ctl) cudaFree(ctl);
 		if (dtMinBits) cudaFree(dtMinBits);
 		if (comm) Nccl::get().CommDestroy(comm);
+		ctxRelease(ctx);
 	}
 	cudaStream_t st() const { return ctx->stream; }
 	size_t uBytes() const { return sizeof(real) * (size_t)nS * (size_t)cells; }

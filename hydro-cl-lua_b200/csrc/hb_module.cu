@@ -172,6 +172,7 @@ int hb_module_compile(hb_ctx* ctx, const char* src, const char* name, const char
 	if (r) return setError(HB_ERR_CUDA, "cuModuleLoadData: " + D.err(r));
 	hb_module* m = new hb_module();
 	m->ctx = ctx; m->cuModule = mod; m->name = name ? name : "module";
+	ctxRetain(ctx);
 	*out = m;
 	return HB_OK;
 }
@@ -181,6 +182,7 @@ int hb_module_free(hb_module* m) {
 	useDevice(m->ctx);
 	cudaStreamSynchronize(m->ctx->stream);
 	Driver::get().ModuleUnload(m->cuModule);
+	ctxRelease(m->ctx);
 	delete m;
 	return HB_OK;
 }
