@@ -32,7 +32,7 @@ class hb_fv_desc(C.Structure):
         ("mins", C.c_double * 3), ("maxs", C.c_double * 3),
         ("cfl", C.c_double), ("fixed_dt", C.c_double), ("use_fixed_dt", C.c_int),
         ("eqn_params", C.c_double * 16),
-        ("strict_fp", C.c_int), ("use_graph", C.c_int),
+        ("strict_fp", C.c_int), ("use_graph", C.c_int), ("stage_kernel", C.c_int),
     ]
 
 
@@ -72,6 +72,7 @@ SIGNATURES = {
     "hb_kernel_set_arg_buf": (C.c_int, [P, C.c_int, P]),
     "hb_kernel_launch": (C.c_int, [P, size3, size3, C.c_size_t]),
     "hb_reduce": (C.c_int, [P, P, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
+    "hb_sizeof_fv_desc": (C.c_size_t, []),
     "hb_fv_create": (C.c_int, [P, C.POINTER(hb_fv_desc), C.POINTER(P)]),
     "hb_fv_destroy": (C.c_int, [P]),
     "hb_fv_num_states": (C.c_int, [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -54,7 +54,7 @@ class Context:
         return ms.value
 
 
-def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None):
+def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None, stage_kernel=0):
     d = hb.hb_fv_desc()
     d.eqn = solver.eqn.eqnId
     d.dim = solver.dim
@@ -79,6 +79,7 @@ def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None):
         d.eqn_params[i] = v
     d.strict_fp = 1 if strict_fp else 0
     d.use_graph = 1 if use_graph else 0
+    d.stage_kernel = stage_kernel
     return d
 
 
@@ -95,7 +96,7 @@ class CudaBackend:
         strict = args.get("strict_fp", self.strict_fp)
         graph = args.get("use_graph", self.use_graph)
         self.comm = comm
-        self.desc = desc_from_solver(solver, strict, graph, solver.localSizeWithoutBorder)
+        self.desc = desc_from_solver(solver, strict, graph, solver.localSizeWithoutBorder, args.get("stage_kernel", 0))
         self.h = hb.P()
         hb.check(self.L.hb_fv_create(self.ctx.h, C.byref(self.desc), C.byref(self.h)))
         ns, ni, nw = C.c_int(), C.c_int(), C.c_int()

@@ -80,6 +80,7 @@ int hb_device_count(int* count) {
 	if (!count) return setError(HB_ERR_INVALID, "hb_device_count: null argument");
 	*count = 0;
 	cudaError_t e = cudaGetDeviceCount(count);
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) { cudaGetLastError(); *count = 0; return HB_OK; }   // no driver / no device: count 0
 	if (e != cudaSuccess) return cudaFail(e, "cudaGetDeviceCount");
 	return HB_OK;
 }
@@ -90,8 +91,12 @@ int hb_ctx_create(int device, int real_bytes, hb_ctx** out) {
 	if (real_bytes != 8 && real_bytes != 4) return setError(HB_ERR_INVALID, "hb_ctx_create: real_bytes must be 8 or 4");
 	int n = 0;
 	cudaError_t e = cudaGetDeviceCount(&n);
+	if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || (e == cudaSuccess && n == 0)) {
+		cudaGetLastError();
+		return setError(HB_ERR_NO_DEVICE, std::string("hb_ctx_create: no usable CUDA device (") + (e == cudaSuccess ? "device count 0" : cudaGetErrorName(e))
+			+ "); there is no CPU fallback");
+	}
 	if (e != cudaSuccess) return cudaFail(e, "cudaGetDeviceCount");
-	if (n == 0) return setError(HB_ERR_NO_DEVICE, "hb_ctx_create: no CUDA device (there is no CPU fallback)");
 	if (device < 0 || device >= n) return setError(HB_ERR_INVALID, "hb_ctx_create: device index out of range");
 	HB_CUDA(cudaSetDevice(device));
 	hb_ctx* c = new hb_ctx();

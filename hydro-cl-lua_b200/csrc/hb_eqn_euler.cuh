@@ -20,13 +20,16 @@
 
 namespace hb {
 
-template<class real_> struct Euler {
+template<class real_, bool FAST_ = false> struct Euler {
 	typedef real_ real;
+	static constexpr bool FAST = FAST_;                // production arithmetic (hb_roe_fast.cuh) in the marching kernel
 	static constexpr int eqnId = 0;
 	static constexpr int nS = 6, nI = 5, nW = 5;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/eqn.lua:46
-	struct Params { real gamma, rhoMin, PMin; };
-	static HB_HD Params makeParams(const double* p) { return Params{real(p[0]), real(p[1]), real(p[2])}; }
+	struct Params { real gamma, rhoMin, PMin; real gamma_1, invGamma_1, rhoFloor; };   // the last three: production forms only
+	static HB_HD Params makeParams(const double* p) {
+		return Params{real(p[0]), real(p[1]), real(p[2]), real(p[0] - 1.), real(1. / (p[0] - 1.)), real(p[1] > 1e-5 ? p[1] : 1e-5)};
+	}
 
 	struct Prim { real rho, v[3], P; };
 	struct Eig { real rho, v[3], hTotal, Cs, vSq; };   // vL == v for the identity metric
@@ -178,8 +181,9 @@ template<class real_> struct Euler {
 		else if (U[0] < s.rhoMin) Cs = inf_of<real>::v();
 		else Cs = rsqrt_ieee(s.gamma * P / U[0]);
 		real dt = inf_of<real>::v();
-		for (int side = 0; side < dim; ++side) {
-			if (dx[side] > 0) {
+		#pragma unroll
+		for (int side = 0; side < 3; ++side) {   // static indices: U stays in registers
+			if (side < dim && dx[side] > 0) {
 				real const v_n = U[0] < s.rhoMin ? real(0.) : U[1 + side] / U[0];
 				real const lambdaMin = v_n - Cs, lambdaMax = v_n + Cs;
 				real absLambdaMax = rmax<real>(rabs(lambdaMin), rabs(lambdaMax));

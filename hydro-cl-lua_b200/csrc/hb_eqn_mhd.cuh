@@ -21,8 +21,9 @@
 
 namespace hb {
 
-template<class real_> struct MHD {
+template<class real_, bool FAST_ = false> struct MHD {
 	typedef real_ real;
+	static constexpr bool FAST = FAST_;                // no production-form flux yet: the marching kernel uses the literal functions
 	static constexpr int eqnId = 1;
 	static constexpr int nS = 10, nI = 8, nW = 7;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/mhd.lua:19

@@ -11,8 +11,10 @@
 // boundary plane pairs are exchanged with ncclSend/ncclRecv and dt is min-allreduced (choppedup.lua:193-233,344-409).
 #include "hb_core.h"
 #include "hb_fv_ops.h"
+#include <cuda.h>
 #include <dlfcn.h>
 #include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <map>
@@ -77,6 +79,22 @@ struct Nccl {
 };
 enum { kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclMin = 3 };
 #define HB_NCCL(expr) do { int r_ = (expr); if (r_ != 0) return setError(HB_ERR_CUDA, std::string(#expr) + ": " + Nccl::get().GetErrorString(r_)); } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library links neither libcuda nor libnvrtc)
+typedef CUresult (*EncodeTiled_t)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+	const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiled_t encodeTiledFn() {
+	static EncodeTiled_t fn = nullptr;
+	static bool tried = false;
+	if (!tried) {
+		tried = true;
+		cudaDriverEntryPointQueryResult q;
+		void* p = nullptr;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && p) fn = (EncodeTiled_t)p;
+		else cudaGetLastError();
+	}
+	return fn;
+}
 
 struct Term { int k; double coef; };
 struct StagePlan {
@@ -166,7 +184,12 @@ template<class real> struct Fv : FvBase {
 	const FvOps<real>* ops;
 	GridP<real> grid;
 	BcP bc;
-	std::vector<real*> upool, lpool;
+	std::vector<real*> upool, lpool;       // element (i=0,j=0,k=0) of variable 0; the allocation starts padX elements earlier
+	std::vector<CUtensorMap> umaps;        // TMA descriptor of every U buffer (marching kernel)
+	int padX = 0;                          // leading pad of every row: interior cell i=2 sits on a 128-byte boundary
+	long long vstride = 0;                 // elements between variables (pitchX * S1 * S2)
+	bool useMarch = false;
+	int marchCfg = 0, marchBox[4] = {0, 0, 0, 0}, marchInfoV[6] = {0, 0, 0, 0, 0, 0};
 	real* scratchL = nullptr;
 	double* stagingAos = nullptr;
 	double* ctl = nullptr;                 // device: t, dt, cfl, fixedDT(<0 adaptive)
@@ -196,9 +219,9 @@ template<class real> struct Fv : FvBase {
 		cudaStreamSynchronize(ctx->stream);
 		if (graphExec) cudaGraphExecDestroy(graphExec);
 		for (auto& e : profEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-		for (auto p : upool) cudaFree(p);
-		for (auto p : lpool) cudaFree(p);
-		if (scratchL) cudaFree(scratchL);
+		for (auto p : upool) cudaFree(p - padX);
+		for (auto p : lpool) cudaFree(p - padX);
+		if (scratchL) cudaFree(scratchL - padX);
 		if (stagingAos) cudaFree(stagingAos);
 		if (ctl) cudaFree(ctl);
 		if (dtMinBits) cudaFree(dtMinBits);
@@ -206,8 +229,29 @@ template<class real> struct Fv : FvBase {
 		ctxRelease(ctx);
 	}
 	cudaStream_t st() const { return ctx->stream; }
-	size_t uBytes() const { return sizeof(real) * (size_t)nS * (size_t)cells; }
-	size_t lBytes() const { return sizeof(real) * (size_t)nI * (size_t)cells; }
+	// allocation sizes: the variables' padded arrays plus one row of slack for the leading pad
+	size_t uBytes() const { return sizeof(real) * ((size_t)nS * (size_t)vstride + (size_t)grid.strideY); }
+	size_t lBytes() const { return sizeof(real) * ((size_t)nI * (size_t)vstride + (size_t)grid.strideY); }
+	int allocPadded(real** out, size_t bytes) {
+		real* p = nullptr;
+		HB_CUDA(cudaMalloc(&p, bytes));
+		HB_CUDA(cudaMemsetAsync(p, 0, bytes, st()));
+		*out = p + padX;
+		return HB_OK;
+	}
+	int encodeMap(real* U, CUtensorMap* map) {
+		EncodeTiled_t enc = encodeTiledFn();
+		if (!enc) return setError(HB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+		cuuint64_t dims[4] = {(cuuint64_t)grid.strideY, (cuuint64_t)grid.S[1], (cuuint64_t)grid.S[2], (cuuint64_t)nI};
+		cuuint64_t strides[3] = {(cuuint64_t)grid.strideY * sizeof(real), (cuuint64_t)grid.strideZ * sizeof(real), (cuuint64_t)vstride * sizeof(real)};
+		cuuint32_t box[4] = {(cuuint32_t)marchBox[0], (cuuint32_t)marchBox[1], (cuuint32_t)marchBox[2], (cuuint32_t)marchBox[3]};
+		cuuint32_t es[4] = {1, 1, 1, 1};
+		CUresult r = enc(map, sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(U - padX),
+			dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+			CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+		if (r != CUDA_SUCCESS) return setError(HB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+		return HB_OK;
+	}
 
 	int init() override {
 		useDevice(ctx);
@@ -218,11 +262,17 @@ template<class real> struct Fv : FvBase {
 			int const gn = k < d.dim ? d.global_n[k] : 1;
 			double const dx = (d.maxs[k] - d.mins[k]) / double(gn);     // gridsolver.lua:406-409, host double then cast
 			grid.dx[k] = real(dx);
+			grid.invdx[k] = real(1.) / grid.dx[k];
 		}
-		grid.strideY = grid.S[0];
-		grid.strideZ = (long long)grid.S[0] * grid.S[1];
+		// HBM layout: structure of arrays, rows padded so that the first interior cell of every row is 128-byte aligned
+		// and the row pitch is a multiple of 128 bytes (coalesced warp stores; TMA needs 16-byte multiples)
+		int const per128 = int(128 / sizeof(real));
+		padX = per128 - HB_G;
+		grid.strideY = (padX + grid.S[0] + per128 - 1) / per128 * per128;
+		grid.strideZ = grid.strideY * grid.S[1];
 		cells = (long long)grid.S[0] * grid.S[1] * grid.S[2];
-		grid.strideV = cells;
+		vstride = grid.strideZ * grid.S[2];
+		grid.strideV = vstride;
 		// fvsolver.cl:34-41,97-102: volume = prod dx (used axes), area_s = prod_{i != s} dx_i, scaled by 1/volume, in `real`
 		real volume = 1;
 		for (int k = 0; k < d.dim; ++k) volume = volume * grid.dx[k];
@@ -244,15 +294,41 @@ template<class real> struct Fv : FvBase {
 		if (nU < 2 && d.rk_order < 2) nU = 2;
 		for (int k = 0; k < nU; ++k) {
 			real* p = nullptr;
-			HB_CUDA(cudaMalloc(&p, uBytes()));
+			if (int r = allocPadded(&p, uBytes())) return r;
 			upool.push_back(p);
-			HB_CUDA(cudaMemsetAsync(p, 0, uBytes(), st()));
 		}
 		for (int k = 0; k < nL; ++k) {
 			real* p = nullptr;
-			HB_CUDA(cudaMalloc(&p, lBytes()));
+			if (int r = allocPadded(&p, lBytes())) return r;
 			lpool.push_back(p);
-			HB_CUDA(cudaMemsetAsync(p, 0, lBytes(), st()));
+		}
+		// stage kernel selection: the plane-marching TMA kernel where it is built (dim >= 2, 'plm cons' with minmod / superbee),
+		// else the tile kernel.  d.stage_kernel: 0 auto, 1 tile kernel, 2 marching kernel (error if unavailable).
+		{
+			bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
+			int cfg0 = 0;
+			if (const char* e = getenv("HB_MARCH_CFG")) cfg0 = atoi(e);
+			// RK operands staged in shared memory per column thread: the largest count over the stages
+			int maxOps = 0;
+			for (auto& s : plan) {
+				int n = (int)s.beta.size();
+				for (auto& t : s.alpha) if (t.k != s.uIn) ++n;
+				if (n > maxOps) maxOps = n;
+			}
+			bool ok = false;
+			if (d.stage_kernel != 1) {
+				for (int pass = 0; pass < 2 && !ok; ++pass)
+					for (int cfg = pass == 0 ? cfg0 : 0; !ok && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
+						size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
+						if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
+					}
+			}
+			if (d.stage_kernel == 2 && !ok) return setError(HB_ERR_INVALID, "hb_fv_create: the marching kernel is not built for this configuration");
+			useMarch = ok;
+			if (useMarch) {
+				umaps.resize(nU);
+				for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &umaps[k])) return r;
+			}
 		}
 		HB_CUDA(cudaMalloc(&ctl, 4 * sizeof(double)));
 		HB_CUDA(cudaMalloc(&dtMinBits, sizeof(unsigned long long)));
@@ -316,17 +392,19 @@ template<class real> struct Fv : FvBase {
 		if (lo < 0) lo = periodic ? nranks - 1 : -1;
 		if (hi >= nranks) hi = periodic ? 0 : -1;
 		int const dtype = sizeof(real) == 8 ? kNcclFloat64 : kNcclFloat32;
+		// Message order per peer: sends [low planes -> lo, high planes -> hi], receives [high ghosts <- hi, low ghosts <- lo].
+		// With two ranks and a periodic axis lo == hi: NCCL pairs the sends and receives of one peer in issue order, and this
+		// order makes my low planes land in the peer's high ghosts and my high planes in its low ghosts.
 		HB_NCCL(N.GroupStart());
 		for (int q = 0; q < nVars; ++q) {
 			real* base = U + (size_t)q * grid.strideV;
-			if (lo >= 0) {
-				HB_NCCL(N.Send(base + (size_t)HB_G * strideA, chunk, dtype, lo, comm, st()));
-				HB_NCCL(N.Recv(base, chunk, dtype, lo, comm, st()));
-			}
-			if (hi >= 0) {
-				HB_NCCL(N.Send(base + (size_t)(S - 2 * HB_G) * strideA, chunk, dtype, hi, comm, st()));
-				HB_NCCL(N.Recv(base + (size_t)(S - HB_G) * strideA, chunk, dtype, hi, comm, st()));
-			}
+			if (lo >= 0) HB_NCCL(N.Send(base + (size_t)HB_G * strideA, chunk, dtype, lo, comm, st()));
+			if (hi >= 0) HB_NCCL(N.Send(base + (size_t)(S - 2 * HB_G) * strideA, chunk, dtype, hi, comm, st()));
+		}
+		for (int q = 0; q < nVars; ++q) {
+			real* base = U + (size_t)q * grid.strideV;
+			if (hi >= 0) HB_NCCL(N.Recv(base + (size_t)(S - HB_G) * strideA, chunk, dtype, hi, comm, st()));
+			if (lo >= 0) HB_NCCL(N.Recv(base, chunk, dtype, lo, comm, st()));
 		}
 		HB_NCCL(N.GroupEnd());
 		return HB_OK;
@@ -382,7 +460,10 @@ template<class real> struct Fv : FvBase {
 		sp.Uout = upool[s.uOut];
 		sp.Lout = s.lOut >= 0 ? lpool[s.lOut] : nullptr;
 		sp.nA = (int)s.alpha.size();
-		for (int k = 0; k < sp.nA; ++k) { sp.aPtr[k] = upool[s.alpha[k].k]; sp.aCoef[k] = s.alpha[k].coef; }
+		for (int k = 0; k < sp.nA; ++k) {
+			sp.aPtr[k] = upool[s.alpha[k].k]; sp.aCoef[k] = s.alpha[k].coef;
+			if (s.alpha[k].k == s.uIn) sp.aOwnMask |= 1 << k;
+		}
 		sp.nB = (int)s.beta.size();
 		for (int k = 0; k < sp.nB; ++k) { sp.bPtr[k] = lpool[s.beta[k].k]; sp.bCoef[k] = s.beta[k].coef; }
 		sp.betaSelf = s.betaSelf;
@@ -398,15 +479,15 @@ template<class real> struct Fv : FvBase {
 		bool const rk = d.rk_order >= 1;
 		if (rk && !rkZeroed && nS > nI) {
 			// rk.lua:94 clears UBuf (all fields, ghosts too); multAdd restores only the integrated fields (App. C #3)
-			HB_CUDA(cudaMemsetAsync(upool[0] + (size_t)nI * cells, 0, sizeof(real) * (size_t)(nS - nI) * cells, st()));
+			HB_CUDA(cudaMemsetAsync(upool[0] + (size_t)nI * vstride, 0, sizeof(real) * (size_t)(nS - nI) * vstride, st()));
 			for (int k = 1; k < nU; ++k)
-				HB_CUDA(cudaMemsetAsync(upool[k] + (size_t)nI * cells, 0, sizeof(real) * (size_t)(nS - nI) * cells, st()));
+				HB_CUDA(cudaMemsetAsync(upool[k] + (size_t)nI * vstride, 0, sizeof(real) * (size_t)(nS - nI) * vstride, st()));
 			rkZeroed = true;
 		}
 		if (!rk && nonIntSync > 0 && nS > nI) {
 			// forward Euler keeps the non-integrated fields; carry them into the ping-pong partner
-			HB_CUDA(cudaMemcpyAsync(upool[1] + (size_t)nI * cells, upool[0] + (size_t)nI * cells,
-				sizeof(real) * (size_t)(nS - nI) * cells, cudaMemcpyDeviceToDevice, st()));
+			HB_CUDA(cudaMemcpyAsync(upool[1] + (size_t)nI * vstride, upool[0] + (size_t)nI * vstride,
+				sizeof(real) * (size_t)(nS - nI) * vstride, cudaMemcpyDeviceToDevice, st()));
 			nonIntSync--;
 		}
 		bool const plm = d.use_plm != 0;
@@ -424,13 +505,17 @@ template<class real> struct Fv : FvBase {
 				e0 = profEvents[profUsed].first; e1 = profEvents[profUsed].second; profUsed++;
 				HB_CUDA(cudaEventRecord(e0, st()));
 			}
-			HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
+			if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, st()));
+			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches++;
 			if (int r = fillGhosts(upool[s.uOut], rk ? nI : nS)) return r;
 		}
 		if (int r = reduceDtMin()) return r;
-		if (plan.back().uOut != 0) std::swap(upool[0], upool[plan.back().uOut]);   // order <= 1: ping-pong
+		if (plan.back().uOut != 0) {   // order <= 1: ping-pong
+			std::swap(upool[0], upool[plan.back().uOut]);
+			if (useMarch) std::swap(umaps[0], umaps[plan.back().uOut]);
+		}
 		dtValid = true;
 		return HB_OK;
 	}
@@ -502,8 +587,8 @@ template<class real> struct Fv : FvBase {
 		if (!aos) return setError(HB_ERR_INVALID, "hb_fv_calc_deriv: null pointer");
 		useDevice(ctx);
 		if (int r = ensureStaging()) return r;
-		if (!scratchL) HB_CUDA(cudaMalloc(&scratchL, uBytes()));
-		HB_CUDA(cudaMemsetAsync(scratchL, 0, uBytes(), st()));
+		if (!scratchL) { if (int r = allocPadded(&scratchL, uBytes())) return r; }
+		else HB_CUDA(cudaMemsetAsync(scratchL - padX, 0, uBytes(), st()));
 		// keep the device dt of a running simulation intact: use a private dt slot (ctl+1 is restored below)
 		double saved[2];
 		HB_CUDA(cudaMemcpyAsync(saved, ctl, sizeof(saved), cudaMemcpyDeviceToHost, st()));
@@ -515,7 +600,8 @@ template<class real> struct Fv : FvBase {
 		sp.computeL = 1; sp.dt = ctl + 1;
 		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter;
 		bool const plm = d.use_plm != 0;
-		HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
+		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, st()));
+		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
 		launches++;
 		HB_CUDA(cudaMemcpyAsync(ctl + 1, &saved[1], sizeof(double), cudaMemcpyHostToDevice, st()));
 		size_t const n = (size_t)nS * (size_t)cells;
@@ -531,7 +617,9 @@ template<class real> struct Fv : FvBase {
 		std::ostringstream o;
 		int ti[5];
 		bool const plm = d.use_plm != 0;
-		ops->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
+ 		ops->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
+		if (useMarch) for (int k = 0; k < 5; ++k) ti[k] = marchInfoV[k];
+		o << "kernel=" << (useMarch ? "fv_march(tma)" : "fv_stage(tile)") << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
 		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
 		  << " Ubufs=" << nU << " Lbufs=" << nL << "\n";
@@ -600,6 +688,7 @@ using namespace hb;
 
 extern "C" {
 
+size_t hb_sizeof_fv_desc(void) { return sizeof(hb_fv_desc); }
 int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (!ctx || !d || !out) return setError(HB_ERR_INVALID, "hb_fv_create: null argument");
 	*out = nullptr;

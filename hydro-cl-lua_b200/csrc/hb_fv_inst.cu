@@ -10,11 +10,12 @@ namespace hb {
 namespace {
 
 typedef HB_REAL real;
-typedef HB_EQN<real> Eqn;
 #ifdef HB_STRICT
 constexpr int MODE = 1;
+typedef HB_EQN<real, false> Eqn;     // literal arithmetic, -fmad=false: bit-comparable with the oracle
 #else
 constexpr int MODE = 0;
+typedef HB_EQN<real, true> Eqn;      // production arithmetic (hb_roe_fast.cuh) in the marching kernel
 #endif
 
 // Tile shapes (interior cells per CTA) and CTA size per dimensionality.
@@ -58,6 +59,98 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	case 1: return launchStageDim<1>(plm, flim, g, sp, ep, st);
 	case 2: return launchStageDim<2>(plm, flim, g, sp, ep, st);
 	case 3: return launchStageDim<3>(plm, flim, g, sp, ep, st);
+	}
+	return cudaErrorInvalidValue;
+}
+
+// ---- plane-marching kernel: tile configurations per dimensionality (cfg index; the host takes the first one whose shared
+// memory fits, starting at $HB_MARCH_CFG or 0)
+typedef MarchCfg<1, 12, 32, 1> March3A;    // 32 x 12 columns, 15 warps, <= 136 registers
+typedef MarchCfg<1, 8, 32, 1> March3B;     // 32 x 8 columns, 11 warps, no register cap
+typedef MarchCfg<1, 16, 32, 1> March3C;    // 32 x 16 columns, 19 warps, <= 104 registers
+typedef MarchCfg<1, 8, 32, 2> March3D;     // 32 x 8 columns, 2 CTAs / SM, <= 88 registers
+typedef MarchCfg<1, 10, 32, 1> March3E;    // 32 x 10 columns, 13 warps, <= 152 registers
+typedef MarchCfg<1, 6, 32, 2> March3F;     // 32 x 6 columns, 9 warps, 2 CTAs / SM, <= 112 registers
+typedef MarchCfg<4, 1, 32, 2> March2A;     // 128 columns, 5 warps
+typedef MarchCfg<2, 1, 32, 4> March2B;     // 64 columns, 3 warps
+typedef MarchCfg<6, 1, 64, 1> March2C;     // 192 columns, 7 warps (TMA boxes are at most 256 elements wide)
+
+constexpr size_t kSmemLimit = 232448 - 1024;   // 227 KB opt-in maximum per CTA minus the kernel's static shared memory (rounded up)
+
+template<int DIM, int LIM, class C>
+cudaError_t launchMarch(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st) {
+	typedef MarchGeom<DIM, C, real> G;
+	auto kern = fv_march<Eqn, DIM, LIM, C, MODE>;
+	int nOps = sp.nB;
+	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
+	size_t const smemMax = G::template smemBytes<Eqn::nI>(2 * HB_MAX_TERMS);
+	static bool attrSet = false;
+	if (!attrSet) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemMax < kSmemLimit ? smemMax : kSmemLimit));
+		if (e != cudaSuccess) return e;
+		attrSet = true;
+	}
+	if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+	long long const ntx = (g.N[0] + G::TX - 1) / G::TX;
+	long long const nty = DIM == 3 ? (g.N[1] + G::TY - 1) / G::TY : 1;
+	long long const nm = (g.N[DIM - 1] + C::KM - 1) / C::KM;
+	kern<<<(unsigned)(ntx * nty * nm), G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX);
+	return cudaGetLastError();
+}
+template<int DIM, class C>
+cudaError_t launchMarchLim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, cudaStream_t st) {
+	if (lim == 8) return launchMarch<DIM, 8, C>(tmap, padX, g, sp, ep, st);      // minmod
+	if (lim == 18) return launchMarch<DIM, 18, C>(tmap, padX, g, sp, ep, st);    // superbee
+	return cudaErrorInvalidValue;
+}
+template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
+	typedef MarchGeom<DIM, C, real> G;
+	box[0] = G::BX; box[1] = DIM == 3 ? G::BY : 1; box[2] = 1; box[3] = Eqn::nI;
+	info[0] = G::TX; info[1] = G::TY; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
+	info[5] = G::NREG * 32;
+}
+#ifdef HB_STRICT
+constexpr int kMarchCfgs3 = 2, kMarchCfgs2 = 1;     // the strict build carries fewer configurations (compile time)
+#else
+constexpr int kMarchCfgs3 = 6, kMarchCfgs2 = 3;
+#endif
+bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[6]) {
+	if (!plm || flim || (lim != 8 && lim != 18) || dim < 2 || cfg < 0 || cfg >= (dim == 3 ? kMarchCfgs3 : kMarchCfgs2)) return false;
+	if (dim == 3) {
+		if (cfg == 0) marchInfoCfg<3, March3A>(box, info);
+		else if (cfg == 1) marchInfoCfg<3, March3B>(box, info);
+#ifndef HB_STRICT
+		else if (cfg == 2) marchInfoCfg<3, March3C>(box, info);
+		else if (cfg == 3) marchInfoCfg<3, March3D>(box, info);
+		else if (cfg == 4) marchInfoCfg<3, March3E>(box, info);
+		else marchInfoCfg<3, March3F>(box, info);
+#endif
+	} else {
+		if (cfg == 0) marchInfoCfg<2, March2A>(box, info);
+#ifndef HB_STRICT
+		else if (cfg == 1) marchInfoCfg<2, March2B>(box, info);
+		else marchInfoCfg<2, March2C>(box, info);
+#endif
+	}
+	return true;
+}
+cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, cudaStream_t st) {
+	if (dim == 3) {
+		if (cfg == 0) return launchMarchLim<3, March3A>(lim, tmap, padX, g, sp, ep, st);
+		if (cfg == 1) return launchMarchLim<3, March3B>(lim, tmap, padX, g, sp, ep, st);
+#ifndef HB_STRICT
+		if (cfg == 2) return launchMarchLim<3, March3C>(lim, tmap, padX, g, sp, ep, st);
+		if (cfg == 3) return launchMarchLim<3, March3D>(lim, tmap, padX, g, sp, ep, st);
+		if (cfg == 4) return launchMarchLim<3, March3E>(lim, tmap, padX, g, sp, ep, st);
+		if (cfg == 5) return launchMarchLim<3, March3F>(lim, tmap, padX, g, sp, ep, st);
+#endif
+	} else if (dim == 2) {
+		if (cfg == 0) return launchMarchLim<2, March2A>(lim, tmap, padX, g, sp, ep, st);
+#ifndef HB_STRICT
+		if (cfg == 1) return launchMarchLim<2, March2B>(lim, tmap, padX, g, sp, ep, st);
+		if (cfg == 2) return launchMarchLim<2, March2C>(lim, tmap, padX, g, sp, ep, st);
+#endif
 	}
 	return cudaErrorInvalidValue;
 }
@@ -138,7 +231,7 @@ cudaError_t debugEval(int kind, int side, int n, const double* ep, const double*
 	return cudaGetLastError();
 }
 
-const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, ghosts, calcDT, constrainAll, tileInfo, debugEval};
+const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval};
 
 }   // namespace
 

@@ -37,6 +37,7 @@ template<class real> struct GridP {
 	int N[3];              // interior size
 	long long strideY, strideZ, strideV;   // element strides of j, k and of the variable index
 	real dx[3];            // gridsolver.lua:406-409
+	real invdx[3];         // 1 / dx (production CFL reduction)
 	real aov[3];           // area_s * (1/volume) as calcDerivFromFlux forms it (fvsolver.cl:97-102)
 	int fluxOn[3];         // area_s > 1e-7 (fvsolver.lua:107-110)
 	int volOn;             // volume > 1e-7 (fvsolver.cl:97)
@@ -47,6 +48,7 @@ template<class real> struct StageP {
 	real* Uout;            // next stage state (interior written)
 	real* Lout;            // optional: dU/dt of Uin (interior), for later stages' beta terms
 	int nA; const real* aPtr[HB_MAX_TERMS]; double aCoef[HB_MAX_TERMS];   // alpha_k * U^k
+	int aOwnMask;          // bit a set: aPtr[a] == Uin (the marching kernel then uses its register copy)
 	int nB; const real* bPtr[HB_MAX_TERMS]; double bCoef[HB_MAX_TERMS];   // (beta_k dt) * L^k, k < this stage
 	double betaSelf;       // beta of this stage's own L; used when computeL
 	int computeL;

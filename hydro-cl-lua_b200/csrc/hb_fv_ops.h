@@ -5,12 +5,20 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "hb_fv_kernels.cuh"
+#include "hb_fv_march.cuh"
 
 namespace hb {
 
 template<class real> struct FvOps {
 	int eqnId, nS, nI, nW;
 	cudaError_t (*stage)(int dim, bool plm, bool flim, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st);
+	// Plane-marching TMA kernel (hb_fv_march.cuh).  marchInfo: is it built for (dim, plm, flim, slope limiter)?  If so it
+	// returns the TMA box {x, y, z, var} the host must encode into the tensor map of every stage-input buffer and
+	// info = {TX, TY, planes per CTA, threads, dynamic smem bytes without staged RK operands, column threads}.
+	// cfg selects a tile configuration (0 = default).
+	bool (*marchInfo)(int dim, bool plm, bool flim, int slopeLimiter, int cfg, int box[4], int info[6]);
+	cudaError_t (*march)(int dim, int slopeLimiter, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp,
+		const double* eqnParams, cudaStream_t st);
 	cudaError_t (*ghosts)(GridP<real> const& g, BcP const& bc, real* U, int nVars, cudaStream_t st);
 	cudaError_t (*calcDT)(GridP<real> const& g, const double* eqnParams, const real* U, unsigned long long* dtMinBits, cudaStream_t st);
 	cudaError_t (*constrainAll)(GridP<real> const& g, const double* eqnParams, real* U, cudaStream_t st);

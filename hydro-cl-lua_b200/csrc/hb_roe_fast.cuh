@@ -1,0 +1,160 @@
+// hb_roe_fast.cuh -- production ("fast") forms of the per-interface and per-cell arithmetic.
+//
+// The literal functions (hb_roe.cuh, hb_eqn_*.cuh) follow the reference's OpenCL-C expression by expression so that the
+// -fmad=false build is bit-identical to the CPU oracle.  On the B200 that literal form is bound by instruction issue, not by
+// HBM: one Euler Roe flux is ~1100 SASS instructions (4 reciprocals, 2 divisions, 3 square roots, the vacuum branches, a
+// full 5x5 left and right transform), one 'plm cons' slope ~100 (a division inside a 20-way limiter switch).
+// The production build (Eqn::FAST) evaluates the SAME mathematical expressions, re-associated:
+//   * slope limiters that are symmetric (phi(r)/r = phi(1/r): minmod, superbee) need no ratio: sigma = f(dUL, dUR);
+//   * the Roe flux of the Euler equations is written in wave-strength form (alpha = L dU in closed form, R |Lambda| alpha
+//     accumulated by groups), with reciprocal reuse and one square root less; states that take any of the reference's
+//     special branches (rho < 1e-5 on either side, rho < rhoMin, h < 1e-5: hydro/eqn/euler.cl:357-426,442,501) are sent to
+//     the literal code, out of line;
+//   * constrainU + calcDTCell share the primitive recovery; the CFL reduction tracks max(lambda/dx) and inverts once.
+// Results agree with the literal form to rounding (a few ulp per flux); the parity tests hold the production build to
+// 1e-12 relative L-infinity against the oracle after N steps (BASELINE.json north_star), the strict build to bit-exactness.
+#pragma once
+#include "hb_roe.cuh"
+#include "hb_eqn_euler.cuh"
+#include "hb_eqn_mhd.cuh"
+
+#if defined(__CUDACC__)
+#define HB_NOINLINE __host__ __device__ __noinline__
+#else
+#define HB_NOINLINE
+#endif
+
+namespace hb {
+
+// ---- 'plm cons' half slope (hydro/solver/plm.cl:56-76) with the limiter fixed at compile time.
+// minmod (hydro/app.lua:622): phi = max(0, min(r, 1)); superbee (:632): phi = max(0, max(min(1, 2r), min(2, r))).
+// Both satisfy phi(r) d = phi(1/r) n for r = n/d, so which of dUL, dUR is the denominator (the dUC >= 0 test) does not matter,
+// and sigma = 0 when n d <= 0 (this also covers the exact d == 0 test).
+template<class real, int LIM, bool FAST> HB_HD real plmHalfSlopeT(int lim, real UL, real U, real UR) {
+	if (FAST && LIM == 8) {
+		real const dR = UR - U, dL = U - UL;
+		real const m = rabs(dL) < rabs(dR) ? dL : dR;
+		return dL * dR > real(0) ? real(.5) * m : real(0);
+	} else if (FAST && LIM == 18) {
+		real const dR = UR - U, dL = U - UL;
+		real const a = rabs(dL), b = rabs(dR);
+		real const m = rmax<real>(rmin<real>(real(2.) * a, b), rmin<real>(a, real(2.) * b));
+		real const sg = dR > real(0) ? real(.5) : real(-.5);
+		return dL * dR > real(0) ? sg * m : real(0);
+	} else {
+		return plmHalfSlope<real>(lim, UL, U, UR);
+	}
+}
+
+template<class real, int n> struct VecN { real v[n]; };
+
+// the literal Roe flux, out of line: the rare special-branch states of the production kernels go here
+template<class Eqn, int SIDE>
+HB_NOINLINE VecN<typename Eqn::real, Eqn::nI> roeFluxOutOfLine(typename Eqn::Params s, VecN<typename Eqn::real, Eqn::nI> UL, VecN<typename Eqn::real, Eqn::nI> UR) {
+	VecN<typename Eqn::real, Eqn::nI> F;
+	roeFlux<Eqn, SIDE>(F.v, s, UL.v, UR.v);
+	return F;
+}
+
+// Roe flux of the Euler equations, wave-strength form.  Same quantities as hydro/eqn/euler.cl:347-542 + hydro/flux/roe.cl:17-163
+// with useFluxLimiter == false and roeUseFluxFromCons == true:
+//   F = .5 (F(UL) + F(UR)) - .5 sum_j |lambda_j| alpha_j r_j,   alpha = L (UR - UL)
+//   G = (gamma-1) (.5 v^2 drho - v.dm + dE),  K = Cs (dm_n - v_n drho)
+//   alpha_0,4 = (G -/+ K) / (2 Cs^2),  alpha_1 = drho - G / Cs^2,  alpha_2,3 = dm_t - v_t drho
+template<class Eqn, int SIDE>
+HB_HD void eulerRoeFluxFast(typename Eqn::real (&F)[5], typename Eqn::Params const& s, typename Eqn::real const (&UL)[5], typename Eqn::real const (&UR)[5])
+{
+	typedef typename Eqn::real real;
+	constexpr int n = SIDE, t1 = (SIDE + 1) % 3, t2 = (SIDE + 2) % 3;
+	real const rhoL = UL[0], rhoR = UR[0];
+	real const g1 = s.gamma_1;
+	// 1/rhoL and 1/rhoR from one reciprocal
+	real const iLR = real(1.) / (rhoL * rhoR);
+	real const iL = iLR * rhoR, iR = iLR * rhoL;
+	real vL[3], vR[3];
+	#pragma unroll
+	for (int q = 0; q < 3; ++q) { vL[q] = UL[1 + q] * iL; vR[q] = UR[1 + q] * iR; }
+	real const PL = g1 * (UL[4] - real(.5) * (UL[1] * vL[0] + UL[2] * vL[1] + UL[3] * vL[2]));
+	real const PR = g1 * (UR[4] - real(.5) * (UR[1] * vR[0] + UR[2] * vR[1] + UR[3] * vR[2]));
+	real const HL = UL[4] + PL, HR = UR[4] + PR;             // rho hTotal
+	// Roe weights wL = sqrt(rhoL) / (sqrt(rhoL) + sqrt(rhoR)) = 1 / (1 + sqrt(rhoR / rhoL)), wR = 1 - wL
+	real const w = rsqrt_ieee(rhoR * iL);
+	real const wL = real(1.) / (real(1.) + w), wR = w * wL;
+	real v[3];
+	#pragma unroll
+	for (int q = 0; q < 3; ++q) v[q] = vL[q] * wL + vR[q] * wR;
+	real const H = (HL * iL) * wL + (HR * iR) * wR;
+	real const eK = real(.5) * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+	real const h = H - eK;
+	// the reference's special branches -> literal code (euler.cl:357-426: rhoEpsilon = 1e-5; :442,501: rho < rhoMin)
+	if (!(rhoL >= s.rhoFloor && rhoR >= s.rhoFloor && h >= real(1e-5))) {
+		VecN<real, 5> a, b;
+		#pragma unroll
+		for (int q = 0; q < 5; ++q) { a.v[q] = UL[q]; b.v[q] = UR[q]; }
+		VecN<real, 5> const r = roeFluxOutOfLine<Eqn, SIDE>(s, a, b);
+		#pragma unroll
+		for (int q = 0; q < 5; ++q) F[q] = r.v[q];
+		return;
+	}
+	real const Cs2 = g1 * h;
+	real const Cs = rsqrt_ieee(Cs2);
+	real const iCs2 = real(1.) / Cs2;
+	real const drho = rhoR - rhoL, dE = UR[4] - UL[4];
+	real dm[3];
+	#pragma unroll
+	for (int q = 0; q < 3; ++q) dm[q] = UR[1 + q] - UL[1 + q];
+	real const G = g1 * (eK * drho - (v[0] * dm[0] + v[1] * dm[1] + v[2] * dm[2]) + dE) * iCs2;   // G / Cs^2
+	real const K = (dm[n] - v[n] * drho) * (Cs * iCs2);                                           // K / Cs^2
+	real const b0 = rabs(v[n] - Cs) * (real(.5) * (G - K));
+	real const b4 = rabs(v[n] + Cs) * (real(.5) * (G + K));
+	real const lam = rabs(v[n]);
+	real const b1 = lam * (drho - G);
+	real const b2 = lam * (dm[t1] - v[t1] * drho);
+	real const b3 = lam * (dm[t2] - v[t2] * drho);
+	real const sum = b0 + b1 + b4, dif = (b4 - b0) * Cs;
+	real const vnL = vL[n], vnR = vR[n];
+	F[0] = real(.5) * ((UL[1 + n] + UR[1 + n]) - sum);
+	F[1 + n] = real(.5) * ((UL[1 + n] * vnL + UR[1 + n] * vnR + (PL + PR)) - (sum * v[n] + dif));
+	F[1 + t1] = real(.5) * ((UL[1 + t1] * vnL + UR[1 + t1] * vnR) - (sum * v[t1] + b2));
+	F[1 + t2] = real(.5) * ((UL[1 + t2] * vnL + UR[1 + t2] * vnR) - (sum * v[t2] + b3));
+	F[4] = real(.5) * ((HL * vnL + HR * vnR) - ((b0 + b4) * H + dif * v[n] + b1 * eK + b2 * v[t1] + b3 * v[t2]));
+}
+
+template<class Eqn, int SIDE>
+HB_HD void roeFluxAuto(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	if constexpr (Eqn::FAST && Eqn::eqnId == 0) eulerRoeFluxFast<Eqn, SIDE>(F, s, UL, UR);
+	else roeFlux<Eqn, SIDE>(F, s, UL, UR);
+}
+
+// constrainU (solverbase.lua:2116-2127 -> euler.cl:698-717) and, when wanted, the cell's CFL rate max_s(lambda_s / dx_s)
+// (calcDT.cl:38-73 computes min_s dx_s / max(lambda_s, 1e-9); the kernel inverts the reduced maximum once).
+// Production form for Euler: one reciprocal; momentum is left as it is (the reference's m = (m / rho) * rho round trip moves it
+// by at most one ulp) and ETotal is rebuilt only when the pressure floor acts.
+template<class Eqn>
+HB_HD void finishCellAuto(typename Eqn::Params const& s, typename Eqn::real (&U)[Eqn::nI], typename Eqn::real const (&dx)[3],
+	typename Eqn::real const (&invdx)[3], int dim, bool wantDt, typename Eqn::real& dtCell, typename Eqn::real& rateCell)
+{
+	typedef typename Eqn::real real;
+	if constexpr (Eqn::FAST && Eqn::eqnId == 0) {
+		if (U[0] < s.rhoMin) U[0] = s.rhoMin;
+		real const iR = real(1.) / U[0];
+		real const v0 = U[1] * iR, v1 = U[2] * iR, v2 = U[3] * iR;
+		real const eK = real(.5) * (U[1] * v0 + U[2] * v1 + U[3] * v2);
+		real P = s.gamma_1 * (U[4] - eK);
+		if (P < s.PMin) { P = s.PMin; U[4] = eK + P * s.invGamma_1; }
+		if (wantDt) {
+			real const Cs = P <= s.PMin ? real(0) : rsqrt_ieee(s.gamma * P * iR);
+			real r = rmax<real>(rabs(v0) + Cs, real(1e-9)) * invdx[0];
+			if (dim > 1) r = rmax<real>(r, rmax<real>(rabs(v1) + Cs, real(1e-9)) * invdx[1]);
+			if (dim > 2) r = rmax<real>(r, rmax<real>(rabs(v2) + Cs, real(1e-9)) * invdx[2]);
+			rateCell = rmax<real>(rateCell, r);
+		}
+	} else {
+		Eqn::constrainU(s, U);
+		if (wantDt) dtCell = rmin<real>(dtCell, Eqn::calcDTCell(s, U, dx, dim));
+	}
+}
+
+}   // namespace hb

@@ -119,8 +119,10 @@ typedef struct hb_fv_desc {
 	double eqn_params[16];
 	int strict_fp;            /* 1: kernels built with -fmad=false (no FMA contraction); 0: production kernels */
 	int use_graph;            /* 1: replay each update() as a captured CUDA graph */
+	int stage_kernel;         /* 0: auto; 1: tile kernel (fv_stage); 2: plane-marching TMA kernel (fv_march), error if not built for the config */
 } hb_fv_desc;
 
+size_t hb_sizeof_fv_desc(void);                              /* sizeof(hb_fv_desc), for bindings that mirror the struct */
 int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* desc, hb_fv** out);
 int hb_fv_destroy(hb_fv* fv);
 int hb_fv_num_states(hb_fv* fv, int* num_states, int* num_int_states, int* num_waves);
@@ -139,11 +141,11 @@ int hb_fv_get_time(hb_fv* fv, double* t_out, double* last_dt_out);   /* blocking
 int hb_fv_set_time(hb_fv* fv, double t);
 int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos_host_out);    /* FiniteVolumeSolver:calcDeriv into a zeroed deriv buffer (blocking) */
 int hb_fv_launch_count(hb_fv* fv, long long* kernel_launches);       /* kernels this object has launched so far */
-int hb_fv_describe(hb_fv* fv, char* out, size_t cap);
+int hb_fv_describe(hb_fv* fv, char* out, size_t cap);          /* text: kernel, tile shape, smem, per-stage plan (reads / writes per cell) */
 /* per-launch device timing of the fused stage kernel (CUDA events on the context's stream; disables graph replay
  * while enabled): total milliseconds and number of stage launches since hb_fv_profile(fv, 1) */
 int hb_fv_profile(hb_fv* fv, int enable);
-int hb_fv_profile_read(hb_fv* fv, double* stage_ms_total, long long* stage_launches);        /* text: tile shape, smem, per-stage plan (reads / writes per cell) */
+int hb_fv_profile_read(hb_fv* fv, double* stage_ms_total, long long* stage_launches);
 /* unit-test hook: evaluate one device function per item on the GPU (kind 0 Roe flux, 1 constrainU, 2 calcDTCell,
  * 3 PLM half slope, 4 Roe flux with flux limiter); host pointers of doubles; strict selects the -fmad=false build */
 int hb_debug_eval(hb_ctx* ctx, int eqn, int strict, int kind, int side, int n, const double* params, const double* aux4,

@@ -4,6 +4,7 @@
 #include "../../hydro-cl-lua_b200/csrc/hb_roe.cuh"
 #include "../../hydro-cl-lua_b200/csrc/hb_eqn_euler.cuh"
 #include "../../hydro-cl-lua_b200/csrc/hb_eqn_mhd.cuh"
+#include "../../hydro-cl-lua_b200/csrc/hb_roe_fast.cuh"
 
 using namespace hb;
 
@@ -58,4 +59,29 @@ double hc_plm_half_slope(int rb, int lim, double UL, double U, double UR) {
 	return rb == 8 ? plmHalfSlope<double>(lim, UL, U, UR) : double(plmHalfSlope<float>(lim, float(UL), float(U), float(UR)));
 }
 double hc_limiter(int id, double r) { return limiter<double>(id, r); }
+// production ("fast") forms, hb_roe_fast.cuh (double only; compiled without contraction here)
+void hc_euler_roe_flux_fast(int side, const double* params, const double* UL_, const double* UR_, double* F_) {
+	typedef Euler<double, true> E;
+	E::Params p = E::makeParams(params);
+	double UL[5], UR[5], F[5];
+	for (int q = 0; q < 5; ++q) { UL[q] = UL_[q]; UR[q] = UR_[q]; }
+	if (side == 0) roeFluxAuto<E, 0>(F, p, UL, UR);
+	else if (side == 1) roeFluxAuto<E, 1>(F, p, UL, UR);
+	else roeFluxAuto<E, 2>(F, p, UL, UR);
+	for (int q = 0; q < 5; ++q) F_[q] = F[q];
+}
+double hc_plm_half_slope_fast(int lim, double UL, double U, double UR) {
+	return lim == 8 ? plmHalfSlopeT<double, 8, true>(lim, UL, U, UR) : plmHalfSlopeT<double, 18, true>(lim, UL, U, UR);
+}
+// returns the CFL dt of the cell; U is constrained in place
+double hc_euler_finish_cell_fast(const double* params, double* U_, const double* dx_, int dim) {
+	typedef Euler<double, true> E;
+	E::Params p = E::makeParams(params);
+	double U[5]; double dx[3] = {dx_[0], dx_[1], dx_[2]}, invdx[3] = {1. / dx_[0], 1. / dx_[1], 1. / dx_[2]};
+	for (int q = 0; q < 5; ++q) U[q] = U_[q];
+	double dtCell = HUGE_VAL, rate = 0;
+	finishCellAuto<E>(p, U, dx, invdx, dim, true, dtCell, rate);
+	for (int q = 0; q < 5; ++q) U_[q] = U[q];
+	return rate > 0 ? 1. / rate : dtCell;
+}
 }

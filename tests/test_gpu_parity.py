@@ -141,3 +141,54 @@ def test_conservation_periodic(hydrob200):
     U1 = S.interior().sum(axis=(0, 1, 2))
     scale = np.abs(S.interior()).sum(axis=(0, 1, 2)) + 1e-300
     assert (np.abs(U1 - U0) / scale).max() < 1e-13
+
+
+# ---- the two stage-kernel implementations against each other (stage_kernel: 1 = tile kernel fv_stage, 2 = marching TMA kernel)
+MARCH_CASES = {
+    # grids that span several marching chunks (KM = 32 planes per CTA) and several, partly empty, column tiles
+    "march3d_freeflow": (dict(eqn="euler", dim=3, gridSize=[70, 19, 41], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                              usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 3),
+    "march3d_superbee_periodic": (dict(eqn="euler", dim=3, gridSize=[33, 9, 34], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="Sod",
+                                       usePLM="plm cons", slopeLimiter="superbee", integrator="Runge-Kutta 3, TVD", cfl=.1,
+                                       boundary=dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic",
+                                                     zmin="periodic", zmax="periodic")), 3),
+    "march2d_kh": (dict(eqn="euler", dim=2, gridSize=[300, 100], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                        slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 4),
+    "march2d_mhd": (dict(eqn="mhd", dim=2, gridSize=[130, 70], initCond="Orszag-Tang", usePLM="plm cons",
+                         slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15), 4),
+    "march3d_mhd": (dict(eqn="mhd", dim=3, gridSize=[36, 12, 35], initCond="Orszag-Tang", usePLM="plm cons",
+                         slopeLimiter="superbee", integrator="forward Euler", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]), 3),
+}
+
+
+@pytest.mark.parametrize("name", list(MARCH_CASES))
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_march_kernel_equals_tile_kernel_strict(hydrob200, name, precision):
+    """Same arithmetic per cell in both kernels: with -fmad=false the states must be bit-identical, ghosts included."""
+    cfg, n = MARCH_CASES[name]
+    cfg = dict(cfg, precision=precision, strict_fp=True)
+    a, ta, SA = run(hydrob200, cfg, n, stage_kernel=1)
+    b, tb, SB = run(hydrob200, cfg, n, stage_kernel=2)
+    assert "fv_stage" in SA.backend.describe() and "fv_march" in SB.backend.describe()
+    assert np.isfinite(a).all()
+    assert ta == tb
+    bad = np.argwhere(a != b)
+    assert bad.size == 0, "first mismatches (k,j,i,var): %s  max|diff| %g" % (bad[:5].tolist(), np.abs(a - b).max())
+
+
+@pytest.mark.parametrize("name", ["march3d_freeflow", "march2d_kh"])
+def test_march_kernel_fast_close_to_tile_kernel(hydrob200, name):
+    cfg, n = MARCH_CASES[name]
+    a, ta, _ = run(hydrob200, cfg, n, stage_kernel=1)
+    b, tb, _ = run(hydrob200, cfg, n, stage_kernel=2)
+    err, per = rel_linf(b, a)
+    assert err <= 1e-13, per
+
+
+def test_march_is_default_for_plm(hydrob200):
+    cfg, _ = CASES["C4_sphere_rk4"]
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    assert "fv_march(tma)" in S.backend.describe(), S.backend.describe()
+    cfg, _ = CASES["C1_sod_fe_superbee"]
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    assert "fv_stage(tile)" in S.backend.describe()

@@ -143,3 +143,75 @@ def test_limiters_and_plm(oracle, hc):
     assert hc.hc_plm_half_slope(8, 8, 0., 1., 1.) == 0.          # dUR == 0
     assert hc.hc_plm_half_slope(8, 8, 1., 1., 0.) == 0.          # dUL == 0, dUC < 0
     assert hc.hc_plm_half_slope(8, 8, 0., 1., 0.) == 0.          # extremum
+
+
+# ---- production ("fast") forms against the literal forms (hb_roe_fast.cuh)
+def test_fast_plm_equals_literal_up_to_rounding(hc):
+    hc.hc_plm_half_slope_fast.restype = C.c_double
+    hc.hc_plm_half_slope_fast.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double]
+    rng = np.random.default_rng(7)
+    trip = rng.uniform(-2, 2, (4000, 3))
+    trip[:200, 1] = trip[:200, 0]          # dUL == 0 exactly
+    trip[200:400, 2] = trip[200:400, 1]    # dUR == 0 exactly
+    trip[400:600, 2] = 2 * trip[400:600, 1] - trip[400:600, 0]   # dUL == dUR (r == 1)
+    for lim in (8, 18):
+        for a, b, c in trip:
+            lit = hc.hc_plm_half_slope(8, lim, a, b, c)
+            fast = hc.hc_plm_half_slope_fast(lim, a, b, c)
+            assert abs(fast - lit) <= 4e-16 * max(abs(lit), abs(c - b), abs(b - a)), (lim, a, b, c, lit, fast)
+
+
+def test_fast_euler_roe_flux_close_to_literal(hc):
+    hc.hc_euler_roe_flux_fast.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(11)
+    n = 3000
+    UL = random_states("euler", n, rng)
+    UR = random_states("euler", n, rng)
+    # near-identical pairs (smooth flow: the cancellation-prone case) and strong jumps
+    UR[:1000] = UL[:1000] * (1 + 1e-6 * rng.standard_normal((1000, 6)))
+    UR[1000:1200, 0] *= 50.
+    # special branches: vacuum on one / both sides, rho < rhoMin -> must equal the literal code exactly
+    UL[1200:1230, 0] = 1e-6; UR[1230:1260, 0] = 1e-6; UL[1260:1280, 0] = 1e-8
+    params = np.array([7. / 5., 1e-7, 1e-7] + [0.] * 13)
+    worst = 0.
+    for side in range(3):
+        for i in range(n):
+            Fl = np.zeros(5); Ff = np.zeros(5)
+            ul = np.ascontiguousarray(UL[i, :5]); ur = np.ascontiguousarray(UR[i, :5])
+            hc.hc_roe_flux(0, 8, side, params.ctypes.data, ul.ctypes.data, ur.ctypes.data, Fl.ctypes.data)
+            hc.hc_euler_roe_flux_fast(side, params.ctypes.data, ul.ctypes.data, ur.ctypes.data, Ff.ctypes.data)
+            if 1200 <= i < 1280:
+                assert np.array_equal(Fl, Ff)
+                continue
+            # scale: the size of the terms that are summed (advective flux + dissipation), not of the possibly cancelled result
+            rho = max(ul[0], ur[0]); vmax = max(np.abs(ul[1:4] / ul[0]).max(), np.abs(ur[1:4] / ur[0]).max(), 1.)
+            cs = np.sqrt(1.4 * 2. / .1 * 1.)
+            scale = np.array([rho, rho * vmax, rho * vmax, rho * vmax, max(ul[4], ur[4])]) * (vmax + cs) + np.abs(Fl)
+            worst = max(worst, (np.abs(Ff - Fl) / scale).max())
+    assert worst < 2e-15, worst
+
+
+def test_fast_euler_finish_cell(hc):
+    hc.hc_euler_finish_cell_fast.restype = C.c_double
+    hc.hc_euler_finish_cell_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(5)
+    U = random_states("euler", 500, rng)
+    U[:20, 4] = .5 * (U[:20, 1:4] ** 2).sum(1) / U[:20, 0] - 1.     # negative pressure -> PMin floor
+    U[20:30, 0] = 1e-9                                               # below rhoMin -> density floor
+    U[20:30, 1:4] *= 1e-8                                            # (momentum of a near-vacuum cell, so that P stays well conditioned)
+    params = np.array([7. / 5., 1e-7, 1e-7] + [0.] * 13)
+    dx = np.array([.01, .02, .03])
+    for dim in (1, 2, 3):
+        for i in range(len(U)):
+            a = U[i, :5].copy(); b = a.copy()
+            hc.hc_constrainU(0, 8, params.ctypes.data, a.ctypes.data)
+            dt_lit = hc.hc_calc_dt_cell(0, 8, params.ctypes.data, a.ctypes.data, dx.ctypes.data, dim)
+            dt_fast = hc.hc_euler_finish_cell_fast(params.ctypes.data, b.ctypes.data, dx.ctypes.data, dim)
+            assert np.allclose(a, b, rtol=1e-14, atol=1e-14 * np.abs(a).max()), (i, a, b)
+            if i < 20:
+                # pressure floor active: the literal form recomputes P from the rebuilt ETotal and lands on either side of
+                # `P <= PMin` by rounding (Cs = 0 or sqrt(gamma PMin / rho)); the production form takes Cs = 0
+                dt_cs0 = min(dx[s_] / max(abs(a[1 + s_] / a[0]), 1e-9) for s_ in range(dim))
+                assert dt_lit * (1 - 1e-14) <= dt_fast <= dt_cs0 * (1 + 1e-14), (i, dt_lit, dt_fast, dt_cs0)
+            else:
+                assert abs(dt_fast - dt_lit) <= 1e-14 * dt_lit, (i, dt_lit, dt_fast)
