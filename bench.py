@@ -231,8 +231,17 @@ def main():
     bytes_per_launch = w["words"] * w["nI"] * 8 / w["stages"] * cellsLocal
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": "fv_stage", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "stage_kernel_ms": stage_ms,
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tr = json.load(f).get(args.workload)
+        if tr and not args.grid:
+            traffic = tr["bytes_per_launch"]
+    except Exception:
+        pass
+    desc = B.describe().split("\n")[0]
+    roofline = {"bound": "hbm", "kernel": desc.split()[0].replace("kernel=", ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "stage_kernel_ms": stage_ms, "kernel_config": desc,
                 "stage_share_of_step": stage_ms * w["stages"] / (ms / args.steps),
                 "algorithmic_bytes_per_cell_update": w["words"] * w["nI"] * 8}
 

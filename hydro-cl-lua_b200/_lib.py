@@ -13,7 +13,7 @@ CSRC = os.path.join(_here, "csrc")
 LIB_PATH = os.path.join(CSRC, "libhydrob200.so")
 
 HB_OK, HB_ERR_INVALID, HB_ERR_NO_DEVICE, HB_ERR_CUDA, HB_ERR_COMPILE = 0, 1, 2, 3, 4
-HB_EQN_EULER, HB_EQN_MHD = 0, 1
+HB_EQN_EULER, HB_EQN_MHD, HB_EQN_ADM3D = 0, 1, 2
 HB_REDUCE_MIN, HB_REDUCE_MAX, HB_REDUCE_SUM = 0, 1, 2
 
 
@@ -82,6 +82,7 @@ SIGNATURES = {
     "hb_fv_state_devptr": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "hb_fv_boundary": (C.c_int, [P]),
     "hb_fv_constrainU": (C.c_int, [P]),
+    "hb_fv_init_derivs": (C.c_int, [P]),
     "hb_fv_calc_dt": (C.c_int, [P, C.POINTER(C.c_double)]),
     "hb_fv_step": (C.c_int, [P, C.c_double]),
     "hb_fv_update": (C.c_int, [P, C.c_int]),

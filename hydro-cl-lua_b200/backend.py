@@ -135,6 +135,9 @@ class CudaBackend:
     def constrainU(self):
         hb.check(self.L.hb_fv_constrainU(self.h))
 
+    def init_derivs(self):
+        hb.check(self.L.hb_fv_init_derivs(self.h))
+
     def calc_dt(self):
         dt = C.c_double()
         hb.check(self.L.hb_fv_calc_dt(self.h, C.byref(dt)))

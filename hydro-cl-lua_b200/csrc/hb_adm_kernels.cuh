@@ -1,0 +1,225 @@
+// hb_adm_kernels.cuh -- finite-volume stage of the ADM Bona-Masso 3-D system (BASELINE config C5) on sm_100a.
+//
+// One Runge-Kutta stage = the reference's calcFlux (Roe + flux limiter, hydro/solver/fvsolver.lua:57-198, hydro/flux/roe.cl:17-163),
+// calcDerivFromFlux (hydro/solver/fvsolver.cl:6-125), addSource (hydro/eqn/adm3d.cl:1402-3072), the stage's multAdd combination
+// (hydro/int/rk.lua:91-112) and, on the last stage, calcDT (hydro/eqn/cl/calcDT.cl:38-73), as two kernels over SoA arrays:
+//   adm_flux<SIDE>  one thread per interface: the 13-wave Roe flux (a_side, d_side,ij, K_ij) -> flux scratch [side][13][cell]
+//   adm_update      one thread per interior cell: flux differences of the 13 x dim components, source term of all 37, RK
+//                   combination, store, CFL min (warp shuffle -> block -> atomicMin)
+// The state is 51 reals per cell (408 B as an AoS record in the reference): only 20 of them enter a side's flux, so the flux
+// kernel reads 4 cells x 20 variables per interface through L1/L2 and never touches the other 31.
+// First version: not yet fused into one tile kernel like fv_march (next step for this equation).
+#pragma once
+#include "hb_fv_kernels.cuh"
+#include "hb_eqn_adm3d.cuh"
+
+namespace hb {
+
+template<class Eqn, int SIDE>
+HB_D void admLoadSide(typename Eqn::Side& s, const typename Eqn::real* __restrict__ U, long long idx, long long sv) {
+	s.alpha = U[idx];
+	#pragma unroll
+	for (int k = 0; k < 6; ++k) s.g[k] = U[idx + (Eqn::iGamma + k) * sv];
+	s.a = U[idx + (Eqn::iA + SIDE) * sv];
+	#pragma unroll
+	for (int k = 0; k < 6; ++k) s.d[k] = U[idx + (Eqn::iD + 6 * SIDE + k) * sv];
+	#pragma unroll
+	for (int k = 0; k < 6; ++k) s.K[k] = U[idx + (Eqn::iK + k) * sv];
+}
+
+// interfaces: the low face of cells c = g .. g+N along SIDE, interior in the transverse directions
+template<class Eqn, int SIDE, int MODE>
+__global__ void __launch_bounds__(128)
+adm_flux(GridP<typename Eqn::real> const g, typename Eqn::Params const ep, const typename Eqn::real* __restrict__ U,
+	typename Eqn::real* __restrict__ Fb, const double* dtPtr, int fluxLimiter)
+{
+	typedef typename Eqn::real real;
+	int const n0 = g.N[0] + (SIDE == 0), n1 = g.N[1] + (SIDE == 1), n2 = g.N[2] + (SIDE == 2);
+	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (w >= (long long)n0 * n1 * n2) return;
+	int const i = int(w % n0) + HB_G;
+	int const j = int((w / n0) % n1) + (g.dim >= 2 ? HB_G : 0);
+	int const k = int(w / ((long long)n0 * n1)) + (g.dim >= 3 ? HB_G : 0);
+	long long const idx = i + g.strideY * j + g.strideZ * k;
+	long long const step = SIDE == 0 ? 1 : (SIDE == 1 ? g.strideY : g.strideZ);
+	long long const sv = g.strideV;
+	real Fa = 0, Fd[6], FK[6];
+	#pragma unroll
+	for (int q = 0; q < 6; ++q) { Fd[q] = 0; FK[q] = 0; }
+	if (g.fluxOn[SIDE]) {
+		typename Eqn::Side U2L, UL, UR, U2R;
+		admLoadSide<Eqn, SIDE>(UL, U, idx - step, sv);
+		admLoadSide<Eqn, SIDE>(UR, U, idx, sv);
+		bool const lim = fluxLimiter > 0;
+		if (lim) {
+			admLoadSide<Eqn, SIDE>(U2L, U, idx - 2 * step, sv);
+			admLoadSide<Eqn, SIDE>(U2R, U, idx + step, sv);
+		} else { U2L = UL; U2R = UR; }
+		real const dt_dx = real(*dtPtr) / g.dx[SIDE];
+		Eqn::template roeFluxLimited<SIDE>(Fa, Fd, FK, ep, fluxLimiter, lim, dt_dx, U2L, UL, UR, U2R);
+	}
+	real* F = Fb + (long long)SIDE * 13 * sv + idx;
+	F[0] = Fa;
+	#pragma unroll
+	for (int q = 0; q < 6; ++q) { F[(1 + q) * sv] = Fd[q]; F[(7 + q) * sv] = FK[q]; }
+}
+
+template<class Eqn, int MODE>
+__global__ void __launch_bounds__(128)
+adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep,
+	const typename Eqn::real* __restrict__ Fb)
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI;
+	__shared__ double redBuf[32];
+	long long const nInt = (long long)g.N[0] * g.N[1] * g.N[2];
+	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	real dtCell = inf_of<real>::v();
+	if (w < nInt) {
+		int const i = int(w % g.N[0]) + HB_G;
+		int const j = int((w / g.N[0]) % g.N[1]) + (g.dim >= 2 ? HB_G : 0);
+		int const k = int(w / ((long long)g.N[0] * g.N[1])) + (g.dim >= 3 ? HB_G : 0);
+		long long const idx = i + g.strideY * j + g.strideZ * k;
+		long long const sv = g.strideV;
+		real const* __restrict__ Uin = sp.Uin;
+		real U[nI], deriv[nI];
+		#pragma unroll
+		for (int q = 0; q < nI; ++q) { U[q] = Uin[idx + q * sv]; deriv[q] = 0; }
+		if (sp.computeL) {
+			// ---- calcDerivFromFlux (fvsolver.cl:97-123): sides in order; only the side's 13 components carry a flux
+			if (g.volOn) {
+				#pragma unroll
+				for (int side = 0; side < 3; ++side) {
+					if (side < g.dim) {
+						long long const step = side == 0 ? 1 : (side == 1 ? g.strideY : g.strideZ);
+						real const aov = g.aov[side];
+						real const* FL = Fb + (long long)side * 13 * sv + idx;
+						real const* FR = FL + step;
+						deriv[Eqn::iA + side] = deriv[Eqn::iA + side] - (FR[0] * aov - FL[0] * aov);
+						#pragma unroll
+						for (int q = 0; q < 6; ++q) {
+							deriv[Eqn::iD + 6 * side + q] = deriv[Eqn::iD + 6 * side + q] - (FR[(1 + q) * sv] * aov - FL[(1 + q) * sv] * aov);
+							deriv[Eqn::iK + q] = deriv[Eqn::iK + q] - (FR[(7 + q) * sv] * aov - FL[(7 + q) * sv] * aov);
+						}
+					}
+				}
+			}
+			// ---- addSource (adm3d.cl:1402-3072)
+			real Sll[6];
+			real const rho = Uin[idx + Eqn::iRho * sv];
+			#pragma unroll
+			for (int q = 0; q < 6; ++q) Sll[q] = Uin[idx + (Eqn::iSll + q) * sv];
+			Eqn::addSource(deriv, ep, U, rho, Sll);
+			if (ep.a_conv != 0 || ep.d_conv != 0) {
+				// first-order constraint convergence (adm3d.cl:3008-3036): radius-1 centred differences of alpha and gamma_ll
+				#pragma unroll
+				for (int side = 0; side < 3; ++side) {
+					if (side < g.dim) {
+						long long const step = side == 0 ? 1 : (side == 1 ? g.strideY : g.strideZ);
+						real const dx = g.dx[side];
+						real const partial_i_log_alpha = (log(Uin[idx + step]) - log(Uin[idx - step])) / (real(2.) * dx);
+						deriv[Eqn::iA + side] += ep.a_conv * (partial_i_log_alpha - U[Eqn::iA + side]);
+						#pragma unroll
+						for (int q = 0; q < 6; ++q) {
+							real const pg = (Uin[idx + step + (Eqn::iGamma + q) * sv] - Uin[idx - step + (Eqn::iGamma + q) * sv]) / (real(2.) * dx);
+							deriv[Eqn::iD + 6 * side + q] += ep.d_conv * (real(.5) * pg - U[Eqn::iD + 6 * side + q]);
+						}
+					} else {
+						deriv[Eqn::iA + side] += ep.a_conv * (real(0.) - U[Eqn::iA + side]);
+						#pragma unroll
+						for (int q = 0; q < 6; ++q) deriv[Eqn::iD + 6 * side + q] += ep.d_conv * (real(.5) * real(0) - U[Eqn::iD + 6 * side + q]);
+					}
+				}
+			}
+		}
+		if (sp.Lout) {
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) sp.Lout[idx + q * sv] = deriv[q];
+		}
+		if (sp.Uout) {
+			double const dt = *sp.dt;
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) {
+				real r = 0;
+				#pragma unroll
+				for (int a = 0; a < HB_MAX_TERMS; ++a)
+					if (a < sp.nA) r = r + (((sp.aOwnMask >> a) & 1) ? U[q] : sp.aPtr[a][idx + q * sv]) * real(sp.aCoef[a]);
+				#pragma unroll
+				for (int b = 0; b < HB_MAX_TERMS; ++b)
+					if (b < sp.nB) r = r + sp.bPtr[b][idx + q * sv] * real(sp.bCoef[b] * dt);
+				if (sp.computeL) r = r + deriv[q] * real(sp.betaSelf * dt);
+				deriv[q] = r;          // reuse as the new state
+			}
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) sp.Uout[idx + q * sv] = deriv[q];
+			if (sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);
+		}
+	}
+	if (sp.dtMinBits) {
+		double v = double(dtCell);
+		#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }
+		if ((threadIdx.x & 31) == 0) redBuf[threadIdx.x >> 5] = v;
+		__syncthreads();
+		if (threadIdx.x < 32) {
+			v = threadIdx.x < (blockDim.x + 31) / 32 ? redBuf[threadIdx.x] : HUGE_VAL;
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }
+			if (threadIdx.x == 0 && v < HUGE_VAL) atomicMin(sp.dtMinBits, dtBits(v));
+		}
+	}
+}
+
+// initDerivs (hydro/eqn/adm3d.cl:196-243): a_l, d_lll from centred differences of alpha, gamma_ll (interior cells), V_i = d_ik^k - d^k_ki.
+// Reads alpha / gamma_ll (never written here) of the neighbours, writes a_l, d_lll, V_l of its own cell: safe in place.
+template<class Eqn, int MODE>
+__global__ void adm_init_derivs(GridP<typename Eqn::real> const g, typename Eqn::real* __restrict__ U)
+{
+	typedef typename Eqn::real real;
+	long long const nInt = (long long)g.N[0] * g.N[1] * g.N[2];
+	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (w >= nInt) return;
+	int const i = int(w % g.N[0]) + HB_G;
+	int const j = int((w / g.N[0]) % g.N[1]) + (g.dim >= 2 ? HB_G : 0);
+	int const k = int(w / ((long long)g.N[0] * g.N[1])) + (g.dim >= 3 ? HB_G : 0);
+	long long const idx = i + g.strideY * j + g.strideZ * k;
+	long long const sv = g.strideV;
+	real gl[6], gU[6], d[3][6], a[3];
+	#pragma unroll
+	for (int q = 0; q < 6; ++q) gl[q] = U[idx + (Eqn::iGamma + q) * sv];
+	Eqn::inv6(gU, gl, Eqn::det6(gl));
+	real const alpha = U[idx];
+	#pragma unroll
+	for (int side = 0; side < 3; ++side) {
+		if (side < g.dim) {
+			long long const step = side == 0 ? 1 : (side == 1 ? g.strideY : g.strideZ);
+			real const dx = g.dx[side];
+			a[side] = (U[idx + step] - U[idx - step]) / (dx * alpha);
+			#pragma unroll
+			for (int q = 0; q < 6; ++q)
+				d[side][q] = real(.5) * (U[idx + step + (Eqn::iGamma + q) * sv] - U[idx - step + (Eqn::iGamma + q) * sv]) / dx;
+		} else {
+			a[side] = 0;
+			#pragma unroll
+			for (int q = 0; q < 6; ++q) d[side][q] = 0;
+		}
+	}
+	#pragma unroll
+	for (int s = 0; s < 3; ++s) {
+		U[idx + (Eqn::iA + s) * sv] = a[s];
+		#pragma unroll
+		for (int q = 0; q < 6; ++q) U[idx + (Eqn::iD + 6 * s + q) * sv] = d[s][q];
+	}
+	#pragma unroll
+	for (int ii = 0; ii < 3; ++ii) {
+		real t = 0.;
+		#pragma unroll
+		for (int jj = 0; jj < 3; ++jj)
+			#pragma unroll
+			for (int kk = 0; kk < 3; ++kk)
+				t = t + gU[Eqn::s6(jj, kk)] * (d[ii][Eqn::s6(jj, kk)] - d[jj][Eqn::s6(kk, ii)]);
+		U[idx + (Eqn::iV + ii) * sv] = t;
+	}
+}
+
+}   // namespace hb

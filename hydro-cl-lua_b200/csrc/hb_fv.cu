@@ -171,6 +171,7 @@ struct FvBase {
 	virtual int describe(char* out, size_t cap) = 0;
 	virtual int profile(int enable) = 0;
 	virtual int profileRead(double* ms, long long* n) = 0;
+	virtual int initDerivs() = 0;
 	virtual int commInit(int nranks, int rank, const char* id) = 0;
 	virtual int commDestroy() = 0;
 	int nS = 0, nI = 0, nW = 0;
@@ -191,6 +192,7 @@ template<class real> struct Fv : FvBase {
 	bool useMarch = false;
 	int marchCfg = 0, marchBox[4] = {0, 0, 0, 0}, marchInfoV[6] = {0, 0, 0, 0, 0, 0};
 	real* scratchL = nullptr;
+	real* opsScratch = nullptr;            // FvOps::scratchElems (ADM flux arrays)
 	double* stagingAos = nullptr;
 	double* ctl = nullptr;                 // device: t, dt, cfl, fixedDT(<0 adaptive)
 	unsigned long long* dtMinBits = nullptr;
@@ -222,6 +224,7 @@ template<class real> struct Fv : FvBase {
 		for (auto p : upool) cudaFree(p - padX);
 		for (auto p : lpool) cudaFree(p - padX);
 		if (scratchL) cudaFree(scratchL - padX);
+		if (opsScratch) cudaFree(opsScratch - padX);
 		if (stagingAos) cudaFree(stagingAos);
 		if (ctl) cudaFree(ctl);
 		if (dtMinBits) cudaFree(dtMinBits);
@@ -329,6 +332,9 @@ template<class real> struct Fv : FvBase {
 				umaps.resize(nU);
 				for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &umaps[k])) return r;
 			}
+		}
+		if (ops->scratchElems) {
+			if (int r = allocPadded(&opsScratch, sizeof(real) * ((size_t)ops->scratchElems(grid) + (size_t)grid.strideY))) return r;
 		}
 		HB_CUDA(cudaMalloc(&ctl, 4 * sizeof(double)));
 		HB_CUDA(cudaMalloc(&dtMinBits, sizeof(unsigned long long)));
@@ -472,6 +478,7 @@ template<class real> struct Fv : FvBase {
 		sp.dtMinBits = wantDtMin ? dtMinBits : nullptr;
 		sp.slopeLimiter = d.slope_limiter;
 		sp.fluxLimiter = d.flux_limiter;
+		sp.scratch = opsScratch;
 	}
 
 	// integrator:integrate(dt, calcDeriv) + boundary/constrainU after every stage (rk.lua:91-165, fe.lua:33-49)
@@ -598,7 +605,7 @@ template<class real> struct Fv : FvBase {
 		memset(&sp, 0, sizeof(sp));
 		sp.Uin = upool[0]; sp.Uout = nullptr; sp.Lout = scratchL;
 		sp.computeL = 1; sp.dt = ctl + 1;
-		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter;
+		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch;
 		bool const plm = d.use_plm != 0;
 		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, st()));
 		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
@@ -656,6 +663,14 @@ template<class real> struct Fv : FvBase {
 		if (n) *n = (long long)profUsed;
 		return HB_OK;
 	}
+	int initDerivs() override {
+		useDevice(ctx);
+		if (!ops->initDerivs) return HB_OK;      // equations without an initDerivs kernel (hydro/init/init.lua:231-235)
+		HB_CUDA(ops->initDerivs(grid, upool[0], st()));
+		launches++;
+		dtValid = false;
+		return HB_OK;
+	}
 	int commInit(int nr, int rk_, const char* id) override {
 		useDevice(ctx);
 		Nccl& N = Nccl::get();
@@ -701,6 +716,10 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (d->use_plm < 0 || d->use_plm > 1) return setError(HB_ERR_INVALID, "hb_fv_create: only usePLM none / 'plm cons' are built");
 	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");
 	if (d->use_plm && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM requires fluxLimiter 'donor cell' (gridsolver.lua:119)");
+	if (d->eqn == HB_EQN_ADM3D) {
+		if (d->use_plm) return setError(HB_ERR_INVALID, "hb_fv_create: adm3d runs the Roe flux with a flux limiter on cell-centred states; usePLM is not built for it");
+		for (int k = 0; k < 2 * d->dim; ++k) if (d->bc[k] == HB_BC_MIRROR) return setError(HB_ERR_INVALID, "hb_fv_create: mirror boundaries are not built for adm3d");
+	}
 	FvBase* impl = nullptr;
 	bool const strict = d->strict_fp != 0;
 	if (ctx->real_bytes == 8) {
@@ -728,6 +747,7 @@ int hb_fv_get_state(hb_fv* fv, double* aos) { HB_FV(fv); return fv->impl->getSta
 int hb_fv_state_devptr(hb_fv* fv, void** p, long long* sy, long long* sz, long long* sv) { HB_FV(fv); return fv->impl->stateDevPtr(p, sy, sz, sv); }
 int hb_fv_boundary(hb_fv* fv) { HB_FV(fv); return fv->impl->boundary(); }
 int hb_fv_constrainU(hb_fv* fv) { HB_FV(fv); return fv->impl->constrainU(); }
+int hb_fv_init_derivs(hb_fv* fv) { HB_FV(fv); return fv->impl->initDerivs(); }
 int hb_fv_calc_dt(hb_fv* fv, double* dt) { HB_FV(fv); return fv->impl->calcDT(dt); }
 int hb_fv_step(hb_fv* fv, double dt) { HB_FV(fv); return fv->impl->step(dt); }
 int hb_fv_update(hb_fv* fv, int nsteps) { HB_FV(fv); return fv->impl->update(nsteps); }

@@ -65,12 +65,12 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 
 // ---- plane-marching kernel: tile configurations per dimensionality (cfg index; the host takes the first one whose shared
 // memory fits, starting at $HB_MARCH_CFG or 0)
-typedef MarchCfg<1, 12, 32, 1> March3A;    // 32 x 12 columns, 15 warps, <= 136 registers
-typedef MarchCfg<1, 8, 32, 1> March3B;     // 32 x 8 columns, 11 warps, no register cap
-typedef MarchCfg<1, 16, 32, 1> March3C;    // 32 x 16 columns, 19 warps, <= 104 registers
-typedef MarchCfg<1, 8, 32, 2> March3D;     // 32 x 8 columns, 2 CTAs / SM, <= 88 registers
-typedef MarchCfg<1, 10, 32, 1> March3E;    // 32 x 10 columns, 13 warps, <= 152 registers
-typedef MarchCfg<1, 6, 32, 2> March3F;     // 32 x 6 columns, 9 warps, 2 CTAs / SM, <= 112 registers
+typedef MarchCfg<1, 10, 32, 1> March3A;    // 32 x 10 columns, 13 warps
+typedef MarchCfg<1, 8, 32, 1> March3B;     // 32 x 8 columns, 11 warps
+typedef MarchCfg<1, 4, 32, 1> March3C;     // 32 x 4 columns, 7 warps: the fallback that fits 8-variable equations (MHD) in shared memory
+typedef MarchCfg<1, 12, 32, 1> March3D;    // 32 x 12 columns, 15 warps (shared memory allows at most one staged RK operand)
+typedef MarchCfg<1, 6, 32, 2> March3E;     // 32 x 6 columns, 9 warps, 2 CTAs / SM, <= 112 registers
+typedef MarchCfg<1, 4, 32, 2> March3F;     // 32 x 4 columns, 7 warps, 2 CTAs / SM
 typedef MarchCfg<4, 1, 32, 2> March2A;     // 128 columns, 5 warps
 typedef MarchCfg<2, 1, 32, 4> March2B;     // 64 columns, 3 warps
 typedef MarchCfg<6, 1, 64, 1> March2C;     // 192 columns, 7 warps (TMA boxes are at most 256 elements wide)
@@ -111,7 +111,7 @@ template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
 	info[5] = G::NREG * 32;
 }
 #ifdef HB_STRICT
-constexpr int kMarchCfgs3 = 2, kMarchCfgs2 = 1;     // the strict build carries fewer configurations (compile time)
+constexpr int kMarchCfgs3 = 3, kMarchCfgs2 = 1;     // the strict build carries fewer configurations (compile time)
 #else
 constexpr int kMarchCfgs3 = 6, kMarchCfgs2 = 3;
 #endif
@@ -120,8 +120,8 @@ bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int i
 	if (dim == 3) {
 		if (cfg == 0) marchInfoCfg<3, March3A>(box, info);
 		else if (cfg == 1) marchInfoCfg<3, March3B>(box, info);
-#ifndef HB_STRICT
 		else if (cfg == 2) marchInfoCfg<3, March3C>(box, info);
+#ifndef HB_STRICT
 		else if (cfg == 3) marchInfoCfg<3, March3D>(box, info);
 		else if (cfg == 4) marchInfoCfg<3, March3E>(box, info);
 		else marchInfoCfg<3, March3F>(box, info);
@@ -139,8 +139,8 @@ cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, 
 	if (dim == 3) {
 		if (cfg == 0) return launchMarchLim<3, March3A>(lim, tmap, padX, g, sp, ep, st);
 		if (cfg == 1) return launchMarchLim<3, March3B>(lim, tmap, padX, g, sp, ep, st);
-#ifndef HB_STRICT
 		if (cfg == 2) return launchMarchLim<3, March3C>(lim, tmap, padX, g, sp, ep, st);
+#ifndef HB_STRICT
 		if (cfg == 3) return launchMarchLim<3, March3D>(lim, tmap, padX, g, sp, ep, st);
 		if (cfg == 4) return launchMarchLim<3, March3E>(lim, tmap, padX, g, sp, ep, st);
 		if (cfg == 5) return launchMarchLim<3, March3F>(lim, tmap, padX, g, sp, ep, st);
@@ -231,7 +231,7 @@ cudaError_t debugEval(int kind, int side, int n, const double* ep, const double*
 	return cudaGetLastError();
 }
 
-const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval};
+const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval, nullptr, nullptr};
 
 }   // namespace
 

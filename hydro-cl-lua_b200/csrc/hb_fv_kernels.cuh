@@ -55,6 +55,7 @@ template<class real> struct StageP {
 	const double* dt;      // device scalar: the full-step dt (solverbase.lua:3197-3202: stages see the step dt)
 	unsigned long long* dtMinBits;   // optional: fused calcDT, min over interior cells as ordered bits of a double
 	int slopeLimiter, fluxLimiter;
+	real* scratch;         // optional per-solver device scratch (FvOps::scratchElems), e.g. the ADM flux arrays
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {

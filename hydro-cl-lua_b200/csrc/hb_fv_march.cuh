@@ -10,8 +10,8 @@
 //     (z in 3-D, y in 2-D).  One thread owns one column: the marching-axis stencil (U[k-1], U[k], U[k+1], the face state
 //     and the flux of the previous interface) lives in registers, so that axis costs no shared-memory traffic and no
 //     redundant halo work except one extra interface flux per KM planes.
-//   * TMA.  Plane k+2 of the tile plus its 2-cell x/y halo (all nI variables, one 4-D box) is fetched by one
-//     cp.async.bulk.tensor instruction into a 3-slot shared-memory ring while plane k is being computed; completion is
+//   * TMA.  Plane k+3 of the tile plus its 2-cell x/y halo (all nI variables, one 4-D box) is fetched by one
+//     cp.async.bulk.tensor instruction into a 4-slot shared-memory ring while plane k is being computed; completion is
 //     signalled on an mbarrier per slot.  Out-of-range box parts are zero-filled by the hardware (those lanes never store).
 //   * Whole-warp halos.  The x/y neighbours' half slopes and interface fluxes are exchanged through shared memory; the halo
 //     work that no column thread owns (slopes of the cells one step outside the tile, the flux of the tile's far faces) is
@@ -51,13 +51,13 @@ template<int DIM, class C, class real> struct MarchGeom {
 	static constexpr int NROWH = DIM == 3 ? 2 * WX : 0;        // row-halo warps (row -1, row TY)
 	static constexpr int NWARPS = NREG + NROWH + 1;            // + the x-halo warp
 	static constexpr int NT = 32 * NWARPS;
-	static constexpr int R = 3;                                // ring slots: planes k, k+1 and the one in flight
+	static constexpr int R = 4;                                // ring slots: planes k-1 (being recycled), k, k+1, k+2 (in flight)
 	static constexpr int SGXN = TY * (TX + 2), FXXN = TY * (TX + 1);
 	static constexpr int SGYN = DIM == 3 ? (TY + 2) * TX : 0, FXYN = DIM == 3 ? (TY + 1) * TX : 0;
 	template<int nI> static constexpr size_t slotBytes() { return (sizeof(real) * nI * PS + 127) / 128 * 128; }
 	// nOps = number of RK operands (alpha terms other than the stage input + beta terms) staged per column thread
 	template<int nI> static constexpr size_t smemBytes(int nOps) {
-		return 128 + R * slotBytes<nI>() + sizeof(real) * nI * size_t(SGXN + FXXN + SGYN + FXYN + nOps * NREG * 32) + 128;
+		return 128 + R * slotBytes<nI>() + sizeof(real) * nI * size_t(2 * (SGXN + FXXN + SGYN + FXYN) + nOps * NREG * 32) + 128;
 	}
 	static_assert(TY <= 16, "the x-halo warp serves at most 16 rows");
 };
@@ -158,11 +158,12 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 	extern __shared__ __align__(128) unsigned char marchSmem[];
 	uint64_t* full = reinterpret_cast<uint64_t*>(marchSmem);               // R mbarriers
 	real* ring = reinterpret_cast<real*>(marchSmem + 128);
-	real* SGX = ring + G::R * SLOT;             // half slopes along x of cells i = -1 .. TX      [q][row][i + 1]
-	real* FXX = SGX + nI * G::SGXN;             // x fluxes at the low faces of cells i = 0 .. TX [q][row][i]
-	real* SGY = FXX + nI * G::FXXN;             // half slopes along y of rows j = -1 .. TY       [q][j + 1][i]
-	real* FXY = SGY + nI * G::SGYN;             // y fluxes at the low faces of rows j = 0 .. TY  [q][j][i]
-	real* OPB = FXY + nI * G::FXYN;             // staged RK operands of the column threads       [operand][q][thread]
+	// exchange arrays, two halves each (plane parity): one barrier per iteration suffices (see the loop)
+	real* SGX = ring + G::R * SLOT;             // half slopes along x of cells i = -1 .. TX      [parity][q][row][i + 1]
+	real* FXX = SGX + 2 * nI * G::SGXN;         // x fluxes at the low faces of cells i = 0 .. TX [parity][q][row][i]
+	real* SGY = FXX + 2 * nI * G::FXXN;         // half slopes along y of rows j = -1 .. TY       [parity][q][j + 1][i]
+	real* FXY = SGY + 2 * nI * G::SGYN;         // y fluxes at the low faces of rows j = 0 .. TY  [parity][q][j][i]
+	real* OPB = FXY + 2 * nI * G::FXYN;         // staged RK operands of the column threads       [operand][q][thread]
 	constexpr int OPS = G::NREG * 32;
 	__shared__ double redBuf[32];
 
@@ -215,7 +216,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
 	__syncthreads();
-	if (tid == 0) { issue(kb - 2, 0); issue(kb - 1, 1); issue(kb, 2); }
+	if (tid == 0) { issue(kb - 2, 0); issue(kb - 1, 1); issue(kb, 2); if (kb + 1 <= ke + 1) issue(kb + 1, 3); }
 
 	double const dt = *sp.dt;
 	real const aovX = g.aov[0], aovY = g.aov[1], aovM = g.aov[MS];
@@ -226,10 +227,11 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 	mbarWait(&full[1], 0);
 
 	real dtCell = inf_of<real>::v(), rateCell = 0;
-	// iteration `it` handles plane k = kb - 1 + it.  Plane p occupies ring slot (p - (kb-2)) % 3 on its ((p - (kb-2)) / 3)-th use.
+	// iteration `it` handles plane k = kb - 1 + it.  Plane p occupies ring slot (p - (kb-2)) % 4 on its ((p - (kb-2)) / 4)-th use.
+	// Plane k+3 is requested at the barrier of iteration k and first needed at the top of iteration k+2: a full iteration of lead.
 	for (int k = kb - 1, it = 0; k <= ke; ++k, ++it) {
-		int const sP = it % 3, sK = (it + 1) % 3, sN = (it + 2) % 3;     // slots of planes k-1 (recycled for k+2), k, k+1
-		uint32_t const parN = uint32_t((it + 2) / 3) & 1u;
+		int const sP = it & 3, sK = (it + 1) & 3, sN = (it + 2) & 3;     // slots of planes k-1 (recycled for k+3), k, k+1
+		uint32_t const parN = uint32_t((it + 2) >> 2) & 1u;
 		bool const xy = k >= kb && k < ke;
 		real const* __restrict__ P = ring + sK * SLOT;
 		mbarWait(&full[sN], parN);
@@ -276,72 +278,83 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) { Um[q] = Uk[q]; zfP[q] = zfN[q]; FzP[q] = Fz[q]; }
 		}
-		// ---- phase 1: half slopes of plane k along x and y (plm.cl:56-76)
-		if (xy) {
-			if (doSX) {
-				#pragma unroll
-				for (int q = 0; q < nI; ++q)
-					SGX[(q * TY + cj) * (TX + 2) + ci + 1] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, P[q * PS + ob - 1], P[q * PS + ob], P[q * PS + ob + 1]);
-			}
-			if (DIM == 3 && doSY) {
-				#pragma unroll
-				for (int q = 0; q < nI; ++q)
-					SGY[(q * (TY + 2) + cj + 1) * TX + ci] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, P[q * PS + ob - BX], P[q * PS + ob], P[q * PS + ob + BX]);
-			}
-		}
-		__syncthreads();
-		if (tid == 0 && k + 2 <= ke + 1) {
-			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-			issue(k + 2, sP);
-		}
-		// ---- phase 2: Roe fluxes at the low x and y faces of the cells of plane k
-		real fxl[nI], fyl[nI];
+		// ---- fluxes of plane k: Roe flux at the low x and y faces (slopes of plane k were published one iteration ago)
+		real* const sgx = SGX + (k & 1) * (nI * G::SGXN);
+		real* const sgy = SGY + (k & 1) * (nI * G::SGYN);
+		real* const fxx = FXX + (k & 1) * (nI * G::FXXN);
+		real* const fxy = FXY + (k & 1) * (nI * G::FXYN);
 		if (xy) {
 			if (doFX) {
+				real F[nI];
 				if (g.fluxOn[0]) {
 					real UL[nI], UR[nI];
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) {
-						real const* sg = SGX + (q * TY + cj) * (TX + 2) + ci;
+						real const* sg = sgx + (q * TY + cj) * (TX + 2) + ci;
 						UL[q] = P[q * PS + ob - 1] + sg[0];
 						UR[q] = P[q * PS + ob] - sg[1];
 					}
-					roeFluxAuto<Eqn, 0>(fxl, ep, UL, UR);
+					roeFluxAuto<Eqn, 0>(F, ep, UL, UR);
 				} else {
 					#pragma unroll
-					for (int q = 0; q < nI; ++q) fxl[q] = 0;
+					for (int q = 0; q < nI; ++q) F[q] = 0;
 				}
 				#pragma unroll
-				for (int q = 0; q < nI; ++q) FXX[(q * TY + cj) * (TX + 1) + ci] = fxl[q];
+				for (int q = 0; q < nI; ++q) fxx[(q * TY + cj) * (TX + 1) + ci] = F[q];
 			}
 			if (DIM == 3 && doFY) {
+				real F[nI];
 				if (g.fluxOn[1]) {
 					real UL[nI], UR[nI];
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) {
-						real const* sg = SGY + (q * (TY + 2) + cj) * TX + ci;
+						real const* sg = sgy + (q * (TY + 2) + cj) * TX + ci;
 						UL[q] = P[q * PS + ob - BX] + sg[0];
 						UR[q] = P[q * PS + ob] - sg[TX];
 					}
-					roeFluxAuto<Eqn, 1>(fyl, ep, UL, UR);
+					roeFluxAuto<Eqn, 1>(F, ep, UL, UR);
 				} else {
 					#pragma unroll
-					for (int q = 0; q < nI; ++q) fyl[q] = 0;
+					for (int q = 0; q < nI; ++q) F[q] = 0;
 				}
 				#pragma unroll
-				for (int q = 0; q < nI; ++q) FXY[(q * (TY + 1) + cj) * TX + ci] = fyl[q];
+				for (int q = 0; q < nI; ++q) fxy[(q * (TY + 1) + cj) * TX + ci] = F[q];
 			}
 		}
-		__syncthreads();
-		// ---- phase 3: flux differences of plane k along x and y (fvsolver.cl:97-123)
+		// ---- half slopes of plane k+1 along x and y (plm.cl:56-76), published for the next iteration (other buffer half)
+		if (k + 1 >= kb && k + 1 < ke) {
+			real const* __restrict__ Q = ring + sN * SLOT;
+			real* const sgxN = SGX + ((k + 1) & 1) * (nI * G::SGXN);
+			real* const sgyN = SGY + ((k + 1) & 1) * (nI * G::SGYN);
+			if (doSX) {
+				#pragma unroll
+				for (int q = 0; q < nI; ++q)
+					sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], Q[q * PS + ob], Q[q * PS + ob + 1]);
+			}
+			if (DIM == 3 && doSY) {
+				#pragma unroll
+				for (int q = 0; q < nI; ++q)
+					sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], Q[q * PS + ob], Q[q * PS + ob + BX]);
+			}
+		}
+		__syncthreads();           // the only barrier of the iteration: fluxes of plane k and slopes of plane k+1 are visible
+		if (tid == 0 && k + 3 <= ke + 1) {
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+			issue(k + 3, sP);
+		}
+		// ---- flux differences of plane k along x and y (fvsolver.cl:97-123)
 		if (doMain) {
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) accP[q] = 0;
 			if (xy && g.volOn) {
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) {
-					real a = real(0) - (FXX[(q * TY + cj) * (TX + 1) + ci + 1] * aovX - fxl[q] * aovX);
-					if (DIM == 3) a = a - (FXY[(q * (TY + 1) + cj + 1) * TX + ci] * aovY - fyl[q] * aovY);
+					real const* fx = fxx + (q * TY + cj) * (TX + 1) + ci;
+					real a = real(0) - (fx[1] * aovX - fx[0] * aovX);
+					if (DIM == 3) {
+						real const* fy = fxy + (q * (TY + 1) + cj) * TX + ci;
+						a = a - (fy[TX] * aovY - fy[0] * aovY);
+					}
 					accP[q] = a;
 				}
 			}

@@ -25,6 +25,9 @@ template<class real> struct FvOps {
 	void (*tileInfo)(int dim, bool plm, bool flim, int out[5]);   // TX, TY, TZ, NT, dynamic smem bytes
 	// unit-test hook: evaluates one device function per item on the GPU (device pointers; doubles in and out)
 	cudaError_t (*debugEval)(int kind, int side, int n, const double* eqnParams, const double* aux, const double* in, double* out, cudaStream_t st);
+	// optional (null when unused): device scratch the stage needs (StageP::scratch), in reals; the equation's initDerivs kernel
+	long long (*scratchElems)(GridP<real> const& g);
+	cudaError_t (*initDerivs)(GridP<real> const& g, real* U, cudaStream_t st);
 };
 
 // exported by hb_fv_inst.cu instantiations
@@ -36,5 +39,10 @@ const FvOps<double>* ops_mhd_f64_fast();
 const FvOps<double>* ops_mhd_f64_strict();
 const FvOps<float>* ops_mhd_f32_fast();
 const FvOps<float>* ops_mhd_f32_strict();
+// exported by hb_adm_inst.cu instantiations
+const FvOps<double>* ops_adm3d_f64_fast();
+const FvOps<double>* ops_adm3d_f64_strict();
+const FvOps<float>* ops_adm3d_f32_fast();
+const FvOps<float>* ops_adm3d_f32_strict();
 
 }   // namespace hb

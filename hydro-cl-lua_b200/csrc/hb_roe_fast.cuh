@@ -7,7 +7,8 @@
 // The production build (Eqn::FAST) evaluates the SAME mathematical expressions, re-associated:
 //   * slope limiters that are symmetric (phi(r)/r = phi(1/r): minmod, superbee) need no ratio: sigma = f(dUL, dUR);
 //   * the Roe flux of the Euler equations is written in wave-strength form (alpha = L dU in closed form, R |Lambda| alpha
-//     accumulated by groups), with reciprocal reuse and one square root less; states that take any of the reference's
+//     accumulated by groups), with branch-free reciprocal / reciprocal-square-root forms (4 per interface, two of them
+//     independent, instead of 4 reciprocals + 2 divisions + 3 square roots behind slow-path branches); states that take any of the reference's
 //     special branches (rho < 1e-5 on either side, rho < rhoMin, h < 1e-5: hydro/eqn/euler.cl:357-426,442,501) are sent to
 //     the literal code, out of line;
 //   * constrainU + calcDTCell share the primitive recovery; the CFL reduction tracks max(lambda/dx) and inverts once.
@@ -46,6 +47,59 @@ template<class real, int LIM, bool FAST> HB_HD real plmHalfSlopeT(int lim, real 
 	}
 }
 
+// ---- branch-free reciprocal and (reciprocal) square root for arguments known to be positive and normal.
+// The compiler's IEEE 1/x and sqrt(x) carry a special-case slow path behind a branch per call; those branches cut the flux
+// routine into basic blocks and serialise its long dependent chains (MUFU seed -> Newton steps).  These forms are straight-line:
+// hardware seed (2^-22 relative) + two Newton steps, accurate to the last ulp or two (not correctly rounded).
+HB_HD double fastRcp(double x) {
+#if defined(__CUDA_ARCH__)
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	double e = fma(-x, r, 1.);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.);
+	return fma(r, e, r);
+#else
+	return 1. / x;
+#endif
+}
+HB_HD float fastRcp(float x) {
+#if defined(__CUDA_ARCH__)
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return fmaf(r, fmaf(-x, r, 1.f), r);
+#else
+	return 1.f / x;
+#endif
+}
+// y = 1/sqrt(x), s = sqrt(x) from one seed (coupled Newton iteration on g ~ sqrt(x), h ~ 1/(2 sqrt(x)))
+HB_HD void fastRsqrt(double x, double& y, double& s) {
+#if defined(__CUDA_ARCH__)
+	double y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+	double g = x * y0, h = .5 * y0;
+	double r = fma(-g, h, .5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	r = fma(-g, h, .5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	s = g; y = h + h;
+#else
+	s = sqrt(x); y = 1. / s;
+#endif
+}
+HB_HD void fastRsqrt(float x, float& y, float& s) {
+#if defined(__CUDA_ARCH__)
+	float y0;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
+	float g = x * y0, h = .5f * y0;
+	float r = fmaf(-g, h, .5f);
+	g = fmaf(g, r, g); h = fmaf(h, r, h);
+	s = g; y = h + h;
+#else
+	s = sqrtf(x); y = 1.f / s;
+#endif
+}
+
 template<class real, int n> struct VecN { real v[n]; };
 
 // the literal Roe flux, out of line: the rare special-branch states of the production kernels go here
@@ -61,50 +115,48 @@ HB_NOINLINE VecN<typename Eqn::real, Eqn::nI> roeFluxOutOfLine(typename Eqn::Par
 //   F = .5 (F(UL) + F(UR)) - .5 sum_j |lambda_j| alpha_j r_j,   alpha = L (UR - UL)
 //   G = (gamma-1) (.5 v^2 drho - v.dm + dE),  K = Cs (dm_n - v_n drho)
 //   alpha_0,4 = (G -/+ K) / (2 Cs^2),  alpha_1 = drho - G / Cs^2,  alpha_2,3 = dm_t - v_t drho
+// The core is straight-line code (no branch): it returns false when the state pair takes one of the reference's special branches,
+// in which case F is meaningless and the caller substitutes the literal flux (eulerRoeFluxFixup).  Two cores issued back to back
+// (x and y interfaces of a cell) interleave in the instruction stream, which hides the latency of their dependent chains.
 template<class Eqn, int SIDE>
-HB_HD void eulerRoeFluxFast(typename Eqn::real (&F)[5], typename Eqn::Params const& s, typename Eqn::real const (&UL)[5], typename Eqn::real const (&UR)[5])
+HB_HD bool eulerRoeFluxCore(typename Eqn::real (&F)[5], typename Eqn::Params const& s, typename Eqn::real const (&UL)[5], typename Eqn::real const (&UR)[5])
 {
 	typedef typename Eqn::real real;
 	constexpr int n = SIDE, t1 = (SIDE + 1) % 3, t2 = (SIDE + 2) % 3;
 	real const rhoL = UL[0], rhoR = UR[0];
 	real const g1 = s.gamma_1;
-	// 1/rhoL and 1/rhoR from one reciprocal
-	real const iLR = real(1.) / (rhoL * rhoR);
-	real const iL = iLR * rhoR, iR = iLR * rhoL;
+	// sqrt(rho) and 1/rho of both sides from two independent reciprocal square roots (1/rho = (1/sqrt(rho))^2)
+	real yL, sL, yR, sR;
+	fastRsqrt(rhoL, yL, sL);
+	fastRsqrt(rhoR, yR, sR);
+	real const iL = yL * yL, iR = yR * yR;
 	real vL[3], vR[3];
 	#pragma unroll
 	for (int q = 0; q < 3; ++q) { vL[q] = UL[1 + q] * iL; vR[q] = UR[1 + q] * iR; }
 	real const PL = g1 * (UL[4] - real(.5) * (UL[1] * vL[0] + UL[2] * vL[1] + UL[3] * vL[2]));
 	real const PR = g1 * (UR[4] - real(.5) * (UR[1] * vR[0] + UR[2] * vR[1] + UR[3] * vR[2]));
 	real const HL = UL[4] + PL, HR = UR[4] + PR;             // rho hTotal
-	// Roe weights wL = sqrt(rhoL) / (sqrt(rhoL) + sqrt(rhoR)) = 1 / (1 + sqrt(rhoR / rhoL)), wR = 1 - wL
-	real const w = rsqrt_ieee(rhoR * iL);
-	real const wL = real(1.) / (real(1.) + w), wR = w * wL;
+	// Roe weights w = sqrt(rho) / (sqrt(rhoL) + sqrt(rhoR))
+	real const iS = fastRcp(sL + sR);
+	real const wL = sL * iS, wR = sR * iS;
 	real v[3];
 	#pragma unroll
 	for (int q = 0; q < 3; ++q) v[q] = vL[q] * wL + vR[q] * wR;
 	real const H = (HL * iL) * wL + (HR * iR) * wR;
 	real const eK = real(.5) * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
 	real const h = H - eK;
-	// the reference's special branches -> literal code (euler.cl:357-426: rhoEpsilon = 1e-5; :442,501: rho < rhoMin)
-	if (!(rhoL >= s.rhoFloor && rhoR >= s.rhoFloor && h >= real(1e-5))) {
-		VecN<real, 5> a, b;
-		#pragma unroll
-		for (int q = 0; q < 5; ++q) { a.v[q] = UL[q]; b.v[q] = UR[q]; }
-		VecN<real, 5> const r = roeFluxOutOfLine<Eqn, SIDE>(s, a, b);
-		#pragma unroll
-		for (int q = 0; q < 5; ++q) F[q] = r.v[q];
-		return;
-	}
+	// the reference's special branches (euler.cl:357-426: rhoEpsilon = 1e-5; :442,501: rho < rhoMin)
+	bool const regular = rhoL >= s.rhoFloor && rhoR >= s.rhoFloor && h >= real(1e-5);
 	real const Cs2 = g1 * h;
-	real const Cs = rsqrt_ieee(Cs2);
-	real const iCs2 = real(1.) / Cs2;
+	real Cs, yC;                                             // Cs, 1 / Cs
+	fastRsqrt(Cs2, yC, Cs);
+	real const iCs2 = yC * yC;
 	real const drho = rhoR - rhoL, dE = UR[4] - UL[4];
 	real dm[3];
 	#pragma unroll
 	for (int q = 0; q < 3; ++q) dm[q] = UR[1 + q] - UL[1 + q];
 	real const G = g1 * (eK * drho - (v[0] * dm[0] + v[1] * dm[1] + v[2] * dm[2]) + dE) * iCs2;   // G / Cs^2
-	real const K = (dm[n] - v[n] * drho) * (Cs * iCs2);                                           // K / Cs^2
+	real const K = (dm[n] - v[n] * drho) * yC;                                                    // K / Cs^2
 	real const b0 = rabs(v[n] - Cs) * (real(.5) * (G - K));
 	real const b4 = rabs(v[n] + Cs) * (real(.5) * (G + K));
 	real const lam = rabs(v[n]);
@@ -118,6 +170,45 @@ HB_HD void eulerRoeFluxFast(typename Eqn::real (&F)[5], typename Eqn::Params con
 	F[1 + t1] = real(.5) * ((UL[1 + t1] * vnL + UR[1 + t1] * vnR) - (sum * v[t1] + b2));
 	F[1 + t2] = real(.5) * ((UL[1 + t2] * vnL + UR[1 + t2] * vnR) - (sum * v[t2] + b3));
 	F[4] = real(.5) * ((HL * vnL + HR * vnR) - ((b0 + b4) * H + dif * v[n] + b1 * eK + b2 * v[t1] + b3 * v[t2]));
+	return regular;
+}
+
+template<class Eqn, int SIDE>
+HB_HD void eulerRoeFluxFixup(bool regular, typename Eqn::real (&F)[5], typename Eqn::Params const& s, typename Eqn::real const (&UL)[5], typename Eqn::real const (&UR)[5])
+{
+	typedef typename Eqn::real real;
+	if (!regular) {
+		VecN<real, 5> a, b;
+		#pragma unroll
+		for (int q = 0; q < 5; ++q) { a.v[q] = UL[q]; b.v[q] = UR[q]; }
+		VecN<real, 5> const r = roeFluxOutOfLine<Eqn, SIDE>(s, a, b);
+		#pragma unroll
+		for (int q = 0; q < 5; ++q) F[q] = r.v[q];
+	}
+}
+
+template<class Eqn, int SIDE>
+HB_HD void eulerRoeFluxFast(typename Eqn::real (&F)[5], typename Eqn::Params const& s, typename Eqn::real const (&UL)[5], typename Eqn::real const (&UR)[5])
+{
+	bool const regular = eulerRoeFluxCore<Eqn, SIDE>(F, s, UL, UR);
+	eulerRoeFluxFixup<Eqn, SIDE>(regular, F, s, UL, UR);
+}
+
+// two independent interfaces (sides SA, SB) of one cell
+template<class Eqn, int SA, int SB>
+HB_HD void roeFluxPairAuto(typename Eqn::real (&FA)[Eqn::nI], typename Eqn::real (&FB)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&ULA)[Eqn::nI], typename Eqn::real const (&URA)[Eqn::nI],
+	typename Eqn::real const (&ULB)[Eqn::nI], typename Eqn::real const (&URB)[Eqn::nI])
+{
+	if constexpr (Eqn::FAST && Eqn::eqnId == 0) {
+		bool const ra = eulerRoeFluxCore<Eqn, SA>(FA, s, ULA, URA);
+		bool const rb = eulerRoeFluxCore<Eqn, SB>(FB, s, ULB, URB);
+		eulerRoeFluxFixup<Eqn, SA>(ra, FA, s, ULA, URA);
+		eulerRoeFluxFixup<Eqn, SB>(rb, FB, s, ULB, URB);
+	} else {
+		roeFlux<Eqn, SA>(FA, s, ULA, URA);
+		roeFlux<Eqn, SB>(FB, s, ULB, URB);
+	}
 }
 
 template<class Eqn, int SIDE>
@@ -139,13 +230,14 @@ HB_HD void finishCellAuto(typename Eqn::Params const& s, typename Eqn::real (&U)
 	typedef typename Eqn::real real;
 	if constexpr (Eqn::FAST && Eqn::eqnId == 0) {
 		if (U[0] < s.rhoMin) U[0] = s.rhoMin;
-		real const iR = real(1.) / U[0];
+		real const iR = fastRcp(U[0]);
 		real const v0 = U[1] * iR, v1 = U[2] * iR, v2 = U[3] * iR;
 		real const eK = real(.5) * (U[1] * v0 + U[2] * v1 + U[3] * v2);
 		real P = s.gamma_1 * (U[4] - eK);
 		if (P < s.PMin) { P = s.PMin; U[4] = eK + P * s.invGamma_1; }
 		if (wantDt) {
-			real const Cs = P <= s.PMin ? real(0) : rsqrt_ieee(s.gamma * P * iR);
+			real Cs = 0, yCs;
+			if (P > s.PMin) fastRsqrt(s.gamma * P * iR, yCs, Cs);
 			real r = rmax<real>(rabs(v0) + Cs, real(1e-9)) * invdx[0];
 			if (dim > 1) r = rmax<real>(r, rmax<real>(rabs(v1) + Cs, real(1e-9)) * invdx[1]);
 			if (dim > 2) r = rmax<real>(r, rmax<real>(rabs(v2) + Cs, real(1e-9)) * invdx[2]);

@@ -12,7 +12,11 @@ import numpy as np
 
 from .. import app as hydro_app
 from ..eqn import eqns
-from ..init.euler import initConds
+from ..init.einstein import initConds as einsteinInitConds
+from ..init.euler import initConds as eulerInitConds
+
+initConds = dict(eulerInitConds)
+initConds.update(einsteinInitConds)
 from ..int import all as int_all
 
 
@@ -97,6 +101,10 @@ class SolverBase:
         self.t = 0.
         self.backend.set_t(0.)
         self.applyInitCond()
+        if getattr(self.eqn, "name", None) == "adm3d":
+            # init.lua:231-235: equations with an initDerivs kernel (adm3d.cl:196-243): boundary, then finite-difference a_l, d_lll, V_l
+            self.boundary()
+            self.backend.init_derivs()
         self.boundary()
         self.constrainU()
 

@@ -95,6 +95,8 @@ int hb_reduce(hb_ctx* ctx, hb_buf* buf, size_t count, int op, double* host_out);
  *      hydro/solver/solverbase.lua:2116-2127,3004-3023,3026-3238, hydro/solver/gridsolver.lua:1272-1320) */
 #define HB_EQN_EULER 0        /* hydro/eqn/euler.lua: eqn_params = { heatCapacityRatio, rhoMin, PMin } */
 #define HB_EQN_MHD 1          /* hydro/eqn/mhd.lua:   eqn_params = { heatCapacityRatio, mu0 / unit_kg_m_per_C2 } */
+#define HB_EQN_ADM3D 2        /* hydro/eqn/adm3d.lua (noZeroRowsInFlux, useShift 'none'): eqn_params = { f_eqn option index
+                               * (hydro/eqn/einstein.lua:42-48, 0-based), a_convCoeff, d_convCoeff, V_convCoeff } */
 #define HB_BC_PERIODIC 0      /* hydro/solver/gridsolver.lua:638-651 */
 #define HB_BC_MIRROR 1        /* :654-744 */
 #define HB_BC_FREEFLOW 2      /* :766-780 */
@@ -133,6 +135,7 @@ int hb_fv_set_state(hb_fv* fv, const double* aos_host);
 int hb_fv_get_state(hb_fv* fv, double* aos_host);           /* blocking */
 int hb_fv_state_devptr(hb_fv* fv, void** soa_dev, long long* stride_y, long long* stride_z, long long* stride_var);
 int hb_fv_boundary(hb_fv* fv);                               /* solver:boundary(), gridsolver.lua:1316 */
+int hb_fv_init_derivs(hb_fv* fv);                            /* initDerivsKernelObj(), hydro/init/init.lua:231-235 (adm3d.cl:196-243); no-op for other equations */
 int hb_fv_constrainU(hb_fv* fv);                             /* solver:constrainU() = kernel + boundary(), solverbase.lua:2116-2127 */
 int hb_fv_calc_dt(hb_fv* fv, double* dt_out);                /* solver:calcDT(), solverbase.lua:3004-3023 (blocking) */
 int hb_fv_step(hb_fv* fv, double dt);                        /* solver:step(dt), solverbase.lua:3193-3238 */

@@ -32,7 +32,7 @@
 extern "C" {
 // Plain-C descriptor shared with oracle/oracle.py (ctypes).  Field order is ABI.
 struct ho_desc {
-	int eqn;            // 0 = euler, 1 = mhd
+	int eqn;            // 0 = euler, 1 = mhd, 2 = ADM Bona-Masso 3D
 	int dim;            // 1..3
 	int n[3];           // interior cells per axis (unused axes = 1)
 	int real_bytes;     // 8 = double, 4 = float   (hydro/app.lua:892 'real' selection)
@@ -52,6 +52,7 @@ struct ho_desc {
 	double mu0_eff;     // solver->mu0 / unit_kg_m_per_C2 (mhd.lua:209-234, math.cl:270)
 	int nthreads;       // OpenMP threads (0 = default)
 	int global_n[3];    // 0 = same as n; otherwise the whole grid's interior size (this object is one slab of it): defines grid_dx
+	double eqn_params[16];   // eqn 2 (ADM3D): f_eqn option index, a_convCoeff, d_convCoeff, V_convCoeff (adm3d.lua:207-227)
 };
 }
 
@@ -141,6 +142,8 @@ template<class real> struct solver_t {
 	int dim;
 	real heatCapacityRatio, rhoMin, PMin;
 	real mu0_eff;
+	int f_eqn;                                   // hydro/eqn/einstein.lua:42-48 option index
+	real a_convCoeff, d_convCoeff, V_convCoeff;  // adm3d.lua:218-226
 };
 
 // =============================================================================================
@@ -151,6 +154,7 @@ template<class real_> struct Euler {
 	typedef solver_t<real> S;
 	enum { numStates = 6, numIntStates = 5, numWaves = 5 };   // euler.lua:13-14,166-171
 	static const bool roeUseFluxFromCons = true;               // eqn.lua:46
+	static constexpr bool hasSource = false;                   // cartesian: no addSource kernel work
 	union cons_t { struct { real rho; real3 m; real ETotal; real ePot; }; real ptr[6]; };
 	struct prim_t { real rho; real3 v; real P; real ePot; };
 	struct eigen_t { real rho; real3 v; real hTotal; real Cs; real vSq; real3 vL; };  // euler.lua:298-307
@@ -346,6 +350,7 @@ template<class real_> struct MHD {
 	typedef solver_t<real> S;
 	enum { numStates = 10, numIntStates = 8, numWaves = 7 };   // mhd.lua:16-17,76-83
 	static const bool roeUseFluxFromCons = true;                // mhd.lua:19
+	static constexpr bool hasSource = false;                    // mhd.cl:885-911 addSource is empty on a cartesian grid
 	union cons_t { struct { real rho; real3 m; real ETotal; real3 B; real psi; real ePot; }; real ptr[10]; };
 	struct prim_t { real rho; real3 v; real P; real3 B; real psi; real ePot; };
 	struct roe_t { real rho; real3 v; real hTotal; real3 B; real X, Y; };   // mhd.lua:27-34
@@ -739,8 +744,14 @@ template<class real_> struct MHD {
 };
 
 // =============================================================================================
+} // namespace ho
+#include "adm3d_oracle.hpp"
+namespace ho {
+
 struct SolverBase {
 	virtual ~SolverBase() {}
+	virtual void initDerivs() {}
+	virtual void sourceTest(const double*, double*) {}
 	virtual void setState(const double* aos) = 0;
 	virtual void getState(double* aos) const = 0;
 	virtual void boundary() = 0;
@@ -790,6 +801,8 @@ template<class Eqn> struct Solver : SolverBase {
 		solver.stepsize[0] = 1; solver.stepsize[1] = S[0]; solver.stepsize[2] = S[0] * S[1];   // gridsolver.lua:377-380
 		solver.numGhost = g; solver.dim = dim;
 		solver.heatCapacityRatio = d.gamma; solver.rhoMin = d.rhoMin; solver.PMin = d.PMin; solver.mu0_eff = d.mu0_eff;
+		solver.f_eqn = int(d.eqn_params[0]); solver.a_convCoeff = real(d.eqn_params[1]); solver.d_convCoeff = real(d.eqn_params[2]);
+		solver.V_convCoeff = real(d.eqn_params[3]);
 		// fvsolver.lua:61-63 useFluxLimiter = fluxLimiter > 1 (1-based) and flux.usesFluxLimiter
 		useFluxLimiter = d.flux_limiter > 0;
 		cons_t zero; std::memset(&zero, 0, sizeof(zero));
@@ -1058,10 +1071,43 @@ template<class Eqn> struct Solver : SolverBase {
 		calcFlux(dt);
 		calcDerivFromFlux(derivBuf);
 	}
+	// ---- addSource kernel (solverbase.lua:3209-3215; SETBOUNDS_NOGHOST): equations with a source term only
+	void addSource(std::vector<cons_t>& derivBuf) {
+		if constexpr (Eqn::hasSource) {
+			#pragma omp parallel for collapse(2)
+			for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+				if (OOB(i, j, k, g, g)) continue;
+				long index = INDEX(i, j, k);
+				Eqn::addSource(derivBuf[index], solver, UBuf[index], [&](int side, int off) -> cons_t const& { return UBuf[index + off * solver.stepsize[side]]; });
+			}
+		}
+	}
+	// initDerivs kernel (hydro/init/init.lua:231-235; SETBOUNDS(numGhost, numGhost)): ADM only
+	void initDerivs() override {
+		if constexpr (Eqn::hasSource) {
+			std::vector<cons_t> src = UBuf;
+			#pragma omp parallel for collapse(2)
+			for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+				if (OOB(i, j, k, g, g)) continue;
+				long index = INDEX(i, j, k);
+				Eqn::initDerivs(UBuf[index], solver, [&](int side, int off) -> cons_t const& { return src[index + off * solver.stepsize[side]]; });
+			}
+		}
+	}
+	// unit-test hook: addSource of one cell (no neighbours: the convergence terms that need them must be off)
+	void sourceTest(const double* U_, double* deriv_) override {
+		if constexpr (Eqn::hasSource) {
+			cons_t U, dv;
+			for (int j = 0; j < nS; ++j) { U.ptr[j] = real(U_[j]); dv.ptr[j] = 0; }
+			Eqn::addSource(dv, solver, U, [&](int, int) -> cons_t const& { return U; });
+			for (int j = 0; j < nS; ++j) deriv_[j] = double(dv.ptr[j]);
+		}
+	}
 	void calcDerivOut(double* aos, double dt_) override {
 		std::vector<cons_t> deriv(ncells);
 		std::memset(deriv.data(), 0, sizeof(cons_t) * ncells);
 		calcDeriv(deriv, real(dt_));
+		addSource(deriv);
 		for (long c = 0; c < ncells; ++c) for (int j = 0; j < nS; ++j) aos[c * nS + j] = double(deriv[c].ptr[j]);
 	}
 
@@ -1109,6 +1155,7 @@ template<class Eqn> struct Solver : SolverBase {
 		if (d.rk_order == 0) {
 			clearBuffer(feDeriv);
 			calcDeriv(feDeriv, dtArg);
+			addSource(feDeriv);
 			multAddInto(UBuf, feDeriv, real(dt_));
 			boundary();
 			constrainU();
@@ -1123,7 +1170,7 @@ template<class Eqn> struct Solver : SolverBase {
 			if (needed) UBufs[0] = UBuf;
 			needed = false;
 			for (int m = 0; m < order; ++m) needed = needed || beta(m, 0) != 0;
-			if (needed) { clearBuffer(derivBufs[0]); calcDeriv(derivBufs[0], dtArg); }
+			if (needed) { clearBuffer(derivBufs[0]); calcDeriv(derivBufs[0], dtArg); addSource(derivBufs[0]); }
 		}
 		for (int i = 1; i <= order; ++i) {   // Lua i = 2..order+1
 			clearBuffer(UBuf);
@@ -1139,7 +1186,7 @@ template<class Eqn> struct Solver : SolverBase {
 				if (needed) UBufs[i] = UBuf;
 				needed = false;
 				for (int m = i; m < order; ++m) needed = needed || beta(m, i) != 0;
-				if (needed) { clearBuffer(derivBufs[i]); calcDeriv(derivBufs[i], dtArg); }
+				if (needed) { clearBuffer(derivBufs[i]); calcDeriv(derivBufs[i], dtArg); addSource(derivBufs[i]); }
 			}
 		}
 	}
@@ -1188,9 +1235,11 @@ void* ho_create(const ho_desc* d) {
 	if (d->real_bytes == 8) {
 		if (d->eqn == 0) return static_cast<SolverBase*>(new Solver<Euler<double>>(*d));
 		if (d->eqn == 1) return static_cast<SolverBase*>(new Solver<MHD<double>>(*d));
+		if (d->eqn == 2) return static_cast<SolverBase*>(new Solver<ADM3D<double>>(*d));
 	} else if (d->real_bytes == 4) {
 		if (d->eqn == 0) return static_cast<SolverBase*>(new Solver<Euler<float>>(*d));
 		if (d->eqn == 1) return static_cast<SolverBase*>(new Solver<MHD<float>>(*d));
+		if (d->eqn == 2) return static_cast<SolverBase*>(new Solver<ADM3D<float>>(*d));
 	}
 	return nullptr;
 }
@@ -1200,6 +1249,8 @@ long ho_num_cells(void* h) { return static_cast<ho::SolverBase*>(h)->numCells();
 void ho_set_state(void* h, const double* aos) { static_cast<ho::SolverBase*>(h)->setState(aos); }
 void ho_get_state(void* h, double* aos) { static_cast<ho::SolverBase*>(h)->getState(aos); }
 void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }
+void ho_init_derivs(void* h) { static_cast<ho::SolverBase*>(h)->initDerivs(); }
+void ho_source_test(void* h, const double* U, double* deriv) { static_cast<ho::SolverBase*>(h)->sourceTest(U, deriv); }
 void ho_constrainU(void* h) { static_cast<ho::SolverBase*>(h)->constrainU(); }
 double ho_calc_dt(void* h) { return static_cast<ho::SolverBase*>(h)->calcDT(); }
 void ho_update(void* h, int nsteps) { auto* s = static_cast<ho::SolverBase*>(h); for (int i = 0; i < nsteps; ++i) s->update(); }

@@ -27,7 +27,7 @@ class ho_desc(C.Structure):
         ("mins", C.c_double * 3), ("maxs", C.c_double * 3),
         ("cfl", C.c_double), ("fixed_dt", C.c_double), ("use_fixed_dt", C.c_int),
         ("gamma", C.c_double), ("rhoMin", C.c_double), ("PMin", C.c_double), ("mu0_eff", C.c_double),
-        ("nthreads", C.c_int), ("global_n", C.c_int * 3),
+        ("nthreads", C.c_int), ("global_n", C.c_int * 3), ("eqn_params", C.c_double * 16),
     ]
 
 
@@ -49,7 +49,7 @@ def lib(fma=False):
         L = C.CDLL(os.path.join(_here, "libhydro_oracle_fma.so" if fma else "libhydro_oracle.so"))
         L.ho_create.restype = C.c_void_p
         L.ho_create.argtypes = [C.POINTER(ho_desc)]
-        for name in ("ho_destroy", "ho_boundary", "ho_constrainU"):
+        for name in ("ho_destroy", "ho_boundary", "ho_constrainU", "ho_init_derivs"):
             getattr(L, name).argtypes = [C.c_void_p]
             getattr(L, name).restype = None
         L.ho_num_states.argtypes = [C.c_void_p]
@@ -68,6 +68,7 @@ def lib(fma=False):
         L.ho_set_t.argtypes = [C.c_void_p, C.c_double]
         L.ho_calc_deriv.argtypes = [C.c_void_p, C.c_void_p, C.c_double]
         L.ho_roe_flux_test.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.ho_source_test.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ho_limiter.argtypes = [C.c_int, C.c_double]
         L.ho_limiter.restype = C.c_double
         L.ho_max_threads.restype = C.c_int
@@ -101,7 +102,9 @@ def desc_from_solver(solver, nthreads=0):
     d.fixed_dt = solver.fixedDT if solver.useFixedDT else 0.
     d.use_fixed_dt = 1 if solver.useFixedDT else 0
     v = solver.eqn.vars
-    d.gamma = v["heatCapacityRatio"]
+    for i, p in enumerate(solver.eqn.eqnParams()):
+        d.eqn_params[i] = p
+    d.gamma = v.get("heatCapacityRatio", 0.)
     d.rhoMin = v.get("rhoMin", 1e-7)
     d.PMin = v.get("PMin", 1e-7)
     d.mu0_eff = getattr(solver.eqn, "mu0_eff", 1.)
@@ -147,6 +150,15 @@ class OracleBackend:
 
     def constrainU(self):
         self.L.ho_constrainU(self.h)
+
+    def init_derivs(self):
+        self.L.ho_init_derivs(self.h)
+
+    def source_test(self, U):
+        U = np.ascontiguousarray(U, dtype=np.float64)
+        D = np.zeros(self.nS)
+        self.L.ho_source_test(self.h, U.ctypes.data, D.ctypes.data)
+        return D
 
     def calc_dt(self):
         return self.L.ho_calc_dt(self.h)
