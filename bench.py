@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- cell-updates/s of the explicit finite-volume update (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4|C2|C3]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4|C2|C3|C5]
 
 Workload (default C4, the config BASELINE.json quotes "at 1/2/4/8 B200" on): 3-D Euler spherical blast, Roe + PLM
 ('plm cons', minmod) + classic RK4, double precision, freeflow boundaries, 512^3 interior cells PER GPU (weak
@@ -48,7 +48,17 @@ WORKLOADS = {
                cfg=dict(eqn="mhd", dim=2, gridSize=[4096, 4096], initCond="Orszag-Tang", usePLM="plm cons",
                         slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15),
                words=8, nI=8, stages=3, cpu_sample=[1024, 1024]),
+    # 16 words x 37 integrated variables + 4 stages x 14 auxiliary reads = 5184 B per cell-update
+    "C5": dict(name="3D ADM Bona-Masso gauge wave (A=.1, d=1, f=2/alpha), Roe + superbee flux limiter, RK4, double, periodic, 256^3 per GPU (z slabs)",
+               cfg=dict(eqn="adm3d", dim=3, gridSize=[256, 256, 256], mins=[-.5] * 3, maxs=[.5] * 3, initCond="testbed - gauge wave",
+                        fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1,
+                        boundary=dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic", zmin="periodic", zmax="periodic")),
+               words=16, nI=37, stages=4, extra_bytes=4 * 14 * 8, cpu_sample=[48, 48, 48]),
 }
+
+
+def alg_bytes(w):
+    return w["words"] * w["nI"] * 8 + w.get("extra_bytes", 0)
 
 
 def peaks():
@@ -228,7 +238,7 @@ def main():
     hb.check(L.hb_fv_profile_read(B.h, C.byref(sms), C.byref(sn)))
     hb.check(L.hb_fv_profile(B.h, 0))
     stage_ms = sms.value / max(1, sn.value)
-    bytes_per_launch = w["words"] * w["nI"] * 8 / w["stages"] * cellsLocal
+    bytes_per_launch = alg_bytes(w) / w["stages"] * cellsLocal
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
     traffic = None
@@ -243,7 +253,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": desc.split()[0].replace("kernel=", ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "stage_kernel_ms": stage_ms, "kernel_config": desc,
                 "stage_share_of_step": stage_ms * w["stages"] / (ms / args.steps),
-                "algorithmic_bytes_per_cell_update": w["words"] * w["nI"] * 8}
+                "algorithmic_bytes_per_cell_update": alg_bytes(w)}
 
     # ---- end to end through the C-ABI with HOST buffers: upload state (pinned host, AoS doubles) -> update -> download
     nS = B.nS

@@ -726,11 +726,13 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 		const FvOps<double>* o = nullptr;
 		if (d->eqn == HB_EQN_EULER) o = strict ? ops_euler_f64_strict() : ops_euler_f64_fast();
 		else if (d->eqn == HB_EQN_MHD) o = strict ? ops_mhd_f64_strict() : ops_mhd_f64_fast();
+		else if (d->eqn == HB_EQN_ADM3D) o = strict ? ops_adm3d_f64_strict() : ops_adm3d_f64_fast();
 		if (o) impl = new Fv<double>(ctx, *d, o);
 	} else {
 		const FvOps<float>* o = nullptr;
 		if (d->eqn == HB_EQN_EULER) o = strict ? ops_euler_f32_strict() : ops_euler_f32_fast();
 		else if (d->eqn == HB_EQN_MHD) o = strict ? ops_mhd_f32_strict() : ops_mhd_f32_fast();
+		else if (d->eqn == HB_EQN_ADM3D) o = strict ? ops_adm3d_f32_strict() : ops_adm3d_f32_fast();
 		if (o) impl = new Fv<float>(ctx, *d, o);
 	}
 	if (!impl) return setError(HB_ERR_INVALID, "hb_fv_create: unknown equation id");

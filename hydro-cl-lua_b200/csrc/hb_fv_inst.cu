@@ -64,16 +64,29 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 }
 
 // ---- plane-marching kernel: tile configurations per dimensionality (cfg index; the host takes the first one whose shared
-// memory fits, starting at $HB_MARCH_CFG or 0)
-typedef MarchCfg<1, 10, 32, 1> March3A;    // 32 x 10 columns, 13 warps
-typedef MarchCfg<1, 8, 32, 1> March3B;     // 32 x 8 columns, 11 warps
-typedef MarchCfg<1, 4, 32, 1> March3C;     // 32 x 4 columns, 7 warps: the fallback that fits 8-variable equations (MHD) in shared memory
-typedef MarchCfg<1, 12, 32, 1> March3D;    // 32 x 12 columns, 15 warps (shared memory allows at most one staged RK operand)
-typedef MarchCfg<1, 6, 32, 2> March3E;     // 32 x 6 columns, 9 warps, 2 CTAs / SM, <= 112 registers
-typedef MarchCfg<1, 4, 32, 2> March3F;     // 32 x 4 columns, 7 warps, 2 CTAs / SM
-typedef MarchCfg<4, 1, 32, 2> March2A;     // 128 columns, 5 warps
-typedef MarchCfg<2, 1, 32, 4> March2B;     // 64 columns, 3 warps
-typedef MarchCfg<6, 1, 64, 1> March2C;     // 192 columns, 7 warps (TMA boxes are at most 256 elements wide)
+// memory fits, starting at $HB_MARCH_CFG or 0).  X(index, WX, TY, KM, MINB, VAR)
+#ifdef HB_STRICT
+// the strict build carries fewer configurations (compile time)
+#define HB_MARCH3_LIST(X) X(0, 1, 10, 32, 1, 0) X(1, 1, 8, 32, 1, 0) X(2, 1, 4, 32, 1, 0) X(3, 1, 8, 32, 1, 1) X(4, 1, 6, 32, 1, 2)
+#define HB_MARCH2_LIST(X) X(0, 4, 1, 32, 2, 0) X(1, 4, 1, 32, 2, 2)
+#else
+#define HB_MARCH3_LIST(X) \
+	X(0, 1, 10, 32, 1, 0)   /* 32 x 10 columns, 13 warps */ \
+	X(1, 1, 8, 32, 1, 0)    /* 32 x 8 columns, 11 warps */ \
+	X(2, 1, 4, 32, 1, 0)    /* 32 x 4 columns, 7 warps: the fallback that fits 8-variable equations (MHD) in shared memory */ \
+	X(3, 1, 12, 32, 1, 0)   /* 32 x 12 columns, 15 warps (shared memory allows at most one staged RK operand) */ \
+	X(4, 1, 6, 32, 2, 0)    /* 32 x 6 columns, 9 warps, 2 CTAs / SM, <= 112 registers */ \
+	X(5, 1, 4, 32, 2, 0)    /* 32 x 4 columns, 7 warps, 2 CTAs / SM */ \
+	X(6, 1, 8, 32, 1, 1)    /* fused column warps: three flux cores interleaved */ \
+	X(7, 1, 8, 32, 1, 2)    /* fused column warps: z flux, then the x/y pair */ \
+	X(8, 1, 6, 32, 1, 1) X(9, 1, 6, 32, 1, 2) X(10, 1, 4, 32, 1, 1) X(11, 1, 8, 64, 1, 1) X(12, 1, 8, 64, 1, 0) X(13, 1, 10, 32, 1, 1) \
+	X(14, 1, 8, 64, 1, 2) X(15, 1, 10, 32, 1, 2)
+#define HB_MARCH2_LIST(X) \
+	X(0, 4, 1, 32, 2, 0)    /* 128 columns, 5 warps */ \
+	X(1, 2, 1, 32, 4, 0)    /* 64 columns, 3 warps */ \
+	X(2, 6, 1, 64, 1, 0)    /* 192 columns, 7 warps (TMA boxes are at most 256 elements wide) */ \
+	X(3, 4, 1, 32, 2, 2) X(4, 4, 1, 64, 2, 2) X(5, 2, 1, 32, 4, 2) X(6, 6, 1, 64, 1, 2) X(7, 4, 1, 64, 1, 2)
+#endif
 
 constexpr size_t kSmemLimit = 232448 - 1024;   // 227 KB opt-in maximum per CTA minus the kernel's static shared memory (rounded up)
 
@@ -110,48 +123,23 @@ template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
 	info[0] = G::TX; info[1] = G::TY; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
 	info[5] = G::NREG * 32;
 }
-#ifdef HB_STRICT
-constexpr int kMarchCfgs3 = 3, kMarchCfgs2 = 1;     // the strict build carries fewer configurations (compile time)
-#else
-constexpr int kMarchCfgs3 = 6, kMarchCfgs2 = 3;
-#endif
 bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[6]) {
-	if (!plm || flim || (lim != 8 && lim != 18) || dim < 2 || cfg < 0 || cfg >= (dim == 3 ? kMarchCfgs3 : kMarchCfgs2)) return false;
-	if (dim == 3) {
-		if (cfg == 0) marchInfoCfg<3, March3A>(box, info);
-		else if (cfg == 1) marchInfoCfg<3, March3B>(box, info);
-		else if (cfg == 2) marchInfoCfg<3, March3C>(box, info);
-#ifndef HB_STRICT
-		else if (cfg == 3) marchInfoCfg<3, March3D>(box, info);
-		else if (cfg == 4) marchInfoCfg<3, March3E>(box, info);
-		else marchInfoCfg<3, March3F>(box, info);
-#endif
-	} else {
-		if (cfg == 0) marchInfoCfg<2, March2A>(box, info);
-#ifndef HB_STRICT
-		else if (cfg == 1) marchInfoCfg<2, March2B>(box, info);
-		else marchInfoCfg<2, March2C>(box, info);
-#endif
-	}
-	return true;
+	if (!plm || flim || (lim != 8 && lim != 18) || dim < 2 || cfg < 0) return false;
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<3, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
+	if (dim == 3) { HB_MARCH3_LIST(HB_X) return false; }
+#undef HB_X
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<2, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
+	HB_MARCH2_LIST(HB_X)
+#undef HB_X
+	return false;
 }
 cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, cudaStream_t st) {
-	if (dim == 3) {
-		if (cfg == 0) return launchMarchLim<3, March3A>(lim, tmap, padX, g, sp, ep, st);
-		if (cfg == 1) return launchMarchLim<3, March3B>(lim, tmap, padX, g, sp, ep, st);
-		if (cfg == 2) return launchMarchLim<3, March3C>(lim, tmap, padX, g, sp, ep, st);
-#ifndef HB_STRICT
-		if (cfg == 3) return launchMarchLim<3, March3D>(lim, tmap, padX, g, sp, ep, st);
-		if (cfg == 4) return launchMarchLim<3, March3E>(lim, tmap, padX, g, sp, ep, st);
-		if (cfg == 5) return launchMarchLim<3, March3F>(lim, tmap, padX, g, sp, ep, st);
-#endif
-	} else if (dim == 2) {
-		if (cfg == 0) return launchMarchLim<2, March2A>(lim, tmap, padX, g, sp, ep, st);
-#ifndef HB_STRICT
-		if (cfg == 1) return launchMarchLim<2, March2B>(lim, tmap, padX, g, sp, ep, st);
-		if (cfg == 2) return launchMarchLim<2, March2C>(lim, tmap, padX, g, sp, ep, st);
-#endif
-	}
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, st);
+	if (dim == 3) { HB_MARCH3_LIST(HB_X) }
+#undef HB_X
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<2, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, st);
+	else if (dim == 2) { HB_MARCH2_LIST(HB_X) }
+#undef HB_X
 	return cudaErrorInvalidValue;
 }
 

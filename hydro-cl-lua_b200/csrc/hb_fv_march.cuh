@@ -30,11 +30,15 @@
 
 namespace hb {
 
-template<int WX_, int TY_, int KM_, int MINB_> struct MarchCfg {
+template<int WX_, int TY_, int KM_, int MINB_, int VAR_ = 0> struct MarchCfg {
 	static constexpr int WX = WX_;     // warps along x: TX = 32 * WX
 	static constexpr int TY = TY_;     // rows (3-D only)
 	static constexpr int KM = KM_;     // planes per CTA along the marching axis
 	static constexpr int MINB = MINB_; // __launch_bounds__ min blocks per SM
+	// instruction-level parallelism of the column warps: 0 = the three interface fluxes of a cell one after the other;
+	// 1 = all of them issued as one straight-line block (the cores interleave: three independent dependent chains);
+	// 2 = marching-axis flux alone, then the x and y fluxes as a pair
+	static constexpr int VAR = VAR_;
 };
 
 template<int DIM, class C, class real> struct MarchGeom {
@@ -235,8 +239,85 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 		bool const xy = k >= kb && k < ke;
 		real const* __restrict__ P = ring + sK * SLOT;
 		mbarWait(&full[sN], parN);
+		// ---- column warps, fused form (MarchCfg::VAR >= 1): the fluxes at the low z, x and y faces of cell (ci, cj, k) are independent
+		// of each other, so their cores are issued as one straight-line block and the scheduler interleaves the dependent chains
+		// (MUFU seed -> Newton steps -> wave strengths).  Same operations per flux as the separate form below.
+		bool const fusedMain = C::VAR >= 1 && w < G::NREG;
+		if (C::VAR >= 1 && fusedMain) {
+			long long const idxK = colIdx + strideM * k;
+			real Fz[nI], UR[nI], zfN[nI], Uk[nI];
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) {
+				Uk[q] = P[q * PS + ob];
+				real const s = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Um[q], Uk[q], ring[sN * SLOT + q * PS + ob]);
+				UR[q] = Uk[q] - s;
+				zfN[q] = Uk[q] + s;
+				Fz[q] = 0;
+			}
+			if (xy) {
+				real* const fxx = FXX + (k & 1) * (nI * G::FXXN);
+				real* const fxy = FXY + (k & 1) * (nI * G::FXYN);
+				real const* const sgx = SGX + (k & 1) * (nI * G::SGXN);
+				real const* const sgy = SGY + (k & 1) * (nI * G::SGYN);
+				real ULx[nI], URx[nI], ULy[nI], URy[nI], Fx[nI], Fy[nI];
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) {
+					real const* sg = sgx + (q * TY + cj) * (TX + 2) + ci;
+					ULx[q] = P[q * PS + ob - 1] + sg[0];
+					URx[q] = P[q * PS + ob] - sg[1];
+					if (DIM == 3) {
+						real const* sh = sgy + (q * (TY + 2) + cj) * TX + ci;
+						ULy[q] = P[q * PS + ob - BX] + sh[0];
+						URy[q] = P[q * PS + ob] - sh[TX];
+					}
+				}
+				if constexpr (DIM == 3) {
+					if constexpr (C::VAR == 1) roeFluxTripleAuto<Eqn, MS, 0, 1>(Fz, Fx, Fy, ep, zfP, UR, ULx, URx, ULy, URy);
+					else {
+						roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+						roeFluxPairAuto<Eqn, 0, 1>(Fx, Fy, ep, ULx, URx, ULy, URy);
+					}
+				} else {
+					roeFluxPairAuto<Eqn, MS, 0>(Fz, Fx, ep, zfP, UR, ULx, URx);
+				}
+				bool const onM = g.fluxOn[MS], on0 = g.fluxOn[0], on1 = g.fluxOn[1];
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) {
+					if (!onM) Fz[q] = 0;
+					fxx[(q * TY + cj) * (TX + 1) + ci] = on0 ? Fx[q] : real(0);
+					if (DIM == 3) fxy[(q * (TY + 1) + cj) * TX + ci] = on1 ? Fy[q] : real(0);
+				}
+			} else if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+			if (k > kb && inside) {
+				real acc[nI];
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) acc[q] = g.volOn ? accP[q] - (Fz[q] * aovM - FzP[q] * aovM) : real(0);
+				cpAsyncWaitAll();
+				stageEpilogue<Eqn>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + tid, OPS);
+			}
+			if (inside && xy && sp.Uout) {
+				int slot = 0;
+				#pragma unroll
+				for (int a = 0; a < HB_MAX_TERMS; ++a)
+					if (a < sp.nA && !((sp.aOwnMask >> a) & 1)) {
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) cpAsyncElem<real>(OPB + (slot * nI + q) * OPS + tid, sp.aPtr[a] + idxK + q * g.strideV);
+						++slot;
+					}
+				#pragma unroll
+				for (int b = 0; b < HB_MAX_TERMS; ++b)
+					if (b < sp.nB) {
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) cpAsyncElem<real>(OPB + (slot * nI + q) * OPS + tid, sp.bPtr[b] + idxK + q * g.strideV);
+						++slot;
+					}
+				cpAsyncCommit();
+			}
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) { Um[q] = Uk[q]; zfP[q] = zfN[q]; FzP[q] = Fz[q]; }
+		}
 		// ---- marching axis, registers only: slope of cell k, flux at interface k-1/2, finish cell k-1
-		if (doMain) {
+		if (doMain && !fusedMain) {
 			long long const idxK = colIdx + strideM * k;
 			real Fz[nI], UR[nI], zfN[nI], Uk[nI];
 			#pragma unroll
@@ -283,7 +364,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 		real* const sgy = SGY + (k & 1) * (nI * G::SGYN);
 		real* const fxx = FXX + (k & 1) * (nI * G::FXXN);
 		real* const fxy = FXY + (k & 1) * (nI * G::FXYN);
-		if (xy) {
+		if (xy && !fusedMain) {
 			if (doFX) {
 				real F[nI];
 				if (g.fluxOn[0]) {

@@ -211,6 +211,28 @@ HB_HD void roeFluxPairAuto(typename Eqn::real (&FA)[Eqn::nI], typename Eqn::real
 	}
 }
 
+// three independent interfaces (the low faces of one cell along SA, SB, SC)
+template<class Eqn, int SA, int SB, int SC>
+HB_HD void roeFluxTripleAuto(typename Eqn::real (&FA)[Eqn::nI], typename Eqn::real (&FB)[Eqn::nI], typename Eqn::real (&FC)[Eqn::nI],
+	typename Eqn::Params const& s,
+	typename Eqn::real const (&ULA)[Eqn::nI], typename Eqn::real const (&URA)[Eqn::nI],
+	typename Eqn::real const (&ULB)[Eqn::nI], typename Eqn::real const (&URB)[Eqn::nI],
+	typename Eqn::real const (&ULC)[Eqn::nI], typename Eqn::real const (&URC)[Eqn::nI])
+{
+	if constexpr (Eqn::FAST && Eqn::eqnId == 0) {
+		bool const ra = eulerRoeFluxCore<Eqn, SA>(FA, s, ULA, URA);
+		bool const rb = eulerRoeFluxCore<Eqn, SB>(FB, s, ULB, URB);
+		bool const rc = eulerRoeFluxCore<Eqn, SC>(FC, s, ULC, URC);
+		eulerRoeFluxFixup<Eqn, SA>(ra, FA, s, ULA, URA);
+		eulerRoeFluxFixup<Eqn, SB>(rb, FB, s, ULB, URB);
+		eulerRoeFluxFixup<Eqn, SC>(rc, FC, s, ULC, URC);
+	} else {
+		roeFlux<Eqn, SA>(FA, s, ULA, URA);
+		roeFlux<Eqn, SB>(FB, s, ULB, URB);
+		roeFlux<Eqn, SC>(FC, s, ULC, URC);
+	}
+}
+
 template<class Eqn, int SIDE>
 HB_HD void roeFluxAuto(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
 	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])

@@ -45,4 +45,20 @@ CASES["slab_fe_3d_mixed"] = (dict(eqn="mhd", dim=3, gridSize=[10, 8, 12], initCo
                                   boundary=dict(xmin="periodic", xmax="periodic", ymin="mirror", ymax="mirror",
                                                 zmin="freeflow", zmax="mirror")), 6)
 
+# C5: 3D ADM Bona-Masso, Roe + superbee flux limiter (no PLM), RK4: gauge wave (periodic, domain +-.5) and warp bubble (freeflow)
+_PER = dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic", zmin="periodic", zmax="periodic")
+ADM_CASES = {
+    "C5_gauge_wave_rk4": (dict(eqn="adm3d", dim=3, gridSize=[20, 10, 9], mins=[-.5] * 3, maxs=[.5] * 3,
+                               initCond="testbed - gauge wave", fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1,
+                               boundary=_PER), 10),
+    "C5_gauge_wave_f1": (dict(eqn="adm3d", dim=3, gridSize=[18, 7, 6], mins=[-.5] * 3, maxs=[.5] * 3,
+                              initCond="testbed - gauge wave", fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1,
+                              boundary=_PER, eqnArgs=dict(f_eqn="1")), 10),
+    "C5_warp_bubble_rk4": (dict(eqn="adm3d", dim=3, gridSize=[14, 12, 10], initCond="Alcubierre warp bubble",
+                                fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1), 10),
+    "C5_gauge_wave_donor_fe_2d": (dict(eqn="adm3d", dim=2, gridSize=[24, 10], mins=[-.5] * 3, maxs=[.5] * 3,
+                                       initCond="testbed - gauge wave", fluxLimiter="donor cell", integrator="forward Euler",
+                                       cfl=.1, boundary=dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic")), 8),
+}
+
 FLOAT_CASES = ["C2_kh_rk4tvd_minmod", "C4_sphere_rk4", "C3_ot_rk3tvd", "C1_sod_fe_superbee"]

@@ -9,7 +9,7 @@ Two bars per case (BASELINE.json north_star):
 import numpy as np
 import pytest
 
-from cases import CASES, FLOAT_CASES
+from cases import ADM_CASES, CASES, FLOAT_CASES
 
 pytestmark = pytest.mark.gpu
 
@@ -90,6 +90,41 @@ def test_float(hydrob200, oracle, name):
     got, tgot, _ = run(hydrob200, cfg, n)
     err, per = rel_linf_grouped(got, ref)
     assert err <= TOL_FLOAT, per
+
+
+@pytest.mark.parametrize("name", list(ADM_CASES))
+def test_adm3d_strict_bitexact_and_fast(hydrob200, oracle, name):
+    """Config C5 (ADM Bona-Masso 3-D, 37 integrated + 14 auxiliary variables): flux kernels + update kernel against the oracle."""
+    cfg, n = ADM_CASES[name]
+    ref, tref, _ = run(hydrob200, cfg, n, backend=oracle.OracleBackend)
+    assert np.isfinite(ref).all()
+    got, tgot, S = run(hydrob200, cfg, n, strict_fp=True)
+    assert tgot == tref, (tgot, tref)
+    bad = np.argwhere(got != ref)
+    assert bad.size == 0, "first mismatches (k,j,i,var): %s  max|diff| %g" % (bad[:5].tolist(), np.abs(got - ref).max())
+    got, tgot, S = run(hydrob200, cfg, n)
+    assert abs(tgot - tref) <= 1e-12 * abs(tref)
+    # variables that are identically zero up to rounding (a_y, d_yxx ... of a wave along x) have no scale of their own:
+    # measure every variable against the largest magnitude of its tensor
+    # (V_i = d_ik^k - d^k_ki is a contraction of d_kij: where it cancels to zero identically it is measured against the scale of d)
+    groups = [[0], list(range(1, 7)), list(range(7, 10)), list(range(10, 28)), list(range(28, 34)), list(range(10, 28)) + list(range(34, 37))]
+    for gidx in groups:
+        scale = np.abs(ref[..., gidx]).max()
+        err = np.abs(got[..., gidx] - ref[..., gidx]).max()
+        assert err <= TOL_DOUBLE * scale, (gidx, err, scale)
+
+
+def test_adm3d_float(hydrob200, oracle):
+    cfg, n = ADM_CASES["C5_gauge_wave_rk4"]
+    cfg = dict(cfg, precision="float")
+    ref, tref, _ = run(hydrob200, cfg, n, backend=oracle.OracleBackend)
+    got, tgot, _ = run(hydrob200, cfg, n, strict_fp=True)
+    assert tgot == tref
+    assert np.array_equal(got, ref)
+    got, tgot, _ = run(hydrob200, cfg, n)
+    for gidx in ([0], list(range(1, 7)), list(range(7, 10)), list(range(10, 28)), list(range(28, 34))):
+        scale = np.abs(ref[..., gidx]).max()
+        assert np.abs(got[..., gidx] - ref[..., gidx]).max() <= TOL_FLOAT * scale, gidx
 
 
 def test_graph_equals_eager(hydrob200):
