@@ -23,12 +23,14 @@ namespace hb {
 
 template<class real_, bool FAST_ = false> struct MHD {
 	typedef real_ real;
-	static constexpr bool FAST = FAST_;                // no production-form flux yet: the marching kernel uses the literal functions
+	static constexpr bool FAST = FAST_;                // production forms: hb_roe_fast.cuh (mhdRoeFluxFast, finishCellAuto)
 	static constexpr int eqnId = 1;
 	static constexpr int nS = 10, nI = 8, nW = 7;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/mhd.lua:19
-	struct Params { real gamma, mu0; };
-	static HB_HD Params makeParams(const double* p) { return Params{real(p[0]), real(p[1])}; }
+	struct Params { real gamma, mu0; real g2_g1, iMu0, iG1; };   // the last three: production forms only (gamma_2/gamma_1, 1/mu0, 1/gamma_1)
+	static HB_HD Params makeParams(const double* p) {
+		return Params{real(p[0]), real(p[1]), real((p[0] - 2.) / (p[0] - 1.)), real(1. / p[1]), real(1. / (p[0] - 1.))};
+	}
 
 	struct Prim { real rho, v[3], P, B[3]; };
 	struct Eig {

@@ -80,12 +80,13 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(6, 1, 8, 32, 1, 1)    /* fused column warps: three flux cores interleaved */ \
 	X(7, 1, 8, 32, 1, 2)    /* fused column warps: z flux, then the x/y pair */ \
 	X(8, 1, 6, 32, 1, 1) X(9, 1, 6, 32, 1, 2) X(10, 1, 4, 32, 1, 1) X(11, 1, 8, 64, 1, 1) X(12, 1, 8, 64, 1, 0) X(13, 1, 10, 32, 1, 1) \
-	X(14, 1, 8, 64, 1, 2) X(15, 1, 10, 32, 1, 2)
+	X(14, 1, 8, 64, 1, 2) X(15, 1, 10, 32, 1, 2) X(16, 1, 8, 32, 1, 3) X(17, 1, 8, 64, 1, 3) X(18, 1, 9, 32, 1, 0) X(19, 1, 9, 64, 1, 0) X(20, 1, 9, 64, 1, 3)
 #define HB_MARCH2_LIST(X) \
 	X(0, 4, 1, 32, 2, 0)    /* 128 columns, 5 warps */ \
 	X(1, 2, 1, 32, 4, 0)    /* 64 columns, 3 warps */ \
 	X(2, 6, 1, 64, 1, 0)    /* 192 columns, 7 warps (TMA boxes are at most 256 elements wide) */ \
-	X(3, 4, 1, 32, 2, 2) X(4, 4, 1, 64, 2, 2) X(5, 2, 1, 32, 4, 2) X(6, 6, 1, 64, 1, 2) X(7, 4, 1, 64, 1, 2)
+	X(3, 4, 1, 32, 2, 2) X(4, 4, 1, 64, 2, 2) X(5, 2, 1, 32, 4, 2) X(6, 6, 1, 64, 1, 2) X(7, 4, 1, 64, 1, 2) \
+	X(8, 3, 1, 32, 2, 0) X(9, 2, 1, 32, 3, 0) X(10, 7, 1, 32, 1, 0) X(11, 5, 1, 32, 1, 0) X(12, 4, 1, 128, 2, 0)
 #endif
 
 constexpr size_t kSmemLimit = 232448 - 1024;   // 227 KB opt-in maximum per CTA minus the kernel's static shared memory (rounded up)

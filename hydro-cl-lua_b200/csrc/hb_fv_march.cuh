@@ -271,7 +271,30 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 						URy[q] = P[q * PS + ob] - sh[TX];
 					}
 				}
-				if constexpr (DIM == 3) {
+				if constexpr (DIM == 3 && C::VAR == 3 && Eqn::FAST && Eqn::eqnId == 0) {
+					// z flux on its own; x and y cores as one block; a state pair on one of the reference's special branches (rare) is
+					// redone by the literal code from operands re-read from shared memory, so no operand stays live across the cores
+					roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+					bool const rx = eulerRoeFluxCore<Eqn, 0>(Fx, ep, ULx, URx);
+					bool const ry = eulerRoeFluxCore<Eqn, 1>(Fy, ep, ULy, URy);
+					if (!(rx && ry)) {
+						real A[nI], B[nI];
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) {
+							real const* sg = sgx + (q * TY + cj) * (TX + 2) + ci;
+							A[q] = P[q * PS + ob - 1] + sg[0];
+							B[q] = P[q * PS + ob] - sg[1];
+						}
+						eulerRoeFluxFixup<Eqn, 0>(rx, Fx, ep, A, B);
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) {
+							real const* sh = sgy + (q * (TY + 2) + cj) * TX + ci;
+							A[q] = P[q * PS + ob - BX] + sh[0];
+							B[q] = P[q * PS + ob] - sh[TX];
+						}
+						eulerRoeFluxFixup<Eqn, 1>(ry, Fy, ep, A, B);
+					}
+				} else if constexpr (DIM == 3) {
 					if constexpr (C::VAR == 1) roeFluxTripleAuto<Eqn, MS, 0, 1>(Fz, Fx, Fy, ep, zfP, UR, ULx, URx, ULy, URy);
 					else {
 						roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
@@ -407,15 +430,33 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 			real const* __restrict__ Q = ring + sN * SLOT;
 			real* const sgxN = SGX + ((k + 1) & 1) * (nI * G::SGXN);
 			real* const sgyN = SGY + ((k + 1) & 1) * (nI * G::SGYN);
-			if (doSX) {
+			// all loads first, then all stores: the compiler cannot move a shared-memory load above a shared-memory store, and
+			// a load -> slope -> store sequence per variable would pay the shared-memory latency nI times in a row
+			if (DIM == 3 && doSX && doSY) {
+				real sx[nI], sy[nI];
 				#pragma unroll
-				for (int q = 0; q < nI; ++q)
-					sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], Q[q * PS + ob], Q[q * PS + ob + 1]);
-			}
-			if (DIM == 3 && doSY) {
+				for (int q = 0; q < nI; ++q) {
+					real const c = Q[q * PS + ob];
+					sx[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], c, Q[q * PS + ob + 1]);
+					sy[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], c, Q[q * PS + ob + BX]);
+				}
 				#pragma unroll
-				for (int q = 0; q < nI; ++q)
-					sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], Q[q * PS + ob], Q[q * PS + ob + BX]);
+				for (int q = 0; q < nI; ++q) {
+					sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = sx[q];
+					sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = sy[q];
+				}
+			} else if (doSX) {
+				real sx[nI];
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) sx[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], Q[q * PS + ob], Q[q * PS + ob + 1]);
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = sx[q];
+			} else if (DIM == 3 && doSY) {
+				real sy[nI];
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) sy[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], Q[q * PS + ob], Q[q * PS + ob + BX]);
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = sy[q];
 			}
 		}
 		__syncthreads();           // the only barrier of the iteration: fluxes of plane k and slopes of plane k+1 are visible

@@ -102,6 +102,10 @@ HB_HD void fastRsqrt(float x, float& y, float& s) {
 
 template<class real, int n> struct VecN { real v[n]; };
 
+template<class Eqn, int SIDE>
+HB_HD void roeFluxAuto(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI]);
+
 // the literal Roe flux, out of line: the rare special-branch states of the production kernels go here
 template<class Eqn, int SIDE>
 HB_NOINLINE VecN<typename Eqn::real, Eqn::nI> roeFluxOutOfLine(typename Eqn::Params s, VecN<typename Eqn::real, Eqn::nI> UL, VecN<typename Eqn::real, Eqn::nI> UR) {
@@ -194,6 +198,147 @@ HB_HD void eulerRoeFluxFast(typename Eqn::real (&F)[5], typename Eqn::Params con
 	eulerRoeFluxFixup<Eqn, SIDE>(regular, F, s, UL, UR);
 }
 
+// sqrt(x) for x >= 0 that may be exactly zero (s = 0 then; the reciprocal y is garbage there and the caller selects around it)
+HB_HD void fastRsqrt0(double x, double& y, double& s) { fastRsqrt(x > 1e-300 ? x : 1e-300, y, s); if (!(x > 1e-300)) s = x > 0. ? sqrt(x) : 0.; }
+HB_HD void fastRsqrt0(float x, float& y, float& s) { fastRsqrt(x > 1e-37f ? x : 1e-37f, y, s); if (!(x > 1e-37f)) s = x > 0.f ? sqrtf(x) : 0.f; }
+
+// Roe flux of ideal MHD, production form.  Same quantities as hydro/eqn/mhd.cl:296-436 (calcRoeValues incl. the swapped sqrt(rho)
+// weights of B.y, B.z at :335-336; eigen_forRoeAvgs), :575-783 (left / right transforms), :441-467 (fluxFromCons) and
+// hydro/flux/roe.cl:17-163 with useFluxLimiter == false, roeUseFluxFromCons == true, re-associated:
+//   * 10 reciprocal square roots + 2 reciprocals (branch-free seeds + Newton steps) replace 13 square roots and ~30 divisions:
+//     1/rho = (1/sqrt(rhoL))(1/sqrt(rhoR)), CAx = |B.x| / sqrt(rho), Cs = aTilde CAx / Cf, BStarPerpLen = BPerpLen sqrt(gamma_1 - gamma_2 Y),
+//     betaStar / betaStarSq = beta sqrt(gamma_1 - gamma_2 Y) (beta is a unit vector), 1/mu0 and gamma_2/gamma_1 precomputed;
+//   * the wave pairs (fast -/+, slow -/+, Alfven -/+) share the symmetric and antisymmetric halves of their rows of L and columns of R;
+//   * the degenerate cases of the reference (BPerpLen == 0; the three alphaF/alphaS tests) are kept, as selects.
+template<class Eqn, int SIDE>
+HB_HD void mhdRoeFluxFast(typename Eqn::real (&F)[8], typename Eqn::Params const& s, typename Eqn::real const (&UL)[8], typename Eqn::real const (&UR)[8])
+{
+	typedef typename Eqn::real real;
+	constexpr int n = SIDE, t1 = (SIDE + 1) % 3, t2 = (SIDE + 2) % 3;
+	real const g1 = s.gamma - real(1.), g2 = s.gamma - real(2.), g2_g1 = s.g2_g1, iMu0 = s.iMu0;
+	// ---- primitives of both sides (mhd.cl:160-179; the floor on rho does not enter the flux)
+	real yL, sL, yR, sR;
+	fastRsqrt(UL[0], yL, sL);
+	fastRsqrt(UR[0], yR, sR);
+	real const iL = yL * yL, iR = yR * yR;
+	real vL[3], vR[3];
+	#pragma unroll
+	for (int q = 0; q < 3; ++q) { vL[q] = UL[1 + q] * iL; vR[q] = UR[1 + q] * iR; }
+	real const vSqL = lenSq3(vL[0], vL[1], vL[2]), vSqR = lenSq3(vR[0], vR[1], vR[2]);
+	real const PMagL = real(.5) * lenSq3(UL[5], UL[6], UL[7]), PMagR = real(.5) * lenSq3(UR[5], UR[6], UR[7]);
+	real const PL = rmax<real>((UL[4] - real(.5) * UL[0] * vSqL - PMagL * iMu0) * g1, real(1e-7));
+	real const PR = rmax<real>((UR[4] - real(.5) * UR[0] * vSqR - PMagR * iMu0) * g1, real(1e-7));
+	real const hTL = (UL[4] + PL + PMagL) * iL, hTR = (UR[4] + PR + PMagR) * iR;
+	// ---- Roe averages (mhd.cl:296-340)
+	real const iS = fastRcp(sL + sR);
+	real const wL = sL * iS, wR = sR * iS;
+	real const rho = sL * sR, iRho = yL * yR;
+	real const vx = vL[n] * wL + vR[n] * wR, vy = vL[t1] * wL + vR[t1] * wR, vz = vL[t2] * wL + vR[t2] * wR;
+	real const hTotal = hTL * wL + hTR * wR;
+	real const Bx = UL[5 + n] * wL + UR[5 + n] * wR;
+	real const By = UL[5 + t1] * wR + UR[5 + t1] * wL;
+	real const Bz = UL[5 + t2] * wR + UR[5 + t2] * wL;
+	real const dby = UL[5 + t1] - UR[5 + t1], dbz = UL[5 + t2] - UR[5 + t2];
+	real const X = real(.5) * (dby * dby + dbz * dbz) * (iS * iS);
+	real const Y = real(.5) * (UL[0] + UR[0]) * iRho;
+	// ---- eigensystem scalars (mhd.cl:346-436)
+	real const vSq = lenSq3(vx, vy, vz);
+	real const BPerpSq = By * By + Bz * Bz;
+	real const gY = g1 - g2 * Y;
+	real const CAxSq = Bx * Bx * iRho;
+	real const hHydro = hTotal - (CAxSq + BPerpSq * iRho);
+	real const aTildeSq = rmax<real>(g1 * (hHydro - real(.5) * vSq) - g2 * X, real(1e-20));
+	real const BSPr = gY * BPerpSq * iRho;
+	real const CATildeSq = CAxSq + BSPr;
+	real const dHalf = real(.5) * (CATildeSq - aTildeSq);
+	real yTmp, sqrtDiscr;
+	fastRsqrt0(dHalf * dHalf + aTildeSq * BSPr, yTmp, sqrtDiscr);
+	real const CfSq = real(.5) * (CATildeSq + aTildeSq) + sqrtDiscr;
+	real yCf, Cf, yA, aTilde, ySR, sqrtRho, yBp, BPerpLen, ySq, sq;
+	fastRsqrt(CfSq, yCf, Cf);
+	fastRsqrt(aTildeSq, yA, aTilde);
+	fastRsqrt(rho, ySR, sqrtRho);
+	fastRsqrt0(BPerpSq, yBp, BPerpLen);
+	fastRsqrt(gY, ySq, sq);
+	real const CAx = rabs(Bx) * ySR;
+	real const CsSq = aTildeSq * CAxSq * (yCf * yCf);
+	real const Cs = aTilde * CAx * yCf;
+	real const BStarPerpLen = BPerpLen * sq;
+	bool const noPerp = BPerpLen == real(0);
+	real const betaY = noPerp ? real(1) : By * yBp, betaZ = noPerp ? real(0) : Bz * yBp;
+	real const betaStarY = betaY * ySq, betaStarZ = betaZ * ySq;
+	real const betaStarSq = betaStarY * betaStarY + betaStarZ * betaStarZ;
+	real const QStarY = betaY * sq, QStarZ = betaZ * sq;
+	real alphaF, alphaS;
+	{
+		real const den = CfSq - CsSq, numF = aTildeSq - CsSq, numS = CfSq - aTildeSq;
+		real const iDen = fastRcp(den);
+		real y0, aF, aS;
+		fastRsqrt0(numF * iDen, y0, aF);
+		fastRsqrt0(numS * iDen, y0, aS);
+		bool const one = den == real(0) || (numF > real(0) && numS <= real(0));
+		bool const zero = den != real(0) && numF <= real(0);
+		alphaF = one ? real(1) : (zero ? real(0) : aF);
+		alphaS = one ? real(0) : (zero ? real(1) : aS);
+	}
+	real const sbx = Bx >= real(0) ? real(1) : real(-1);
+	real const Qf = Cf * alphaF * sbx, Qs = Cs * alphaS * sbx;
+	real const Af = aTilde * alphaF * ySR, As = aTilde * alphaS * ySR;
+	// ---- characteristic differences dUe = L (UR - UL) (mhd.cl:575-679), by wave pairs
+	real const norm = real(.5) * (yA * yA);
+	real const Cff = norm * alphaF * Cf, Css = norm * alphaS * Cs;
+	real const Qf2 = Qf * norm, Qs2 = Qs * norm;
+	real const AHatF = norm * Af * rho, AHatS = norm * As * rho;
+	real const afpb = norm * Af * BStarPerpLen, aspb = norm * As * BStarPerpLen;
+	real const norm2 = norm * g1, alphaF2 = alphaF * norm2, alphaS2 = alphaS * norm2, norm3 = norm2 * real(2.);
+	real const vqstr = vy * QStarY + vz * QStarZ;
+	real const drho = UR[0] - UL[0], dE = UR[4] - UL[4];
+	real const dm0 = UR[1 + n] - UL[1 + n], dm1 = UR[1 + t1] - UL[1 + t1], dm2 = UR[1 + t2] - UL[1 + t2];
+	real const dB1 = UR[5 + t1] - UL[5 + t1], dB2 = UR[5 + t2] - UL[5 + t2];
+	real const mv = dm0 * vx + dm1 * vy + dm2 * vz;
+	real const qm = dm1 * QStarY + dm2 * QStarZ;
+	real const T = drho * (vSq - hHydro) - mv + dE;
+	real const symF = alphaF2 * T + drho * (Cff * Cf - aspb) + dB1 * (AHatS * QStarY - alphaF2 * By) + dB2 * (AHatS * QStarZ - alphaF2 * Bz);
+	real const symS = alphaS2 * T + drho * (Css * Cs + afpb) - dB1 * (AHatF * QStarY + alphaS2 * By) - dB2 * (AHatF * QStarZ + alphaS2 * Bz);
+	real const antiF = drho * (Cff * vx - Qs2 * vqstr) - dm0 * Cff + Qs2 * qm;
+	real const antiS = drho * (Css * vx + Qf2 * vqstr) - dm0 * Css - Qf2 * qm;
+	real const A15 = real(.5) * (drho * (vy * betaZ - vz * betaY) + dm1 * betaZ + dm2 * betaY);
+	real const B15 = real(.5) * sqrtRho * sbx * (dB2 * betaY - dB1 * betaZ);
+	real const r3 = drho * (real(1.) - norm3 * (real(.5) * vSq - g2_g1 * X)) + norm3 * (mv - dE + dB1 * By + dB2 * Bz);
+	// ---- wave strengths a_j = -.5 |lambda_j| dUe_j (roe.cl:91-134 without the limiter term), summed / differenced by pairs
+	real const a0 = real(-.5) * rabs(vx - Cf) * (symF + antiF), a6 = real(-.5) * rabs(vx + Cf) * (symF - antiF);
+	real const a2 = real(-.5) * rabs(vx - Cs) * (symS + antiS), a4 = real(-.5) * rabs(vx + Cs) * (symS - antiS);
+	real const a1 = real(-.5) * rabs(vx - CAx) * (A15 + B15), a5 = real(-.5) * rabs(vx + CAx) * (B15 - A15);
+	real const a3 = real(-.5) * rabs(vx) * r3;
+	real const pf = a0 + a6, mf = a6 - a0, ps = a2 + a4, ms = a4 - a2, pa = a1 + a5, ma = a5 - a1;
+	// ---- F = R a (mhd.cl:683-783)
+	real const Frho = alphaF * pf + alphaS * ps + a3;
+	real const cross = Qf * ms - Qs * mf;
+	real const vDotBeta = vy * betaStarY + vz * betaStarZ;
+	real const bsq = BStarPerpLen * betaStarSq;
+	real const Rm0 = vx * Frho + alphaF * Cf * mf + alphaS * Cs * ms;
+	real const Rm1 = vy * Frho + betaStarY * cross + betaZ * ma;
+	real const Rm2 = vz * Frho + betaStarZ * cross - betaY * ma;
+	real const RE = hHydro * (alphaF * pf + alphaS * ps) + bsq * (As * pf - Af * ps) + vx * (alphaF * Cf * mf + alphaS * Cs * ms)
+		+ vDotBeta * cross + (vy * betaZ - vz * betaY) * ma + a3 * (real(.5) * vSq + g2_g1 * X);
+	real const mag = As * pf - Af * ps, alf = sbx * ySR * pa;
+	real const RB1 = betaStarY * mag - betaZ * alf;
+	real const RB2 = betaStarZ * mag + betaY * alf;
+	// ---- + .5 (F(UL) + F(UR)) (mhd.cl:441-467)
+	real const vnL = vL[n], vnR = vR[n], BnL = UL[5 + n], BnR = UR[5 + n];
+	real const PTL = PL + PMagL * iMu0, PTR = PR + PMagR * iMu0;
+	real const bL = BnL * iMu0, bR = BnR * iMu0;
+	real const BdVL = dot3(UL[5], UL[6], UL[7], vL[0], vL[1], vL[2]), BdVR = dot3(UR[5], UR[6], UR[7], vR[0], vR[1], vR[2]);
+	F[0] = Frho + real(.5) * (UL[1 + n] + UR[1 + n]);
+	F[1 + n] = Rm0 + real(.5) * ((UL[1 + n] * vnL - UL[5 + n] * bL + PTL) + (UR[1 + n] * vnR - UR[5 + n] * bR + PTR));
+	F[1 + t1] = Rm1 + real(.5) * ((UL[1 + t1] * vnL - UL[5 + t1] * bL) + (UR[1 + t1] * vnR - UR[5 + t1] * bR));
+	F[1 + t2] = Rm2 + real(.5) * ((UL[1 + t2] * vnL - UL[5 + t2] * bL) + (UR[1 + t2] * vnR - UR[5 + t2] * bR));
+	F[4] = RE + real(.5) * (((UL[4] + PTL) * vnL - BdVL * bL) + ((UR[4] + PTR) * vnR - BdVR * bR));
+	F[5 + n] = real(0);
+	F[5 + t1] = RB1 + real(.5) * ((UL[5 + t1] * vnL - vL[t1] * BnL) + (UR[5 + t1] * vnR - vR[t1] * BnR));
+	F[5 + t2] = RB2 + real(.5) * ((UL[5 + t2] * vnL - vL[t2] * BnL) + (UR[5 + t2] * vnR - vR[t2] * BnR));
+}
+
 // two independent interfaces (sides SA, SB) of one cell
 template<class Eqn, int SA, int SB>
 HB_HD void roeFluxPairAuto(typename Eqn::real (&FA)[Eqn::nI], typename Eqn::real (&FB)[Eqn::nI], typename Eqn::Params const& s,
@@ -206,8 +351,8 @@ HB_HD void roeFluxPairAuto(typename Eqn::real (&FA)[Eqn::nI], typename Eqn::real
 		eulerRoeFluxFixup<Eqn, SA>(ra, FA, s, ULA, URA);
 		eulerRoeFluxFixup<Eqn, SB>(rb, FB, s, ULB, URB);
 	} else {
-		roeFlux<Eqn, SA>(FA, s, ULA, URA);
-		roeFlux<Eqn, SB>(FB, s, ULB, URB);
+		roeFluxAuto<Eqn, SA>(FA, s, ULA, URA);
+		roeFluxAuto<Eqn, SB>(FB, s, ULB, URB);
 	}
 }
 
@@ -227,9 +372,9 @@ HB_HD void roeFluxTripleAuto(typename Eqn::real (&FA)[Eqn::nI], typename Eqn::re
 		eulerRoeFluxFixup<Eqn, SB>(rb, FB, s, ULB, URB);
 		eulerRoeFluxFixup<Eqn, SC>(rc, FC, s, ULC, URC);
 	} else {
-		roeFlux<Eqn, SA>(FA, s, ULA, URA);
-		roeFlux<Eqn, SB>(FB, s, ULB, URB);
-		roeFlux<Eqn, SC>(FC, s, ULC, URC);
+		roeFluxAuto<Eqn, SA>(FA, s, ULA, URA);
+		roeFluxAuto<Eqn, SB>(FB, s, ULB, URB);
+		roeFluxAuto<Eqn, SC>(FC, s, ULC, URC);
 	}
 }
 
@@ -238,7 +383,18 @@ HB_HD void roeFluxAuto(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params co
 	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
 {
 	if constexpr (Eqn::FAST && Eqn::eqnId == 0) eulerRoeFluxFast<Eqn, SIDE>(F, s, UL, UR);
+	else if constexpr (Eqn::FAST && Eqn::eqnId == 1) mhdRoeFluxFast<Eqn, SIDE>(F, s, UL, UR);
 	else roeFlux<Eqn, SIDE>(F, s, UL, UR);
+}
+
+// the literal constrainU + calcDTCell, out of line: cells on the density / pressure floor
+template<class Eqn>
+HB_NOINLINE void mhdFinishCellOutOfLine(typename Eqn::Params s, typename Eqn::real (&U)[Eqn::nI], typename Eqn::real const (&dx)[3], int dim,
+	bool wantDt, typename Eqn::real& dtCell)
+{
+	typedef typename Eqn::real real;
+	Eqn::constrainU(s, U);
+	if (wantDt) dtCell = rmin<real>(dtCell, Eqn::calcDTCell(s, U, dx, dim));
 }
 
 // constrainU (solverbase.lua:2116-2127 -> euler.cl:698-717) and, when wanted, the cell's CFL rate max_s(lambda_s / dx_s)
@@ -264,6 +420,37 @@ HB_HD void finishCellAuto(typename Eqn::Params const& s, typename Eqn::real (&U)
 			if (dim > 1) r = rmax<real>(r, rmax<real>(rabs(v1) + Cs, real(1e-9)) * invdx[1]);
 			if (dim > 2) r = rmax<real>(r, rmax<real>(rabs(v2) + Cs, real(1e-9)) * invdx[2]);
 			rateCell = rmax<real>(rateCell, r);
+		}
+	} else if constexpr (Eqn::FAST && Eqn::eqnId == 1) {
+		// MHD (mhd.cl:915-931, :473-554): one reciprocal; a cell on neither floor is left as it is (the reference's
+		// prim -> cons round trip moves it by rounding only); the CFL rate is |v_s| + Cf_s per side from two square roots
+		real const rho = U[0], g1 = s.gamma - real(1.), g2 = s.gamma - real(2.);
+		real const iR = fastRcp(rho);
+		real const v0 = U[1] * iR, v1 = U[2] * iR, v2 = U[3] * iR;
+		real const vSq = lenSq3(v0, v1, v2), BSq = lenSq3(U[5], U[6], U[7]);
+		real const P = (U[4] - real(.5) * rho * vSq - real(.5) * BSq * s.iMu0) * g1;
+		if (!(rho >= real(1e-7) && P >= real(1e-7))) {
+			mhdFinishCellOutOfLine<Eqn>(s, U, dx, dim, wantDt, dtCell);
+		} else if (wantDt) {
+			real const hTotal = real(.5) * vSq + (P * s.gamma * s.iG1 + BSq) * iR;
+			real const vv[3] = {v0, v1, v2};
+			#pragma unroll
+			for (int sd = 0; sd < 3; ++sd) {
+				if (sd < dim) {
+					real const Bn = U[5 + sd], Bt1 = U[5 + (sd + 1) % 3], Bt2 = U[5 + (sd + 2) % 3];
+					real const BPerpSq = Bt1 * Bt1 + Bt2 * Bt2;
+					real const CAxSq = Bn * Bn * iR;
+					real const hHydro = hTotal - (CAxSq + BPerpSq * iR);
+					real const aT = rmax<real>(g1 * (hHydro - real(.5) * vSq) - g2, real(1e-20));
+					real const BSPr = (g1 - g2) * BPerpSq * iR;
+					real const CAT = CAxSq + BSPr;
+					real const dH = real(.5) * (CAT - aT);
+					real y0, disc, Cf;
+					fastRsqrt0(dH * dH + aT * BSPr, y0, disc);
+					fastRsqrt(real(.5) * (CAT + aT) + disc, y0, Cf);
+					rateCell = rmax<real>(rateCell, rmax<real>(rabs(vv[sd]) + Cf, real(1e-9)) * invdx[sd]);
+				}
+			}
 		}
 	} else {
 		Eqn::constrainU(s, U);

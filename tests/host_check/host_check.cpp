@@ -70,6 +70,26 @@ void hc_euler_roe_flux_fast(int side, const double* params, const double* UL_, c
 	else roeFluxAuto<E, 2>(F, p, UL, UR);
 	for (int q = 0; q < 5; ++q) F_[q] = F[q];
 }
+void hc_mhd_roe_flux_fast(int side, const double* params, const double* UL_, const double* UR_, double* F_) {
+	typedef MHD<double, true> E;
+	E::Params p = E::makeParams(params);
+	double UL[8], UR[8], F[8];
+	for (int q = 0; q < 8; ++q) { UL[q] = UL_[q]; UR[q] = UR_[q]; }
+	if (side == 0) roeFluxAuto<E, 0>(F, p, UL, UR);
+	else if (side == 1) roeFluxAuto<E, 1>(F, p, UL, UR);
+	else roeFluxAuto<E, 2>(F, p, UL, UR);
+	for (int q = 0; q < 8; ++q) F_[q] = F[q];
+}
+double hc_mhd_finish_cell_fast(const double* params, double* U_, const double* dx_, int dim) {
+	typedef MHD<double, true> E;
+	E::Params p = E::makeParams(params);
+	double U[8]; double dx[3] = {dx_[0], dx_[1], dx_[2]}, invdx[3] = {1. / dx_[0], 1. / dx_[1], 1. / dx_[2]};
+	for (int q = 0; q < 8; ++q) U[q] = U_[q];
+	double dtCell = HUGE_VAL, rate = 0;
+	finishCellAuto<E>(p, U, dx, invdx, dim, true, dtCell, rate);
+	for (int q = 0; q < 8; ++q) U_[q] = U[q];
+	return rate > 0 ? (1. / rate < dtCell ? 1. / rate : dtCell) : dtCell;
+}
 double hc_plm_half_slope_fast(int lim, double UL, double U, double UR) {
 	return lim == 8 ? plmHalfSlopeT<double, 8, true>(lim, UL, U, UR) : plmHalfSlopeT<double, 18, true>(lim, UL, U, UR);
 }

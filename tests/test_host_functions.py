@@ -215,3 +215,55 @@ def test_fast_euler_finish_cell(hc):
                 assert dt_lit * (1 - 1e-14) <= dt_fast <= dt_cs0 * (1 + 1e-14), (i, dt_lit, dt_fast, dt_cs0)
             else:
                 assert abs(dt_fast - dt_lit) <= 1e-14 * dt_lit, (i, dt_lit, dt_fast)
+
+
+def test_fast_mhd_roe_flux_close_to_literal(hc):
+    """mhdRoeFluxFast (reciprocal-square-root forms, paired waves) against the literal 7-wave transforms, incl. the degenerate
+    states of the reference's eigensystem (B perpendicular == 0, B.x == 0, identical states)."""
+    hc.hc_mhd_roe_flux_fast.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(13)
+    n = 2000
+    UL = random_states("mhd", n, rng)
+    UR = random_states("mhd", n, rng)
+    UR[:600] = UL[:600] * (1 + 1e-6 * rng.standard_normal((600, UL.shape[1])))
+    UL[600:650, 6:8] = 0; UR[600:650, 6:8] = 0            # no perpendicular field for side 0
+    UL[650:700, 5] = 0; UR[650:700, 5] = 0                # no normal field for side 0
+    UR[700:750] = UL[700:750]                             # identical states
+    for gamma in (5. / 3., 2.):
+        params = np.array([gamma, 1.] + [0.] * 14)
+        worst = 0.
+        for side in range(3):
+            for i in range(n):
+                Fl = np.zeros(8); Ff = np.zeros(8)
+                ul = np.ascontiguousarray(UL[i, :8]); ur = np.ascontiguousarray(UR[i, :8])
+                hc.hc_roe_flux(1, 8, side, params.ctypes.data, ul.ctypes.data, ur.ctypes.data, Fl.ctypes.data)
+                hc.hc_mhd_roe_flux_fast(side, params.ctypes.data, ul.ctypes.data, ur.ctypes.data, Ff.ctypes.data)
+                assert np.isfinite(Ff).all(), (i, side, ul, ur, Ff)
+                rho = max(ul[0], ur[0]); vmax = max(np.abs(ul[1:4] / ul[0]).max(), np.abs(ur[1:4] / ur[0]).max(), 1.)
+                B = max(np.abs(ul[5:8]).max(), np.abs(ur[5:8]).max(), 1.)
+                E = max(ul[4], ur[4])
+                cf = np.sqrt((gamma * E + B * B) / min(ul[0], ur[0]))
+                scale = np.array([rho, rho * vmax, rho * vmax, rho * vmax, E, B, B, B]) * (vmax + cf) + np.abs(Fl)
+                err = (np.abs(Ff - Fl) / scale).max()
+                worst = max(worst, err)
+        assert worst < 1e-14, worst
+
+
+def test_fast_mhd_finish_cell(hc):
+    hc.hc_mhd_finish_cell_fast.restype = C.c_double
+    hc.hc_mhd_finish_cell_fast.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(6)
+    U = random_states("mhd", 400, rng)
+    U[:20, 4] = .5 * (U[:20, 1:4] ** 2).sum(1) / U[:20, 0] + .5 * (U[:20, 5:8] ** 2).sum(1) - 1.     # negative pressure -> floor
+    U[20:30, 0] = 1e-9
+    U[20:30, 1:4] *= 1e-8
+    params = np.array([5. / 3., 1.] + [0.] * 14)
+    dx = np.array([.01, .02, .03])
+    for dim in (1, 2, 3):
+        for i in range(len(U)):
+            a = U[i, :8].copy(); b = a.copy()
+            hc.hc_constrainU(1, 8, params.ctypes.data, a.ctypes.data)
+            dt_lit = hc.hc_calc_dt_cell(1, 8, params.ctypes.data, a.ctypes.data, dx.ctypes.data, dim)
+            dt_fast = hc.hc_mhd_finish_cell_fast(params.ctypes.data, b.ctypes.data, dx.ctypes.data, dim)
+            assert np.allclose(a, b, rtol=1e-14, atol=1e-14 * np.abs(a).max()), (i, a, b)
+            assert abs(dt_fast - dt_lit) <= 1e-13 * dt_lit, (i, dt_lit, dt_fast)
