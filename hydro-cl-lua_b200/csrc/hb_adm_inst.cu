@@ -2,6 +2,7 @@
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -DHB_REAL=double -DHB_OPS=ops_adm3d_f64_fast [-fmad=false -DHB_STRICT=1]
 #include "hb_fv_ops.h"
 #include "hb_adm_kernels.cuh"
+#include <cstdlib>
 
 namespace hb {
 namespace {
@@ -12,7 +13,11 @@ constexpr int MODE = 1;
 #else
 constexpr int MODE = 0;
 #endif
-typedef ADM3D<real, false> Eqn;
+#ifdef HB_STRICT
+typedef ADM3D<real, false> Eqn;     // literal arithmetic, -fmad=false: bit-comparable with the oracle
+#else
+typedef ADM3D<real, true> Eqn;      // production forms (reciprocal / rsqrt seeds, ratio-free minmod / superbee)
+#endif
 
 template<int SIDE>
 cudaError_t launchFlux(GridP<real> const& g, StageP<real> const& sp, Eqn::Params const& ep, cudaStream_t st) {
@@ -36,7 +41,13 @@ cudaError_t stage(int dim, bool, bool, GridP<real> const& g, StageP<real> const&
 	}
 	long long const n = (long long)g.N[0] * g.N[1] * g.N[2];
 	int const nt = 128;
-	adm_update<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
+	static int const split = getenv("HB_ADM_SPLIT") ? atoi(getenv("HB_ADM_SPLIT")) : 1;
+	if (split) {
+		adm_update<Eqn, MODE, 0><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 1><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
+	} else {
+		adm_update<Eqn, MODE, 2><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
+	}
 	return cudaGetLastError();
 }
 bool marchInfo(int, bool, bool, int, int, int*, int*) { return false; }

@@ -64,13 +64,20 @@ adm_flux(GridP<typename Eqn::real> const g, typename Eqn::Params const ep, const
 	for (int q = 0; q < 6; ++q) { F[(1 + q) * sv] = Fd[q]; F[(7 + q) * sv] = FK[q]; }
 }
 
-template<class Eqn, int MODE>
-__global__ void __launch_bounds__(128)
+// PART selects the integrated variables this launch produces: 0 = all but K_ij, 1 = K_ij only, 2 = all 37.
+// The source of K_ij (adm3d.cl:1589-2776) needs the raised forms of all 18 d_kij at once (~75 live doubles); together with the
+// other 31 derivatives and the RK combination of 37 variables one thread spills ~1 KB and the spill traffic evicts the state from L1:
+// measured 2.0 ms per 128^3 launch against 0.27 ms for a 13-wave flux kernel.  Split in two launches every thread computes only
+// what its part stores -- the arithmetic per stored value is the same expression sequence (the unused branches of the fully
+// unrolled, compile-time indexed code are dead and dropped by the compiler), so the strict build stays bit-identical to the oracle.
+template<class Eqn, int MODE, int PART>
+__global__ void __launch_bounds__(128, PART == 0 ? 3 : 1)
 adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep,
 	const typename Eqn::real* __restrict__ Fb)
 {
 	typedef typename Eqn::real real;
 	constexpr int nI = Eqn::nI;
+	auto inPart = [](int q) { return PART == 2 || (PART == 1) == (q >= Eqn::iK && q < Eqn::iK + 6); };
 	__shared__ double redBuf[32];
 	long long const nInt = (long long)g.N[0] * g.N[1] * g.N[2];
 	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -134,12 +141,12 @@ adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const s
 		}
 		if (sp.Lout) {
 			#pragma unroll
-			for (int q = 0; q < nI; ++q) sp.Lout[idx + q * sv] = deriv[q];
+			for (int q = 0; q < nI; ++q) if (inPart(q)) sp.Lout[idx + q * sv] = deriv[q];
 		}
 		if (sp.Uout) {
 			double const dt = *sp.dt;
 			#pragma unroll
-			for (int q = 0; q < nI; ++q) {
+			for (int q = 0; q < nI; ++q) if (inPart(q)) {
 				real r = 0;
 				#pragma unroll
 				for (int a = 0; a < HB_MAX_TERMS; ++a)
@@ -151,11 +158,11 @@ adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const s
 				deriv[q] = r;          // reuse as the new state
 			}
 			#pragma unroll
-			for (int q = 0; q < nI; ++q) sp.Uout[idx + q * sv] = deriv[q];
-			if (sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);
+			for (int q = 0; q < nI; ++q) if (inPart(q)) sp.Uout[idx + q * sv] = deriv[q];
+			if (PART != 1 && sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);   // reads alpha, gamma_ll only
 		}
 	}
-	if (sp.dtMinBits) {
+	if (PART != 1 && sp.dtMinBits) {
 		double v = double(dtCell);
 		#pragma unroll
 		for (int o = 16; o > 0; o >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }

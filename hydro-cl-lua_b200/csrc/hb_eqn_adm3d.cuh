@@ -38,7 +38,7 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 
 	// what one side's 13-wave system sees of a cell: alpha, gamma_ll, a_side, d_side,ij, K_ij
 	struct Side { real alpha, g[6], a, d[6], K[6]; };
-	struct Eig { real alpha, alpha_sqrt_f, gU[6], sq[3]; };
+	struct Eig { real alpha, alpha_sqrt_f, gU[6], sq[3]; real iAsf, iSq; };   // iAsf = 1 / alpha_sqrt_f, iSq = 1 / sq[SIDE]: production forms only
 
 	static HB_HD int s6(int i, int j) { return i == j ? (i == 0 ? 0 : i == 1 ? 3 : 5) : (i + j == 1 ? 1 : i + j == 2 ? 2 : 4); }
 
@@ -53,7 +53,7 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		return m[0] * (m[3] * m[5] - m[4] * m[4]) - m[1] * (m[1] * m[5] - m[2] * m[4]) + m[2] * (m[1] * m[4] - m[3] * m[2]);
 	}
 	static HB_HD void inv6(real* o, const real* m, real det) {
-		real const invDet = real(1.) / det;
+		real const invDet = FAST ? fastRcp(det) : real(1.) / det;
 		o[0] = (m[3] * m[5] - m[4] * m[4]) * invDet;
 		o[1] = (m[2] * m[4] - m[1] * m[5]) * invDet;
 		o[2] = (m[1] * m[4] - m[2] * m[3]) * invDet;
@@ -71,6 +71,16 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		else { o[0] = m[5]; o[1] = m[4]; o[2] = m[2]; o[3] = m[3]; o[4] = m[1]; o[5] = m[0]; }
 	}
 
+	// production form: the side's own sqrt(gamma^jj) only (the other two are never read), reciprocals from the same seeds
+	template<int SIDE> static HB_HD void eigen_forInterfaceFast(Eig& e, Params const& s, Side const& UL, Side const& UR) {
+		e.alpha = real(.5) * (UL.alpha + UR.alpha);
+		real avg[6];
+		#pragma unroll
+		for (int k = 0; k < 6; ++k) avg[k] = (UL.g[k] + UR.g[k]) * real(.5);
+		inv6(e.gU, avg, det6(avg));
+		fastRsqrt(calc_f_alphaSq(s.f_eqn, e.alpha), e.iAsf, e.alpha_sqrt_f);
+		fastRsqrt(e.gU[SIDE == 0 ? 0 : SIDE == 1 ? 3 : 5], e.iSq, e.sq[SIDE]);
+	}
 	static HB_HD void eigen_forInterface(Eig& e, Params const& s, Side const& UL, Side const& UR) {
 		e.alpha = real(.5) * (UL.alpha + UR.alpha);
 		real avg[6];
@@ -97,10 +107,10 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 	}
 	// inputs: a_side, d_side,ij and K_ij in the state's own (unswapped) component order
 	template<int SIDE> static HB_HD void leftTransform(real (&r)[nW], Eig const& e, real a_j, const real* dIn, const real* KIn) {
-		real const _1_sqrt_f = e.alpha / e.alpha_sqrt_f;
+		real const _1_sqrt_f = FAST ? e.alpha * e.iAsf : e.alpha / e.alpha_sqrt_f;
 		real const _1_f = _1_sqrt_f * _1_sqrt_f;
 		real const sqrt_gammaUjj = e.sq[SIDE];
-		real const _1_gammaUjj = real(1.) / e.gU[SIDE == 0 ? 0 : SIDE == 1 ? 3 : 5];
+		real const _1_gammaUjj = FAST ? e.iSq * e.iSq : real(1.) / e.gU[SIDE == 0 ? 0 : SIDE == 1 ? 3 : 5];
 		real d[6], K[6], gU[6];
 		swap6<SIDE>(d, dIn); swap6<SIDE>(K, KIn); swap6<SIDE>(gU, e.gU);
 		real const K_dot_eig_gamma = dot6(K, gU);
@@ -118,10 +128,10 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		swap6<SIDE>(gU, e.gU);
 		real const input1_dot_gammaU = in[1] * real(2.) * gU[1] + in[2] * real(2.) * gU[2] + in[3] * gU[3] + in[4] * real(2.) * gU[4] + in[5] * gU[5];
 		real const input7_dot_gammaU = in[7] * real(2.) * gU[1] + in[8] * real(2.) * gU[2] + in[9] * gU[3] + in[10] * real(2.) * gU[4] + in[11] * gU[5];
-		real const sqrt_f = e.alpha_sqrt_f / e.alpha;
-		real const _1_sqrt_f = real(1.) / sqrt_f;
+		real const sqrt_f = FAST ? e.alpha_sqrt_f * fastRcp(e.alpha) : e.alpha_sqrt_f / e.alpha;
+		real const _1_sqrt_f = FAST ? e.alpha * e.iAsf : real(1.) / sqrt_f;
 		real const sqrt_gammaUjj = e.sq[SIDE];
-		real const _1_sqrt_gammaUjj = real(1.) / sqrt_gammaUjj;
+		real const _1_sqrt_gammaUjj = FAST ? e.iSq : real(1.) / sqrt_gammaUjj;
 		real const _1_gammaUjj = _1_sqrt_gammaUjj * _1_sqrt_gammaUjj;
 		aOut = sqrt_f * sqrt_gammaUjj * (in[12] - in[0]);
 		real d[6], K[6];
@@ -140,7 +150,7 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		Side const& U2L, Side const& UL, Side const& UR, Side const& U2R)
 	{
 		Eig eig;
-		eigen_forInterface(eig, s, UL, UR);
+		if constexpr (FAST) eigen_forInterfaceFast<SIDE>(eig, s, UL, UR); else eigen_forInterface(eig, s, UL, UR);
 		real lam[nW];
 		waves<SIDE>(lam, eig);
 		real fluxEig[nW];
@@ -159,13 +169,13 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		}
 		if (useLimiter) {
 			Eig eL;
-			eigen_forInterface(eL, s, U2L, UL);
+			if constexpr (FAST) eigen_forInterfaceFast<SIDE>(eL, s, U2L, UL); else eigen_forInterface(eL, s, U2L, UL);
 			real dd[6], dK[6];
 			#pragma unroll
 			for (int k = 0; k < 6; ++k) { dd[k] = UL.d[k] - U2L.d[k]; dK[k] = UL.K[k] - U2L.K[k]; }
 			leftTransform<SIDE>(dUeL, eL, UL.a - U2L.a, dd, dK);
 			Eig eR;
-			eigen_forInterface(eR, s, UR, U2R);
+			if constexpr (FAST) eigen_forInterfaceFast<SIDE>(eR, s, UR, U2R); else eigen_forInterface(eR, s, UR, U2R);
 			#pragma unroll
 			for (int k = 0; k < 6; ++k) { dd[k] = U2R.d[k] - UR.d[k]; dK[k] = U2R.K[k] - UR.K[k]; }
 			leftTransform<SIDE>(dUeR, eR, U2R.a - UR.a, dd, dK);
@@ -175,7 +185,14 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 			real const lambda = lam[j];
 			real const base = fluxEig[j] * lambda;
 			real const sgn = lambda >= 0 ? real(1) : real(-1);
-			if (useLimiter) {
+			if (FAST && useLimiter && (fluxLimiter == 8 || fluxLimiter == 18)) {
+				// minmod / superbee without the ratio: phi(r) dUe = sign(dUe) m(|dUe|, |up|) when up dUe > 0, else 0 (hydro/app.lua:622,632)
+				real const up = lambda >= 0 ? dUeL[j] : dUeR[j];
+				real const a = rabs(dUe[j]), b = rabs(up);
+				real const m = fluxLimiter == 8 ? rmin<real>(a, b) : rmax<real>(rmin<real>(a, real(2.) * b), rmin<real>(real(2.) * a, b));
+				real const phiD = up * dUe[j] > real(0) ? (dUe[j] > real(0) ? m : -m) : real(0);
+				fluxEig[j] = base - real(.5) * lambda * (dUe[j] * sgn + phiD * (lambda * dt_dx - sgn));
+			} else if (useLimiter) {
 				real rEig;
 				if (dUe[j] == 0) rEig = 0;
 				else if (lambda >= 0) rEig = dUeL[j] / dUe[j];
@@ -218,6 +235,8 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 					for (int m = 0; m < 3; ++m) { t += U[iD + 6 * k + s6(i, m)] * gU[s6(m, j)]; u += gU[s6(k, m)] * U[iD + 6 * m + s6(i, j)]; }
 					d_llu[k][i][j] = t; d_ull[k][i][j] = u;
 				}
+		// production form: d_ikl d_j^kl = d_il^m d_jm^l, so the doubly raised d_k^ij is never formed (18 fewer live values)
+		if constexpr (!FAST) {
 		#pragma unroll
 		for (int k = 0; k < 3; ++k)
 			#pragma unroll
@@ -229,6 +248,7 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 					for (int m = 0; m < 3; ++m) t += gU[s6(i, m)] * d_llu[k][m][j];
 					d_luu[k][i][j] = t;
 				}
+		}
 		real d_l[3], e_l[3];
 		#pragma unroll
 		for (int k = 0; k < 3; ++k) {
@@ -263,7 +283,8 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 					t += conn * (a[k] + d_l[k] - real(2.) * e_l[k]);
 					#pragma unroll
 					for (int l = 0; l < 3; ++l) {
-						t += U[iD + 6 * i + s6(k, l)] * d_luu[j][k][l];
+						if constexpr (FAST) t += d_llu[i][l][k] * d_llu[j][k][l];
+						else t += U[iD + 6 * i + s6(k, l)] * d_luu[j][k][l];
 						t += real(2.) * d_llu[k][i][l] * (d_ull[k][j][l] - d_llu[l][j][k]);
 					}
 					t += real(-2.) * K[s6(i, k)] * K_ul[k][j];
@@ -282,6 +303,21 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		real const det_gamma = det6(g);
 		real const alpha_sqrt_f = rsqrt_ieee(f_alphaSq);
 		real dt = inf_of<real>::v();
+		if constexpr (FAST) {
+			// production form: one reciprocal, one square root per side; dt = min_s dx_s / max(lambda_s, 1e-9)
+			real const iDet = fastRcp(det_gamma);
+			real const speed = rmax<real>(alpha_sqrt_f, U[iAlpha]);
+			#pragma unroll
+			for (int side = 0; side < 3; ++side) {
+				if (side < dim && dx[side] > 0) {
+					real const gjj = (side == 0 ? g[3] * g[5] - g[4] * g[4] : side == 1 ? g[0] * g[5] - g[2] * g[2] : g[0] * g[3] - g[1] * g[1]) * iDet;
+					real y, sq;
+					fastRsqrt(gjj, y, sq);
+					dt = rmin<real>(dt, dx[side] * fastRcp(rmax<real>(real(1e-9), sq * speed)));
+				}
+			}
+			return dt;
+		}
 		#pragma unroll
 		for (int side = 0; side < 3; ++side) {
 			if (side < dim && dx[side] > 0) {

@@ -67,27 +67,28 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 // memory fits, starting at $HB_MARCH_CFG or 0).  X(index, WX, TY, KM, MINB, VAR)
 #ifdef HB_STRICT
 // the strict build carries fewer configurations (compile time)
-#define HB_MARCH3_LIST(X) X(0, 1, 10, 32, 1, 0) X(1, 1, 8, 32, 1, 0) X(2, 1, 4, 32, 1, 0) X(3, 1, 8, 32, 1, 1) X(4, 1, 6, 32, 1, 2)
-#define HB_MARCH2_LIST(X) X(0, 4, 1, 32, 2, 0) X(1, 4, 1, 32, 2, 2)
+#define HB_MARCH3_LIST(X) X(0, 1, 8, 64, 1, 16) X(1, 1, 8, 32, 1, 0) X(2, 1, 4, 32, 1, 0)
+#define HB_MARCH2_LIST(X) X(0, 4, 1, 32, 2, 0) X(1, 3, 1, 32, 2, 0)
 #else
+// Measured on B200, 512 x 512 x 128 Euler double RK4 stage (profiles/r01c_sweep_c4.txt): cfg 0 2.74 ms, cfg 1 2.80, cfg 4 2.74, cfg 5 3.46,
+// cfg 6 (three flux cores issued as one block) 4.13: longer operand live ranges cost more than the interleaving gains.
 #define HB_MARCH3_LIST(X) \
-	X(0, 1, 10, 32, 1, 0)   /* 32 x 10 columns, 13 warps */ \
-	X(1, 1, 8, 32, 1, 0)    /* 32 x 8 columns, 11 warps */ \
+	X(0, 1, 8, 64, 1, 16)   /* 32 x 8 columns, 64 planes per CTA, 11 warps, staggered slope phase */ \
+	X(1, 1, 8, 32, 1, 0)    /* 32 x 8 columns, 32 planes per CTA */ \
 	X(2, 1, 4, 32, 1, 0)    /* 32 x 4 columns, 7 warps: the fallback that fits 8-variable equations (MHD) in shared memory */ \
-	X(3, 1, 12, 32, 1, 0)   /* 32 x 12 columns, 15 warps (shared memory allows at most one staged RK operand) */ \
-	X(4, 1, 6, 32, 2, 0)    /* 32 x 6 columns, 9 warps, 2 CTAs / SM, <= 112 registers */ \
+	X(3, 1, 10, 32, 1, 0)   /* 32 x 10 columns, 13 warps (fits with at most two staged RK operands) */ \
+	X(4, 1, 8, 128, 1, 16)  /* 128 planes per CTA */ \
 	X(5, 1, 4, 32, 2, 0)    /* 32 x 4 columns, 7 warps, 2 CTAs / SM */ \
-	X(6, 1, 8, 32, 1, 1)    /* fused column warps: three flux cores interleaved */ \
-	X(7, 1, 8, 32, 1, 2)    /* fused column warps: z flux, then the x/y pair */ \
-	X(8, 1, 6, 32, 1, 1) X(9, 1, 6, 32, 1, 2) X(10, 1, 4, 32, 1, 1) X(11, 1, 8, 64, 1, 1) X(12, 1, 8, 64, 1, 0) X(13, 1, 10, 32, 1, 1) \
-	X(14, 1, 8, 64, 1, 2) X(15, 1, 10, 32, 1, 2) X(16, 1, 8, 32, 1, 3) X(17, 1, 8, 64, 1, 3) X(18, 1, 9, 32, 1, 0) X(19, 1, 9, 64, 1, 0) X(20, 1, 9, 64, 1, 3)
+	X(6, 1, 8, 32, 1, 1)    /* column warps issue their three flux cores as one block (kept for the record: slower) */
+// 2-D, 2048^2 stage: Euler cfg 0 0.266 ms, cfg 1 0.28; MHD cfg 0 0.730 ms (168 registers, spills), cfg 1 0.706 (254 registers, none)
 #define HB_MARCH2_LIST(X) \
-	X(0, 4, 1, 32, 2, 0)    /* 128 columns, 5 warps */ \
-	X(1, 2, 1, 32, 4, 0)    /* 64 columns, 3 warps */ \
-	X(2, 6, 1, 64, 1, 0)    /* 192 columns, 7 warps (TMA boxes are at most 256 elements wide) */ \
-	X(3, 4, 1, 32, 2, 2) X(4, 4, 1, 64, 2, 2) X(5, 2, 1, 32, 4, 2) X(6, 6, 1, 64, 1, 2) X(7, 4, 1, 64, 1, 2) \
-	X(8, 3, 1, 32, 2, 0) X(9, 2, 1, 32, 3, 0) X(10, 7, 1, 32, 1, 0) X(11, 5, 1, 32, 1, 0) X(12, 4, 1, 128, 2, 0)
+	X(0, 4, 1, 32, 2, 0)    /* 128 columns, 5 warps, 2 CTAs / SM */ \
+	X(1, 3, 1, 32, 2, 0)    /* 96 columns, 4 warps */ \
+	X(2, 2, 1, 32, 4, 0)    /* 64 columns, 3 warps */ \
+	X(3, 6, 1, 64, 1, 0)    /* 192 columns, 7 warps (TMA boxes are at most 256 elements wide) */
 #endif
+// per-equation default: the host starts at cfg 0; 2-D MHD prefers list entry 1
+constexpr int remapCfg(int dim, int cfg) { return (Eqn::eqnId == 1 && dim == 2 && cfg < 2) ? 1 - cfg : cfg; }
 
 constexpr size_t kSmemLimit = 232448 - 1024;   // 227 KB opt-in maximum per CTA minus the kernel's static shared memory (rounded up)
 
@@ -126,6 +127,7 @@ template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
 }
 bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[6]) {
 	if (!plm || flim || (lim != 8 && lim != 18) || dim < 2 || cfg < 0) return false;
+	cfg = remapCfg(dim, cfg);
 #define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<3, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) return false; }
 #undef HB_X
@@ -135,6 +137,7 @@ bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int i
 	return false;
 }
 cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, cudaStream_t st) {
+	cfg = remapCfg(dim, cfg);
 #define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, st);
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) }
 #undef HB_X

@@ -38,7 +38,8 @@ template<int WX_, int TY_, int KM_, int MINB_, int VAR_ = 0> struct MarchCfg {
 	// instruction-level parallelism of the column warps: 0 = the three interface fluxes of a cell one after the other;
 	// 1 = all of them issued as one straight-line block (the cores interleave: three independent dependent chains);
 	// 2 = marching-axis flux alone, then the x and y fluxes as a pair
-	static constexpr int VAR = VAR_;
+	static constexpr int VAR = VAR_ & 15;
+	static constexpr bool STAGGER = (VAR_ & 16) != 0;   // column warps w, w + 4 run the slope phase at opposite ends of the iteration
 };
 
 template<int DIM, class C, class real> struct MarchGeom {
@@ -231,6 +232,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 	mbarWait(&full[1], 0);
 
 	real dtCell = inf_of<real>::v(), rateCell = 0;
+	bool const earlySlopes = C::STAGGER && w < G::NREG && ((w >> 2) & 1);
 	// iteration `it` handles plane k = kb - 1 + it.  Plane p occupies ring slot (p - (kb-2)) % 4 on its ((p - (kb-2)) / 4)-th use.
 	// Plane k+3 is requested at the barrier of iteration k and first needed at the top of iteration k+2: a full iteration of lead.
 	for (int k = kb - 1, it = 0; k <= ke; ++k, ++it) {
@@ -239,16 +241,58 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 		bool const xy = k >= kb && k < ke;
 		real const* __restrict__ P = ring + sK * SLOT;
 		mbarWait(&full[sN], parN);
+		real Uk[nI];                                   // own cell of plane k (every role reads it at least once)
+		#pragma unroll
+		for (int q = 0; q < nI; ++q) Uk[q] = P[q * PS + ob];
+		// ---- half slopes of plane k+1 along x and y (plm.cl:56-76), published for the next iteration (other buffer half).
+		// Independent of the fluxes of plane k: the column warps that share an SM sub-partition with another column warp (w and w + 4)
+		// run it at opposite ends of the iteration, so that one warp's FP64-dense flux phase overlaps the other's shared-memory-bound
+		// phases instead of both competing for the FP64 pipe and then both leaving it idle.
+		auto slopesPhase = [&]() {
+			if (k + 1 >= kb && k + 1 < ke) {
+				real const* __restrict__ Q = ring + sN * SLOT;
+				real* const sgxN = SGX + ((k + 1) & 1) * (nI * G::SGXN);
+				real* const sgyN = SGY + ((k + 1) & 1) * (nI * G::SGYN);
+				// all loads first, then all stores: the compiler cannot move a shared-memory load above a shared-memory store, and
+				// a load -> slope -> store sequence per variable would pay the shared-memory latency nI times in a row
+				if (DIM == 3 && doSX && doSY) {
+					real sx[nI], sy[nI];
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) {
+						real const c = Q[q * PS + ob];
+						sx[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], c, Q[q * PS + ob + 1]);
+						sy[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], c, Q[q * PS + ob + BX]);
+					}
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) {
+						sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = sx[q];
+						sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = sy[q];
+					}
+				} else if (doSX) {
+					real sx[nI];
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) sx[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], Q[q * PS + ob], Q[q * PS + ob + 1]);
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = sx[q];
+				} else if (DIM == 3 && doSY) {
+					real sy[nI];
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) sy[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], Q[q * PS + ob], Q[q * PS + ob + BX]);
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = sy[q];
+				}
+			}
+		};
+		if (earlySlopes) slopesPhase();
 		// ---- column warps, fused form (MarchCfg::VAR >= 1): the fluxes at the low z, x and y faces of cell (ci, cj, k) are independent
 		// of each other, so their cores are issued as one straight-line block and the scheduler interleaves the dependent chains
 		// (MUFU seed -> Newton steps -> wave strengths).  Same operations per flux as the separate form below.
 		bool const fusedMain = C::VAR >= 1 && w < G::NREG;
 		if (C::VAR >= 1 && fusedMain) {
 			long long const idxK = colIdx + strideM * k;
-			real Fz[nI], UR[nI], zfN[nI], Uk[nI];
+			real Fz[nI], UR[nI], zfN[nI];
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) {
-				Uk[q] = P[q * PS + ob];
 				real const s = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Um[q], Uk[q], ring[sN * SLOT + q * PS + ob]);
 				UR[q] = Uk[q] - s;
 				zfN[q] = Uk[q] + s;
@@ -342,10 +386,9 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 		// ---- marching axis, registers only: slope of cell k, flux at interface k-1/2, finish cell k-1
 		if (doMain && !fusedMain) {
 			long long const idxK = colIdx + strideM * k;
-			real Fz[nI], UR[nI], zfN[nI], Uk[nI];
+			real Fz[nI], UR[nI], zfN[nI];
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) {
-				Uk[q] = P[q * PS + ob];
 				real const s = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Um[q], Uk[q], ring[sN * SLOT + q * PS + ob]);
 				UR[q] = Uk[q] - s;
 				zfN[q] = Uk[q] + s;
@@ -425,40 +468,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 				for (int q = 0; q < nI; ++q) fxy[(q * (TY + 1) + cj) * TX + ci] = F[q];
 			}
 		}
-		// ---- half slopes of plane k+1 along x and y (plm.cl:56-76), published for the next iteration (other buffer half)
-		if (k + 1 >= kb && k + 1 < ke) {
-			real const* __restrict__ Q = ring + sN * SLOT;
-			real* const sgxN = SGX + ((k + 1) & 1) * (nI * G::SGXN);
-			real* const sgyN = SGY + ((k + 1) & 1) * (nI * G::SGYN);
-			// all loads first, then all stores: the compiler cannot move a shared-memory load above a shared-memory store, and
-			// a load -> slope -> store sequence per variable would pay the shared-memory latency nI times in a row
-			if (DIM == 3 && doSX && doSY) {
-				real sx[nI], sy[nI];
-				#pragma unroll
-				for (int q = 0; q < nI; ++q) {
-					real const c = Q[q * PS + ob];
-					sx[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], c, Q[q * PS + ob + 1]);
-					sy[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], c, Q[q * PS + ob + BX]);
-				}
-				#pragma unroll
-				for (int q = 0; q < nI; ++q) {
-					sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = sx[q];
-					sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = sy[q];
-				}
-			} else if (doSX) {
-				real sx[nI];
-				#pragma unroll
-				for (int q = 0; q < nI; ++q) sx[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - 1], Q[q * PS + ob], Q[q * PS + ob + 1]);
-				#pragma unroll
-				for (int q = 0; q < nI; ++q) sgxN[(q * TY + cj) * (TX + 2) + ci + 1] = sx[q];
-			} else if (DIM == 3 && doSY) {
-				real sy[nI];
-				#pragma unroll
-				for (int q = 0; q < nI; ++q) sy[q] = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Q[q * PS + ob - BX], Q[q * PS + ob], Q[q * PS + ob + BX]);
-				#pragma unroll
-				for (int q = 0; q < nI; ++q) sgyN[(q * (TY + 2) + cj + 1) * TX + ci] = sy[q];
-			}
-		}
+		if (!earlySlopes) slopesPhase();
 		__syncthreads();           // the only barrier of the iteration: fluxes of plane k and slopes of plane k+1 are visible
 		if (tid == 0 && k + 3 <= ke + 1) {
 			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

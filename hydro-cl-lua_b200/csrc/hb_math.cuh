@@ -31,6 +31,63 @@ HB_HD float rsqrt_ieee(float x) { return sqrtf(x); }
 HB_HD double rabs(double x) { return fabs(x); }
 HB_HD float rabs(float x) { return fabsf(x); }
 
+// ---- branch-free reciprocal and (reciprocal) square root for arguments known to be positive and normal.
+// The compiler's IEEE 1/x and sqrt(x) carry a special-case slow path behind a branch per call; those branches cut the flux
+// routine into basic blocks and serialise its long dependent chains (MUFU seed -> Newton steps).  These forms are straight-line:
+// hardware seed (2^-22 relative) + two Newton steps, accurate to the last ulp or two (not correctly rounded).
+HB_HD double fastRcp(double x) {
+#if defined(__CUDA_ARCH__)
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	double e = fma(-x, r, 1.);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.);
+	return fma(r, e, r);
+#else
+	return 1. / x;
+#endif
+}
+HB_HD float fastRcp(float x) {
+#if defined(__CUDA_ARCH__)
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return fmaf(r, fmaf(-x, r, 1.f), r);
+#else
+	return 1.f / x;
+#endif
+}
+// y = 1/sqrt(x), s = sqrt(x) from one seed (coupled Newton iteration on g ~ sqrt(x), h ~ 1/(2 sqrt(x)))
+HB_HD void fastRsqrt(double x, double& y, double& s) {
+#if defined(__CUDA_ARCH__)
+	double y0;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(x));
+	double g = x * y0, h = .5 * y0;
+	double r = fma(-g, h, .5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	r = fma(-g, h, .5);
+	g = fma(g, r, g); h = fma(h, r, h);
+	s = g; y = h + h;
+#else
+	s = sqrt(x); y = 1. / s;
+#endif
+}
+HB_HD void fastRsqrt(float x, float& y, float& s) {
+#if defined(__CUDA_ARCH__)
+	float y0;
+	asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(x));
+	float g = x * y0, h = .5f * y0;
+	float r = fmaf(-g, h, .5f);
+	g = fmaf(g, r, g); h = fmaf(h, r, h);
+	s = g; y = h + h;
+#else
+	s = sqrtf(x); y = 1.f / s;
+#endif
+}
+
+// sqrt(x) for x >= 0 that may be exactly zero (s = 0 then; the reciprocal y is garbage there and the caller selects around it)
+HB_HD void fastRsqrt0(double x, double& y, double& s) { fastRsqrt(x > 1e-300 ? x : 1e-300, y, s); if (!(x > 1e-300)) s = x > 0. ? sqrt(x) : 0.; }
+HB_HD void fastRsqrt0(float x, float& y, float& s) { fastRsqrt(x > 1e-37f ? x : 1e-37f, y, s); if (!(x > 1e-37f)) s = x > 0.f ? sqrtf(x) : 0.f; }
+
 template<class real> HB_HD real lenSq3(real x, real y, real z) { return x * x + y * y + z * z; }
 // math.cl real3_dot: right-nested sum
 template<class real> HB_HD real dot3(real ax, real ay, real az, real bx, real by, real bz) {

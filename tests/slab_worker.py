@@ -18,8 +18,8 @@ def main():
     import hydrob200
     from importlib import import_module
     SlabComm = import_module("hydro-cl-lua_b200.hydro.solver.choppedup").SlabComm
-    from cases import CASES
-    cfg, _ = CASES[case]
+    from cases import ADM_CASES, CASES
+    cfg, _ = dict(CASES, **ADM_CASES)[case]
     if mode == "cpu":
         import oracle
         dist.init_process_group("gloo", rank=rank, world_size=world)
