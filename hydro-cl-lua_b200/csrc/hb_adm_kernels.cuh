@@ -64,20 +64,85 @@ adm_flux(GridP<typename Eqn::real> const g, typename Eqn::Params const ep, const
 	for (int q = 0; q < 6; ++q) { F[(1 + q) * sv] = Fd[q]; F[(7 + q) * sv] = FK[q]; }
 }
 
-// PART selects the integrated variables this launch produces: 0 = all but K_ij, 1 = K_ij only, 2 = all 37.
+// The same flux with the characteristic differences shared between neighbouring interfaces: a thread computes the eigensystem and
+// L (UR - UL) of ITS interface once and publishes the 13 differences in shared memory; the limiter of interface i reads those of
+// i-1 and i+1 from there instead of rebuilding two more eigensystems from two more cells (3 -> 1 eigensystems, 4 -> 2 left
+// transforms, 80 -> 40 loads per interface, ~half the registers).  The first and last thread along SIDE only publish.
+// Thread layout: SIDE 0: NB threads along x;  SIDE 1, 2: 32 threads along x (coalescing) x NB interfaces along SIDE.
+// Every published value is the same expression of the same cells as in adm_flux, so the strict build stays bit-identical.
+// V: 1 = 32 x 8 threads, 2 blocks / SM (128 registers); 2 = 32 x 8, 1 block / SM; 3 = 16 x 8 threads (a 128-byte line per row), 3 blocks / SM
+template<int SIDE, int V> struct AdmFluxGeom {
+	static constexpr int LX = SIDE == 0 ? 1 : (V == 3 ? 16 : 32);     // threads along x (sides 1, 2)
+	static constexpr int NB = SIDE == 0 ? 128 : 8;                     // interfaces along SIDE per block, two of them halo
+	static constexpr int NT = SIDE == 0 ? 128 : LX * NB;
+	static constexpr int STEP = SIDE == 0 ? 1 : LX;                    // thread distance of the neighbouring interface
+	static constexpr int MINB = SIDE == 0 ? 3 : (V == 1 ? 2 : (V == 2 ? 1 : 3));
+};
+template<class Eqn, int SIDE, int MODE, int V>
+__global__ void __launch_bounds__((AdmFluxGeom<SIDE, V>::NT), (AdmFluxGeom<SIDE, V>::MINB))
+adm_flux_shared(GridP<typename Eqn::real> const g, typename Eqn::Params const ep, const typename Eqn::real* __restrict__ U,
+	typename Eqn::real* __restrict__ Fb, const double* dtPtr, int fluxLimiter)
+{
+	typedef typename Eqn::real real;
+	typedef AdmFluxGeom<SIDE, V> G;
+	constexpr int nW = Eqn::nW;
+	__shared__ real sdU[nW][G::NT];
+	int const tid = threadIdx.x;
+	int const pos = SIDE == 0 ? tid : tid / G::LX;                               // position along SIDE inside the block
+	int const gy = g.dim >= 2 ? HB_G : 0, gz = g.dim >= 3 ? HB_G : 0;
+	int const c = HB_G - 1 + int(blockIdx.x) * (G::NB - 2) * (SIDE == 0) + int(blockIdx.y) * (G::NB - 2) * (SIDE != 0) + pos;   // interface = low face of cell c along SIDE
+	int i, j, k;
+	if (SIDE == 0) { i = c; j = int(blockIdx.y) + gy; k = int(blockIdx.z) + gz; }
+	else if (SIDE == 1) { i = HB_G + int(blockIdx.x) * G::LX + tid % G::LX; j = c; k = int(blockIdx.z) + gz; }
+	else { i = HB_G + int(blockIdx.x) * G::LX + tid % G::LX; j = int(blockIdx.z) + gy; k = c; }
+	bool const active = c <= HB_G + g.N[SIDE] + 1 && (SIDE == 0 || i < HB_G + g.N[0]);
+	long long const idx = i + g.strideY * j + g.strideZ * k;
+	long long const step = SIDE == 0 ? 1 : (SIDE == 1 ? g.strideY : g.strideZ);
+	long long const sv = g.strideV;
+	typename Eqn::Eig eig;
+	real fluxEig[nW], dUe[nW];
+	if (active) {
+		typename Eqn::Side UL, UR;
+		admLoadSide<Eqn, SIDE>(UL, U, idx - step, sv);
+		admLoadSide<Eqn, SIDE>(UR, U, idx, sv);
+		Eqn::template interfaceEig<SIDE>(eig, ep, UL, UR);
+		Eqn::template charAvg<SIDE>(fluxEig, eig, UL, UR);
+		Eqn::template charDiff<SIDE>(dUe, eig, UL, UR);
+		#pragma unroll
+		for (int w = 0; w < nW; ++w) sdU[w][tid] = dUe[w];
+	}
+	__syncthreads();
+	if (!active || pos == 0 || pos == G::NB - 1 || c > HB_G + g.N[SIDE]) return;
+	real dUeL[nW], dUeR[nW];
+	#pragma unroll
+	for (int w = 0; w < nW; ++w) { dUeL[w] = sdU[w][tid - G::STEP]; dUeR[w] = sdU[w][tid + G::STEP]; }
+	real Fa, Fd[6], FK[6];
+	real const dt_dx = real(*dtPtr) / g.dx[SIDE];
+	Eqn::template limitedFlux<SIDE>(Fa, Fd, FK, eig, fluxEig, dUe, dUeL, dUeR, fluxLimiter, true, dt_dx);
+	real* F = Fb + (long long)SIDE * 13 * sv + idx;
+	F[0] = Fa;
+	#pragma unroll
+	for (int q = 0; q < 6; ++q) { F[(1 + q) * sv] = Fd[q]; F[(7 + q) * sv] = FK[q]; }
+}
+
+// PART selects the integrated variables this launch produces (see inPart below); 2 = all 37 in one launch.
 // The source of K_ij (adm3d.cl:1589-2776) needs the raised forms of all 18 d_kij at once (~75 live doubles); together with the
 // other 31 derivatives and the RK combination of 37 variables one thread spills ~1 KB and the spill traffic evicts the state from L1:
 // measured 2.0 ms per 128^3 launch against 0.27 ms for a 13-wave flux kernel.  Split in two launches every thread computes only
 // what its part stores -- the arithmetic per stored value is the same expression sequence (the unused branches of the fully
 // unrolled, compile-time indexed code are dead and dropped by the compiler), so the strict build stays bit-identical to the oracle.
 template<class Eqn, int MODE, int PART>
-__global__ void __launch_bounds__(128, PART == 0 ? 3 : 1)
+__global__ void __launch_bounds__(128, PART == 0 ? 3 : (PART == 3 ? 4 : 1))
 adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep,
 	const typename Eqn::real* __restrict__ Fb)
 {
 	typedef typename Eqn::real real;
 	constexpr int nI = Eqn::nI;
-	auto inPart = [](int q) { return PART == 2 || (PART == 1) == (q >= Eqn::iK && q < Eqn::iK + 6); };
+	// PART 0: alpha, gamma_ll, a_l, V_l (13); PART 1: K_ll (6); PART 3: d_lll (18, a pure streaming update); PART 2: all 37
+	auto inPart = [](int q) {
+		bool const isK = q >= Eqn::iK && q < Eqn::iK + 6, isD = q >= Eqn::iD && q < Eqn::iK;
+		return PART == 2 || (PART == 1 && isK) || (PART == 3 && isD) || (PART == 0 && !isK && !isD);
+	};
 	__shared__ double redBuf[32];
 	long long const nInt = (long long)g.N[0] * g.N[1] * g.N[2];
 	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -159,10 +224,10 @@ adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const s
 			}
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) if (inPart(q)) sp.Uout[idx + q * sv] = deriv[q];
-			if (PART != 1 && sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);   // reads alpha, gamma_ll only
+			if (PART != 1 && PART != 3 && sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);   // reads alpha, gamma_ll only
 		}
 	}
-	if (PART != 1 && sp.dtMinBits) {
+	if (PART != 1 && PART != 3 && sp.dtMinBits) {
 		double v = double(dtCell);
 		#pragma unroll
 		for (int o = 16; o > 0; o >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }

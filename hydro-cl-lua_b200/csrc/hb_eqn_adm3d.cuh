@@ -144,42 +144,32 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 		swap6<SIDE>(dOut, d); swap6<SIDE>(KOut, K);
 	}
 
-	// Roe flux with flux limiter (hydro/flux/roe.cl:17-163, roeUseFluxFromCons == false, useFluxLimiter == true) of the 13-wave system
-	// at the interface between UL and UR; U2L, U2R are the next cells outwards.  F = (a_side, d_side,ij, K_ij) components.
-	template<int SIDE> static HB_HD void roeFluxLimited(real& Fa, real* Fd, real* FK, Params const& s, int fluxLimiter, bool useLimiter, real dt_dx,
-		Side const& U2L, Side const& UL, Side const& UR, Side const& U2R)
-	{
-		Eig eig;
+	// ---- the Roe flux with flux limiter (hydro/flux/roe.cl:17-163, roeUseFluxFromCons == false) of the 13-wave system, in two pieces so
+	// that a kernel can share the characteristic differences of an interface with the two interfaces next to it:
+	//   interfaceChar  eig = eigen_forInterface(UL, UR); base = L (UL + UR)/2; dUe = L (UR - UL)           (roe.cl:40-72)
+	//   limitedFlux    per wave: base_j lambda_j - .5 lambda_j dUe_j (sgn + phi(r_j)(lambda_j dt/dx - sgn)),
+	//                  r_j = dUe_j of the upwind neighbour interface / dUe_j; then F = R (...)                 (roe.cl:73-163)
+	template<int SIDE> static HB_HD void interfaceEig(Eig& eig, Params const& s, Side const& UL, Side const& UR) {
 		if constexpr (FAST) eigen_forInterfaceFast<SIDE>(eig, s, UL, UR); else eigen_forInterface(eig, s, UL, UR);
+	}
+	template<int SIDE> static HB_HD void charAvg(real (&base)[nW], Eig const& eig, Side const& UL, Side const& UR) {
+		real dA[6], KA[6];
+		#pragma unroll
+		for (int k = 0; k < 6; ++k) { dA[k] = real(.5) * (UL.d[k] + UR.d[k]); KA[k] = real(.5) * (UL.K[k] + UR.K[k]); }
+		leftTransform<SIDE>(base, eig, real(.5) * (UL.a + UR.a), dA, KA);
+	}
+	template<int SIDE> static HB_HD void charDiff(real (&dUe)[nW], Eig const& eig, Side const& UL, Side const& UR) {
+		real dd[6], dK[6];
+		#pragma unroll
+		for (int k = 0; k < 6; ++k) { dd[k] = UR.d[k] - UL.d[k]; dK[k] = UR.K[k] - UL.K[k]; }
+		leftTransform<SIDE>(dUe, eig, UR.a - UL.a, dd, dK);
+	}
+	// fluxEig: in = L (UL + UR)/2, out = the limited characteristic flux
+	template<int SIDE> static HB_HD void limitedFlux(real& Fa, real* Fd, real* FK, Eig const& eig, real (&fluxEig)[nW], real const (&dUe)[nW],
+		real const (&dUeL)[nW], real const (&dUeR)[nW], int fluxLimiter, bool useLimiter, real dt_dx)
+	{
 		real lam[nW];
 		waves<SIDE>(lam, eig);
-		real fluxEig[nW];
-		{
-			real dA[6], KA[6];
-			#pragma unroll
-			for (int k = 0; k < 6; ++k) { dA[k] = real(.5) * (UL.d[k] + UR.d[k]); KA[k] = real(.5) * (UL.K[k] + UR.K[k]); }
-			leftTransform<SIDE>(fluxEig, eig, real(.5) * (UL.a + UR.a), dA, KA);
-		}
-		real dUe[nW], dUeL[nW], dUeR[nW];
-		{
-			real dd[6], dK[6];
-			#pragma unroll
-			for (int k = 0; k < 6; ++k) { dd[k] = UR.d[k] - UL.d[k]; dK[k] = UR.K[k] - UL.K[k]; }
-			leftTransform<SIDE>(dUe, eig, UR.a - UL.a, dd, dK);
-		}
-		if (useLimiter) {
-			Eig eL;
-			if constexpr (FAST) eigen_forInterfaceFast<SIDE>(eL, s, U2L, UL); else eigen_forInterface(eL, s, U2L, UL);
-			real dd[6], dK[6];
-			#pragma unroll
-			for (int k = 0; k < 6; ++k) { dd[k] = UL.d[k] - U2L.d[k]; dK[k] = UL.K[k] - U2L.K[k]; }
-			leftTransform<SIDE>(dUeL, eL, UL.a - U2L.a, dd, dK);
-			Eig eR;
-			if constexpr (FAST) eigen_forInterfaceFast<SIDE>(eR, s, UR, U2R); else eigen_forInterface(eR, s, UR, U2R);
-			#pragma unroll
-			for (int k = 0; k < 6; ++k) { dd[k] = U2R.d[k] - UR.d[k]; dK[k] = U2R.K[k] - UR.K[k]; }
-			leftTransform<SIDE>(dUeR, eR, U2R.a - UR.a, dd, dK);
-		}
 		#pragma unroll
 		for (int j = 0; j < nW; ++j) {
 			real const lambda = lam[j];
@@ -204,6 +194,25 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 			}
 		}
 		rightTransform<SIDE>(Fa, Fd, FK, eig, fluxEig);
+	}
+	// one interface on its own (every characteristic difference computed here): U2L, U2R are the next cells outwards
+	template<int SIDE> static HB_HD void roeFluxLimited(real& Fa, real* Fd, real* FK, Params const& s, int fluxLimiter, bool useLimiter, real dt_dx,
+		Side const& U2L, Side const& UL, Side const& UR, Side const& U2R)
+	{
+		Eig eig;
+		interfaceEig<SIDE>(eig, s, UL, UR);
+		real fluxEig[nW], dUe[nW], dUeL[nW], dUeR[nW];
+		charAvg<SIDE>(fluxEig, eig, UL, UR);
+		charDiff<SIDE>(dUe, eig, UL, UR);
+		if (useLimiter) {
+			Eig eL;
+			interfaceEig<SIDE>(eL, s, U2L, UL);
+			charDiff<SIDE>(dUeL, eL, U2L, UL);
+			Eig eR;
+			interfaceEig<SIDE>(eR, s, UR, U2R);
+			charDiff<SIDE>(dUeR, eR, UR, U2R);
+		}
+		limitedFlux<SIDE>(Fa, Fd, FK, eig, fluxEig, dUe, dUeL, dUeR, fluxLimiter, useLimiter, dt_dx);
 	}
 
 	// U: the cell's 37 integrated variables; rho, Sll: matter terms (zero in the configs)

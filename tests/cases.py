@@ -56,6 +56,9 @@ ADM_CASES = {
                               boundary=_PER, eqnArgs=dict(f_eqn="1")), 10),
     "C5_warp_bubble_rk4": (dict(eqn="adm3d", dim=3, gridSize=[14, 12, 10], initCond="Alcubierre warp bubble",
                                 fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1), 10),
+    "C5_gauge_wave_slab": (dict(eqn="adm3d", dim=3, gridSize=[12, 8, 8], mins=[-.5] * 3, maxs=[.5] * 3,
+                                initCond="testbed - gauge wave", fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1,
+                                boundary=_PER), 5),
     "C5_gauge_wave_donor_fe_2d": (dict(eqn="adm3d", dim=2, gridSize=[24, 10], mins=[-.5] * 3, maxs=[.5] * 3,
                                        initCond="testbed - gauge wave", fluxLimiter="donor cell", integrator="forward Euler",
                                        cfl=.1, boundary=dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic")), 8),

@@ -68,7 +68,7 @@ def test_cpu_gloo_two_ranks_equal_single(hydrob200, oracle, tmp_path, case):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,mode", [("C4_sphere_rk4", "gpu_strict"), ("C2_kh_rk4tvd_minmod", "gpu"), ("C3_ot_rk3tvd", "gpu"),
-                                       ("C4_sphere_rk4_mirror_periodic", "gpu"), ("C5_gauge_wave_rk4", "gpu"),
+                                       ("C4_sphere_rk4_mirror_periodic", "gpu"), ("C5_gauge_wave_slab", "gpu"),
                                        ("C5_warp_bubble_rk4", "gpu_strict")])
 def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
     import torch
