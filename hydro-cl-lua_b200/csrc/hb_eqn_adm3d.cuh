@@ -326,7 +326,7 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 				}
 			}
 			return dt;
-		}
+		} else {
 		#pragma unroll
 		for (int side = 0; side < 3; ++side) {
 			if (side < dim && dx[side] > 0) {
@@ -347,6 +347,7 @@ template<class real_, bool FAST_ = false> struct ADM3D {
 			}
 		}
 		return dt;
+		}
 	}
 	static HB_HD void constrainU(Params const&, real (&)[nI]) {}
 	static HB_HD bool mirrorFlips(int, int) { return false; }   // mirror boundaries are rejected for this equation at hb_fv_create
