@@ -47,41 +47,9 @@ cudaError_t launchFlux(GridP<real> const& g, StageP<real> const& sp, Eqn::Params
 
 // plm / flim are ignored: the equation runs the Roe flux on cell-centred states with the flux limiter given in sp (the reference's
 // configuration for this equation; hb_fv_create rejects usePLM).  Needs sp.scratch = 3 x 13 x strideV reals.
-template<int SIDE, int V>
-cudaError_t launchFluxDiff(GridP<real> const& g, StageP<real> const& sp, Eqn::Params const& ep, cudaStream_t st) {
-	typedef AdmDiffGeom<SIDE, V> G;
-	int const nOut = G::NB - 3;
-	dim3 grid;
-	if (SIDE == 0) grid = dim3((unsigned)((g.N[0] + nOut - 1) / nOut), (unsigned)g.N[1], (unsigned)g.N[2]);
-	else if (SIDE == 1) grid = dim3((unsigned)((g.N[0] + G::LX - 1) / G::LX), (unsigned)((g.N[1] + nOut - 1) / nOut), (unsigned)g.N[2]);
-	else grid = dim3((unsigned)((g.N[0] + G::LX - 1) / G::LX), (unsigned)((g.N[2] + nOut - 1) / nOut), (unsigned)g.N[1]);
-	adm_flux_diff<Eqn, SIDE, MODE, V><<<grid, G::NT, 0, st>>>(g, sp, ep);
-	return cudaGetLastError();
-}
-template<int V>
-cudaError_t stageFused(GridP<real> const& g, StageP<real> const& sp, Eqn::Params const& ep, cudaStream_t st) {
-	cudaError_t e = launchFluxDiff<0, V>(g, sp, ep, st);
-	if (e == cudaSuccess) e = launchFluxDiff<1, V>(g, sp, ep, st);
-	if (e == cudaSuccess) e = launchFluxDiff<2, V>(g, sp, ep, st);
-	if (e != cudaSuccess) return e;
-	long long const n = (long long)g.N[0] * g.N[1] * g.N[2];
-	int const nt = 128;
-	adm_update<Eqn, MODE, 0, true><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
-	adm_update<Eqn, MODE, 1, true><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
-	return cudaGetLastError();
-}
-
 cudaError_t stage(int dim, bool, bool, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st) {
 	Eqn::Params const ep = Eqn::makeParams(eqnParams);
 	cudaError_t e = cudaSuccess;
-	// fused form: the flux kernels form the flux differences and finish d_kij (adm_flux_diff); HB_ADM_FUSED = 0 | 1 | 2 | 3 (geometry)
-	static int const fused = getenv("HB_ADM_FUSED") ? atoi(getenv("HB_ADM_FUSED")) : 1;
-	if (fused && dim == 3 && sp.computeL && sp.scratch && sp.fluxLimiter > 0 && g.volOn && g.fluxOn[0] && g.fluxOn[1] && g.fluxOn[2]
-		&& ep.a_conv == 0 && ep.d_conv == 0) {
-		if (fused == 2) return stageFused<2>(g, sp, ep, st);
-		if (fused == 3) return stageFused<3>(g, sp, ep, st);
-		return stageFused<1>(g, sp, ep, st);
-	}
 	if (sp.computeL) {
 		if (!sp.scratch) return cudaErrorInvalidValue;
 		e = launchFlux<0>(g, sp, ep, st);
@@ -92,26 +60,41 @@ cudaError_t stage(int dim, bool, bool, GridP<real> const& g, StageP<real> const&
 	long long const n = (long long)g.N[0] * g.N[1] * g.N[2];
 	int const nt = 128;
 	static int const split = getenv("HB_ADM_SPLIT") ? atoi(getenv("HB_ADM_SPLIT")) : 1;
-	if (split) {
-		adm_update<Eqn, MODE, 0><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
-		adm_update<Eqn, MODE, 1><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
-		adm_update<Eqn, MODE, 3><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
+	unsigned const nb = (unsigned)((n + nt - 1) / nt);
+	if (split == 2) {
+		adm_update<Eqn, MODE, 0><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 7><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 1><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 3><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+	} else if (split) {
+		adm_update<Eqn, MODE, 0><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 7><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 1><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 4><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 5><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
+		adm_update<Eqn, MODE, 6><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);
 	} else {
 		adm_update<Eqn, MODE, 2><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, sp, ep, sp.scratch);
 	}
 	return cudaGetLastError();
 }
 bool marchInfo(int, bool, bool, int, int, int*, int*) { return false; }
-cudaError_t march(int, int, int, const CUtensorMap*, int, GridP<real> const&, StageP<real> const&, const double*, cudaStream_t) { return cudaErrorInvalidValue; }
+cudaError_t march(int, int, int, const CUtensorMap*, int, GridP<real> const&, StageP<real> const&, const double*, int, cudaStream_t) { return cudaErrorInvalidValue; }
 
-cudaError_t ghosts(GridP<real> const& g, BcP const& bc, real* U, int nVars, cudaStream_t st) {
+cudaError_t ghosts(GridP<real> const& g, BcP const& bc, real* U, int nVars, int rimAxis, bool planesOnly, cudaStream_t st) {
 	long long const S0 = g.S[0], S1 = g.S[1], S2 = g.S[2];
+	int const nt = 256;
+	if (rimAxis >= 0 && planesOnly) {
+		long long const n = 2LL * HB_G * S0 * (rimAxis == 2 ? S1 : 1);
+		fill_ghosts_planes<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars, rimAxis);
+		return cudaGetLastError();
+	}
 	int const gy = g.dim >= 2 ? HB_G : 0, gz = g.dim >= 3 ? HB_G : 0;
 	long long const n = 2LL * gz * S0 * S1 + 2LL * gy * S0 * (S2 - 2 * gz) + 2LL * HB_G * (S1 - 2 * gy) * (S2 - 2 * gz);
-	int const nt = 256;
-	fill_ghosts<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars);
+	fill_ghosts<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars, rimAxis);
 	return cudaGetLastError();
 }
+
 cudaError_t calcDT(GridP<real> const& g, const double* ep, const real* U, unsigned long long* dtMinBits, cudaStream_t st) {
 	long long const n = (long long)g.N[0] * g.N[1] * g.N[2];
 	int const nt = 128;

@@ -125,126 +125,27 @@ adm_flux_shared(GridP<typename Eqn::real> const g, typename Eqn::Params const ep
 	for (int q = 0; q < 6; ++q) { F[(1 + q) * sv] = Fd[q]; F[(7 + q) * sv] = FK[q]; }
 }
 
-// adm_flux_diff: adm_flux_shared carried one step further.  The thread of interface c (the low face of cell c) also fetches the
-// flux of interface c+1 from its neighbour through shared memory and forms the cell's flux difference F_{c+1} A/V - F_c A/V
-// (hydro/solver/fvsolver.cl:97-123) on the spot:
-//   * d_side,ij (6 variables): their whole update needs nothing else -- the source is -alpha a_side K_ij (adm3d.cl:1589-2776, the
-//     d_lll lines), all of it in the thread's registers already -- so the RK combination is done here and the new d_side,ij stored;
-//   * a_side and K_ij: the difference (7 values) goes to the scratch array in place of the flux; adm_update<PART, DIFF> reads one
-//     value where it read two fluxes.
-// Per cell and stage this removes 18 scratch stores, 57 scratch loads, the d_kij launch and its 28 state loads.  Each difference is
-// the same expression of the same fluxes as in adm_update, so the strict build stays bit-identical to the oracle.
-// Needs: dim == 3, flux limiter on, volume / area guards open, a_convCoeff == d_convCoeff == 0 (hb_adm_inst.cu falls back otherwise).
-template<int SIDE, int V> struct AdmDiffGeom {
-	static constexpr int LX = SIDE == 0 ? 1 : (V == 1 ? 16 : (V == 2 ? 8 : 16));
-	static constexpr int NB = SIDE == 0 ? 128 : (V == 3 ? 8 : 16);     // interfaces along SIDE per block; NB - 3 cells are finished
-	static constexpr int NT = SIDE == 0 ? 128 : LX * NB;
-	static constexpr int STEP = SIDE == 0 ? 1 : LX;
-	static constexpr int MINB = NT == 256 ? 1 : 2;
-};
-template<class Eqn, int SIDE, int MODE, int V>
-__global__ void __launch_bounds__((AdmDiffGeom<SIDE, V>::NT), (AdmDiffGeom<SIDE, V>::MINB))
-adm_flux_diff(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep)
-{
-	typedef typename Eqn::real real;
-	typedef AdmDiffGeom<SIDE, V> G;
-	constexpr int nW = Eqn::nW;
-	__shared__ real sh[nW][G::NT];
-	int const tid = threadIdx.x;
-	int const pos = SIDE == 0 ? tid : tid / G::LX;
-	int const blk = SIDE == 0 ? int(blockIdx.x) : int(blockIdx.y);
-	int const c = HB_G - 1 + blk * (G::NB - 3) + pos;
-	int i, j, k;
-	if (SIDE == 0) { i = c; j = int(blockIdx.y) + HB_G; k = int(blockIdx.z) + HB_G; }
-	else if (SIDE == 1) { i = HB_G + int(blockIdx.x) * G::LX + tid % G::LX; j = c; k = int(blockIdx.z) + HB_G; }
-	else { i = HB_G + int(blockIdx.x) * G::LX + tid % G::LX; j = int(blockIdx.z) + HB_G; k = c; }
-	bool const inX = SIDE == 0 || i < HB_G + g.N[0];
-	bool const active = inX && c <= HB_G + g.N[SIDE] + 1;                                          // publishes dUe
-	bool const hasFlux = inX && pos >= 1 && pos <= G::NB - 2 && c <= HB_G + g.N[SIDE];            // computes the flux at its face
-	bool const hasCell = inX && pos >= 1 && pos <= G::NB - 3 && c <= HB_G + g.N[SIDE] - 1;        // finishes cell c
-	long long const idx = i + g.strideY * j + g.strideZ * k;
-	long long const step = SIDE == 0 ? 1 : (SIDE == 1 ? g.strideY : g.strideZ);
-	long long const sv = g.strideV;
-	const real* __restrict__ U = sp.Uin;
-	typename Eqn::Eig eig;
-	real fluxEig[nW], dUe[nW];
-	real alphaC = 0, aC = 0, KC[6], dC[6];                // of cell c (= the interface's right state)
-	if (active) {
-		typename Eqn::Side UL, UR;
-		admLoadSide<Eqn, SIDE>(UL, U, idx - step, sv);
-		admLoadSide<Eqn, SIDE>(UR, U, idx, sv);
-		Eqn::template interfaceEig<SIDE>(eig, ep, UL, UR);
-		Eqn::template charAvg<SIDE>(fluxEig, eig, UL, UR);
-		Eqn::template charDiff<SIDE>(dUe, eig, UL, UR);
-		#pragma unroll
-		for (int w = 0; w < nW; ++w) sh[w][tid] = dUe[w];
-		alphaC = UR.alpha; aC = UR.a;
-		#pragma unroll
-		for (int q = 0; q < 6; ++q) { KC[q] = UR.K[q]; dC[q] = UR.d[q]; }
-	}
-	__syncthreads();
-	real F[nW];
-	#pragma unroll
-	for (int w = 0; w < nW; ++w) F[w] = 0;
-	if (hasFlux) {
-		real dUeL[nW], dUeR[nW];
-		#pragma unroll
-		for (int w = 0; w < nW; ++w) { dUeL[w] = sh[w][tid - G::STEP]; dUeR[w] = sh[w][tid + G::STEP]; }
-		real const dt_dx = real(*sp.dt) / g.dx[SIDE];
-		Eqn::template limitedFlux<SIDE>(F[0], F + 1, F + 7, eig, fluxEig, dUe, dUeL, dUeR, sp.fluxLimiter, true, dt_dx);
-	}
-	__syncthreads();                                       // every dUe has been read: the buffer now carries the fluxes
-	#pragma unroll
-	for (int w = 0; w < nW; ++w) sh[w][tid] = F[w];
-	__syncthreads();
-	if (!hasCell) return;
-	real const aov = g.aov[SIDE];
-	real* __restrict__ D = sp.scratch + (long long)SIDE * 13 * sv + idx;
-	// a_side and K_ij: flux difference -> scratch (read by adm_update<.., DIFF = true>)
-	D[0] = sh[0][tid + G::STEP] * aov - F[0] * aov;
-	#pragma unroll
-	for (int q = 0; q < 6; ++q) D[(7 + q) * sv] = sh[7 + q][tid + G::STEP] * aov - F[7 + q] * aov;
-	// d_side,ij: calcDerivFromFlux + addSource + RK combination (the same statements as adm_update)
-	double const dt = *sp.dt;
-	#pragma unroll
-	for (int q = 0; q < 6; ++q) {
-		int const v = Eqn::iD + 6 * SIDE + q;
-		real deriv = 0;
-		deriv = deriv - (sh[1 + q][tid + G::STEP] * aov - F[1 + q] * aov);
-		deriv += -alphaC * aC * KC[q];
-		if (sp.Lout) sp.Lout[idx + v * sv] = deriv;
-		if (sp.Uout) {
-			real r = 0;
-			#pragma unroll
-			for (int a = 0; a < HB_MAX_TERMS; ++a)
-				if (a < sp.nA) r = r + (((sp.aOwnMask >> a) & 1) ? dC[q] : sp.aPtr[a][idx + v * sv]) * real(sp.aCoef[a]);
-			#pragma unroll
-			for (int b = 0; b < HB_MAX_TERMS; ++b)
-				if (b < sp.nB) r = r + sp.bPtr[b][idx + v * sv] * real(sp.bCoef[b] * dt);
-			if (sp.computeL) r = r + deriv * real(sp.betaSelf * dt);
-			sp.Uout[idx + v * sv] = r;
-		}
-	}
-}
-
 // PART selects the integrated variables this launch produces (see inPart below); 2 = all 37 in one launch.
 // The source of K_ij (adm3d.cl:1589-2776) needs the raised forms of all 18 d_kij at once (~75 live doubles); together with the
 // other 31 derivatives and the RK combination of 37 variables one thread spills ~1 KB and the spill traffic evicts the state from L1:
 // measured 2.0 ms per 128^3 launch against 0.27 ms for a 13-wave flux kernel.  Split in two launches every thread computes only
 // what its part stores -- the arithmetic per stored value is the same expression sequence (the unused branches of the fully
 // unrolled, compile-time indexed code are dead and dropped by the compiler), so the strict build stays bit-identical to the oracle.
-// DIFF: the scratch array carries the cell's flux differences of a_side and K_ij (written by adm_flux_diff) instead of fluxes
-template<class Eqn, int MODE, int PART, bool DIFF = false>
-__global__ void __launch_bounds__(128, PART == 0 ? 3 : (PART == 3 ? 4 : 1))
+template<class Eqn, int MODE, int PART>
+__global__ void __launch_bounds__(128, PART == 0 ? 3 : (PART == 3 ? 4 : (PART >= 4 && PART <= 6 ? 8 : (PART == 7 ? 4 : (PART == 1 ? 3 : 1)))))
 adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep,
 	const typename Eqn::real* __restrict__ Fb)
 {
 	typedef typename Eqn::real real;
 	constexpr int nI = Eqn::nI;
-	// PART 0: alpha, gamma_ll, a_l, V_l (13); PART 1: K_ll (6); PART 3: d_lll (18, a pure streaming update); PART 2: all 37
+	// PART 0: a_l, V_l (6); 1: K_ll (6); 7: alpha, gamma_ll (7, + the CFL minimum, which reads exactly these); 4, 5, 6: d_xij, d_yij, d_zij
+	// (6 each); 3: all d_lll (18); 2: all 37.
+	// The streaming parts (gamma_ll: -2 alpha K_ij; d_kij: flux difference - alpha a_k K_ij) are launched 6 variables at a time so that
+	// they run at <= 64 registers: a memory-bound kernel needs occupancy, not a wide thread.
 	auto inPart = [](int q) {
-		bool const isK = q >= Eqn::iK && q < Eqn::iK + 6, isD = q >= Eqn::iD && q < Eqn::iK;
-		return PART == 2 || (PART == 1 && isK) || (PART == 3 && isD) || (PART == 0 && !isK && !isD);
+		bool const isK = q >= Eqn::iK && q < Eqn::iK + 6, isD = q >= Eqn::iD && q < Eqn::iK, isG = q == Eqn::iAlpha || (q >= Eqn::iGamma && q < Eqn::iGamma + 6);
+		if (PART >= 4 && PART <= 6) return q >= Eqn::iD + 6 * (PART - 4) && q < Eqn::iD + 6 * (PART - 3);
+		return PART == 2 || (PART == 1 && isK) || (PART == 3 && isD) || (PART == 7 && isG) || (PART == 0 && !isK && !isD && !isG);
 	};
 	__shared__ double redBuf[32];
 	long long const nInt = (long long)g.N[0] * g.N[1] * g.N[2];
@@ -270,17 +171,11 @@ adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const s
 						real const aov = g.aov[side];
 						real const* FL = Fb + (long long)side * 13 * sv + idx;
 						real const* FR = FL + step;
-						if constexpr (DIFF) {
-							deriv[Eqn::iA + side] = deriv[Eqn::iA + side] - FL[0];
-							#pragma unroll
-							for (int q = 0; q < 6; ++q) deriv[Eqn::iK + q] = deriv[Eqn::iK + q] - FL[(7 + q) * sv];
-						} else {
 						deriv[Eqn::iA + side] = deriv[Eqn::iA + side] - (FR[0] * aov - FL[0] * aov);
 						#pragma unroll
 						for (int q = 0; q < 6; ++q) {
 							deriv[Eqn::iD + 6 * side + q] = deriv[Eqn::iD + 6 * side + q] - (FR[(1 + q) * sv] * aov - FL[(1 + q) * sv] * aov);
 							deriv[Eqn::iK + q] = deriv[Eqn::iK + q] - (FR[(7 + q) * sv] * aov - FL[(7 + q) * sv] * aov);
-						}
 						}
 					}
 				}
@@ -333,10 +228,10 @@ adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const s
 			}
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) if (inPart(q)) sp.Uout[idx + q * sv] = deriv[q];
-			if (PART != 1 && PART != 3 && sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);   // reads alpha, gamma_ll only
+			if ((PART == 7 || PART == 2) && sp.dtMinBits) dtCell = Eqn::calcDTCell(ep, deriv, g.dx, g.dim);   // reads alpha, gamma_ll only
 		}
 	}
-	if (PART != 1 && PART != 3 && sp.dtMinBits) {
+	if ((PART == 7 || PART == 2) && sp.dtMinBits) {
 		double v = double(dtCell);
 		#pragma unroll
 		for (int o = 16; o > 0; o >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, o); v = u < v ? u : v; }

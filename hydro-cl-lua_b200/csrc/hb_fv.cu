@@ -210,6 +210,11 @@ template<class real> struct Fv : FvBase {
 	Nccl::comm_t comm = nullptr;
 	int nranks = 1, rank = 0;
 	int axis;
+	// overlapped exchange (marching kernel, >= 3 chunks along the decomposed axis): the chunks next to the slab faces run first,
+	// their ghost planes travel on commStream while the chunks in between are computed on the solver's stream
+	cudaStream_t commStream = nullptr;
+	cudaEvent_t evRim = nullptr, evXchg = nullptr;
+	bool overlap = false;
 
 	Fv(hb_ctx* c, const hb_fv_desc& desc, const FvOps<real>* o) : ctx(c), d(desc), ops(o) {
 		nS = o->nS; nI = o->nI; nW = o->nW;
@@ -229,6 +234,9 @@ template<class real> struct Fv : FvBase {
 		if (ctl) cudaFree(ctl);
 		if (dtMinBits) cudaFree(dtMinBits);
 		if (comm) Nccl::get().CommDestroy(comm);
+		if (evRim) cudaEventDestroy(evRim);
+		if (evXchg) cudaEventDestroy(evXchg);
+		if (commStream) cudaStreamDestroy(commStream);
 		ctxRelease(ctx);
 	}
 	cudaStream_t st() const { return ctx->stream; }
@@ -387,8 +395,9 @@ template<class real> struct Fv : FvBase {
 	}
 
 	// ghost planes of the decomposed axis: 2 planes x (everything faster) are contiguous per variable
-	int exchange(real* U, int nVars) {
+	int exchange(real* U, int nVars, cudaStream_t xs = nullptr) {
 		if (!comm) return HB_OK;
+		if (!xs) xs = st();
 		Nccl& N = Nccl::get();
 		long long const strideA = axis == 0 ? 1 : (axis == 1 ? grid.strideY : grid.strideZ);
 		size_t const chunk = (size_t)(HB_G * strideA);
@@ -404,13 +413,13 @@ template<class real> struct Fv : FvBase {
 		HB_NCCL(N.GroupStart());
 		for (int q = 0; q < nVars; ++q) {
 			real* base = U + (size_t)q * grid.strideV;
-			if (lo >= 0) HB_NCCL(N.Send(base + (size_t)HB_G * strideA, chunk, dtype, lo, comm, st()));
-			if (hi >= 0) HB_NCCL(N.Send(base + (size_t)(S - 2 * HB_G) * strideA, chunk, dtype, hi, comm, st()));
+			if (lo >= 0) HB_NCCL(N.Send(base + (size_t)HB_G * strideA, chunk, dtype, lo, comm, xs));
+			if (hi >= 0) HB_NCCL(N.Send(base + (size_t)(S - 2 * HB_G) * strideA, chunk, dtype, hi, comm, xs));
 		}
 		for (int q = 0; q < nVars; ++q) {
 			real* base = U + (size_t)q * grid.strideV;
-			if (hi >= 0) HB_NCCL(N.Recv(base + (size_t)(S - HB_G) * strideA, chunk, dtype, hi, comm, st()));
-			if (lo >= 0) HB_NCCL(N.Recv(base, chunk, dtype, lo, comm, st()));
+			if (hi >= 0) HB_NCCL(N.Recv(base + (size_t)(S - HB_G) * strideA, chunk, dtype, hi, comm, xs));
+			if (lo >= 0) HB_NCCL(N.Recv(base, chunk, dtype, lo, comm, xs));
 		}
 		HB_NCCL(N.GroupEnd());
 		return HB_OK;
@@ -423,7 +432,7 @@ template<class real> struct Fv : FvBase {
 	}
 
 	int fillGhosts(real* U, int nVars) {
-		HB_CUDA(ops->ghosts(grid, bc, U, nVars, st()));
+		HB_CUDA(ops->ghosts(grid, bc, U, nVars, -1, false, st()));
 		launches++;
 		return exchange(U, nVars);
 	}
@@ -512,7 +521,22 @@ template<class real> struct Fv : FvBase {
 				e0 = profEvents[profUsed].first; e1 = profEvents[profUsed].second; profUsed++;
 				HB_CUDA(cudaEventRecord(e0, st()));
 			}
-			if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, st()));
+			if (useMarch && overlap) {
+				int const nv = rk ? nI : nS;
+				HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 1, st()));
+				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, true, st()));
+				HB_CUDA(cudaEventRecord(evRim, st()));
+				HB_CUDA(cudaStreamWaitEvent(commStream, evRim, 0));
+				if (int r = exchange(upool[s.uOut], nv, commStream)) return r;
+				HB_CUDA(cudaEventRecord(evXchg, commStream));
+				HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 2, st()));
+				if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
+				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, false, st()));
+				HB_CUDA(cudaStreamWaitEvent(st(), evXchg, 0));
+				launches += 4;
+				continue;
+			}
+			if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 0, st()));
 			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches++;
@@ -607,7 +631,7 @@ template<class real> struct Fv : FvBase {
 		sp.computeL = 1; sp.dt = ctl + 1;
 		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch;
 		bool const plm = d.use_plm != 0;
-		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, st()));
+		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
 		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
 		launches++;
 		HB_CUDA(cudaMemcpyAsync(ctl + 1, &saved[1], sizeof(double), cudaMemcpyHostToDevice, st()));
@@ -629,7 +653,7 @@ template<class real> struct Fv : FvBase {
 		o << "kernel=" << (useMarch ? "fv_march(tma)" : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
 		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
-		  << " Ubufs=" << nU << " Lbufs=" << nL << "\n";
+		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : "")) << "\n";
 		int words = 0;
 		for (size_t i = 0; i < plan.size(); ++i) {
 			auto& s = plan[i];
@@ -685,6 +709,15 @@ template<class real> struct Fv : FvBase {
 		bool const periodic = d.bc[2 * axis] == HB_BC_PERIODIC && d.bc[2 * axis + 1] == HB_BC_PERIODIC;
 		if (rank > 0 || periodic) bc.bc[2 * axis] = HB_BC_NONE;
 		if (rank < nr - 1 || periodic) bc.bc[2 * axis + 1] = HB_BC_NONE;
+		// overlap needs chunks that are neither first nor last along the decomposed (= marching) axis; HB_OVERLAP=0 switches it off
+		const char* ov = getenv("HB_OVERLAP");
+		int const km = marchInfoV[2] > 0 ? marchInfoV[2] : 1;
+		overlap = useMarch && (!ov || atoi(ov) != 0) && (grid.N[axis] + km - 1) / km >= 3;
+		if (overlap) {
+			HB_CUDA(cudaStreamCreateWithFlags(&commStream, cudaStreamNonBlocking));
+			HB_CUDA(cudaEventCreateWithFlags(&evRim, cudaEventDisableTiming));
+			HB_CUDA(cudaEventCreateWithFlags(&evXchg, cudaEventDisableTiming));
+		}
 		invalidateGraph();
 		dtValid = false;
 		return HB_OK;

@@ -93,7 +93,7 @@ constexpr int remapCfg(int dim, int cfg) { return (Eqn::eqnId == 1 && dim == 2 &
 constexpr size_t kSmemLimit = 232448 - 1024;   // 227 KB opt-in maximum per CTA minus the kernel's static shared memory (rounded up)
 
 template<int DIM, int LIM, class C>
-cudaError_t launchMarch(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st) {
+cudaError_t launchMarch(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
 	typedef MarchGeom<DIM, C, real> G;
 	auto kern = fv_march<Eqn, DIM, LIM, C, MODE>;
 	int nOps = sp.nB;
@@ -109,14 +109,17 @@ cudaError_t launchMarch(const CUtensorMap* tmap, int padX, GridP<real> const& g,
 	if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
 	long long const ntx = (g.N[0] + G::TX - 1) / G::TX;
 	long long const nty = DIM == 3 ? (g.N[1] + G::TY - 1) / G::TY : 1;
-	long long const nm = (g.N[DIM - 1] + C::KM - 1) / C::KM;
-	kern<<<(unsigned)(ntx * nty * nm), G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX);
+	long long nm = (g.N[DIM - 1] + C::KM - 1) / C::KM;
+	if (chunkSel == 1) nm = nm < 2 ? nm : 2;
+	else if (chunkSel == 2) nm = nm > 2 ? nm - 2 : 0;
+	if (nm == 0) return cudaSuccess;
+	kern<<<(unsigned)(ntx * nty * nm), G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX, chunkSel);
 	return cudaGetLastError();
 }
 template<int DIM, class C>
-cudaError_t launchMarchLim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, cudaStream_t st) {
-	if (lim == 8) return launchMarch<DIM, 8, C>(tmap, padX, g, sp, ep, st);      // minmod
-	if (lim == 18) return launchMarch<DIM, 18, C>(tmap, padX, g, sp, ep, st);    // superbee
+cudaError_t launchMarchLim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
+	if (lim == 8) return launchMarch<DIM, 8, C>(tmap, padX, g, sp, ep, chunkSel, st);      // minmod
+	if (lim == 18) return launchMarch<DIM, 18, C>(tmap, padX, g, sp, ep, chunkSel, st);    // superbee
 	return cudaErrorInvalidValue;
 }
 template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
@@ -136,12 +139,12 @@ bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int i
 #undef HB_X
 	return false;
 }
-cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, cudaStream_t st) {
+cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
 	cfg = remapCfg(dim, cfg);
-#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, st);
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) }
 #undef HB_X
-#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<2, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, st);
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<2, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
 	else if (dim == 2) { HB_MARCH2_LIST(HB_X) }
 #undef HB_X
 	return cudaErrorInvalidValue;
@@ -159,12 +162,17 @@ void tileInfo(int dim, bool plm, bool, int out[5]) {
 	else tileInfoDim<3>(plm, out);
 }
 
-cudaError_t ghosts(GridP<real> const& g, BcP const& bc, real* U, int nVars, cudaStream_t st) {
+cudaError_t ghosts(GridP<real> const& g, BcP const& bc, real* U, int nVars, int rimAxis, bool planesOnly, cudaStream_t st) {
 	long long const S0 = g.S[0], S1 = g.S[1], S2 = g.S[2];
+	int const nt = 256;
+	if (rimAxis >= 0 && planesOnly) {
+		long long const n = 2LL * HB_G * S0 * (rimAxis == 2 ? S1 : 1);
+		fill_ghosts_planes<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars, rimAxis);
+		return cudaGetLastError();
+	}
 	int const gy = g.dim >= 2 ? HB_G : 0, gz = g.dim >= 3 ? HB_G : 0;
 	long long const n = 2LL * gz * S0 * S1 + 2LL * gy * S0 * (S2 - 2 * gz) + 2LL * HB_G * (S1 - 2 * gy) * (S2 - 2 * gz);
-	int const nt = 256;
-	fill_ghosts<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars);
+	fill_ghosts<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars, rimAxis);
 	return cudaGetLastError();
 }
 

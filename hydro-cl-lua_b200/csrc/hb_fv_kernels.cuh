@@ -323,7 +323,7 @@ HB_HD int ghostSource(int j, int S, int bcMin, int bcMax, bool& flip, bool& skip
 
 // Enumerates the ghost cells: z slabs (whole planes), then y slabs of the remaining planes, then x slabs.
 template<class Eqn, int MODE>
-__global__ void fill_ghosts(GridP<typename Eqn::real> const g, BcP const bc, typename Eqn::real* __restrict__ U, int nVars)
+__global__ void fill_ghosts(GridP<typename Eqn::real> const g, BcP const bc, typename Eqn::real* __restrict__ U, int nVars, int skipRimAxis)
 {
 	typedef typename Eqn::real real;
 	long long const S0 = g.S[0], S1 = g.S[1], S2 = g.S[2];
@@ -354,6 +354,11 @@ __global__ void fill_ghosts(GridP<typename Eqn::real> const g, BcP const bc, typ
 	int const sj = g.dim >= 2 ? ghostSource(j, g.S[1], bc.bc[2], bc.bc[3], fy, sy) : j;
 	int const sk = g.dim >= 3 ? ghostSource(k, g.S[2], bc.bc[4], bc.bc[5], fz, sz) : k;
 	if (sx || sy || sz) return;
+	if (skipRimAxis >= 0) {
+		// overlapped slab exchange: the ghost cells of the planes that are sent to the neighbours were filled by fill_ghosts_planes
+		int const c = skipRimAxis == 1 ? j : k, S = g.S[skipRimAxis];
+		if ((c >= HB_G && c < 2 * HB_G) || (c >= S - 2 * HB_G && c < S - HB_G)) return;
+	}
 	long long const dst = i + g.strideY * j + g.strideZ * k;
 	long long const src = si + g.strideY * sj + g.strideZ * sk;
 	for (int q = 0; q < nVars; ++q) {
@@ -361,6 +366,33 @@ __global__ void fill_ghosts(GridP<typename Eqn::real> const g, BcP const bc, typ
 		if (fx && Eqn::mirrorFlips(q, 0)) v = real(-1.) * v;
 		if (fy && Eqn::mirrorFlips(q, 1)) v = real(-1.) * v;
 		if (fz && Eqn::mirrorFlips(q, 2)) v = real(-1.) * v;
+		U[dst + q * g.strideV] = v;
+	}
+}
+
+// The ghost cells (along the axes other than `axis`) of the 2 x numGhost planes next to the slab faces along `axis`: the planes the
+// slab exchange sends.  Same source map as fill_ghosts; one thread per cell of those planes.
+template<class Eqn, int MODE>
+__global__ void fill_ghosts_planes(GridP<typename Eqn::real> const g, BcP const bc, typename Eqn::real* __restrict__ U, int nVars, int axis)
+{
+	typedef typename Eqn::real real;
+	long long const S0 = g.S[0], Sm = axis == 2 ? g.S[1] : 1;          // extent of a plane: S0 x S1 (axis z) or S0 (axis y)
+	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (w >= 2LL * HB_G * S0 * Sm) return;
+	int const i = int(w % S0), m = int((w / S0) % Sm), pp = int(w / (S0 * Sm));
+	int const S = g.S[axis];
+	int const c = pp < HB_G ? HB_G + pp : S - 2 * HB_G + (pp - HB_G);
+	int const j = axis == 2 ? m : c, k = axis == 2 ? c : 0;
+	bool fx = false, fy = false, fz = false, sx = false, sy = false, sz = false;
+	int const si = ghostSource(i, g.S[0], bc.bc[0], bc.bc[1], fx, sx);
+	int const sj = (g.dim >= 2 && axis != 1) ? ghostSource(j, g.S[1], bc.bc[2], bc.bc[3], fy, sy) : j;
+	if (sx || sy || sz || (si == i && sj == j)) return;
+	long long const dst = i + g.strideY * j + g.strideZ * k;
+	long long const src = si + g.strideY * sj + g.strideZ * k;
+	for (int q = 0; q < nVars; ++q) {
+		real v = U[src + q * g.strideV];
+		if (fx && Eqn::mirrorFlips(q, 0)) v = real(-1.) * v;
+		if (fy && Eqn::mirrorFlips(q, 1)) v = real(-1.) * v;
 		U[dst + q * g.strideV] = v;
 	}
 }

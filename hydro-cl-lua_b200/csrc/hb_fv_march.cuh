@@ -152,7 +152,7 @@ HB_D void stageEpilogue(GridP<typename Eqn::real> const& g, StageP<typename Eqn:
 template<class Eqn, int DIM, int LIM, class C, int MODE>
 __global__ void __launch_bounds__((MarchGeom<DIM, C, typename Eqn::real>::NT), C::MINB)
 fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp,
-	typename Eqn::Params const ep, int const padX)
+	typename Eqn::Params const ep, int const padX, int const chunkSel)
 {
 	typedef typename Eqn::real real;
 	typedef MarchGeom<DIM, C, real> G;
@@ -180,7 +180,11 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 	int const nty = DIM == 3 ? (g.N[1] + TY - 1) / TY : 1;
 	int bid = blockIdx.x;
 	int const bx = bid % ntx; bid /= ntx;
-	int const by = bid % nty; int const bm = bid / nty;
+	int const by = bid % nty; int bm = bid / nty;
+	// chunkSel (overlapped slab exchange, hb_fv.cu): 0 = every chunk of KM planes; 1 = the first and the last chunk (whose planes are
+	// sent to the neighbours); 2 = the chunks in between
+	if (chunkSel == 1) { if (bm != 0) bm = (g.N[MS] + C::KM - 1) / C::KM - 1; }
+	else if (chunkSel == 2) bm += 1;
 	int const i0 = bx * TX + HB_G;
 	int const j0 = DIM == 3 ? by * TY + HB_G : 0;
 	int const kb = bm * C::KM + HB_G;

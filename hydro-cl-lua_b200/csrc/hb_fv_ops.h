@@ -17,9 +17,12 @@ template<class real> struct FvOps {
 	// info = {TX, TY, planes per CTA, threads, dynamic smem bytes without staged RK operands, column threads}.
 	// cfg selects a tile configuration (0 = default).
 	bool (*marchInfo)(int dim, bool plm, bool flim, int slopeLimiter, int cfg, int box[4], int info[6]);
+	// chunkSel: 0 all chunks along the marching axis, 1 first + last chunk, 2 the chunks in between (overlapped slab exchange)
 	cudaError_t (*march)(int dim, int slopeLimiter, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp,
-		const double* eqnParams, cudaStream_t st);
-	cudaError_t (*ghosts)(GridP<real> const& g, BcP const& bc, real* U, int nVars, cudaStream_t st);
+		const double* eqnParams, int chunkSel, cudaStream_t st);
+	// rimAxis < 0: every ghost cell.  rimAxis = 1 | 2 with planesOnly: only the ghost cells of the planes the slab exchange sends;
+	// with !planesOnly: every ghost cell but those.
+	cudaError_t (*ghosts)(GridP<real> const& g, BcP const& bc, real* U, int nVars, int rimAxis, bool planesOnly, cudaStream_t st);
 	cudaError_t (*calcDT)(GridP<real> const& g, const double* eqnParams, const real* U, unsigned long long* dtMinBits, cudaStream_t st);
 	cudaError_t (*constrainAll)(GridP<real> const& g, const double* eqnParams, real* U, cudaStream_t st);
 	void (*tileInfo)(int dim, bool plm, bool flim, int out[5]);   // TX, TY, TZ, NT, dynamic smem bytes

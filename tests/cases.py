@@ -65,3 +65,14 @@ ADM_CASES = {
 }
 
 FLOAT_CASES = ["C2_kh_rk4tvd_minmod", "C4_sphere_rk4", "C3_ot_rk3tvd", "C1_sod_fe_superbee"]
+
+# slabs with >= 3 marching chunks per rank (KM = 64 planes in 3-D, 32 rows in 2-D): the overlapped exchange path of hb_fv.cu
+CASES["slab_march3d_overlap"] = (dict(eqn="euler", dim=3, gridSize=[34, 10, 264], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                      usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 3)
+CASES["slab_march3d_overlap_periodic"] = (dict(eqn="mhd", dim=3, gridSize=[33, 6, 264], mins=[-2, -2, -2], maxs=[2, 2, 2],
+                                               initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="superbee",
+                                               integrator="Runge-Kutta 3, TVD", cfl=.1,
+                                               boundary=dict(xmin="periodic", xmax="periodic", ymin="mirror", ymax="mirror",
+                                                             zmin="periodic", zmax="periodic")), 3)
+CASES["slab_march2d_overlap"] = (dict(eqn="euler", dim=2, gridSize=[40, 140], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                                      slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 4)

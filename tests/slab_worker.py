@@ -43,6 +43,9 @@ def main():
         S = hydrob200.FiniteVolumeSolver(dict(cfg, comm=comm, device=rank % torch.cuda.device_count(),
                                               strict_fp=(mode == "gpu_strict"), use_graph=False))
         S.update(nsteps)
+        if rank == 0:
+            with open(out + ".describe", "w") as f:
+                f.write(S.backend.describe())
         # the gather below runs on the host through a second, gloo group
     if mode != "cpu":
         g = dist.new_group(backend="gloo")

@@ -69,14 +69,19 @@ def test_cpu_gloo_two_ranks_equal_single(hydrob200, oracle, tmp_path, case):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,mode", [("C4_sphere_rk4", "gpu_strict"), ("C2_kh_rk4tvd_minmod", "gpu"), ("C3_ot_rk3tvd", "gpu"),
                                        ("C4_sphere_rk4_mirror_periodic", "gpu"), ("C5_gauge_wave_slab", "gpu"),
-                                       ("C5_warp_bubble_rk4", "gpu_strict")])
+                                       ("C5_warp_bubble_rk4", "gpu_strict"), ("slab_march3d_overlap", "gpu_strict"),
+                                       ("slab_march3d_overlap", "gpu"), ("slab_march3d_overlap_periodic", "gpu"),
+                                       ("slab_march2d_overlap", "gpu_strict")])
 def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
     out = str(tmp_path / "dec")
-    launch(mode, case, 5, out)
+    n = 3 if "overlap" in case else 5
+    launch(mode, case, n, out)
     got = np.load(out + ".npy")
-    ref, tref = single(hydrob200, case, 5, strict_fp=(mode == "gpu_strict"), use_graph=False)
+    if "overlap" in case:
+        assert "exchange=overlapped" in open(out + ".describe").read()
+    ref, tref = single(hydrob200, case, n, strict_fp=(mode == "gpu_strict"), use_graph=False)
     assert np.load(out + ".t.npy")[0] == tref
     assert np.array_equal(got, ref)
