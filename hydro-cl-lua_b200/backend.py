@@ -66,6 +66,7 @@ def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None, stag
     d.use_plm = 1 if solver.usePLM else 0
     d.slope_limiter = solver.slopeLimiter
     d.flux_limiter = solver.fluxLimiter
+    d.flux = solver.flux.fluxId
     for i, b in enumerate(solver.boundaryIdList()):
         d.bc[i] = b
     d.rk_order = solver.rkOrder

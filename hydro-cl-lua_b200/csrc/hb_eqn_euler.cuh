@@ -173,6 +173,18 @@ template<class real_, bool FAST_ = false> struct Euler {
 		consFromPrim(U, s, W);
 	}
 
+	// eqn.lua:1134-1146 consWaveCodeMinMax with euler.lua:329-336: Cs from the cons state (euler.cl:98-112), v_n = 0 below rhoMin
+	template<int SIDE> static HB_HD void consWaveMinMax(real& lmin, real& lmax, Params const& s, real const (&U)[nI]) {
+		real Cs;
+		real const P = calc_P(s, U);
+		if (P <= s.PMin) Cs = real(0.);
+		else if (U[0] < s.rhoMin) Cs = inf_of<real>::v();
+		else Cs = rsqrt_ieee(s.gamma * P / U[0]);
+		Cs *= real(1.);
+		real const v_n = U[0] < s.rhoMin ? real(0.) : U[1 + SIDE] / U[0];
+		lmin = v_n - Cs; lmax = v_n + Cs;
+	}
+
 	// euler.cl:98-112 calc_Cs_fromCons; calcDT.cl:38-73
 	static HB_HD real calcDTCell(Params const& s, real const (&U)[nI], real const (&dx)[3], int dim) {
 		real Cs;

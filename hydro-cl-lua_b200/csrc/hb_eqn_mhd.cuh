@@ -387,6 +387,12 @@ template<class real_, bool FAST_ = false> struct MHD {
 		lmax = v_n + Cf;
 	}
 
+	// mhd.lua:377-387 consWaveCodeMinMax -> calcCellMinMaxEigenvalues
+	template<int SIDE> static HB_HD void consWaveMinMax(real& lmin, real& lmax, Params const& s, real const (&U)[nI]) {
+		Prim W; primFromCons(W, s, U);
+		cellMinMaxEigenvalues<SIDE>(lmin, lmax, s, W);
+	}
+
 	static HB_HD real calcDTCell(Params const& s, real const (&U)[nI], real const (&dx)[3], int dim) {
 		real dt = inf_of<real>::v();
 		Prim W; primFromCons(W, s, U);

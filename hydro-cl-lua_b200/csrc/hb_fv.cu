@@ -327,7 +327,7 @@ template<class real> struct Fv : FvBase {
 				if (n > maxOps) maxOps = n;
 			}
 			bool ok = false;
-			if (d.stage_kernel != 1) {
+			if (d.stage_kernel != 1 && d.flux == HB_FLUX_ROE) {   // the marching kernel is built for the Roe flux
 				for (int pass = 0; pass < 2 && !ok; ++pass)
 					for (int cfg = pass == 0 ? cfg0 : 0; !ok && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
 						size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
@@ -488,6 +488,7 @@ template<class real> struct Fv : FvBase {
 		sp.slopeLimiter = d.slope_limiter;
 		sp.fluxLimiter = d.flux_limiter;
 		sp.scratch = opsScratch;
+		sp.flux = d.flux;
 	}
 
 	// integrator:integrate(dt, calcDeriv) + boundary/constrainU after every stage (rk.lua:91-165, fe.lua:33-49)
@@ -629,7 +630,7 @@ template<class real> struct Fv : FvBase {
 		memset(&sp, 0, sizeof(sp));
 		sp.Uin = upool[0]; sp.Uout = nullptr; sp.Lout = scratchL;
 		sp.computeL = 1; sp.dt = ctl + 1;
-		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch;
+		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux;
 		bool const plm = d.use_plm != 0;
 		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
 		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
@@ -749,6 +750,9 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (d->use_plm < 0 || d->use_plm > 1) return setError(HB_ERR_INVALID, "hb_fv_create: only usePLM none / 'plm cons' are built");
 	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");
 	if (d->use_plm && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM requires fluxLimiter 'donor cell' (gridsolver.lua:119)");
+	if (d->flux < 0 || d->flux > HB_FLUX_RUSANOV) return setError(HB_ERR_INVALID, "hb_fv_create: unknown flux");
+	if (d->flux != HB_FLUX_ROE && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: only the Roe flux uses a flux limiter (hydro/flux/roe.lua:5-19)");
+	if (d->flux != HB_FLUX_ROE && d->eqn == HB_EQN_ADM3D) return setError(HB_ERR_INVALID, "hb_fv_create: hll / rusanov are built for euler and mhd");
 	if (d->eqn == HB_EQN_ADM3D) {
 		if (d->use_plm) return setError(HB_ERR_INVALID, "hb_fv_create: adm3d runs the Roe flux with a flux limiter on cell-centred states; usePLM is not built for it");
 		for (int k = 0; k < 2 * d->dim; ++k) if (d->bc[k] == HB_BC_MIRROR) return setError(HB_ERR_INVALID, "hb_fv_create: mirror boundaries are not built for adm3d");

@@ -56,6 +56,7 @@ template<class real> struct StageP {
 	unsigned long long* dtMinBits;   // optional: fused calcDT, min over interior cells as ordered bits of a double
 	int slopeLimiter, fluxLimiter;
 	real* scratch;         // optional per-solver device scratch (FvOps::scratchElems), e.g. the ADM flux arrays
+	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov (tile kernel; the marching kernel is built for roe)
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {
@@ -155,7 +156,7 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 					UL[q] = u[-step]; UR[q] = u[0];
 				}
 			}
-			roeFlux<Eqn, SIDE>(F, ep, UL, UR);
+			interfaceFlux<Eqn, SIDE>(sp.flux, F, ep, UL, UR);
 		}
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) FX[q * G::FXN + f * PF + p] = F[q];

@@ -64,6 +64,73 @@ HB_HD void roeFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const&
 	}
 }
 
+// HLL flux, hydro/flux/hll.cl:5-74 with hllCalcWaveMethod = 'Davis direct bounded' (hydro/flux/hll.lua:10):
+//   sL = min(lambdaMin(UL), lambdaMin(interface)), sR = max(lambdaMax(UR), lambdaMax(interface)); interface speeds from the Roe-averaged
+//   eigensystem (eqn.lua:1108-1120), cell speeds from the cons state (eqn.lua:1134-1146).
+template<class Eqn, int SIDE>
+HB_HD void hllFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI, nW = Eqn::nW;
+	typename Eqn::Eig eigInt;
+	Eqn::template eigen_forInterface<SIDE>(eigInt, s, UL, UR);
+	real lam[nW];
+	Eqn::template waves<SIDE>(lam, s, eigInt);
+	real const lambdaIntMin = lam[0], lambdaIntMax = lam[nW - 1];
+	real lambdaLMin, lambdaRMax, unused;
+	Eqn::template consWaveMinMax<SIDE>(lambdaLMin, unused, s, UL);
+	Eqn::template consWaveMinMax<SIDE>(unused, lambdaRMax, s, UR);
+	real const sL = rmin<real>(lambdaLMin, lambdaIntMin);
+	real const sR = rmax<real>(lambdaRMax, lambdaIntMax);
+	for (int j = 0; j < nI; ++j) F[j] = 0;
+	if (0 <= sL) {
+		Eqn::template fluxFromCons<SIDE>(F, s, UL);
+	} else if (sR <= 0) {
+		Eqn::template fluxFromCons<SIDE>(F, s, UR);
+	} else if (sL <= 0 && 0 <= sR) {
+		real FL[nI], FR[nI];
+		Eqn::template fluxFromCons<SIDE>(FL, s, UL);
+		Eqn::template fluxFromCons<SIDE>(FR, s, UR);
+		for (int j = 0; j < nI; ++j) F[j] = (sR * FL[j] - sL * FR[j] + sL * sR * (UR[j] - UL[j])) / (sR - sL);
+	}
+}
+
+// Rusanov flux, hydro/flux/rusanov.cl:4-33.  The reference's loop over {L, R} assigns lambdaMax in each pass, so the wave speed of the
+// RIGHT state is the one that enters the flux; reproduced.
+template<class Eqn, int SIDE>
+HB_HD void rusanovFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI;
+	real lambdaMax;
+	{
+		real lmin, lmax;
+		Eqn::template consWaveMinMax<SIDE>(lmin, lmax, s, UL);
+		lambdaMax = rmax<real>(rabs(lmin), rabs(lmax));
+	}
+	{
+		real lmin, lmax;
+		Eqn::template consWaveMinMax<SIDE>(lmin, lmax, s, UR);
+		lambdaMax = rmax<real>(rabs(lmin), rabs(lmax));
+	}
+	real FL[nI], FR[nI];
+	Eqn::template fluxFromCons<SIDE>(FL, s, UL);
+	Eqn::template fluxFromCons<SIDE>(FR, s, UR);
+	for (int j = 0; j < nI; ++j) F[j] = real(.5) * (FL[j] + FR[j] - lambdaMax * (UR[j] - UL[j]));
+}
+
+// the solver's flux plug-in (hydro/flux/*.lua), selected at run time in the tile kernel: 0 roe, 1 hll, 2 rusanov
+template<class Eqn, int SIDE>
+HB_HD void interfaceFlux(int flux, typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	if (flux == 1) hllFlux<Eqn, SIDE>(F, s, UL, UR);
+	else if (flux == 2) rusanovFlux<Eqn, SIDE>(F, s, UL, UR);
+	else roeFlux<Eqn, SIDE>(F, s, UL, UR);
+}
+
 // Roe flux with flux limiter phi (no PLM): needs the two neighbouring interfaces' states
 // (U2L,UL) and (UR,U2R)  (fvsolver.lua:138-155 -> roe.cl:73-80,113-134).
 template<class Eqn, int SIDE>

@@ -26,4 +26,23 @@ class Roe(Flux):
             raise NotImplementedError("Harten entropy fix (roe.cl:100-106) is off in every BASELINE config")
 
 
-fluxes = {"roe": Roe}
+class HLL(Flux):
+    """hydro/flux/hll.lua:5-12: name 'hll', hllCalcWaveMethod = 'Davis direct bounded' (the reference's live setting)."""
+    name = "hll"
+    fluxId = 1
+    hllCalcWaveMethod = "Davis direct bounded"
+
+    def __init__(self, solver, args=None):
+        super().__init__(solver, args)
+        m = self.args.get("hllCalcWaveMethod", self.hllCalcWaveMethod)
+        if m != self.hllCalcWaveMethod:
+            raise NotImplementedError("hllCalcWaveMethod %r: only 'Davis direct bounded' (hll.lua:10) is built" % (m,))
+
+
+class Rusanov(Flux):
+    """hydro/flux/rusanov.lua: name 'rusanov' (local Lax-Friedrichs with the cell wave speeds)."""
+    name = "rusanov"
+    fluxId = 2
+
+
+fluxes = {"roe": Roe, "hll": HLL, "rusanov": Rusanov}

@@ -20,7 +20,7 @@ class FiniteVolumeSolver(GridSolver):
 
     def createFlux(self, fluxName, fluxArgs=None):
         if fluxName not in fluxes:
-            raise NotImplementedError("flux %r is a 'next' row (SURVEY 8f2); only 'roe' is built" % (fluxName,))
+            raise NotImplementedError("flux %r is not built (SURVEY 8f2: 'roe', 'hll', 'rusanov' are)" % (fluxName,))
         self.flux = fluxes[fluxName](self, fluxArgs)
 
     def createBackend(self, args):

@@ -97,6 +97,9 @@ int hb_reduce(hb_ctx* ctx, hb_buf* buf, size_t count, int op, double* host_out);
 #define HB_EQN_MHD 1          /* hydro/eqn/mhd.lua:   eqn_params = { heatCapacityRatio, mu0 / unit_kg_m_per_C2 } */
 #define HB_EQN_ADM3D 2        /* hydro/eqn/adm3d.lua (noZeroRowsInFlux, useShift 'none'): eqn_params = { f_eqn option index
                                * (hydro/eqn/einstein.lua:42-48, 0-based), a_convCoeff, d_convCoeff, V_convCoeff } */
+#define HB_FLUX_ROE 0         /* hydro/flux/roe.cl:17-163 (usesFluxLimiter) */
+#define HB_FLUX_HLL 1         /* hydro/flux/hll.cl:5-74, hllCalcWaveMethod 'Davis direct bounded' (hll.lua:10); Euler and MHD */
+#define HB_FLUX_RUSANOV 2     /* hydro/flux/rusanov.cl:4-33; Euler and MHD */
 #define HB_BC_PERIODIC 0      /* hydro/solver/gridsolver.lua:638-651 */
 #define HB_BC_MIRROR 1        /* :654-744 */
 #define HB_BC_FREEFLOW 2      /* :766-780 */
@@ -122,6 +125,7 @@ typedef struct hb_fv_desc {
 	int strict_fp;            /* 1: kernels built with -fmad=false (no FMA contraction); 0: production kernels */
 	int use_graph;            /* 1: replay each update() as a captured CUDA graph */
 	int stage_kernel;         /* 0: auto; 1: tile kernel (fv_stage); 2: plane-marching TMA kernel (fv_march), error if not built for the config */
+	int flux;                 /* HB_FLUX_*: the solver's flux plug-in (hydro/flux/*.lua; solver.flux = 'roe' | 'hll' | 'rusanov') */
 } hb_fv_desc;
 
 size_t hb_sizeof_fv_desc(void);                              /* sizeof(hb_fv_desc), for bindings that mirror the struct */

@@ -53,6 +53,7 @@ struct ho_desc {
 	int nthreads;       // OpenMP threads (0 = default)
 	int global_n[3];    // 0 = same as n; otherwise the whole grid's interior size (this object is one slab of it): defines grid_dx
 	double eqn_params[16];   // eqn 2 (ADM3D): f_eqn option index, a_convCoeff, d_convCoeff, V_convCoeff (adm3d.lua:207-227)
+	int flux;           // 0 = roe (hydro/flux/roe.cl), 1 = hll 'Davis direct bounded' (hydro/flux/hll.cl, hll.lua:10), 2 = rusanov (hydro/flux/rusanov.cl)
 };
 }
 
@@ -154,6 +155,7 @@ template<class real_> struct Euler {
 	typedef solver_t<real> S;
 	enum { numStates = 6, numIntStates = 5, numWaves = 5 };   // euler.lua:13-14,166-171
 	static const bool roeUseFluxFromCons = true;               // eqn.lua:46
+	static const bool hasWaveMinMax = true;                    // hll / rusanov fluxes restated for this equation
 	static constexpr bool hasSource = false;                   // cartesian: no addSource kernel work
 	union cons_t { struct { real rho; real3 m; real ETotal; real ePot; }; real ptr[6]; };
 	struct prim_t { real rho; real3 v; real P; real ePot; };
@@ -316,6 +318,18 @@ template<class real_> struct Euler {
 		lambda[1] = v_n; lambda[2] = v_n; lambda[3] = v_n;
 		lambda[4] = v_n + Cs_nLen;
 	}
+	// eqn.lua:1108-1120 eigenWaveCodeMinMax with euler.lua:309-325: first and last wave of the interface eigensystem
+	static void eigenWaveMinMax(real& lmin, real& lmax, S const& s, eigen_t const& e, normal_t n) {
+		real lambda[5]; eigenWaves(lambda, s, e, n);
+		lmin = lambda[0]; lmax = lambda[4];
+	}
+	// eqn.lua:1134-1146 consWaveCodeMinMax with euler.lua:329-336 (consWaveCodePrefix): Cs from the cons state, v_n = 0 below rhoMin
+	static void consWaveMinMax(real& lmin, real& lmax, S const& s, cons_t const& U, normal_t n) {
+		real Cs_nLen = calc_Cs_fromCons(s, U);
+		Cs_nLen *= real(1.);
+		real const v_n = U.rho < s.rhoMin ? real(0.) : U.m.s(n.side) / U.rho;
+		lmin = v_n - Cs_nLen; lmax = v_n + Cs_nLen;
+	}
 	// euler.cl:698-717
 	static void constrainU(S const& s, cons_t& U) {
 		if (U.rho < s.rhoMin) U.rho = s.rhoMin;
@@ -350,6 +364,7 @@ template<class real_> struct MHD {
 	typedef solver_t<real> S;
 	enum { numStates = 10, numIntStates = 8, numWaves = 7 };   // mhd.lua:16-17,76-83
 	static const bool roeUseFluxFromCons = true;                // mhd.lua:19
+	static const bool hasWaveMinMax = true;
 	static constexpr bool hasSource = false;                    // mhd.cl:885-911 addSource is empty on a cartesian grid
 	union cons_t { struct { real rho; real3 m; real ETotal; real3 B; real psi; real ePot; }; real ptr[10]; };
 	struct prim_t { real rho; real3 v; real P; real3 B; real psi; real ePot; };
@@ -688,6 +703,14 @@ template<class real_> struct MHD {
 		lambda[5] = e.v.x + e.CAx;
 		lambda[6] = e.v.x + e.Cf;
 	}
+	// eqn.lua:1108-1120 with mhd.lua:361-373: v.x -/+ Cf of the interface eigensystem
+	static void eigenWaveMinMax(real& lmin, real& lmax, S const&, eigen_t const& e, normal_t) {
+		lmin = e.v.x - e.Cf; lmax = e.v.x + e.Cf;
+	}
+	// mhd.lua:377-387 consWaveCodeMinMax -> calcCellMinMaxEigenvalues
+	static void consWaveMinMax(real& lmin, real& lmax, S const& s, cons_t const& U, normal_t n) {
+		calcCellMinMaxEigenvalues(lmin, lmax, s, U, n);
+	}
 	// mhd.cl:915-931
 	static void constrainU(S const& s, cons_t& U) {
 		prim_t W; primFromCons(W, s, U);
@@ -804,7 +827,7 @@ template<class Eqn> struct Solver : SolverBase {
 		solver.f_eqn = int(d.eqn_params[0]); solver.a_convCoeff = real(d.eqn_params[1]); solver.d_convCoeff = real(d.eqn_params[2]);
 		solver.V_convCoeff = real(d.eqn_params[3]);
 		// fvsolver.lua:61-63 useFluxLimiter = fluxLimiter > 1 (1-based) and flux.usesFluxLimiter
-		useFluxLimiter = d.flux_limiter > 0;
+		useFluxLimiter = d.flux_limiter > 0 && d.flux == 0;   // only the Roe flux usesFluxLimiter (hydro/flux/roe.lua:5-19)
 		cons_t zero; std::memset(&zero, 0, sizeof(zero));
 		UBuf.assign(ncells, zero);
 		fluxBuf.assign(ncells * dim, zero);
@@ -985,6 +1008,52 @@ template<class Eqn> struct Solver : SolverBase {
 		}
 	}
 
+	// ---- calcFluxForInterface, HLL: hydro/flux/hll.cl:5-74 with hllCalcWaveMethod = 'Davis direct bounded' (hll.lua:10)
+	void hllFlux(cons_t& resultFlux, cons_t const& UL, cons_t const& UR, normal_t n) const {
+		if constexpr (Eqn::hasWaveMinMax) {
+			eigen_t eigInt;
+			Eqn::eigen_forInterface(eigInt, solver, UL, UR, n);
+			real lambdaIntMin, lambdaIntMax;
+			Eqn::eigenWaveMinMax(lambdaIntMin, lambdaIntMax, solver, eigInt, n);
+			real lambdaLMin, lambdaRMax, unused;
+			Eqn::consWaveMinMax(lambdaLMin, unused, solver, UL, n);
+			Eqn::consWaveMinMax(unused, lambdaRMax, solver, UR, n);
+			real const sL = clmin<real>(lambdaLMin, lambdaIntMin);
+			real const sR = clmax<real>(lambdaRMax, lambdaIntMax);
+			if (0 <= sL) {
+				Eqn::fluxFromCons(resultFlux, solver, UL, n);
+			} else if (sR <= 0) {
+				Eqn::fluxFromCons(resultFlux, solver, UR, n);
+			} else if (sL <= 0 && 0 <= sR) {
+				cons_t FL; Eqn::fluxFromCons(FL, solver, UL, n);
+				cons_t FR; Eqn::fluxFromCons(FR, solver, UR, n);
+				for (int j = 0; j < nI; ++j)
+					resultFlux.ptr[j] = (sR * FL.ptr[j] - sL * FR.ptr[j] + sL * sR * (UR.ptr[j] - UL.ptr[j])) / (sR - sL);
+			}
+		}
+	}
+	// ---- calcFluxForInterface, Rusanov: hydro/flux/rusanov.cl:4-33.  The loop over {L, R} there assigns lambdaMax each time, so the
+	// right state's value is the one used.
+	void rusanovFlux(cons_t& resultFlux, cons_t const& UL, cons_t const& UR, normal_t n) const {
+		if constexpr (Eqn::hasWaveMinMax) {
+			real lambdaMax;
+			{
+				real lambdaMinL, lambdaMaxL;
+				Eqn::consWaveMinMax(lambdaMinL, lambdaMaxL, solver, UL, n);
+				lambdaMax = clmax<real>(std::fabs(lambdaMinL), std::fabs(lambdaMaxL));
+			}
+			{
+				real lambdaMinR, lambdaMaxR;
+				Eqn::consWaveMinMax(lambdaMinR, lambdaMaxR, solver, UR, n);
+				lambdaMax = clmax<real>(std::fabs(lambdaMinR), std::fabs(lambdaMaxR));
+			}
+			cons_t FL; Eqn::fluxFromCons(FL, solver, UL, n);
+			cons_t FR; Eqn::fluxFromCons(FR, solver, UR, n);
+			for (int j = 0; j < nI; ++j)
+				resultFlux.ptr[j] = real(.5) * (FL.ptr[j] + FR.ptr[j] - lambdaMax * (UR.ptr[j] - UL.ptr[j]));
+		}
+	}
+
 	// cell_area<side>: symmath product of the other axes' grid_dx (coord.lua:990-1015); 1 for dim==1
 	real cellArea(int side) const {
 		real area = 1.;
@@ -1015,7 +1084,9 @@ template<class Eqn> struct Solver : SolverBase {
 					} else {
 						UL = &UBuf[indexL]; UR = &UBuf[indexR];
 					}
-					if (useFluxLimiter) {
+					if (d.flux == 1) hllFlux(flux, *UL, *UR, n);
+					else if (d.flux == 2) rusanovFlux(flux, *UL, *UR, n);
+					else if (useFluxLimiter) {
 						real const dt_dx = dt / dx;   // fvsolver.lua:135
 						long const indexR2 = indexR + solver.stepsize[side];
 						long const indexL2 = indexL - solver.stepsize[side];

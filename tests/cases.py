@@ -37,6 +37,20 @@ CASES = {
                                  usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 2),
 }
 
+# the other interface fluxes of the calcFluxForInterface slot (hydro/flux/hll.cl 'Davis direct bounded', rusanov.cl)
+CASES["F2_sod_hll_fe"] = (dict(eqn="euler", dim=1, gridSize=[256], initCond="Sod", flux="hll", integrator="forward Euler", cfl=.3), 60)
+CASES["F2_kh_hll_plm_rk4"] = (dict(eqn="euler", dim=2, gridSize=[64, 40], initCond="Kelvin-Helmholtz", flux="hll", usePLM="plm cons",
+                                   slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.15), 12)
+CASES["F2_sphere_rusanov_3d"] = (dict(eqn="euler", dim=3, gridSize=[24, 18, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                      flux="rusanov", usePLM="plm cons", slopeLimiter="superbee", integrator="Runge-Kutta 3, TVD", cfl=.1,
+                                      boundary=dict(xmin="mirror", xmax="mirror", ymin="periodic", ymax="periodic",
+                                                    zmin="freeflow", zmax="freeflow")), 6)
+CASES["F2_briowu_hll"] = (dict(eqn="mhd", dim=1, gridSize=[256], initCond="Brio-Wu", flux="hll", integrator="forward Euler", cfl=.3), 50)
+CASES["F2_ot_rusanov_plm"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond="Orszag-Tang", flux="rusanov", usePLM="plm cons",
+                                   slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15), 12)
+CASES["F2_ot_hll_3d"] = (dict(eqn="mhd", dim=3, gridSize=[16, 12, 10], initCond="Orszag-Tang", flux="hll", integrator="Runge-Kutta 2, TVD",
+                              cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]), 5)
+
 # forward-Euler cases for the host-side (gloo) decomposition test; axis sizes divisible by 2 ranks
 CASES["slab_fe_2d_periodic"] = (dict(eqn="euler", dim=2, gridSize=[24, 16], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                                      slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 6)
@@ -64,7 +78,7 @@ ADM_CASES = {
                                        cfl=.1, boundary=dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic")), 8),
 }
 
-FLOAT_CASES = ["C2_kh_rk4tvd_minmod", "C4_sphere_rk4", "C3_ot_rk3tvd", "C1_sod_fe_superbee"]
+FLOAT_CASES = ["C2_kh_rk4tvd_minmod", "C4_sphere_rk4", "C3_ot_rk3tvd", "C1_sod_fe_superbee", "F2_kh_hll_plm_rk4", "F2_ot_rusanov_plm"]
 
 # slabs with >= 3 marching chunks per rank (KM = 64 planes in 3-D, 32 rows in 2-D): the overlapped exchange path of hb_fv.cu
 CASES["slab_march3d_overlap"] = (dict(eqn="euler", dim=3, gridSize=[34, 10, 264], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",

@@ -39,6 +39,7 @@ KATS = [
     (dict(integrator="Runge-Kutta 3, TVD", fluxLimiter="Lax-Wendroff"), 9.6682375641956e-05, None, 1e-9, None),             # :107
     (dict(integrator="Runge-Kutta 2, TVD", fluxLimiter="Lax-Wendroff"), 9.6682087934274e-05, None, 1e-9, None),             # :112
     (dict(integrator="Runge-Kutta 4, non-TVD", fluxLimiter="Lax-Wendroff"), 9.6682357228525e-05, None, 1e-9, None),         # :108
+    (dict(flux="hll", integrator="forward Euler"), 0.00037540541165354, 0.0029204942118918, 1e-11, 1e-12),                  # :35
 ]
 
 
