@@ -63,7 +63,7 @@ def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None, stag
         d.n[i] = (local_n or solver.sizeWithoutBorder)[i]
         d.mins[i] = solver.mins[i]
         d.maxs[i] = solver.maxs[i]
-    d.use_plm = 1 if solver.usePLM else 0
+    d.use_plm = solver.plmId
     d.slope_limiter = solver.slopeLimiter
     d.flux_limiter = solver.fluxLimiter
     d.flux = solver.flux.fluxId

@@ -51,6 +51,16 @@ template<class real_, bool FAST_ = false> struct Euler {
 		U[1] = W.v[0] * W.rho; U[2] = W.v[1] * W.rho; U[3] = W.v[2] * W.rho;
 		U[4] = (W.rho * (real(.5) * lenSq3(W.v[0], W.v[1], W.v[2]))) + (W.P / (s.gamma - real(1.)));
 	}
+	// prim_t as an array in the reference's field order (rho, v.xyz, P): plm.cl casts prim_t and cons_t into each other
+	static constexpr bool hasEigenForCell = true;
+	static HB_HD void primArray(real (&w)[nI], Params const& s, real const (&U)[nI]) {
+		Prim W; primFromCons(W, s, U);
+		w[0] = W.rho; w[1] = W.v[0]; w[2] = W.v[1]; w[3] = W.v[2]; w[4] = W.P;
+	}
+	static HB_HD void consFromPrimArray(real (&U)[nI], Params const& s, real const (&w)[nI]) {
+		Prim W; W.rho = w[0]; W.v[0] = w[1]; W.v[1] = w[2]; W.v[2] = w[3]; W.P = w[4];
+		consFromPrim(U, s, W);
+	}
 	// euler.cl:87-94
 	static HB_HD real calc_Cs(Params const& s, Prim const& W) {
 		if (W.P <= s.PMin) return real(0.);
@@ -171,6 +181,16 @@ template<class real_, bool FAST_ = false> struct Euler {
 		Prim W; primFromCons(W, s, U);
 		if (W.P < s.PMin) W.P = s.PMin;
 		consFromPrim(U, s, W);
+	}
+
+	// euler.cl:319-341 eigen_forCell (used by 'plm athena'): the cell's own eigensystem, Cs from hTotal - eKin (no floors)
+	static HB_HD void eigen_forCell(Eig& r, Params const& s, real const (&U)[nI]) {
+		Prim W; primFromCons(W, s, U);
+		real const vSq = dot3(W.v[0], W.v[1], W.v[2], W.v[0], W.v[1], W.v[2]);
+		real const eKin = real(.5) * vSq;
+		real const hTotal = (W.P + U[4]) / W.rho;            // calc_hTotal, euler.cl:17-30
+		real const CsSq = (s.gamma - real(1.)) * (hTotal - eKin);
+		r.rho = W.rho; r.v[0] = W.v[0]; r.v[1] = W.v[1]; r.v[2] = W.v[2]; r.vSq = vSq; r.hTotal = hTotal; r.Cs = rsqrt_ieee(CsSq);
 	}
 
 	// eqn.lua:1134-1146 consWaveCodeMinMax with euler.lua:329-336: Cs from the cons state (euler.cl:98-112), v_n = 0 below rhoMin

@@ -27,6 +27,7 @@ template<class real_, bool FAST_ = false> struct MHD {
 	static constexpr int eqnId = 1;
 	static constexpr int nS = 10, nI = 8, nW = 7;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/mhd.lua:19
+	static constexpr bool hasEigenForCell = false;     // 'plm athena' is built for euler
 	struct Params { real gamma, mu0; real g2_g1, iMu0, iG1; };   // the last three: production forms only (gamma_2/gamma_1, 1/mu0, 1/gamma_1)
 	static HB_HD Params makeParams(const double* p) {
 		return Params{real(p[0]), real(p[1]), real((p[0] - 2.) / (p[0] - 1.)), real(1. / p[1]), real(1. / (p[0] - 1.))};

@@ -327,7 +327,7 @@ template<class real> struct Fv : FvBase {
 				if (n > maxOps) maxOps = n;
 			}
 			bool ok = false;
-			if (d.stage_kernel != 1 && d.flux == HB_FLUX_ROE) {   // the marching kernel is built for the Roe flux
+			if (d.stage_kernel != 1 && d.flux == HB_FLUX_ROE && d.use_plm == 1) {   // the marching kernel is built for Roe + 'plm cons'
 				for (int pass = 0; pass < 2 && !ok; ++pass)
 					for (int cfg = pass == 0 ? cfg0 : 0; !ok && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
 						size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
@@ -489,6 +489,7 @@ template<class real> struct Fv : FvBase {
 		sp.fluxLimiter = d.flux_limiter;
 		sp.scratch = opsScratch;
 		sp.flux = d.flux;
+		sp.plmMode = d.use_plm;
 	}
 
 	// integrator:integrate(dt, calcDeriv) + boundary/constrainU after every stage (rk.lua:91-165, fe.lua:33-49)
@@ -630,7 +631,7 @@ template<class real> struct Fv : FvBase {
 		memset(&sp, 0, sizeof(sp));
 		sp.Uin = upool[0]; sp.Uout = nullptr; sp.Lout = scratchL;
 		sp.computeL = 1; sp.dt = ctl + 1;
-		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux;
+		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux; sp.plmMode = d.use_plm;
 		bool const plm = d.use_plm != 0;
 		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
 		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
@@ -747,7 +748,8 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 		for (int m = 0; m < 2; ++m) if (d->bc[2 * k + m] < 0 || d->bc[2 * k + m] > 3) return setError(HB_ERR_INVALID, "hb_fv_create: unknown boundary method");
 	}
 	if (d->rk_order < 0 || d->rk_order > 4) return setError(HB_ERR_INVALID, "hb_fv_create: rk_order must be 0..4");
-	if (d->use_plm < 0 || d->use_plm > 1) return setError(HB_ERR_INVALID, "hb_fv_create: only usePLM none / 'plm cons' are built");
+	if (d->use_plm < 0 || d->use_plm > 3) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM must be none, 'plm cons' or 'plm athena'");
+	if (d->use_plm >= 2 && d->eqn != HB_EQN_EULER) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' is built for euler");
 	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");
 	if (d->use_plm && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM requires fluxLimiter 'donor cell' (gridsolver.lua:119)");
 	if (d->flux < 0 || d->flux > HB_FLUX_RUSANOV) return setError(HB_ERR_INVALID, "hb_fv_create: unknown flux");

@@ -32,10 +32,11 @@ cudaError_t launchStage(GridP<real> const& g, StageP<real> const& sp, const doub
 	typedef typename TileFor<DIM>::type T;
 	typedef TileGeom<DIM, T> G;
 	auto kern = fv_stage<Eqn, DIM, PLM, FLIM, T, MODE>;
-	size_t const smem = G::template smemBytes<real, Eqn::nI>(PLM);
+	size_t const smem = G::template smemBytes<real, Eqn::nI>(PLM ? (sp.plmMode >= 2 ? 2 : 1) : 0);
+	if (sp.plmMode >= 2 && !Eqn::hasEigenForCell) return cudaErrorInvalidValue;
 	static bool attrSet = false;
 	if (!attrSet) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::template smemBytes<real, Eqn::nI>(PLM ? (Eqn::hasEigenForCell ? 2 : 1) : 0));
 		if (e != cudaSuccess) return e;
 		attrSet = true;
 	}
@@ -154,7 +155,7 @@ template<int DIM> void tileInfoDim(bool plm, int out[5]) {
 	typedef typename TileFor<DIM>::type T;
 	typedef TileGeom<DIM, T> G;
 	out[0] = G::TX; out[1] = G::TY; out[2] = G::TZ; out[3] = T::NT;
-	out[4] = (int)G::template smemBytes<real, Eqn::nI>(plm);
+	out[4] = (int)G::template smemBytes<real, Eqn::nI>(plm ? 1 : 0);
 }
 void tileInfo(int dim, bool plm, bool, int out[5]) {
 	if (dim == 1) tileInfoDim<1>(plm, out);

@@ -57,6 +57,7 @@ template<class real> struct StageP {
 	int slopeLimiter, fluxLimiter;
 	real* scratch;         // optional per-solver device scratch (FvOps::scratchElems), e.g. the ADM flux arrays
 	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov (tile kernel; the marching kernel is built for roe)
+	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {
@@ -78,8 +79,9 @@ template<int DIM, class T> struct TileGeom {
 	static constexpr int SGN = cmax((TX + 2) * P0, cmax(DIM >= 2 ? (TY + 2) * P1 : 0, DIM >= 3 ? (TZ + 2) * P2 : 0));
 	static constexpr int FXN = cmax((TX + 1) * P0P, cmax(DIM >= 2 ? (TY + 1) * P1 : 0, DIM >= 3 ? (TZ + 1) * P2 : 0));
 	static constexpr int CPT = (CELLS + T::NT - 1) / T::NT;
-	template<class real, int nI> static constexpr size_t smemBytes(bool plm) {
-		return sizeof(real) * size_t(nI) * (BOX + (plm ? SGN : 0) + FXN) + 64;
+	// plm: 0 none, 1 'plm cons' (one half slope per variable), 2 'plm athena' (both face states per variable)
+	template<class real, int nI> static constexpr size_t smemBytes(int plm) {
+		return sizeof(real) * size_t(nI) * (BOX + plm * SGN + FXN) + 64;
 	}
 };
 
@@ -118,10 +120,25 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 			decodeItem<DIM, T, SIDE>(w, c, p, i, j, k);
 			if (SIDE == 0) i -= 1; else if (SIDE == 1) j -= 1; else k -= 1;
 			int const b = boxIdx<DIM, T>(i, j, k);
-			#pragma unroll
-			for (int q = 0; q < nI; ++q) {
-				real const* u = Us + q * G::BOX + b;
-				SG[q * G::SGN + w] = plmHalfSlope<real>(sp.slopeLimiter, u[-step], u[0], u[step]);
+			if (sp.plmMode >= 2) {
+				// 'plm athena': both face states of the cell -> SG (L faces), SG + nI * SGN (R faces)
+				if constexpr (Eqn::hasEigenForCell) {
+					real UL[nI], U[nI], UR[nI], L[nI], R[nI];
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) {
+						real const* u = Us + q * G::BOX + b;
+						UL[q] = u[-step]; U[q] = u[0]; UR[q] = u[step];
+					}
+					plmAthenaFaces<Eqn, SIDE>(L, R, ep, UL, U, UR, sp.plmMode == 3 ? 1 : 0);
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) { SG[q * G::SGN + w] = L[q]; SG[(nI + q) * G::SGN + w] = R[q]; }
+				}
+			} else {
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) {
+					real const* u = Us + q * G::BOX + b;
+					SG[q * G::SGN + w] = plmHalfSlope<real>(sp.slopeLimiter, u[-step], u[0], u[step]);
+				}
 			}
 		}
 		__syncthreads();
@@ -149,7 +166,10 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) {
 				real const* u = Us + q * G::BOX + b;
-				if (PLM) {
+				if (PLM && sp.plmMode >= 2) {
+					UL[q] = SG[(nI + q) * G::SGN + w];            // R face state of cell f-1 (item layer f-1+1)
+					UR[q] = SG[q * G::SGN + w + P];               // L face state of cell f
+				} else if (PLM) {
 					UL[q] = u[-step] + SG[q * G::SGN + w];        // R face state of cell f-1 (item layer f-1+1)
 					UR[q] = u[0] - SG[q * G::SGN + w + P];        // L face state of cell f
 				} else {
@@ -196,7 +216,7 @@ fv_stage(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp,
 	extern __shared__ __align__(16) unsigned char smemRaw[];
 	real* Us = reinterpret_cast<real*>(smemRaw);
 	real* SG = Us + nI * G::BOX;
-	real* FX = SG + (PLM ? nI * G::SGN : 0);
+	real* FX = SG + (PLM ? (sp.plmMode >= 2 ? 2 : 1) * nI * G::SGN : 0);
 	__shared__ double redBuf[32];
 
 	int const tid = threadIdx.x;

@@ -64,6 +64,61 @@ HB_HD void roeFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const&
 	}
 }
 
+// 'plm athena' (hydro/solver/plm.cl:782-879): face states of one cell along SIDE from slopes of the PRIMITIVE variables limited in the
+// characteristic variables of the cell's own eigensystem (the primitive differences go through eigen_leftTransform as if they were
+// conserved ones, as in the reference), Athena's monotonicity clamps, back to conserved variables.
+// faceOrder 0: as the reference tree assigns them, result->L = cons(Wrv), result->R = cons(Wlv) (plm.cl:877-878);
+// faceOrder 1: L = cons(Wlv), R = cons(Wrv) -- the order that reproduces the errors the reference recorded for this scheme
+// (tests/test-order/schemes.lua 'plm-athena' rows; tests/test_oracle_kat.py).  Built for equations with eigen_forCell (euler).
+template<class real> HB_HD real clSign(real x) { return x > real(0) ? real(1) : (x < real(0) ? real(-1) : x); }   // OpenCL sign()
+template<class Eqn, int SIDE>
+HB_HD void plmAthenaFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R)[Eqn::nI], typename Eqn::Params const& s,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI], int faceOrder)
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI, nW = Eqn::nW;
+	typename Eqn::Eig eig;
+	Eqn::eigen_forCell(eig, s, U);
+	real W[nI], WL[nI], WR[nI];
+	Eqn::primArray(W, s, U); Eqn::primArray(WL, s, UL); Eqn::primArray(WR, s, UR);
+	real dWL[nI], dWR[nI], dWC[nI], dWG[nI];
+	for (int j = 0; j < nI; ++j) {
+		dWL[j] = W[j] - WL[j];
+		dWR[j] = WR[j] - W[j];
+		dWC[j] = real(.5) * (WR[j] - WL[j]);
+		dWG[j] = (dWL[j] * dWR[j]) <= real(0.) ? real(0.) : (real(2.) * dWL[j] * dWR[j] / (dWL[j] + dWR[j]));
+	}
+	real dal[nW], dar[nW], dac[nW], dag[nW], da[nW];
+	Eqn::template leftTransform<SIDE>(dal, s, eig, dWL);
+	Eqn::template leftTransform<SIDE>(dar, s, eig, dWR);
+	Eqn::template leftTransform<SIDE>(dac, s, eig, dWC);
+	Eqn::template leftTransform<SIDE>(dag, s, eig, dWG);
+	for (int j = 0; j < nW; ++j) {
+		da[j] = 0;
+		if (dal[j] * dar[j] > 0) {
+			real const lim_slope1 = rmin<real>(rabs(dal[j]), rabs(dar[j]));
+			real const lim_slope2 = rmin<real>(rabs(dac[j]), rabs(dag[j]));
+			da[j] = clSign<real>(dac[j]) * rmin<real>(real(2.) * lim_slope1, lim_slope2);
+		}
+	}
+	real dWm[nI];
+	Eqn::template rightTransform<SIDE>(dWm, s, eig, da);
+	real Wlv[nI], Wrv[nI];
+	for (int j = 0; j < nI; ++j) {
+		Wlv[j] = W[j] - real(.5) * dWm[j];
+		Wrv[j] = W[j] + real(.5) * dWm[j];
+		real const C = Wrv[j] + Wlv[j];
+		Wlv[j] = rmax<real>(rmin<real>(W[j], WL[j]), Wlv[j]);
+		Wlv[j] = rmin<real>(rmax<real>(W[j], WL[j]), Wlv[j]);
+		Wrv[j] = C - Wlv[j];
+		Wrv[j] = rmax<real>(rmin<real>(W[j], WR[j]), Wrv[j]);
+		Wrv[j] = rmin<real>(rmax<real>(W[j], WR[j]), Wrv[j]);
+		Wlv[j] = C - Wrv[j];
+	}
+	if (faceOrder == 0) { Eqn::consFromPrimArray(L, s, Wrv); Eqn::consFromPrimArray(R, s, Wlv); }
+	else { Eqn::consFromPrimArray(L, s, Wlv); Eqn::consFromPrimArray(R, s, Wrv); }
+}
+
 // HLL flux, hydro/flux/hll.cl:5-74 with hllCalcWaveMethod = 'Davis direct bounded' (hydro/flux/hll.lua:10):
 //   sL = min(lambdaMin(UL), lambdaMin(interface)), sR = max(lambdaMax(UR), lambdaMax(interface)); interface speeds from the Roe-averaged
 //   eigensystem (eqn.lua:1108-1120), cell speeds from the cons state (eqn.lua:1134-1146).

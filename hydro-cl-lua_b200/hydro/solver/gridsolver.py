@@ -13,7 +13,9 @@ from .solverbase import SolverBase
 boundaryIds = {"periodic": 0, "mirror": 1, "freeflow": 2, "none": 3}
 xNames = ("x", "y", "z")
 minmaxs = ("min", "max")
-plmIds = {None: 0, False: 0, "plm cons": 1}
+# 'plm athena': plm.cl:782-879 as the reference tree has it (result->L = cons(Wrv), result->R = cons(Wlv), :877-878);
+# 'plm athena, recorded face order': L = left, R = right face -- reproduces the errors recorded in tests/test-order/schemes.lua
+plmIds = {None: 0, False: 0, "plm cons": 1, "plm athena": 2, "plm athena, recorded face order": 3}
 
 
 class GridSolver(SolverBase):
@@ -55,7 +57,8 @@ class GridSolver(SolverBase):
         self.mindx = min(self.grid_dx)
         self.usePLM = args.get("usePLM") or None
         if self.usePLM not in plmIds:
-            raise NotImplementedError("usePLM=%r: only 'plm cons' is in the hot-path scope so far" % (self.usePLM,))
+            raise NotImplementedError("usePLM=%r: 'plm cons' and 'plm athena' are built" % (self.usePLM,))
+        self.plmId = plmIds[self.usePLM]
         self.slopeLimiter = hydro_app.limiterIndex(args.get("slopeLimiter", "minmod")) if self.usePLM else 0
         if self.usePLM and self.fluxLimiter != 0:
             # gridsolver.lua:119: "are you sure you want to use flux and slope limiters at the same time?"

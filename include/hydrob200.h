@@ -110,7 +110,9 @@ typedef struct hb_fv_desc {
 	int dim;                  /* 1..3 */
 	int n[3];                 /* interior cells of THIS rank's slab per axis (1 on unused axes) */
 	int global_n[3];          /* interior cells of the whole grid (== n without decomposition); defines grid_dx */
-	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91) */
+	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879, euler), 3 = 'plm athena'
+	                           * with the face states assigned L = left, R = right: the order that reproduces the errors the reference
+	                           * recorded for this scheme (its tree has them the other way round at plm.cl:877-878) */
 	int slope_limiter;        /* 0-based index into hydro/app.lua:614-635 */
 	int flux_limiter;         /* 0-based; 0 = 'donor cell' = no flux limiter (hydro/solver/fvsolver.lua:61-63) */
 	int bc[6];                /* xmin,xmax,ymin,ymax,zmin,zmax: HB_BC_* */

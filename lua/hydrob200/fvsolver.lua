@@ -39,8 +39,9 @@ function B200Solver:refreshSolverProgram()
 		d.n[i] = tonumber(self.sizeWithoutBorder.s[i]); d.global_n[i] = d.n[i]
 		d.mins[i] = self.mins.s[i]; d.maxs[i] = self.maxs.s[i]
 	end
-	d.use_plm = self.usePLM == 'plm cons' and 1 or 0
-	assert(not self.usePLM or self.usePLM == 'plm cons', "hydrob200: only usePLM='plm cons' is built")
+	-- 'plm athena' follows plm.cl:782-879 literally (faces as the tree assigns them, :877-878); use_plm = 3 selects L = left, R = right
+	local plmIds = {['plm cons'] = 1, ['plm athena'] = 2}
+	d.use_plm = self.usePLM and assert(plmIds[self.usePLM], "hydrob200: usePLM not built: "..tostring(self.usePLM)) or 0
 	d.slope_limiter = self.slopeLimiter - 1            -- hydro/app.lua:614-635 is 1-based
 	d.flux_limiter = self.fluxLimiter - 1
 	-- hydro/flux/*.lua: the flux plug-in object carries its name ('roe', 'hll', 'rusanov')

@@ -36,7 +36,7 @@ struct ho_desc {
 	int dim;            // 1..3
 	int n[3];           // interior cells per axis (unused axes = 1)
 	int real_bytes;     // 8 = double, 4 = float   (hydro/app.lua:892 'real' selection)
-	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91)
+	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded
 	int slope_limiter;  // 0-based index into hydro/app.lua:614-635
 	int flux_limiter;   // 0-based index; 0 = 'donor cell' => useFluxLimiter=false (fvsolver.lua:61-63)
 	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none
@@ -209,6 +209,18 @@ template<class real_> struct Euler {
 		F.ETotal = HTotal * v_n;
 		F.ePot = 0;
 	}
+	// euler.cl:319-341 (used by the PLM variants that limit in characteristic variables)
+	static const bool hasEigenForCell = true;
+	static void eigen_forCell(eigen_t& r, S const& s, cons_t const& U, normal_t) {
+		prim_t W; primFromCons(W, s, U);
+		real3 const vL = W.v;
+		real const vSq = real3_dot(W.v, vL);
+		real const eKin = real(.5) * vSq;
+		real const hTotal = calc_hTotal(W.rho, W.P, U.ETotal);
+		real const CsSq = (s.heatCapacityRatio - real(1.)) * (hTotal - eKin);
+		real const Cs = std::sqrt(CsSq);
+		r.rho = W.rho; r.v = W.v; r.vSq = vSq; r.vL = vL; r.hTotal = hTotal; r.Cs = Cs;
+	}
 	// euler.cl:347-430
 	static void eigen_forInterface(eigen_t& r, S const& s, cons_t const& UL, cons_t const& UR, normal_t) {
 		real const rhoEpsilon = 1e-5;
@@ -365,6 +377,7 @@ template<class real_> struct MHD {
 	enum { numStates = 10, numIntStates = 8, numWaves = 7 };   // mhd.lua:16-17,76-83
 	static const bool roeUseFluxFromCons = true;                // mhd.lua:19
 	static const bool hasWaveMinMax = true;
+	static const bool hasEigenForCell = false;                  // 'plm athena' is restated for euler only
 	static constexpr bool hasSource = false;                    // mhd.cl:885-911 addSource is empty on a cartesian grid
 	union cons_t { struct { real rho; real3 m; real ETotal; real3 B; real psi; real ePot; }; real ptr[10]; };
 	struct prim_t { real rho; real3 v; real P; real3 B; real psi; real ePot; };
@@ -918,6 +931,74 @@ template<class Eqn> struct Solver : SolverBase {
 		boundary();
 	}
 
+	// ---- 'plm athena': plm.cl:782-879.  Slopes of the PRIMITIVE variables limited in characteristic variables of the cell's own
+	// eigensystem (the prim differences are handed to eigen_leftTransform as if they were cons_t, as the reference does), the
+	// monotonicity clamps of Athena, and the reference's final assignment result->L = cons(Wrv), result->R = cons(Wlv).
+	static real clsign(real x) { return x > 0 ? real(1) : (x < 0 ? real(-1) : x); }   // OpenCL sign(): +-0 -> +-0
+	void calcCellLR_athena(consLR_t& result, cons_t const& U, cons_t const& UL, cons_t const& UR, normal_t n) const {
+		if constexpr (Eqn::hasEigenForCell) {
+			typedef typename Eqn::prim_t prim_t;
+			static_assert(sizeof(prim_t) == sizeof(cons_t), "prim_t and cons_t are cast into each other (plm.cl:835-842,854)");
+			eigen_t eig;
+			Eqn::eigen_forCell(eig, solver, U, n);
+			prim_t W, WL, WR;
+			Eqn::primFromCons(W, solver, U);
+			Eqn::primFromCons(WL, solver, UL);
+			Eqn::primFromCons(WR, solver, UR);
+			real const* w = reinterpret_cast<real const*>(&W);
+			real const* wl = reinterpret_cast<real const*>(&WL);
+			real const* wr = reinterpret_cast<real const*>(&WR);
+			cons_t dWL, dWR, dWC, dWG;
+			for (int j = 0; j < nI; ++j) {
+				dWL.ptr[j] = w[j] - wl[j];
+				dWR.ptr[j] = wr[j] - w[j];
+				dWC.ptr[j] = real(.5) * (wr[j] - wl[j]);
+				dWG.ptr[j] = (dWL.ptr[j] * dWR.ptr[j]) <= real(0.) ? real(0.) : (real(2.) * dWL.ptr[j] * dWR.ptr[j] / (dWL.ptr[j] + dWR.ptr[j]));
+			}
+			for (int j = nI; j < nS; ++j) dWL.ptr[j] = dWR.ptr[j] = dWC.ptr[j] = dWG.ptr[j] = 0.;
+			waves_t dal, dar, dac, dag;
+			Eqn::eigen_leftTransform(dal, solver, eig, dWL, n);
+			Eqn::eigen_leftTransform(dar, solver, eig, dWR, n);
+			Eqn::eigen_leftTransform(dac, solver, eig, dWC, n);
+			Eqn::eigen_leftTransform(dag, solver, eig, dWG, n);
+			waves_t da;
+			for (int j = 0; j < nW; ++j) {
+				da.ptr[j] = 0;
+				if (dal.ptr[j] * dar.ptr[j] > 0) {
+					real const lim_slope1 = clmin<real>(std::fabs(dal.ptr[j]), std::fabs(dar.ptr[j]));
+					real const lim_slope2 = clmin<real>(std::fabs(dac.ptr[j]), std::fabs(dag.ptr[j]));
+					da.ptr[j] = clsign(dac.ptr[j]) * clmin<real>(real(2.) * lim_slope1, lim_slope2);
+				}
+			}
+			cons_t dWm;
+			Eqn::eigen_rightTransform(dWm, solver, eig, da, n);
+			prim_t Wlv, Wrv;
+			real* lv = reinterpret_cast<real*>(&Wlv);
+			real* rv = reinterpret_cast<real*>(&Wrv);
+			for (int j = 0; j < nI; ++j) {
+				lv[j] = w[j] - real(.5) * dWm.ptr[j];
+				rv[j] = w[j] + real(.5) * dWm.ptr[j];
+				real const C = rv[j] + lv[j];
+				lv[j] = clmax<real>(clmin<real>(w[j], wl[j]), lv[j]);
+				lv[j] = clmin<real>(clmax<real>(w[j], wl[j]), lv[j]);
+				rv[j] = C - lv[j];
+				rv[j] = clmax<real>(clmin<real>(w[j], wr[j]), rv[j]);
+				rv[j] = clmin<real>(clmax<real>(w[j], wr[j]), rv[j]);
+				lv[j] = C - rv[j];
+			}
+			for (int j = nI; j < nS; ++j) { lv[j] = w[j]; rv[j] = w[j]; }
+			if (d.use_plm == 3) {
+				// the assignment that reproduces the errors the reference recorded for 'plm-athena' (tests/test-order/schemes.lua)
+				Eqn::consFromPrim(result.L, solver, Wlv);
+				Eqn::consFromPrim(result.R, solver, Wrv);
+			} else {
+				// plm.cl:877-878 as the tree has it
+				Eqn::consFromPrim(result.L, solver, Wrv);
+				Eqn::consFromPrim(result.R, solver, Wlv);
+			}
+		}
+	}
+
 	// ---- calcLR: plm.cl:976-997 kernel, 'plm cons' :32-91
 	void calcLR() {
 		int const sl = d.slope_limiter;
@@ -930,6 +1011,7 @@ template<class Eqn> struct Solver : SolverBase {
 				consLR_t& result = ULRBuf[side + dim * index];
 				cons_t const& UL = UBuf[index - solver.stepsize[side]];
 				cons_t const& UR = UBuf[index + solver.stepsize[side]];
+				if (d.use_plm >= 2) { calcCellLR_athena(result, U, UL, UR, normal_t{side}); continue; }
 				result.L = U; result.R = U;
 				for (int q = 0; q < nI; ++q) {
 					real const dUR = UR.ptr[q] - U.ptr[q];

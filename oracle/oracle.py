@@ -86,7 +86,7 @@ def desc_from_solver(solver, nthreads=0):
         d.mins[i] = solver.mins[i]
         d.maxs[i] = solver.maxs[i]
     d.real_bytes = solver.real_bytes
-    d.use_plm = 1 if solver.usePLM else 0
+    d.use_plm = solver.plmId
     d.slope_limiter = solver.slopeLimiter
     d.flux_limiter = solver.fluxLimiter
     d.flux = solver.flux.fluxId

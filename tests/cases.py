@@ -51,6 +51,17 @@ CASES["F2_ot_rusanov_plm"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond
 CASES["F2_ot_hll_3d"] = (dict(eqn="mhd", dim=3, gridSize=[16, 12, 10], initCond="Orszag-Tang", flux="hll", integrator="Runge-Kutta 2, TVD",
                               cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]), 5)
 
+# 'plm athena' (plm.cl:782-879), both face orders (as in the tree / as recorded), Euler
+CASES["F1_sod_athena_fe"] = (dict(eqn="euler", dim=1, gridSize=[256], initCond="Sod", usePLM="plm athena", integrator="forward Euler", cfl=.3), 60)
+CASES["F1_sod_athena_rec_rk4"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm athena, recorded face order",
+                                       integrator="Runge-Kutta 4", cfl=.3, boundary=dict(xmin="mirror", xmax="mirror")), 40)
+CASES["F1_kh_athena_rec_rk4tvd"] = (dict(eqn="euler", dim=2, gridSize=[64, 40], initCond="Kelvin-Helmholtz",
+                                         usePLM="plm athena, recorded face order", integrator="Runge-Kutta 4, TVD", cfl=.15), 12)
+CASES["F1_sphere_athena_rec_3d"] = (dict(eqn="euler", dim=3, gridSize=[24, 18, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                         usePLM="plm athena, recorded face order", integrator="Runge-Kutta 3, TVD", cfl=.1), 6)
+CASES["F1_sphere_athena_hll_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 10], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                         usePLM="plm athena", flux="hll", integrator="Runge-Kutta 2, TVD", cfl=.05), 4)
+
 # forward-Euler cases for the host-side (gloo) decomposition test; axis sizes divisible by 2 ranks
 CASES["slab_fe_2d_periodic"] = (dict(eqn="euler", dim=2, gridSize=[24, 16], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                                      slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 6)

@@ -40,6 +40,13 @@ KATS = [
     (dict(integrator="Runge-Kutta 2, TVD", fluxLimiter="Lax-Wendroff"), 9.6682087934274e-05, None, 1e-9, None),             # :112
     (dict(integrator="Runge-Kutta 4, non-TVD", fluxLimiter="Lax-Wendroff"), 9.6682357228525e-05, None, 1e-9, None),         # :108
     (dict(flux="hll", integrator="forward Euler"), 0.00037540541165354, 0.0029204942118918, 1e-11, 1e-12),                  # :35
+    # SURVEY 8f1 'plm athena'.  The tree assigns the face states the other way round (plm.cl:877-878: L = cons(Wrv), R = cons(Wlv))
+    # than the version these rows were recorded with; with L = left, R = right every row is reproduced.
+    (dict(usePLM="plm athena, recorded face order", integrator="forward Euler"), 9.7002822784791e-05, 0.00093771140713331, 1e-10, 1e-11),   # :97
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 4"), 1.2279744814311e-06, 0.00069783409481987, 1e-9, 1e-11),     # :116
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 2"), 1.3132898617302e-06, 0.00067817159415456, 1e-9, 1e-11),     # :112
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 3, TVD"), 1.226178781197e-06, 0.00070049425851808, 1e-9, 1e-11),  # :120
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 4, TVD"), 1.2279971850421e-06, 0.00069848808747002, 1e-9, 1e-11),  # :119
 ]
 
 
