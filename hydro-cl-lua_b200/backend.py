@@ -67,6 +67,7 @@ def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None, stag
     d.slope_limiter = solver.slopeLimiter
     d.flux_limiter = solver.fluxLimiter
     d.flux = solver.flux.fluxId
+    d.flux_param = getattr(solver.flux, 'fluxParam', 0)
     for i, b in enumerate(solver.boundaryIdList()):
         d.bc[i] = b
     d.rk_order = solver.rkOrder

@@ -132,7 +132,7 @@ adm_flux_shared(GridP<typename Eqn::real> const g, typename Eqn::Params const ep
 // what its part stores -- the arithmetic per stored value is the same expression sequence (the unused branches of the fully
 // unrolled, compile-time indexed code are dead and dropped by the compiler), so the strict build stays bit-identical to the oracle.
 template<class Eqn, int MODE, int PART>
-__global__ void __launch_bounds__(128, PART == 0 ? 3 : (PART == 3 ? 4 : (PART >= 4 && PART <= 6 ? 8 : (PART == 7 ? 4 : (PART == 1 ? 3 : 1)))))
+__global__ void __launch_bounds__(128, PART == 0 ? 4 : (PART == 3 ? 4 : (PART >= 4 && PART <= 6 ? 8 : (PART == 7 ? 4 : (PART == 1 ? 3 : 1)))))
 adm_update(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp, typename Eqn::Params const ep,
 	const typename Eqn::real* __restrict__ Fb)
 {

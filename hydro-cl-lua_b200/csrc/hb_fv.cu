@@ -489,6 +489,7 @@ template<class real> struct Fv : FvBase {
 		sp.fluxLimiter = d.flux_limiter;
 		sp.scratch = opsScratch;
 		sp.flux = d.flux;
+		sp.fluxParam = d.flux_param;
 		sp.plmMode = d.use_plm;
 	}
 
@@ -631,7 +632,7 @@ template<class real> struct Fv : FvBase {
 		memset(&sp, 0, sizeof(sp));
 		sp.Uin = upool[0]; sp.Uout = nullptr; sp.Lout = scratchL;
 		sp.computeL = 1; sp.dt = ctl + 1;
-		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux; sp.plmMode = d.use_plm;
+		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux; sp.fluxParam = d.flux_param; sp.plmMode = d.use_plm;
 		bool const plm = d.use_plm != 0;
 		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
 		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
@@ -752,7 +753,9 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (d->use_plm >= 2 && d->eqn != HB_EQN_EULER) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' is built for euler");
 	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");
 	if (d->use_plm && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM requires fluxLimiter 'donor cell' (gridsolver.lua:119)");
-	if (d->flux < 0 || d->flux > HB_FLUX_RUSANOV) return setError(HB_ERR_INVALID, "hb_fv_create: unknown flux");
+	if (d->flux < 0 || d->flux > HB_FLUX_EULER_HLLC) return setError(HB_ERR_INVALID, "hb_fv_create: unknown flux");
+	if (d->flux == HB_FLUX_EULER_HLLC && d->eqn != HB_EQN_EULER) return setError(HB_ERR_INVALID, "hb_fv_create: euler-hllc only works with the euler equation (euler-hllc.cl:8-10)");
+	if (d->flux == HB_FLUX_EULER_HLLC && (d->flux_param < 0 || d->flux_param > 2)) return setError(HB_ERR_INVALID, "hb_fv_create: hllcMethod must be 0, 1 or 2");
 	if (d->flux != HB_FLUX_ROE && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: only the Roe flux uses a flux limiter (hydro/flux/roe.lua:5-19)");
 	if (d->flux != HB_FLUX_ROE && d->eqn == HB_EQN_ADM3D) return setError(HB_ERR_INVALID, "hb_fv_create: hll / rusanov are built for euler and mhd");
 	if (d->eqn == HB_EQN_ADM3D) {

@@ -56,7 +56,8 @@ template<class real> struct StageP {
 	unsigned long long* dtMinBits;   // optional: fused calcDT, min over interior cells as ordered bits of a double
 	int slopeLimiter, fluxLimiter;
 	real* scratch;         // optional per-solver device scratch (FvOps::scratchElems), e.g. the ADM flux arrays
-	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov (tile kernel; the marching kernel is built for roe)
+	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc (tile kernel; the marching kernel is built for roe)
+	int fluxParam;         // euler-hllc: hllcMethod
 	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded
 };
 
@@ -176,7 +177,7 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 					UL[q] = u[-step]; UR[q] = u[0];
 				}
 			}
-			interfaceFlux<Eqn, SIDE>(sp.flux, F, ep, UL, UR);
+			interfaceFlux<Eqn, SIDE>(sp.flux, sp.fluxParam, F, ep, UL, UR);
 		}
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) FX[q * G::FXN + f * PF + p] = F[q];

@@ -176,13 +176,96 @@ HB_HD void rusanovFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params co
 	for (int j = 0; j < nI; ++j) F[j] = real(.5) * (FL[j] + FR[j] - lambdaMax * (UR[j] - UL[j]));
 }
 
-// the solver's flux plug-in (hydro/flux/*.lua), selected at run time in the tile kernel: 0 roe, 1 hll, 2 rusanov
+// HLLC flux of the Euler equations, hydro/flux/euler-hllc.cl:14-243: 'Davis direct bounded' wave speeds as in hllFlux, contact speed sStar,
+// hllcMethod 0 / 1 / 2 (Toro 2012 eqns 38-39 / variation 1 / variation 2; euler-hllc.lua:17 default 2).  State order rho, m.xyz, ETotal.
 template<class Eqn, int SIDE>
-HB_HD void interfaceFlux(int flux, typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
+HB_HD void hllcFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s, int method,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI, nW = Eqn::nW;
+	if constexpr (Eqn::eqnId == 0) {
+		typename Eqn::Prim WL, WR;
+		Eqn::primFromCons(WL, s, UL);
+		Eqn::primFromCons(WR, s, UR);
+		typename Eqn::Eig eigInt;
+		Eqn::template eigen_forInterface<SIDE>(eigInt, s, UL, UR);
+		real lam[nW];
+		Eqn::template waves<SIDE>(lam, s, eigInt);
+		real lambdaLMin, lambdaRMax, unused;
+		Eqn::template consWaveMinMax<SIDE>(lambdaLMin, unused, s, UL);
+		Eqn::template consWaveMinMax<SIDE>(unused, lambdaRMax, s, UR);
+		real const sL = rmin<real>(lambdaLMin, lam[0]);
+		real const sR = rmax<real>(lambdaRMax, lam[nW - 1]);
+		real vnL[3], vnR[3];
+		rot<SIDE>::fwd(WL.v, vnL); rot<SIDE>::fwd(WR.v, vnR);
+		real const sStar = (WR.rho * vnR[0] * (sR - vnR[0]) - WL.rho * vnL[0] * (sL - vnL[0]) + WL.P - WR.P)
+			/ (WR.rho * (sR - vnR[0]) - WL.rho * (sL - vnL[0]));
+		for (int j = 0; j < nI; ++j) F[j] = 0;
+		if (0 <= sL) {
+			Eqn::template fluxFromCons<SIDE>(F, s, UL);
+		} else if ((sL <= real(0.) && real(0.) <= sStar) || (sStar <= real(0.) && real(0.) <= sR)) {
+			// the two star regions are the same formulas with (L, sL) or (R, sR)
+			bool const left = sL <= real(0.) && real(0.) <= sStar;
+			real const (&U)[nI] = left ? UL : UR;
+			typename Eqn::Prim const& W = left ? WL : WR;
+			real const (&vn)[3] = left ? vnL : vnR;
+			real const sK = left ? sL : sR;
+			real FK[nI];
+			Eqn::template fluxFromCons<SIDE>(FK, s, U);
+			if (method == 0) {
+				real UStar[nI];
+				UStar[0] = U[0] * (sK - vn[0]) / (sK - sStar);
+				real const vs[3] = {sStar, vn[1], vn[2]};
+				real vStar[3]; rot<SIDE>::inv(vs, vStar);
+				UStar[1] = UStar[0] * vStar[0];
+				UStar[2] = UStar[0] * vStar[1];
+				UStar[3] = UStar[0] * vStar[2];
+				UStar[4] = UStar[0] * (U[4] / U[0] + (sStar - vn[0]) * (sStar + W.P / (U[0] * (sK - vn[0]))));
+				for (int i = 0; i < nI; ++i) F[i] = FK[i] + sK * (UStar[i] - U[i]);
+			} else {
+				real const Um_[3] = {U[1], U[2], U[3]}, Fm_[3] = {FK[1], FK[2], FK[3]};
+				real Umn[3], Fmn[3]; rot<SIDE>::fwd(Um_, Umn); rot<SIDE>::fwd(Fm_, Fmn);
+				real mn[3];
+				if (method == 1) {
+					F[0] = (sStar * (sK * U[0] - FK[0])) / (sK - sStar);
+					mn[0] = (sStar * (sK * Umn[0] - Fmn[0]) + sK * (W.P + W.rho * (sK - vn[0]) * (sStar - vn[0]))) / (sK - sStar);
+					mn[1] = (sStar * (sK * Umn[1] - Fmn[1])) / (sK - sStar);
+					mn[2] = (sStar * (sK * Umn[2] - Fmn[2])) / (sK - sStar);
+					F[4] = (sStar * (sK * U[4] - FK[4]) + sK * (W.P + W.rho * (sK - vn[0]) * (sStar - vn[0])) * sStar) / (sK - sStar);
+				} else {
+					real const PLR = real(.5) * (WL.P + WR.P + WL.rho * (sL - vnL[0]) * (sStar - vnL[0]) + WR.rho * (sR - vnR[0]) * (sStar - vnR[0]));
+					// euler-hllc.cl:196 vs :216: the density flux is written (sL rho - F) sStar on the left, sStar (sR rho - F) on the right
+					F[0] = left ? (sK * U[0] - FK[0]) * sStar / (sK - sStar) : sStar * (sK * U[0] - FK[0]) / (sK - sStar);
+					mn[0] = left ? ((sK * Umn[0] - Fmn[0]) * sStar + sK * PLR) / (sK - sStar) : (sStar * (sK * Umn[0] - Fmn[0]) + sK * PLR) / (sK - sStar);
+					mn[1] = sStar * (sK * Umn[1] - Fmn[1]) / (sK - sStar);
+					mn[2] = sStar * (sK * Umn[2] - Fmn[2]) / (sK - sStar);
+					F[4] = (sStar * (sK * U[4] - FK[4]) + sK * PLR * sStar) / (sK - sStar);
+				}
+				real m[3]; rot<SIDE>::inv(mn, m);
+				F[1] = m[0]; F[2] = m[1]; F[3] = m[2];
+			}
+		} else if (sR <= 0) {
+			Eqn::template fluxFromCons<SIDE>(F, s, UR);
+		} else if (sL <= 0 && 0 <= sR) {
+			real FL[nI], FR[nI];
+			Eqn::template fluxFromCons<SIDE>(FL, s, UL);
+			Eqn::template fluxFromCons<SIDE>(FR, s, UR);
+			for (int j = 0; j < nI; ++j) F[j] = (sR * FL[j] - sL * FR[j] + sL * sR * (UR[j] - UL[j])) / (sR - sL);
+		}
+	} else {
+		for (int j = 0; j < nI; ++j) F[j] = 0;       // rejected at hb_fv_create for other equations
+	}
+}
+
+// the solver's flux plug-in (hydro/flux/*.lua), selected at run time in the tile kernel: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc
+template<class Eqn, int SIDE>
+HB_HD void interfaceFlux(int flux, int fluxParam, typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,
 	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
 {
 	if (flux == 1) hllFlux<Eqn, SIDE>(F, s, UL, UR);
 	else if (flux == 2) rusanovFlux<Eqn, SIDE>(F, s, UL, UR);
+	else if (flux == 3) hllcFlux<Eqn, SIDE>(F, s, fluxParam, UL, UR);
 	else roeFlux<Eqn, SIDE>(F, s, UL, UR);
 }
 

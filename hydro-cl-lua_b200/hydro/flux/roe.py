@@ -45,4 +45,19 @@ class Rusanov(Flux):
     fluxId = 2
 
 
-fluxes = {"roe": Roe, "hll": HLL, "rusanov": Rusanov}
+class EulerHLLC(HLL):
+    """hydro/flux/euler-hllc.lua: name 'euler-hllc', args.hllcMethod 0 | 1 | 2 (default 2), Euler only (euler-hllc.cl:7-11)."""
+    name = "euler-hllc"
+    fluxId = 3
+
+    def __init__(self, solver, args=None):
+        super().__init__(solver, args)
+        if getattr(solver.eqn, "name", None) != "euler":
+            raise ValueError("euler-hllc only works with euler eqn (euler-hllc.cl:8-10)")
+        self.hllcMethod = int(self.args.get("hllcMethod", 2))
+        if self.hllcMethod not in (0, 1, 2):
+            raise ValueError("hllcMethod must be 0, 1 or 2")
+        self.fluxParam = self.hllcMethod
+
+
+fluxes = {"roe": Roe, "hll": HLL, "rusanov": Rusanov, "euler-hllc": EulerHLLC}

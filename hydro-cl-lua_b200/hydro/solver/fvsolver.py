@@ -14,7 +14,10 @@ class FiniteVolumeSolver(GridSolver):
 
     def initObjs(self, args):
         super().initObjs(args)
-        self.createFlux(args.get("flux", "roe"), args.get("fluxArgs"))
+        fluxArgs = dict(args.get("fluxArgs") or {})
+        if "hllcMethod" in args:      # tests/test-order/schemes.lua passes it at the top level of the solver args
+            fluxArgs.setdefault("hllcMethod", args["hllcMethod"])
+        self.createFlux(args.get("flux", "roe"), fluxArgs)
         if not self.flux.usesFluxLimiter:
             self.fluxLimiter = 0
 

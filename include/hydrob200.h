@@ -100,6 +100,7 @@ int hb_reduce(hb_ctx* ctx, hb_buf* buf, size_t count, int op, double* host_out);
 #define HB_FLUX_ROE 0         /* hydro/flux/roe.cl:17-163 (usesFluxLimiter) */
 #define HB_FLUX_HLL 1         /* hydro/flux/hll.cl:5-74, hllCalcWaveMethod 'Davis direct bounded' (hll.lua:10); Euler and MHD */
 #define HB_FLUX_RUSANOV 2     /* hydro/flux/rusanov.cl:4-33; Euler and MHD */
+#define HB_FLUX_EULER_HLLC 3  /* hydro/flux/euler-hllc.cl:14-243; Euler; flux_param = hllcMethod 0 | 1 | 2 (euler-hllc.lua:17) */
 #define HB_BC_PERIODIC 0      /* hydro/solver/gridsolver.lua:638-651 */
 #define HB_BC_MIRROR 1        /* :654-744 */
 #define HB_BC_FREEFLOW 2      /* :766-780 */
@@ -127,7 +128,8 @@ typedef struct hb_fv_desc {
 	int strict_fp;            /* 1: kernels built with -fmad=false (no FMA contraction); 0: production kernels */
 	int use_graph;            /* 1: replay each update() as a captured CUDA graph */
 	int stage_kernel;         /* 0: auto; 1: tile kernel (fv_stage); 2: plane-marching TMA kernel (fv_march), error if not built for the config */
-	int flux;                 /* HB_FLUX_*: the solver's flux plug-in (hydro/flux/*.lua; solver.flux = 'roe' | 'hll' | 'rusanov') */
+	int flux;                 /* HB_FLUX_*: the solver's flux plug-in (hydro/flux/*.lua; solver.flux = 'roe' | 'hll' | 'rusanov' | 'euler-hllc') */
+	int flux_param;           /* euler-hllc: solver.flux.hllcMethod */
 } hb_fv_desc;
 
 size_t hb_sizeof_fv_desc(void);                              /* sizeof(hb_fv_desc), for bindings that mirror the struct */

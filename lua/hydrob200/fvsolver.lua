@@ -45,7 +45,8 @@ function B200Solver:refreshSolverProgram()
 	d.slope_limiter = self.slopeLimiter - 1            -- hydro/app.lua:614-635 is 1-based
 	d.flux_limiter = self.fluxLimiter - 1
 	-- hydro/flux/*.lua: the flux plug-in object carries its name ('roe', 'hll', 'rusanov')
-	d.flux = assert(({roe = lib.HB_FLUX_ROE, hll = lib.HB_FLUX_HLL, rusanov = lib.HB_FLUX_RUSANOV})[self.flux.name],
+	d.flux_param = self.flux.hllcMethod or 0          -- hydro/flux/euler-hllc.lua:17
+	d.flux = assert(({roe = lib.HB_FLUX_ROE, hll = lib.HB_FLUX_HLL, rusanov = lib.HB_FLUX_RUSANOV, ['euler-hllc'] = lib.HB_FLUX_EULER_HLLC})[self.flux.name],
 		"hydrob200: flux not built: "..tostring(self.flux.name))
 	if d.flux ~= lib.HB_FLUX_ROE then d.flux_limiter = 0 end   -- only roe usesFluxLimiter (hydro/flux/roe.lua)
 	local sides = {'xmin', 'xmax', 'ymin', 'ymax', 'zmin', 'zmax'}

@@ -53,7 +53,9 @@ struct ho_desc {
 	int nthreads;       // OpenMP threads (0 = default)
 	int global_n[3];    // 0 = same as n; otherwise the whole grid's interior size (this object is one slab of it): defines grid_dx
 	double eqn_params[16];   // eqn 2 (ADM3D): f_eqn option index, a_convCoeff, d_convCoeff, V_convCoeff (adm3d.lua:207-227)
-	int flux;           // 0 = roe (hydro/flux/roe.cl), 1 = hll 'Davis direct bounded' (hydro/flux/hll.cl, hll.lua:10), 2 = rusanov (hydro/flux/rusanov.cl)
+	int flux;           // 0 = roe (hydro/flux/roe.cl), 1 = hll 'Davis direct bounded' (hydro/flux/hll.cl, hll.lua:10), 2 = rusanov (hydro/flux/rusanov.cl),
+	                    // 3 = euler-hllc (hydro/flux/euler-hllc.cl)
+	int flux_param;     // euler-hllc: hllcMethod 0 | 1 | 2 (euler-hllc.lua:17, default 2)
 };
 }
 
@@ -1136,6 +1138,103 @@ template<class Eqn> struct Solver : SolverBase {
 		}
 	}
 
+	// ---- calcFluxForInterface, HLLC for the Euler equations: hydro/flux/euler-hllc.cl:14-243 ('Davis direct bounded' wave speeds,
+	// hllcMethod 0 / 1 / 2 = Toro 2012 eqns 38-39 / variation 1 / variation 2)
+	void hllcFlux(cons_t& flux, cons_t const& UL, cons_t const& UR, normal_t n) const {
+		if constexpr (Eqn::hasEigenForCell) {   // euler only
+			typedef typename Eqn::prim_t prim_t;
+			typedef typename Eqn::real3 real3;
+			prim_t WL; Eqn::primFromCons(WL, solver, UL);
+			prim_t WR; Eqn::primFromCons(WR, solver, UR);
+			eigen_t eigInt;
+			Eqn::eigen_forInterface(eigInt, solver, UL, UR, n);
+			real lambdaIntMin, lambdaIntMax;
+			Eqn::eigenWaveMinMax(lambdaIntMin, lambdaIntMax, solver, eigInt, n);
+			real lambdaLMin, lambdaRMax, unused;
+			Eqn::consWaveMinMax(lambdaLMin, unused, solver, UL, n);
+			Eqn::consWaveMinMax(unused, lambdaRMax, solver, UR, n);
+			real const sL = clmin<real>(lambdaLMin, lambdaIntMin);
+			real const sR = clmax<real>(lambdaRMax, lambdaIntMax);
+			real3 const vnL = normal_vecDotNs(n, WL.v);
+			real3 const vnR = normal_vecDotNs(n, WR.v);
+			real const sStar = (WR.rho * vnR.x * (sR - vnR.x) - WL.rho * vnL.x * (sL - vnL.x) + WL.P - WR.P)
+				/ (WR.rho * (sR - vnR.x) - WL.rho * (sL - vnL.x));
+			int const method = d.flux_param;
+			if (0 <= sL) {
+				Eqn::fluxFromCons(flux, solver, UL, n);
+			} else if (sL <= 0. && 0. <= sStar) {
+				cons_t FL; Eqn::fluxFromCons(FL, solver, UL, n);
+				if (method == 0) {
+					cons_t ULStar;
+					ULStar.rho = UL.rho * (sL - vnL.x) / (sL - sStar);
+					real3 const vStar = normal_vecFromNs(n, real3{sStar, vnL.y, vnL.z});
+					ULStar.m.x = ULStar.rho * vStar.x;
+					ULStar.m.y = ULStar.rho * vStar.y;
+					ULStar.m.z = ULStar.rho * vStar.z;
+					ULStar.ETotal = ULStar.rho * (UL.ETotal / UL.rho + (sStar - vnL.x) * (sStar + WL.P / (UL.rho * (sL - vnL.x))));
+					for (int i = 0; i < nI; ++i) flux.ptr[i] = FL.ptr[i] + sL * (ULStar.ptr[i] - UL.ptr[i]);
+				} else if (method == 1) {
+					flux.rho = (sStar * (sL * UL.rho - FL.rho)) / (sL - sStar);
+					real3 const ULmn = normal_vecDotNs(n, UL.m);
+					real3 const FLmn = normal_vecDotNs(n, FL.m);
+					flux.m = normal_vecFromNs(n, real3{
+						(sStar * (sL * ULmn.x - FLmn.x) + sL * (WL.P + WL.rho * (sL - vnL.x) * (sStar - vnL.x))) / (sL - sStar),
+						(sStar * (sL * ULmn.y - FLmn.y)) / (sL - sStar),
+						(sStar * (sL * ULmn.z - FLmn.z)) / (sL - sStar)});
+					flux.ETotal = (sStar * (sL * UL.ETotal - FL.ETotal) + sL * (WL.P + WL.rho * (sL - vnL.x) * (sStar - vnL.x)) * sStar) / (sL - sStar);
+				} else {
+					real const PLR = real(.5) * (WL.P + WR.P + WL.rho * (sL - vnL.x) * (sStar - vnL.x) + WR.rho * (sR - vnR.x) * (sStar - vnR.x));
+					flux.rho = (sL * UL.rho - FL.rho) * sStar / (sL - sStar);
+					real3 const ULmn = normal_vecDotNs(n, UL.m);
+					real3 const FLmn = normal_vecDotNs(n, FL.m);
+					flux.m = normal_vecFromNs(n, real3{
+						((sL * ULmn.x - FLmn.x) * sStar + sL * PLR) / (sL - sStar),
+						sStar * (sL * ULmn.y - FLmn.y) / (sL - sStar),
+						sStar * (sL * ULmn.z - FLmn.z) / (sL - sStar)});
+					flux.ETotal = (sStar * (sL * UL.ETotal - FL.ETotal) + sL * PLR * sStar) / (sL - sStar);
+				}
+			} else if (sStar <= 0. && 0. <= sR) {
+				cons_t FR; Eqn::fluxFromCons(FR, solver, UR, n);
+				if (method == 0) {
+					cons_t URStar;
+					URStar.rho = UR.rho * (sR - vnR.x) / (sR - sStar);
+					real3 const vStar = normal_vecFromNs(n, real3{sStar, vnR.y, vnR.z});
+					URStar.m.x = URStar.rho * vStar.x;
+					URStar.m.y = URStar.rho * vStar.y;
+					URStar.m.z = URStar.rho * vStar.z;
+					URStar.ETotal = URStar.rho * (UR.ETotal / UR.rho + (sStar - vnR.x) * (sStar + WR.P / (UR.rho * (sR - vnR.x))));
+					for (int i = 0; i < nI; ++i) flux.ptr[i] = FR.ptr[i] + sR * (URStar.ptr[i] - UR.ptr[i]);
+				} else if (method == 1) {
+					flux.rho = (sStar * (sR * UR.rho - FR.rho)) / (sR - sStar);
+					real3 const URmn = normal_vecDotNs(n, UR.m);
+					real3 const FRmn = normal_vecDotNs(n, FR.m);
+					flux.m = normal_vecFromNs(n, real3{
+						(sStar * (sR * URmn.x - FRmn.x) + sR * (WR.P + WR.rho * (sR - vnR.x) * (sStar - vnR.x))) / (sR - sStar),
+						(sStar * (sR * URmn.y - FRmn.y)) / (sR - sStar),
+						(sStar * (sR * URmn.z - FRmn.z)) / (sR - sStar)});
+					flux.ETotal = (sStar * (sR * UR.ETotal - FR.ETotal) + sR * (WR.P + WR.rho * (sR - vnR.x) * (sStar - vnR.x)) * sStar) / (sR - sStar);
+				} else {
+					real const PLR = real(.5) * (WL.P + WR.P + WL.rho * (sL - vnL.x) * (sStar - vnL.x) + WR.rho * (sR - vnR.x) * (sStar - vnR.x));
+					flux.rho = sStar * (sR * UR.rho - FR.rho) / (sR - sStar);
+					real3 const URmn = normal_vecDotNs(n, UR.m);
+					real3 const FRmn = normal_vecDotNs(n, FR.m);
+					flux.m = normal_vecFromNs(n, real3{
+						(sStar * (sR * URmn.x - FRmn.x) + sR * PLR) / (sR - sStar),
+						sStar * (sR * URmn.y - FRmn.y) / (sR - sStar),
+						sStar * (sR * URmn.z - FRmn.z) / (sR - sStar)});
+					flux.ETotal = (sStar * (sR * UR.ETotal - FR.ETotal) + sR * PLR * sStar) / (sR - sStar);
+				}
+			} else if (sR <= 0) {
+				Eqn::fluxFromCons(flux, solver, UR, n);
+			} else if (sL <= 0 && 0 <= sR) {
+				cons_t FL; Eqn::fluxFromCons(FL, solver, UL, n);
+				cons_t FR; Eqn::fluxFromCons(FR, solver, UR, n);
+				for (int j = 0; j < nI; ++j)
+					flux.ptr[j] = (sR * FL.ptr[j] - sL * FR.ptr[j] + sL * sR * (UR.ptr[j] - UL.ptr[j])) / (sR - sL);
+			}
+		}
+	}
+
 	// cell_area<side>: symmath product of the other axes' grid_dx (coord.lua:990-1015); 1 for dim==1
 	real cellArea(int side) const {
 		real area = 1.;
@@ -1168,6 +1267,7 @@ template<class Eqn> struct Solver : SolverBase {
 					}
 					if (d.flux == 1) hllFlux(flux, *UL, *UR, n);
 					else if (d.flux == 2) rusanovFlux(flux, *UL, *UR, n);
+					else if (d.flux == 3) hllcFlux(flux, *UL, *UR, n);
 					else if (useFluxLimiter) {
 						real const dt_dx = dt / dx;   // fvsolver.lua:135
 						long const indexR2 = indexR + solver.stepsize[side];

@@ -27,7 +27,7 @@ class ho_desc(C.Structure):
         ("mins", C.c_double * 3), ("maxs", C.c_double * 3),
         ("cfl", C.c_double), ("fixed_dt", C.c_double), ("use_fixed_dt", C.c_int),
         ("gamma", C.c_double), ("rhoMin", C.c_double), ("PMin", C.c_double), ("mu0_eff", C.c_double),
-        ("nthreads", C.c_int), ("global_n", C.c_int * 3), ("eqn_params", C.c_double * 16), ("flux", C.c_int),
+        ("nthreads", C.c_int), ("global_n", C.c_int * 3), ("eqn_params", C.c_double * 16), ("flux", C.c_int), ("flux_param", C.c_int),
     ]
 
 
@@ -90,6 +90,7 @@ def desc_from_solver(solver, nthreads=0):
     d.slope_limiter = solver.slopeLimiter
     d.flux_limiter = solver.fluxLimiter
     d.flux = solver.flux.fluxId
+    d.flux_param = getattr(solver.flux, 'fluxParam', 0)
     bcs = solver.boundaryIdList()
     if getattr(solver, "comm", None) is not None:
         bcs = solver.comm.localBoundaryIds(bcs, solver.dim)     # faces owned by a neighbouring slab: 'none'

@@ -51,6 +51,14 @@ CASES["F2_ot_rusanov_plm"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond
 CASES["F2_ot_hll_3d"] = (dict(eqn="mhd", dim=3, gridSize=[16, 12, 10], initCond="Orszag-Tang", flux="hll", integrator="Runge-Kutta 2, TVD",
                               cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]), 5)
 
+for _m in (0, 1, 2):
+    CASES["F2_sod_hllc%d_fe" % _m] = (dict(eqn="euler", dim=1, gridSize=[256], initCond="Sod", flux="euler-hllc", hllcMethod=_m,
+                                           integrator="forward Euler", cfl=.3), 60)
+    CASES["F2_sphere_hllc%d_plm_3d" % _m] = (dict(eqn="euler", dim=3, gridSize=[20, 16, 12], mins=[-2, -2, -2], maxs=[2, 2, 2],
+                                                  initCond="sphere", flux="euler-hllc", hllcMethod=_m, usePLM="plm cons",
+                                                  slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.1), 5)
+CASES["F2_kh_hllc_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 40], initCond="Kelvin-Helmholtz", flux="euler-hllc",
+                               integrator="Runge-Kutta 4", cfl=.15), 10)
 # 'plm athena' (plm.cl:782-879), both face orders (as in the tree / as recorded), Euler
 CASES["F1_sod_athena_fe"] = (dict(eqn="euler", dim=1, gridSize=[256], initCond="Sod", usePLM="plm athena", integrator="forward Euler", cfl=.3), 60)
 CASES["F1_sod_athena_rec_rk4"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm athena, recorded face order",
