@@ -227,3 +227,54 @@ def test_march_is_default_for_plm(hydrob200):
     cfg, _ = CASES["C1_sod_fe_superbee"]
     S = hydrob200.FiniteVolumeSolver(cfg)
     assert "fv_stage(tile)" in S.backend.describe()
+
+
+# ---- BASELINE.json's full sizes: size-independent properties (the oracle cannot run these in seconds)
+def _sums(U):
+    return U.reshape(-1, U.shape[-1]).sum(axis=0, dtype=np.float64)
+
+
+def test_full_size_c2_conservation_and_translation_symmetry(hydrob200):
+    """C2 (2048^2 Kelvin-Helmholtz, periodic, RK4-TVD): the flux form conserves every integrated variable to rounding, and the
+    initial condition's x -> x + 1 symmetry (frequency 2 on [-1, 1]) is preserved to rounding (every cell sees the same
+    operations as the cell half a domain away)."""
+    cfg = dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons", slopeLimiter="minmod",
+               integrator="Runge-Kutta 4, TVD", cfl=.15)
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    assert "fv_march" in S.backend.describe()
+    U0 = S.interior()
+    s0, a0 = _sums(U0[..., :5]), _sums(np.abs(U0[..., :5]))
+    S.update(10)
+    U1 = S.interior()
+    assert np.isfinite(U1).all() and S.t > 0
+    s1 = _sums(U1[..., :5])
+    # rounding of 4.2 M cells x 40 stage updates accumulates like a random walk: ~1e-12 relative
+    assert (np.abs(s1 - s0) / (a0 + 1e-300)).max() < 1e-11
+    # (to rounding, not bit for bit: the initial condition evaluates sin(4 pi x) at x and x + 1, which differ in the last bits)
+    assert np.abs(U1[:, :, :1024, :5] - U1[:, :, 1024:, :5]).max() <= 1e-11 * np.abs(U1[..., :5]).max()
+    assert np.abs(U1[..., :5] - U0[..., :5]).max() > 1e-6          # and it did move
+
+
+def test_full_size_c4_conservation_and_mirror_symmetry(hydrob200):
+    """C4 (512^3 spherical blast, RK4): before the wave reaches the freeflow boundaries mass, momentum and energy are conserved to
+    rounding; the solution keeps the mirror symmetries of the initial condition (rho, E even; m_x odd under x -> -x, ...) to
+    rounding -- a wrong halo, a missed tile or a stale ghost plane anywhere in the 512^3 grid breaks one of them."""
+    cfg = dict(eqn="euler", dim=3, gridSize=[512, 512, 512], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+               usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1)
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    U0 = S.interior()
+    s0, a0 = _sums(U0[..., :5]), _sums(np.abs(U0[..., :5]))
+    del U0
+    S.update(4)
+    U = S.interior()
+    assert np.isfinite(U).all() and S.t > 0
+    s1 = _sums(U[..., :5])
+    scale = np.maximum(a0, a0[[0, 4]].max())          # momentum sums are ~0: measure them against the mass / energy scale
+    assert (np.abs(s1 - s0) / scale).max() < 1e-12
+    rho, mx, my, mz, E = (U[..., q] for q in range(5))
+    for ax, m in ((2, mx), (1, my), (0, mz)):
+        tol = 1e-12
+        assert np.abs(rho - np.flip(rho, axis=ax)).max() <= tol * np.abs(rho).max()
+        assert np.abs(E - np.flip(E, axis=ax)).max() <= tol * np.abs(E).max()
+        assert np.abs(m + np.flip(m, axis=ax)).max() <= tol * max(np.abs(m).max(), 1e-300)
+    assert np.abs(mx).max() > 1e-4                      # the blast is moving
