@@ -322,7 +322,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 				if constexpr (DIM == 3 && C::VAR == 3 && Eqn::FAST && Eqn::eqnId == 0) {
 					// z flux on its own; x and y cores as one block; a state pair on one of the reference's special branches (rare) is
 					// redone by the literal code from operands re-read from shared memory, so no operand stays live across the cores
-					roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+					roeFluxAuto<Eqn, MS, DIM == 3>(Fz, ep, zfP, UR);
 					bool const rx = eulerRoeFluxCore<Eqn, 0>(Fx, ep, ULx, URx);
 					bool const ry = eulerRoeFluxCore<Eqn, 1>(Fy, ep, ULy, URy);
 					if (!(rx && ry)) {
@@ -345,7 +345,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 				} else if constexpr (DIM == 3) {
 					if constexpr (C::VAR == 1) roeFluxTripleAuto<Eqn, MS, 0, 1>(Fz, Fx, Fy, ep, zfP, UR, ULx, URx, ULy, URy);
 					else {
-						roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+						roeFluxAuto<Eqn, MS, DIM == 3>(Fz, ep, zfP, UR);
 						roeFluxPairAuto<Eqn, 0, 1>(Fx, Fy, ep, ULx, URx, ULy, URy);
 					}
 				} else {
@@ -358,7 +358,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 					fxx[(q * TY + cj) * (TX + 1) + ci] = on0 ? Fx[q] : real(0);
 					if (DIM == 3) fxy[(q * (TY + 1) + cj) * TX + ci] = on1 ? Fy[q] : real(0);
 				}
-			} else if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+			} else if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS, DIM == 3>(Fz, ep, zfP, UR);
 			if (k > kb && inside) {
 				real acc[nI];
 				#pragma unroll
@@ -398,7 +398,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 				zfN[q] = Uk[q] + s;
 				Fz[q] = 0;
 			}
-			if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+			if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS, DIM == 3>(Fz, ep, zfP, UR);
 			if (k > kb && inside) {
 				real acc[nI];
 				#pragma unroll
@@ -445,7 +445,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 						UL[q] = P[q * PS + ob - 1] + sg[0];
 						UR[q] = P[q * PS + ob] - sg[1];
 					}
-					roeFluxAuto<Eqn, 0>(F, ep, UL, UR);
+					roeFluxAuto<Eqn, 0, DIM == 3>(F, ep, UL, UR);
 				} else {
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) F[q] = 0;
@@ -463,7 +463,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 						UL[q] = P[q * PS + ob - BX] + sg[0];
 						UR[q] = P[q * PS + ob] - sg[TX];
 					}
-					roeFluxAuto<Eqn, 1>(F, ep, UL, UR);
+					roeFluxAuto<Eqn, 1, DIM == 3>(F, ep, UL, UR);
 				} else {
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) F[q] = 0;
