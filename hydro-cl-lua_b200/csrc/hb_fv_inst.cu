@@ -88,8 +88,22 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(2, 2, 1, 32, 4, 0)    /* 64 columns, 3 warps */ \
 	X(3, 6, 1, 64, 1, 0)    /* 192 columns, 7 warps (TMA boxes are at most 256 elements wide) */
 #endif
+// 2-D warp-per-pencil kernel (hb_fv_march2d.cuh): X(index, NW, KM, MINB); these come first in the 2-D cfg numbering
+#ifdef HB_STRICT
+#define HB_MARCH2W_LIST(X) X(0, 4, 32, 1)
+#else
+#define HB_MARCH2W_LIST(X) X(0, 4, 32, 1) X(1, 2, 32, 1) X(2, 8, 32, 1)
+#endif
+constexpr int kMarch2W =
+#define HB_X(i, nw, km, mb) +1
+	0 HB_MARCH2W_LIST(HB_X);
+#undef HB_X
 // per-equation default: the host starts at cfg 0; 2-D MHD prefers list entry 1
-constexpr int remapCfg(int dim, int cfg) { return (Eqn::eqnId == 1 && dim == 2 && cfg < 2) ? 1 - cfg : cfg; }
+constexpr int remapCfg(int dim, int cfg) {
+	if (dim != 2 || cfg < kMarch2W) return cfg;
+	int const c = cfg - kMarch2W;                                // index into HB_MARCH2_LIST
+	return kMarch2W + ((Eqn::eqnId == 1 && c < 2) ? 1 - c : c);
+}
 
 constexpr size_t kSmemLimit = 232448 - 1024;   // 227 KB opt-in maximum per CTA minus the kernel's static shared memory (rounded up)
 
@@ -123,6 +137,58 @@ cudaError_t launchMarchLim(int lim, const CUtensorMap* tmap, int padX, GridP<rea
 	if (lim == 18) return launchMarch<DIM, 18, C>(tmap, padX, g, sp, ep, chunkSel, st);    // superbee
 	return cudaErrorInvalidValue;
 }
+template<int LIM, class C>
+cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
+	typedef March2Geom<C, real> G;
+	auto kern = fv_march2d<Eqn, LIM, C, MODE>;
+	int nOps = sp.nB;
+	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
+	size_t const smemMax = G::template smemBytes<Eqn::nI>(2 * HB_MAX_TERMS);
+	static bool attrSet = false;
+	if (!attrSet) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemMax < kSmemLimit ? smemMax : kSmemLimit));
+		if (e != cudaSuccess) return e;
+		attrSet = true;
+	}
+	if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+	long long const nSeg = (g.N[0] + G::CW - 1) / G::CW;
+	// rows per warp.  The warps are independent, so the grid is nSeg x ceil(N1 / KM) warps; a short chunk costs one extra interface
+	// row per KM rows, a long one leaves the last warps of a small grid alone on the GPU.  Measured on 2048^2 (profiles/r01c_sweep_2d_warp.txt):
+	// Euler 16 rows 0.253 ms, 32 rows 0.279, 48 rows 0.303; MHD 0.543 / 0.547 / 0.553 (64).  16 rows until the grid fills the GPU
+	// eight times over, then 32.  $HB_MARCH2_KM overrides.
+	static int kmCache = 0; static long long kmFor[2] = {0, 0};
+	if (!kmCache || kmFor[0] != g.N[0] || kmFor[1] != g.N[1]) {
+		int perSM = 0, dev = 0, sms = 148;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, G::NT, smem) != cudaSuccess || perSM < 1) perSM = 1;
+		long long const conc = (long long)sms * perSM * C::NW;
+		int km = nSeg * ((g.N[1] + 15) / 16) <= 8 * conc ? 16 : 32;
+		if (const char* e = getenv("HB_MARCH2_KM")) if (atoi(e) >= 2) km = atoi(e);
+		kmCache = km; kmFor[0] = g.N[0]; kmFor[1] = g.N[1];
+	}
+	int const KM = kmCache;
+	long long nm = (g.N[1] + KM - 1) / KM;
+	if (chunkSel == 1) nm = nm < 2 ? nm : 2;
+	else if (chunkSel == 2) nm = nm > 2 ? nm - 2 : 0;
+	if (nm == 0) return cudaSuccess;
+	long long const blocks = (nSeg * nm + C::NW - 1) / C::NW;
+	kern<<<(unsigned)blocks, G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX, chunkSel, KM);
+	return cudaGetLastError();
+}
+template<class C>
+cudaError_t launchMarch2WLim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
+	if (lim == 8) return launchMarch2W<8, C>(tmap, padX, g, sp, ep, chunkSel, st);
+	if (lim == 18) return launchMarch2W<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
+	return cudaErrorInvalidValue;
+}
+template<class C> void march2WInfoCfg(int box[4], int info[6]) {
+	typedef March2Geom<C, real> G;
+	box[0] = G::BX; box[1] = 1; box[2] = 1; box[3] = Eqn::nI;
+	info[0] = G::CW * C::NW; info[1] = 1; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
+	info[5] = C::NW * 32;
+}
 template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
 	typedef MarchGeom<DIM, C, real> G;
 	box[0] = G::BX; box[1] = DIM == 3 ? G::BY : 1; box[2] = 1; box[3] = Eqn::nI;
@@ -135,7 +201,10 @@ bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int i
 #define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<3, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) return false; }
 #undef HB_X
-#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<2, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
+#define HB_X(i, nw, km, mb) if (cfg == i) { march2WInfoCfg<March2Cfg<nw, km, mb>>(box, info); return true; }
+	HB_MARCH2W_LIST(HB_X)
+#undef HB_X
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == kMarch2W + i) { marchInfoCfg<2, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
 	HB_MARCH2_LIST(HB_X)
 #undef HB_X
 	return false;
@@ -145,8 +214,11 @@ cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, 
 #define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) }
 #undef HB_X
-#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<2, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
-	else if (dim == 2) { HB_MARCH2_LIST(HB_X) }
+#define HB_X(i, nw, km, mb) if (cfg == i) return launchMarch2WLim<March2Cfg<nw, km, mb>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
+	else if (dim == 2) { HB_MARCH2W_LIST(HB_X) }
+#undef HB_X
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == kMarch2W + i) return launchMarchLim<2, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
+	if (dim == 2) { HB_MARCH2_LIST(HB_X) }
 #undef HB_X
 	return cudaErrorInvalidValue;
 }

@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 #include "hb_fv_kernels.cuh"
 #include "hb_fv_march.cuh"
+#include "hb_fv_march2d.cuh"
 
 namespace hb {
 

@@ -211,6 +211,19 @@ def test_march_kernel_equals_tile_kernel_strict(hydrob200, name, precision):
     assert bad.size == 0, "first mismatches (k,j,i,var): %s  max|diff| %g" % (bad[:5].tolist(), np.abs(a - b).max())
 
 
+@pytest.mark.parametrize("name", ["march2d_kh", "march2d_mhd"])
+def test_cta_march_kernel_2d_equals_warp_kernel_strict(hydrob200, monkeypatch, name):
+    """2-D has two marching kernels: fv_march2d (one warp per pencil, the default) and the CTA-tiled fv_march (HB_MARCH_CFG past the
+    warp kernel's configurations: index 1 in the strict build).  Same arithmetic per cell: bit-identical."""
+    cfg, n = MARCH_CASES[name]
+    cfg = dict(cfg, strict_fp=True)
+    a, ta, SA = run(hydrob200, cfg, n, stage_kernel=2)
+    monkeypatch.setenv("HB_MARCH_CFG", "1")
+    b, tb, SB = run(hydrob200, cfg, n, stage_kernel=2)
+    assert "fv_march2d(warp-per-pencil" in SA.backend.describe() and "fv_march(tma)" in SB.backend.describe(), (SA.backend.describe(), SB.backend.describe())
+    assert ta == tb and np.array_equal(a, b)
+
+
 @pytest.mark.parametrize("name", ["march3d_freeflow", "march2d_kh"])
 def test_march_kernel_fast_close_to_tile_kernel(hydrob200, name):
     cfg, n = MARCH_CASES[name]
