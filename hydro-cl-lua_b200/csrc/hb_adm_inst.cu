@@ -60,6 +60,7 @@ cudaError_t stage(int dim, bool, bool, GridP<real> const& g, StageP<real> const&
 	long long const n = (long long)g.N[0] * g.N[1] * g.N[2];
 	int const nt = 128;
 	static int const split = getenv("HB_ADM_SPLIT") ? atoi(getenv("HB_ADM_SPLIT")) : 1;
+	tlsStageLaunches = (sp.computeL ? dim : 0) + (split == 2 ? 4 : (split ? 6 : 1));
 	unsigned const nb = (unsigned)((n + nt - 1) / nt);
 	if (split == 2) {
 		adm_update<Eqn, MODE, 0><<<nb, nt, 0, st>>>(g, sp, ep, sp.scratch);

@@ -23,6 +23,8 @@
 
 namespace hb {
 
+thread_local int tlsStageLaunches = 1;
+
 // Step bookkeeping on the device (solverbase.lua:3160-3173): dt = fixedDT | cfl * min ; t += dt.
 // Runs at the top of every update so that a whole update is one stream-ordered (graph-capturable) sequence
 // with no host read-back.  `ctl` = { t, dt, cfl, fixedDT(<0: adaptive) }.
@@ -539,10 +541,11 @@ template<class real> struct Fv : FvBase {
 				launches += 4;
 				continue;
 			}
+			tlsStageLaunches = 1;
 			if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 0, st()));
 			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
-			launches++;
+			launches += tlsStageLaunches;
 			if (int r = fillGhosts(upool[s.uOut], rk ? nI : nS)) return r;
 		}
 		if (int r = reduceDtMin()) return r;

@@ -10,6 +10,10 @@
 
 namespace hb {
 
+// kernels launched by the last FvOps::stage call on this thread (a stage of the ADM equation is several launches); read by hb_fv.cu
+// for hb_fv_launch_count
+extern thread_local int tlsStageLaunches;
+
 template<class real> struct FvOps {
 	int eqnId, nS, nI, nW;
 	cudaError_t (*stage)(int dim, bool plm, bool flim, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st);
