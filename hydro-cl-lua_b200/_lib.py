@@ -79,6 +79,9 @@ SIGNATURES = {
     "hb_fv_num_cells": (C.c_longlong, [P]),
     "hb_fv_set_state": (C.c_int, [P, P]),
     "hb_fv_get_state": (C.c_int, [P, P]),
+    "hb_fv_set_state_async": (C.c_int, [P, P]),
+    "hb_fv_get_state_async": (C.c_int, [P, P]),
+    "hb_fv_wait_transfers": (C.c_int, [P]),
     "hb_fv_state_devptr": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "hb_fv_boundary": (C.c_int, [P]),
     "hb_fv_constrainU": (C.c_int, [P]),

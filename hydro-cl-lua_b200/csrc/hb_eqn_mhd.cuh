@@ -27,7 +27,6 @@ template<class real_, bool FAST_ = false> struct MHD {
 	static constexpr int eqnId = 1;
 	static constexpr int nS = 10, nI = 8, nW = 7;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/mhd.lua:19
-	static constexpr bool hasEigenForCell = false;     // 'plm athena' is built for euler
 	struct Params { real gamma, mu0; real g2_g1, iMu0, iG1; };   // the last three: production forms only (gamma_2/gamma_1, 1/mu0, 1/gamma_1)
 	static HB_HD Params makeParams(const double* p) {
 		return Params{real(p[0]), real(p[1]), real((p[0] - 2.) / (p[0] - 1.)), real(1. / p[1]), real(1. / (p[0] - 1.))};
@@ -110,7 +109,11 @@ template<class real_, bool FAST_ = false> struct MHD {
 		B[2] = (sqrtRhoR * BL[2] + sqrtRhoL * BR[2]) * invDenom;
 		real const X = real(.5) * (dby * dby + dbz * dbz) * invDenom * invDenom;
 		real const Y = real(.5) * (UL[0] + UR[0]) / rho;
-		// ---- eigen_forRoeAvgs
+		eigen_forRoeAvgs(e, s, rho, v, hTotal, B, X, Y);
+	}
+
+	// eigen_forRoeAvgs, hydro/eqn/mhd.cl:346-436: v, B are taken as x-aligned with the interface normal
+	static HB_HD void eigen_forRoeAvgs(Eig& e, Params const& s, real rho, real const (&v)[3], real hTotal, real const (&B)[3], real X, real Y) {
 		real const gamma_1 = s.gamma - real(1.);
 		real const gamma_2 = s.gamma - real(2.);
 		real const _1_rho = real(1.) / rho;
@@ -156,6 +159,25 @@ template<class real_, bool FAST_ = false> struct MHD {
 		e.As = aTilde * e.alphaS * _1_sqrtRho;
 		e.rho = rho; e.hTotal = hTotal; e.X = X; e.Y = Y;
 		for (int q = 0; q < 3; ++q) { e.v[q] = v[q]; e.B[q] = B[q]; }
+	}
+
+	// eigen_forCell, hydro/eqn/mhd.cl:859-881 (used by 'plm athena').  The cell's v and B enter as they are, NOT rotated into the
+	// normal's frame as calcRoeValues does -- reproduced.
+	static constexpr bool hasEigenForCell = true;
+	static HB_HD void eigen_forCell(Eig& e, Params const& s, real const (&U)[nI]) {
+		Prim W; primFromCons(W, s, U);
+		real const PMag = real(.5) * lenSq3(W.B[0], W.B[1], W.B[2]);
+		real const hTotal = (U[4] + W.P + PMag) / W.rho;
+		eigen_forRoeAvgs(e, s, W.rho, W.v, hTotal, W.B, real(0), real(1));
+	}
+	// prim_t as an array in the reference's field order (rho, v.xyz, P, B.xyz): plm.cl casts prim_t and cons_t into each other
+	static HB_HD void primArray(real (&w)[nI], Params const& s, real const (&U)[nI]) {
+		Prim W; primFromCons(W, s, U);
+		w[0] = W.rho; w[1] = W.v[0]; w[2] = W.v[1]; w[3] = W.v[2]; w[4] = W.P; w[5] = W.B[0]; w[6] = W.B[1]; w[7] = W.B[2];
+	}
+	static HB_HD void consFromPrimArray(real (&U)[nI], Params const& s, real const (&w)[nI]) {
+		Prim W; W.rho = w[0]; W.v[0] = w[1]; W.v[1] = w[2]; W.v[2] = w[3]; W.P = w[4]; W.B[0] = w[5]; W.B[1] = w[6]; W.B[2] = w[7];
+		consFromPrim(U, s, W);
 	}
 
 	template<int SIDE> static HB_HD void waves(real (&lam)[nW], Params const&, Eig const& e) {

@@ -161,6 +161,9 @@ struct FvBase {
 	virtual int init() = 0;
 	virtual int setState(const double* aos) = 0;
 	virtual int getState(double* aos) = 0;
+	virtual int setStateAsync(const double* aos) = 0;
+	virtual int getStateAsync(double* aos) = 0;
+	virtual int waitTransfers() = 0;
 	virtual int stateDevPtr(void** p, long long* sy, long long* sz, long long* sv) = 0;
 	virtual int boundary() = 0;
 	virtual int constrainU() = 0;
@@ -196,6 +199,13 @@ template<class real> struct Fv : FvBase {
 	real* scratchL = nullptr;
 	real* opsScratch = nullptr;            // FvOps::scratchElems (ADM flux arrays)
 	double* stagingAos = nullptr;
+	// asynchronous state transfer (hb_fv_set_state_async / get_state_async): one staging buffer and one copy stream per direction,
+	// so that an upload, the solver's work and a download overlap (PCIe is full duplex; the two directions use different copy engines)
+	double* stagingIn = nullptr;
+	double* stagingOut = nullptr;
+	cudaStream_t upStream = nullptr, downStream = nullptr;
+	cudaEvent_t evUpDone = nullptr, evInFree = nullptr, evOutReady = nullptr, evDownDone = nullptr;
+	bool inUsed = false, downUsed = false;
 	double* ctl = nullptr;                 // device: t, dt, cfl, fixedDT(<0 adaptive)
 	unsigned long long* dtMinBits = nullptr;
 	std::vector<StagePlan> plan;
@@ -233,6 +243,11 @@ template<class real> struct Fv : FvBase {
 		if (scratchL) cudaFree(scratchL - padX);
 		if (opsScratch) cudaFree(opsScratch - padX);
 		if (stagingAos) cudaFree(stagingAos);
+		if (upStream) { cudaStreamSynchronize(upStream); cudaStreamDestroy(upStream); }
+		if (downStream) { cudaStreamSynchronize(downStream); cudaStreamDestroy(downStream); }
+		if (stagingIn) cudaFree(stagingIn);
+		if (stagingOut) cudaFree(stagingOut);
+		for (cudaEvent_t e : {evUpDone, evInFree, evOutReady, evDownDone}) if (e) cudaEventDestroy(e);
 		if (ctl) cudaFree(ctl);
 		if (dtMinBits) cudaFree(dtMinBits);
 		if (comm) Nccl::get().CommDestroy(comm);
@@ -386,6 +401,59 @@ template<class real> struct Fv : FvBase {
 		launches++;
 		HB_CUDA(cudaMemcpyAsync(aos, stagingAos, sizeof(double) * n, cudaMemcpyDeviceToHost, st()));
 		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
+	}
+	int ensureAsync() {
+		if (upStream) return HB_OK;
+		size_t const bytes = sizeof(double) * (size_t)nS * (size_t)cells;
+		HB_CUDA(cudaMalloc(&stagingIn, bytes));
+		HB_CUDA(cudaMalloc(&stagingOut, bytes));
+		HB_CUDA(cudaStreamCreateWithFlags(&upStream, cudaStreamNonBlocking));
+		HB_CUDA(cudaStreamCreateWithFlags(&downStream, cudaStreamNonBlocking));
+		for (cudaEvent_t* e : {&evUpDone, &evInFree, &evOutReady, &evDownDone}) HB_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+		return HB_OK;
+	}
+	// UBufObj:fromCPU without blocking the host: the copy runs on the upload stream, the solver's stream waits for it before the
+	// AoS -> SoA kernel.  The host buffer (pinned) must stay unchanged until hb_fv_wait_transfers or a later blocking call.
+	int setStateAsync(const double* aos) override {
+		if (!aos) return setError(HB_ERR_INVALID, "hb_fv_set_state_async: null pointer");
+		useDevice(ctx);
+		if (int r = ensureAsync()) return r;
+		size_t const n = (size_t)nS * (size_t)cells;
+		if (inUsed) HB_CUDA(cudaStreamWaitEvent(upStream, evInFree, 0));     // the previous AoS -> SoA kernel has read the staging buffer
+		HB_CUDA(cudaMemcpyAsync(stagingIn, aos, sizeof(double) * n, cudaMemcpyHostToDevice, upStream));
+		HB_CUDA(cudaEventRecord(evUpDone, upStream));
+		HB_CUDA(cudaStreamWaitEvent(st(), evUpDone, 0));
+		aos_to_soa<real><<<(unsigned)((n + 255) / 256), 256, 0, st()>>>(grid, nS, stagingIn, upool[0]);
+		HB_CUDA(cudaGetLastError());
+		HB_CUDA(cudaEventRecord(evInFree, st()));
+		inUsed = true;
+		launches++;
+		dtValid = false; rkZeroed = false; nonIntSync = 2;
+		return HB_OK;
+	}
+	// UBufObj:toCPU without blocking the host: SoA -> AoS on the solver's stream, the copy on the download stream.
+	int getStateAsync(double* aos) override {
+		if (!aos) return setError(HB_ERR_INVALID, "hb_fv_get_state_async: null pointer");
+		useDevice(ctx);
+		if (int r = ensureAsync()) return r;
+		size_t const n = (size_t)nS * (size_t)cells;
+		if (downUsed) HB_CUDA(cudaStreamWaitEvent(st(), evDownDone, 0));     // the previous download has left the staging buffer
+		soa_to_aos<real><<<(unsigned)((n + 255) / 256), 256, 0, st()>>>(grid, nS, upool[0], stagingOut);
+		HB_CUDA(cudaGetLastError());
+		launches++;
+		HB_CUDA(cudaEventRecord(evOutReady, st()));
+		HB_CUDA(cudaStreamWaitEvent(downStream, evOutReady, 0));
+		HB_CUDA(cudaMemcpyAsync(aos, stagingOut, sizeof(double) * n, cudaMemcpyDeviceToHost, downStream));
+		HB_CUDA(cudaEventRecord(evDownDone, downStream));
+		downUsed = true;
+		return HB_OK;
+	}
+	int waitTransfers() override {
+		useDevice(ctx);
+		if (upStream) HB_CUDA(cudaStreamSynchronize(upStream));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		if (downStream) HB_CUDA(cudaStreamSynchronize(downStream));
 		return HB_OK;
 	}
 	int stateDevPtr(void** p, long long* sy, long long* sz, long long* sv) override {
@@ -753,7 +821,8 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	}
 	if (d->rk_order < 0 || d->rk_order > 4) return setError(HB_ERR_INVALID, "hb_fv_create: rk_order must be 0..4");
 	if (d->use_plm < 0 || d->use_plm > 3) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM must be none, 'plm cons' or 'plm athena'");
-	if (d->use_plm >= 2 && d->eqn != HB_EQN_EULER) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' is built for euler");
+	if (d->use_plm >= 2 && d->eqn == HB_EQN_ADM3D) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' is built for euler and mhd");
+	if (d->use_plm >= 2 && d->eqn == HB_EQN_MHD && d->dim == 3) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' for mhd is built for 1-D and 2-D grids (the 3-D tile does not hold both face states of 8 variables in shared memory)");
 	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");
 	if (d->use_plm && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM requires fluxLimiter 'donor cell' (gridsolver.lua:119)");
 	if (d->flux < 0 || d->flux > HB_FLUX_EULER_HLLC) return setError(HB_ERR_INVALID, "hb_fv_create: unknown flux");
@@ -791,6 +860,9 @@ int hb_fv_num_states(hb_fv* fv, int* ns, int* ni, int* nw) { HB_FV(fv); if (ns) 
 long long hb_fv_num_cells(hb_fv* fv) { return fv ? fv->impl->cells : 0; }
 int hb_fv_set_state(hb_fv* fv, const double* aos) { HB_FV(fv); return fv->impl->setState(aos); }
 int hb_fv_get_state(hb_fv* fv, double* aos) { HB_FV(fv); return fv->impl->getState(aos); }
+int hb_fv_set_state_async(hb_fv* fv, const double* aos) { HB_FV(fv); return fv->impl->setStateAsync(aos); }
+int hb_fv_get_state_async(hb_fv* fv, double* aos) { HB_FV(fv); return fv->impl->getStateAsync(aos); }
+int hb_fv_wait_transfers(hb_fv* fv) { HB_FV(fv); return fv->impl->waitTransfers(); }
 int hb_fv_state_devptr(hb_fv* fv, void** p, long long* sy, long long* sz, long long* sv) { HB_FV(fv); return fv->impl->stateDevPtr(p, sy, sz, sv); }
 int hb_fv_boundary(hb_fv* fv) { HB_FV(fv); return fv->impl->boundary(); }
 int hb_fv_constrainU(hb_fv* fv) { HB_FV(fv); return fv->impl->constrainU(); }

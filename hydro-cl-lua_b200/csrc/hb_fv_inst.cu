@@ -34,9 +34,12 @@ cudaError_t launchStage(GridP<real> const& g, StageP<real> const& sp, const doub
 	auto kern = fv_stage<Eqn, DIM, PLM, FLIM, T, MODE>;
 	size_t const smem = G::template smemBytes<real, Eqn::nI>(PLM ? (sp.plmMode >= 2 ? 2 : 1) : 0);
 	if (sp.plmMode >= 2 && !Eqn::hasEigenForCell) return cudaErrorInvalidValue;
+	constexpr size_t kLimit = 232448 - 1024;
+	if (smem > kLimit) return cudaErrorInvalidConfiguration;     // 'plm athena' keeps both face states: 3-D MHD does not fit this tile
 	static bool attrSet = false;
 	if (!attrSet) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::template smemBytes<real, Eqn::nI>(PLM ? (Eqn::hasEigenForCell ? 2 : 1) : 0));
+		size_t const athena = G::template smemBytes<real, Eqn::nI>(PLM ? 2 : 0), cons = G::template smemBytes<real, Eqn::nI>(PLM ? 1 : 0);
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(Eqn::hasEigenForCell && athena <= kLimit ? athena : cons));
 		if (e != cudaSuccess) return e;
 		attrSet = true;
 	}

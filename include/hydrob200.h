@@ -111,7 +111,7 @@ typedef struct hb_fv_desc {
 	int dim;                  /* 1..3 */
 	int n[3];                 /* interior cells of THIS rank's slab per axis (1 on unused axes) */
 	int global_n[3];          /* interior cells of the whole grid (== n without decomposition); defines grid_dx */
-	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879, euler), 3 = 'plm athena'
+	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879; euler, mhd in 1-D / 2-D), 3 = 'plm athena'
 	                           * with the face states assigned L = left, R = right: the order that reproduces the errors the reference
 	                           * recorded for this scheme (its tree has them the other way round at plm.cl:877-878) */
 	int slope_limiter;        /* 0-based index into hydro/app.lua:614-635 */
@@ -141,6 +141,13 @@ long long hb_fv_num_cells(hb_fv* fv);                        /* ghost-inclusive 
  * ghost cells included; converted to/from the SoA `real` device layout on the device */
 int hb_fv_set_state(hb_fv* fv, const double* aos_host);
 int hb_fv_get_state(hb_fv* fv, double* aos_host);           /* blocking */
+/* The same transfers without blocking the host (clEnqueueWrite/ReadBuffer with blocking = false): upload and download run on their
+ * own copy streams with their own staging buffers, ordered against the solver's stream by events, so that the upload of the next
+ * problem, the update of the current one and the download of the previous one overlap.  Host buffers must be pinned (hb_host_alloc)
+ * and stay untouched until hb_fv_wait_transfers returns. */
+int hb_fv_set_state_async(hb_fv* fv, const double* aos_host);
+int hb_fv_get_state_async(hb_fv* fv, double* aos_host);
+int hb_fv_wait_transfers(hb_fv* fv);
 int hb_fv_state_devptr(hb_fv* fv, void** soa_dev, long long* stride_y, long long* stride_z, long long* stride_var);
 int hb_fv_boundary(hb_fv* fv);                               /* solver:boundary(), gridsolver.lua:1316 */
 int hb_fv_init_derivs(hb_fv* fv);                            /* initDerivsKernelObj(), hydro/init/init.lua:231-235 (adm3d.cl:196-243); no-op for other equations */

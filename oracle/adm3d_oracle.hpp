@@ -33,6 +33,7 @@ template<class real_> struct ADM3D {
 	enum { numStates = 51, numIntStates = 37, numWaves = 13 };
 	static constexpr bool roeUseFluxFromCons = false;   // adm3d.lua:21
 	static constexpr bool hasEigenForCell = false;
+	static constexpr bool isEuler = false;
 	static constexpr bool hasWaveMinMax = false;        // hll / rusanov are not restated for this equation
 	static constexpr bool hasSource = true;
 	enum { iAlpha = 0, iGamma = 1, iA = 7, iD = 10, iK = 28, iV = 34, iRho = 37, iSu = 38, iSll = 41, iH = 47, iMu = 48 };

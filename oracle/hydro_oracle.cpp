@@ -158,6 +158,7 @@ template<class real_> struct Euler {
 	enum { numStates = 6, numIntStates = 5, numWaves = 5 };   // euler.lua:13-14,166-171
 	static const bool roeUseFluxFromCons = true;               // eqn.lua:46
 	static const bool hasWaveMinMax = true;                    // hll / rusanov fluxes restated for this equation
+	static const bool isEuler = true;                          // euler-hllc is an Euler-only flux (euler-hllc.cl:7-11)
 	static constexpr bool hasSource = false;                   // cartesian: no addSource kernel work
 	union cons_t { struct { real rho; real3 m; real ETotal; real ePot; }; real ptr[6]; };
 	struct prim_t { real rho; real3 v; real P; real ePot; };
@@ -379,7 +380,8 @@ template<class real_> struct MHD {
 	enum { numStates = 10, numIntStates = 8, numWaves = 7 };   // mhd.lua:16-17,76-83
 	static const bool roeUseFluxFromCons = true;                // mhd.lua:19
 	static const bool hasWaveMinMax = true;
-	static const bool hasEigenForCell = false;                  // 'plm athena' is restated for euler only
+	static const bool hasEigenForCell = true;                   // mhd.cl:859-881
+	static const bool isEuler = false;
 	static constexpr bool hasSource = false;                    // mhd.cl:885-911 addSource is empty on a cartesian grid
 	union cons_t { struct { real rho; real3 m; real ETotal; real3 B; real psi; real ePot; }; real ptr[10]; };
 	struct prim_t { real rho; real3 v; real P; real3 B; real psi; real ePot; };
@@ -500,6 +502,15 @@ template<class real_> struct MHD {
 		e.rho = roe.rho; e.v = roe.v; e.hTotal = roe.hTotal; e.B = roe.B; e.X = roe.X; e.Y = roe.Y;
 	}
 	// mhd.cl:558-571
+	// mhd.cl:859-881 (used by 'plm athena').  The cell's v and B go into the Roe record as they are, NOT rotated into the normal's
+	// frame as calcRoeValues does (:303-309) -- reproduced.
+	static void eigen_forCell(eigen_t& e, S const& s, cons_t const& U, normal_t) {
+		prim_t W; primFromCons(W, s, U);
+		real const PMag = real(.5) * coordLenSq(W.B);
+		real const hTotal = (U.ETotal + W.P + PMag) / W.rho;
+		roe_t roe; roe.rho = W.rho; roe.v = W.v; roe.hTotal = hTotal; roe.B = W.B; roe.X = 0; roe.Y = 1;
+		eigen_forRoeAvgs(e, s, roe);
+	}
 	static void eigen_forInterface(eigen_t& e, S const& s, cons_t const& UL, cons_t const& UR, normal_t n) {
 		roe_t roe; calcRoeValues(roe, s, UL, UR, n);
 		eigen_forRoeAvgs(e, s, roe);
@@ -1141,7 +1152,7 @@ template<class Eqn> struct Solver : SolverBase {
 	// ---- calcFluxForInterface, HLLC for the Euler equations: hydro/flux/euler-hllc.cl:14-243 ('Davis direct bounded' wave speeds,
 	// hllcMethod 0 / 1 / 2 = Toro 2012 eqns 38-39 / variation 1 / variation 2)
 	void hllcFlux(cons_t& flux, cons_t const& UL, cons_t const& UR, normal_t n) const {
-		if constexpr (Eqn::hasEigenForCell) {   // euler only
+		if constexpr (Eqn::isEuler) {
 			typedef typename Eqn::prim_t prim_t;
 			typedef typename Eqn::real3 real3;
 			prim_t WL; Eqn::primFromCons(WL, solver, UL);

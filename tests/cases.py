@@ -70,6 +70,13 @@ CASES["F1_sphere_athena_rec_3d"] = (dict(eqn="euler", dim=3, gridSize=[24, 18, 1
 CASES["F1_sphere_athena_hll_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 10], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
                                          usePLM="plm athena", flux="hll", integrator="Runge-Kutta 2, TVD", cfl=.05), 4)
 
+CASES["F1_briowu_athena_rk2"] = (dict(eqn="mhd", dim=1, gridSize=[256], initCond="Brio-Wu", usePLM="plm athena, recorded face order",
+                                      integrator="Runge-Kutta 2, TVD", cfl=.3), 50)
+CASES["F1_ot_athena_2d"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond="Orszag-Tang", usePLM="plm athena, recorded face order",
+                                 integrator="Runge-Kutta 3, TVD", cfl=.15), 10)
+CASES["F1_ot_athena_tree_hll_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 28], initCond="Orszag-Tang", usePLM="plm athena", flux="hll",
+                                          integrator="Runge-Kutta 2, TVD", cfl=.1), 6)
+
 # forward-Euler cases for the host-side (gloo) decomposition test; axis sizes divisible by 2 ranks
 CASES["slab_fe_2d_periodic"] = (dict(eqn="euler", dim=2, gridSize=[24, 16], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                                      slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 6)

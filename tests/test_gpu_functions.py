@@ -83,3 +83,38 @@ def test_device_functions_strict_match_host(hydrob200, oracle, hc, eqn, precisio
         report.append(("roe limited side %d" % side, int((~ok).sum()), np.argwhere(~ok)[:4].tolist()))
     bad = [r for r in report if r[1]]
     assert not bad, bad
+
+
+def test_async_state_transfer_equals_blocking(hydrob200):
+    """hb_fv_set_state_async / hb_fv_get_state_async / hb_fv_wait_transfers: three problems streamed through one solver (upload of
+    the next overlapping the update and download of the previous) give exactly what the blocking calls give."""
+    import ctypes as C
+    from importlib import import_module
+    hb = import_module("hydro-cl-lua_b200._lib")
+    from cases import CASES
+    cfg, _ = CASES["C4_sphere_rk4"]
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    B, L = S.backend, S.backend.L
+    U0 = S.getState().copy()
+    n = U0.size
+    inputs = [U0, U0 * np.array([1.1, 1., 1., 1., 1.2, 1.]), U0 * np.array([.9, 1., 1., 1., 1.05, 1.])]
+    ref = []
+    for Ui in inputs:
+        S.setState(Ui); S.update(2); ref.append(S.getState().copy())
+    hin = [C.c_void_p() for _ in inputs]; hout = [C.c_void_p() for _ in inputs]
+    for h in hin + hout:
+        hb.check(L.hb_host_alloc(n * 8, C.byref(h)))
+    try:
+        for h, Ui in zip(hin, inputs):
+            C.memmove(h, np.ascontiguousarray(Ui).ctypes.data, n * 8)
+        for hi, ho in zip(hin, hout):
+            hb.check(L.hb_fv_set_state_async(B.h, hi))
+            hb.check(L.hb_fv_update(B.h, 2))
+            hb.check(L.hb_fv_get_state_async(B.h, ho))
+        hb.check(L.hb_fv_wait_transfers(B.h))
+        for ho, r in zip(hout, ref):
+            got = np.frombuffer((C.c_double * n).from_address(ho.value), dtype=np.float64).reshape(r.shape)
+            assert np.array_equal(got, r)
+    finally:
+        for h in hin + hout:
+            hb.check(L.hb_host_free(h))
