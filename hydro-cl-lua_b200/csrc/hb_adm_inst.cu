@@ -37,6 +37,7 @@ cudaError_t launchFlux(GridP<real> const& g, StageP<real> const& sp, Eqn::Params
 	if (shared && sp.fluxLimiter > 0 && g.fluxOn[SIDE]) {
 		if (shared == 2) return launchFluxShared<SIDE, 2>(g, sp, ep, st);
 		if (shared == 3) return launchFluxShared<SIDE, 3>(g, sp, ep, st);
+		if (shared == 5) return launchFluxShared<SIDE, 5>(g, sp, ep, st);
 		return launchFluxShared<SIDE, 1>(g, sp, ep, st);
 	}
 	long long const n = (long long)(g.N[0] + (SIDE == 0)) * (g.N[1] + (SIDE == 1)) * (g.N[2] + (SIDE == 2));

@@ -70,10 +70,11 @@ adm_flux(GridP<typename Eqn::real> const g, typename Eqn::Params const ep, const
 // transforms, 80 -> 40 loads per interface, ~half the registers).  The first and last thread along SIDE only publish.
 // Thread layout: SIDE 0: NB threads along x;  SIDE 1, 2: 32 threads along x (coalescing) x NB interfaces along SIDE.
 // Every published value is the same expression of the same cells as in adm_flux, so the strict build stays bit-identical.
-// V: 1 = 32 x 8 threads, 2 blocks / SM (128 registers); 2 = 32 x 8, 1 block / SM; 3 = 16 x 8 threads (a 128-byte line per row), 3 blocks / SM
+// V: 1 = 32 x 8 threads, 2 blocks / SM (128 registers); 2 = 32 x 8, 1 block / SM; 3 = 16 x 8 threads (a 128-byte line per row), 3 blocks / SM;
+//    5 = 8 x 16 threads (14 of 16 interfaces along SIDE productive instead of 6 of 8; 64-byte row segments), 3 blocks / SM
 template<int SIDE, int V> struct AdmFluxGeom {
-	static constexpr int LX = SIDE == 0 ? 1 : (V == 3 ? 16 : 32);     // threads along x (sides 1, 2)
-	static constexpr int NB = SIDE == 0 ? 128 : 8;                     // interfaces along SIDE per block, two of them halo
+	static constexpr int LX = SIDE == 0 ? 1 : (V == 3 ? 16 : (V == 5 ? 8 : 32));     // threads along x (sides 1, 2)
+	static constexpr int NB = SIDE == 0 ? 128 : (V == 5 ? 16 : 8);      // interfaces along SIDE per block, two of them halo
 	static constexpr int NT = SIDE == 0 ? 128 : LX * NB;
 	static constexpr int STEP = SIDE == 0 ? 1 : LX;                    // thread distance of the neighbouring interface
 	static constexpr int MINB = SIDE == 0 ? 3 : (V == 1 ? 2 : (V == 2 ? 1 : 3));
