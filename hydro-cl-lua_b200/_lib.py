@@ -84,6 +84,7 @@ SIGNATURES = {
     "hb_fv_wait_transfers": (C.c_int, [P]),
     "hb_fv_state_devptr": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "hb_fv_boundary": (C.c_int, [P]),
+    "hb_fv_set_fixed_boundary": (C.c_int, [P, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "hb_fv_constrainU": (C.c_int, [P]),
     "hb_fv_init_derivs": (C.c_int, [P]),
     "hb_fv_calc_dt": (C.c_int, [P, C.POINTER(C.c_double)]),

@@ -134,6 +134,10 @@ class CudaBackend:
     def boundary(self):
         hb.check(self.L.hb_fv_boundary(self.h))
 
+    def set_fixed_boundary(self, face, U):
+        a = (C.c_double * len(U))(*U)
+        hb.check(self.L.hb_fv_set_fixed_boundary(self.h, int(face), a, len(U)))
+
     def constrainU(self):
         hb.check(self.L.hb_fv_constrainU(self.h))
 

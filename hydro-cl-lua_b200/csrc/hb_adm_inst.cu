@@ -86,6 +86,12 @@ cudaError_t march(int, int, int, const CUtensorMap*, int, GridP<real> const&, St
 cudaError_t ghosts(GridP<real> const& g, BcP const& bc, real* U, int nVars, int rimAxis, bool planesOnly, cudaStream_t st) {
 	long long const S0 = g.S[0], S1 = g.S[1], S2 = g.S[2];
 	int const nt = 256;
+	if (rimAxis <= -2) {   // one pass of the per-axis sequence (extrapolating / fixed methods): axis = -2 - rimAxis
+		int const axis = -2 - rimAxis;
+		long long const n = axis == 0 ? S1 * S2 : (axis == 1 ? S0 * S2 : S0 * S1);
+		fill_ghosts_axis<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars, axis);
+		return cudaGetLastError();
+	}
 	if (rimAxis >= 0 && planesOnly) {
 		long long const n = 2LL * HB_G * S0 * (rimAxis == 2 ? S1 : 1);
 		fill_ghosts_planes<Eqn, MODE><<<(unsigned)((n + nt - 1) / nt), nt, 0, st>>>(g, bc, U, nVars, rimAxis);

@@ -166,6 +166,7 @@ struct FvBase {
 	virtual int waitTransfers() = 0;
 	virtual int stateDevPtr(void** p, long long* sy, long long* sz, long long* sv) = 0;
 	virtual int boundary() = 0;
+	virtual int setFixedBoundary(int face, const double* U, int n) = 0;
 	virtual int constrainU() = 0;
 	virtual int calcDT(double* out) = 0;
 	virtual int step(double dt) = 0;
@@ -190,6 +191,8 @@ template<class real> struct Fv : FvBase {
 	const FvOps<real>* ops;
 	GridP<real> grid;
 	BcP bc;
+	bool seqBc = false;                    // a linear / quadratic / fixed face: ghost fill = the reference's x, y, z passes (fill_ghosts_axis)
+	double* fixedDev = nullptr;            // [6][HB_FIXED_STRIDE] states of the 'fixed' faces
 	std::vector<real*> upool, lpool;       // element (i=0,j=0,k=0) of variable 0; the allocation starts padX elements earlier
 	std::vector<CUtensorMap> umaps;        // TMA descriptor of every U buffer (marching kernel)
 	int padX = 0;                          // leading pad of every row: interior cell i=2 sits on a 128-byte boundary
@@ -249,6 +252,7 @@ template<class real> struct Fv : FvBase {
 		if (stagingOut) cudaFree(stagingOut);
 		for (cudaEvent_t e : {evUpDone, evInFree, evOutReady, evDownDone}) if (e) cudaEventDestroy(e);
 		if (ctl) cudaFree(ctl);
+		if (fixedDev) cudaFree(fixedDev);
 		if (dtMinBits) cudaFree(dtMinBits);
 		if (comm) Nccl::get().CommDestroy(comm);
 		if (evRim) cudaEventDestroy(evRim);
@@ -314,6 +318,14 @@ template<class real> struct Fv : FvBase {
 			grid.aov[s] = grid.volOn ? a * (real(1.) / volume) : real(0);
 		}
 		for (int k = 0; k < 6; ++k) bc.bc[k] = d.bc[k];
+		bc.fixedState = nullptr;
+		seqBc = false;
+		for (int k = 0; k < 2 * d.dim; ++k) if (d.bc[k] >= HB_BC_LINEAR) seqBc = true;
+		if (seqBc) {
+			HB_CUDA(cudaMalloc(&fixedDev, sizeof(double) * 6 * HB_FIXED_STRIDE));
+			HB_CUDA(cudaMemset(fixedDev, 0, sizeof(double) * 6 * HB_FIXED_STRIDE));
+			bc.fixedState = fixedDev;
+		}
 		buildPlan(d.rk_order, d.alphas, d.betas, plan, nU, nL);
 		for (auto& s : plan) {
 			if ((int)s.alpha.size() > HB_MAX_TERMS || (int)s.beta.size() > HB_MAX_TERMS)
@@ -502,9 +514,21 @@ template<class real> struct Fv : FvBase {
 	}
 
 	int fillGhosts(real* U, int nVars) {
+		if (seqBc) {
+			for (int a = 0; a < d.dim; ++a) { HB_CUDA(ops->ghosts(grid, bc, U, nVars, -2 - a, false, st())); launches++; }
+			return exchange(U, nVars);
+		}
 		HB_CUDA(ops->ghosts(grid, bc, U, nVars, -1, false, st()));
 		launches++;
 		return exchange(U, nVars);
+	}
+	int setFixedBoundary(int face, const double* U, int n) override {
+		if (face < 0 || face >= 2 * d.dim || !U || n < 1 || n > nS) return setError(HB_ERR_INVALID, "hb_fv_set_fixed_boundary: bad face or state size");
+		if (d.bc[face] != HB_BC_FIXED) return setError(HB_ERR_INVALID, "hb_fv_set_fixed_boundary: that face's boundary method is not 'fixed'");
+		useDevice(ctx);
+		HB_CUDA(cudaMemcpyAsync(fixedDev + (size_t)face * HB_FIXED_STRIDE, U, sizeof(double) * n, cudaMemcpyHostToDevice, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
 	}
 	int boundary() override {
 		useDevice(ctx);
@@ -786,7 +810,7 @@ template<class real> struct Fv : FvBase {
 		// overlap needs chunks that are neither first nor last along the decomposed (= marching) axis; HB_OVERLAP=0 switches it off
 		const char* ov = getenv("HB_OVERLAP");
 		int const km = marchInfoV[2] > 0 ? marchInfoV[2] : 1;
-		overlap = useMarch && (!ov || atoi(ov) != 0) && (grid.N[axis] + km - 1) / km >= 3;
+		overlap = useMarch && !seqBc && (!ov || atoi(ov) != 0) && (grid.N[axis] + km - 1) / km >= 3;
 		if (overlap) {
 			HB_CUDA(cudaStreamCreateWithFlags(&commStream, cudaStreamNonBlocking));
 			HB_CUDA(cudaEventCreateWithFlags(&evRim, cudaEventDisableTiming));
@@ -817,7 +841,7 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (d->dim < 1 || d->dim > 3) return setError(HB_ERR_INVALID, "hb_fv_create: dim must be 1..3");
 	for (int k = 0; k < d->dim; ++k) {
 		if (d->n[k] < 1 || d->global_n[k] < d->n[k]) return setError(HB_ERR_INVALID, "hb_fv_create: bad grid size");
-		for (int m = 0; m < 2; ++m) if (d->bc[2 * k + m] < 0 || d->bc[2 * k + m] > 3) return setError(HB_ERR_INVALID, "hb_fv_create: unknown boundary method");
+		for (int m = 0; m < 2; ++m) if (d->bc[2 * k + m] < 0 || d->bc[2 * k + m] > HB_BC_FIXED) return setError(HB_ERR_INVALID, "hb_fv_create: unknown boundary method");
 	}
 	if (d->rk_order < 0 || d->rk_order > 4) return setError(HB_ERR_INVALID, "hb_fv_create: rk_order must be 0..4");
 	if (d->use_plm < 0 || d->use_plm > 3) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM must be none, 'plm cons' or 'plm athena'");
@@ -865,6 +889,7 @@ int hb_fv_get_state_async(hb_fv* fv, double* aos) { HB_FV(fv); return fv->impl->
 int hb_fv_wait_transfers(hb_fv* fv) { HB_FV(fv); return fv->impl->waitTransfers(); }
 int hb_fv_state_devptr(hb_fv* fv, void** p, long long* sy, long long* sz, long long* sv) { HB_FV(fv); return fv->impl->stateDevPtr(p, sy, sz, sv); }
 int hb_fv_boundary(hb_fv* fv) { HB_FV(fv); return fv->impl->boundary(); }
+int hb_fv_set_fixed_boundary(hb_fv* fv, int face, const double* cons, int n) { HB_FV(fv); return fv->impl->setFixedBoundary(face, cons, n); }
 int hb_fv_constrainU(hb_fv* fv) { HB_FV(fv); return fv->impl->constrainU(); }
 int hb_fv_init_derivs(hb_fv* fv) { HB_FV(fv); return fv->impl->initDerivs(); }
 int hb_fv_calc_dt(hb_fv* fv, double* dt) { HB_FV(fv); return fv->impl->calcDT(dt); }

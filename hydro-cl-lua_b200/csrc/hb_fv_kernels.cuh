@@ -313,12 +313,18 @@ fv_stage(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp,
 //   mirror    j < g: 2g-1-j ; j >= S-g: 2(S-g)-1-j, negating the reflected vector components (:662-671,741)
 //   freeflow  j < g: g ; j >= S-g: S-g-1                                                  (:772-778)
 //   none      ghost left untouched (:618-621) -- also used for slab faces owned by a neighbouring rank
-struct BcP { int bc[6]; };
+//   linear / quadratic / fixed (:746-764, :782-846) do not compose to a source map (a corner ghost is an extrapolation of
+//   extrapolated values): a grid with one of those runs the reference's own sequence, fill_ghosts_axis for x, then y, then z.
+struct BcP { int bc[6]; const double* fixedState; /* device, [6][HB_FIXED_STRIDE]: what a 'fixed' face writes */ };
+constexpr int HB_FIXED_STRIDE = 64;
 #ifndef HB_BC_PERIODIC   // same values as include/hydrob200.h
 #define HB_BC_PERIODIC 0
 #define HB_BC_MIRROR 1
 #define HB_BC_FREEFLOW 2
 #define HB_BC_NONE 3
+#define HB_BC_LINEAR 4
+#define HB_BC_QUADRATIC 5
+#define HB_BC_FIXED 6
 #endif
 
 HB_HD int ghostSource(int j, int S, int bcMin, int bcMax, bool& flip, bool& skip) {
@@ -416,6 +422,59 @@ __global__ void fill_ghosts_planes(GridP<typename Eqn::real> const g, BcP const 
 		if (fx && Eqn::mirrorFlips(q, 0)) v = real(-1.) * v;
 		if (fy && Eqn::mirrorFlips(q, 1)) v = real(-1.) * v;
 		U[dst + q * g.strideV] = v;
+	}
+}
+
+// One pass of the reference's boundary kernel for one axis (boundary_x / _y / _z, gridsolver.lua:1100-1190): one thread per cell
+// of the perpendicular plane, ghost cells of the other axes included, `for j < numGhost { min face; max face }` in that order, so
+// that the extrapolating methods see the ghost values written one iteration earlier exactly as the reference's loop does.
+template<class Eqn, int MODE>
+__global__ void fill_ghosts_axis(GridP<typename Eqn::real> const g, BcP const bc, typename Eqn::real* __restrict__ U, int nVars, int axis)
+{
+	typedef typename Eqn::real real;
+	int const o1 = axis == 0 ? 1 : 0, o2 = axis == 2 ? 1 : 2;
+	long long const S1 = g.S[o1], S2 = g.S[o2];
+	long long const w = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+	if (w >= S1 * S2) return;
+	long long const strd[3] = {1, g.strideY, g.strideZ};
+	long long const base = (w % S1) * strd[o1] + (w / S1) * strd[o2], sa = strd[axis];
+	int const S = g.S[axis], G = HB_G, N = S - 2 * G;
+	for (int q = 0; q < nVars; ++q) {
+		real* const u = U + q * g.strideV + base;
+		bool const flips = Eqn::mirrorFlips(q, axis);
+		for (int j = 0; j < G; ++j) {
+			#pragma unroll
+			for (int mm = 0; mm < 2; ++mm) {
+				int const method = bc.bc[2 * axis + mm];
+				switch (method) {
+				case HB_BC_PERIODIC:
+					if (mm == 0) u[j * sa] = u[(G + (j - G + 2 * N) % N) * sa];
+					else u[(S - 1 - j) * sa] = u[(G + (G - 1 - j) % N) * sa];
+					break;
+				case HB_BC_MIRROR: {
+					real v = mm == 0 ? u[(2 * G - 1 - j) * sa] : u[(S - G - 1 - j) * sa];
+					if (flips) v = real(-1.) * v;
+					u[(mm == 0 ? j : S - G + j) * sa] = v;
+					break; }
+				case HB_BC_FREEFLOW:
+					if (mm == 0) u[j * sa] = u[G * sa];
+					else u[(S - G + j) * sa] = u[(S - G - 1) * sa];
+					break;
+				case HB_BC_LINEAR:
+					if (mm == 0) u[(G - j - 1) * sa] = real(2.) * u[(G - j) * sa] - u[(G - j + 1) * sa];
+					else u[(S - G + j) * sa] = real(2.) * u[(S - G + j - 1) * sa] - u[(S - G + j - 2) * sa];
+					break;
+				case HB_BC_QUADRATIC:
+					if (mm == 0) u[(G - j - 1) * sa] = real(3.) * u[(G - j) * sa] - real(3.) * u[(G - j + 1) * sa] + u[(G - j + 2) * sa];
+					else u[(S - G + j) * sa] = real(3.) * u[(S - G + j - 1) * sa] - real(3.) * u[(S - G + j - 2) * sa] + u[(S - G + j - 3) * sa];
+					break;
+				case HB_BC_FIXED:
+					u[(mm == 0 ? j : S - G + j) * sa] = real(bc.fixedState[(2 * axis + mm) * HB_FIXED_STRIDE + q]);
+					break;
+				default: break;
+				}
+			}
+		}
 	}
 }
 

@@ -26,7 +26,7 @@ template<class real> struct FvOps {
 	cudaError_t (*march)(int dim, int slopeLimiter, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp,
 		const double* eqnParams, int chunkSel, cudaStream_t st);
 	// rimAxis < 0: every ghost cell.  rimAxis = 1 | 2 with planesOnly: only the ghost cells of the planes the slab exchange sends;
-	// with !planesOnly: every ghost cell but those.
+	// with !planesOnly: every ghost cell but those.  rimAxis = -2 - axis: the reference's pass for that axis alone (fill_ghosts_axis).
 	cudaError_t (*ghosts)(GridP<real> const& g, BcP const& bc, real* U, int nVars, int rimAxis, bool planesOnly, cudaStream_t st);
 	cudaError_t (*calcDT)(GridP<real> const& g, const double* eqnParams, const real* U, unsigned long long* dtMinBits, cudaStream_t st);
 	cudaError_t (*constrainAll)(GridP<real> const& g, const double* eqnParams, real* U, cudaStream_t st);

@@ -10,7 +10,7 @@ import numpy as np
 from .. import app as hydro_app
 from .solverbase import SolverBase
 
-boundaryIds = {"periodic": 0, "mirror": 1, "freeflow": 2, "none": 3}
+boundaryIds = {"periodic": 0, "mirror": 1, "freeflow": 2, "none": 3, "linear": 4, "quadratic": 5, "fixed": 6}   # gridsolver.lua:638-846
 xNames = ("x", "y", "z")
 minmaxs = ("min", "max")
 # 'plm athena': plm.cl:782-879 as the reference tree has it (result->L = cons(Wrv), result->R = cons(Wlv), :877-878);
@@ -84,9 +84,35 @@ class GridSolver(SolverBase):
         for x in xNames:
             for mm in minmaxs:
                 m = self.boundaryMethods[x + mm]
+                if isinstance(m, dict):     # {name = 'fixed', args = {...}} as in init/euler.lua:1859-1879
+                    m = m["name"]
                 if m not in boundaryIds:
                     raise NotImplementedError("boundary method %r is outside the hot-path scope" % (m,))
                 out.append(boundaryIds[m])
+        return out
+
+    def fixedBoundaryStates(self):
+        """-> {face index: list of numStates doubles} for the faces whose method is 'fixed' (gridsolver.lua:746-764).
+        The reference takes a `fixedCode` generator; the states it writes in its own uses do not depend on the cell
+        (init/euler.lua:1859-1879: consFromPrim of constants), so here args = {W = prims} or {U = conserved state}."""
+        out = {}
+        k = 0
+        for x in xNames:
+            for mm in minmaxs:
+                m = self.boundaryMethods[x + mm]
+                if isinstance(m, dict) and m["name"] == "fixed":
+                    a = m.get("args") or {}
+                    if "U" in a:
+                        U = [float(v) for v in a["U"]]
+                    elif "W" in a:
+                        W = {key: np.float64(v) for key, v in a["W"].items()}
+                        U = [float(v) for v in np.ravel(self.eqn.consArray(W))]
+                    else:
+                        raise ValueError("boundary 'fixed' needs args = {W = ...} or {U = ...} (gridsolver.lua:753)")
+                    out[k] = U
+                elif m == "fixed":
+                    raise ValueError("you didn't provide any fixedCode arg for boundary==fixed (gridsolver.lua:753)")
+                k += 1
         return out
 
     def cellPositions(self):

@@ -34,7 +34,12 @@ class SolverBase:
         self.initMeshVars(args)
         self.initObjs(args)
         self.backend = self.createBackend(args)
+        for face, U in self.fixedBoundaryStates().items():
+            self.backend.set_fixed_boundary(face, U)
         self.resetState()
+
+    def fixedBoundaryStates(self):
+        return {}
 
     # ---- solverbase.lua:511-556 / gridsolver.lua:60-96 (overridden by GridSolver)
     def initMeshVars(self, args):

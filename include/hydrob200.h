@@ -105,6 +105,10 @@ int hb_reduce(hb_ctx* ctx, hb_buf* buf, size_t count, int op, double* host_out);
 #define HB_BC_MIRROR 1        /* :654-744 */
 #define HB_BC_FREEFLOW 2      /* :766-780 */
 #define HB_BC_NONE 3          /* :618-621; also: face owned by a neighbouring slab (hb_fv_exchange fills it) */
+#define HB_BC_LINEAR 4        /* :782-813 linear extrapolation, every state variable */
+#define HB_BC_QUADRATIC 5     /* :815-846 quadratic extrapolation */
+#define HB_BC_FIXED 6         /* :746-764 Dirichlet: the state set with hb_fv_set_fixed_boundary (a fixedCode that does not depend on the
+                               * cell, e.g. hydro/init/euler.lua:1859-1879 'square cavity' lid, hydro/eqn/einstein.lua:62-80 flat space) */
 
 typedef struct hb_fv_desc {
 	int eqn;                  /* HB_EQN_* */
@@ -149,6 +153,7 @@ int hb_fv_set_state_async(hb_fv* fv, const double* aos_host);
 int hb_fv_get_state_async(hb_fv* fv, double* aos_host);
 int hb_fv_wait_transfers(hb_fv* fv);
 int hb_fv_state_devptr(hb_fv* fv, void** soa_dev, long long* stride_y, long long* stride_z, long long* stride_var);
+int hb_fv_set_fixed_boundary(hb_fv* fv, int face, const double* cons, int n);   /* face 0..5 = xmin,xmax,..,zmax; n <= numStates doubles; zeros until set */
 int hb_fv_boundary(hb_fv* fv);                               /* solver:boundary(), gridsolver.lua:1316 */
 int hb_fv_init_derivs(hb_fv* fv);                            /* initDerivsKernelObj(), hydro/init/init.lua:231-235 (adm3d.cl:196-243); no-op for other equations */
 int hb_fv_constrainU(hb_fv* fv);                             /* solver:constrainU() = kernel + boundary(), solverbase.lua:2116-2127 */

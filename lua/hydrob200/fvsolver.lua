@@ -27,7 +27,8 @@ local FiniteVolumeSolver = require 'hydro.solver.fvsolver'
 local B200Solver = FiniteVolumeSolver:subclass()
 B200Solver.name = 'fvsolver_b200'
 
-local bcIds = {periodic = lib.HB_BC_PERIODIC, mirror = lib.HB_BC_MIRROR, freeflow = lib.HB_BC_FREEFLOW, none = lib.HB_BC_NONE}
+local bcIds = {periodic = lib.HB_BC_PERIODIC, mirror = lib.HB_BC_MIRROR, freeflow = lib.HB_BC_FREEFLOW, none = lib.HB_BC_NONE,
+	linear = lib.HB_BC_LINEAR, quadratic = lib.HB_BC_QUADRATIC, fixed = lib.HB_BC_FIXED}
 local eqnIds = {euler = lib.HB_EQN_EULER, mhd = lib.HB_EQN_MHD}
 
 function B200Solver:refreshSolverProgram()
@@ -70,6 +71,15 @@ function B200Solver:refreshSolverProgram()
 	local h = ffi.new'hb_fv*[1]'
 	check(lib.hb_fv_create(self.app.env.ctx, d, h), 'hb_fv_create')
 	self.fv = ffi.gc(h[0], lib.hb_fv_destroy)
+	-- 'fixed' faces (gridsolver.lua:746-764): the Boundary object carries the state its fixedCode writes as .fixedState (numStates reals);
+	-- the reference's own uses are cell-independent (init/euler.lua:1859-1879, eqn/einstein.lua:62-80)
+	for i, s in ipairs(sides) do
+		local b = self.boundaryMethods[s]
+		if b.name == 'fixed' then
+			local U = ffi.new('double[?]', self.eqn.numStates, assert(b.fixedState, "hydrob200: boundary 'fixed' needs .fixedState"))
+			check(lib.hb_fv_set_fixed_boundary(self.fv, i-1, U, self.eqn.numStates), 'hb_fv_set_fixed_boundary')
+		end
+	end
 end
 
 function B200Solver:uploadState(aosPtr) check(lib.hb_fv_set_state(self.fv, aosPtr), 'hb_fv_set_state') end

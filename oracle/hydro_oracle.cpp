@@ -39,7 +39,7 @@ struct ho_desc {
 	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded
 	int slope_limiter;  // 0-based index into hydro/app.lua:614-635
 	int flux_limiter;   // 0-based index; 0 = 'donor cell' => useFluxLimiter=false (fvsolver.lua:61-63)
-	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none
+	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none, 4 linear, 5 quadratic, 6 fixed
 	int rk_order;       // 0 = forward Euler (int/fe.lua), else Butcher order (int/rk.lua)
 	double alphas[16];  // row-major [order][order] (int/all.lua)
 	double betas[16];
@@ -804,6 +804,7 @@ struct SolverBase {
 	virtual void setState(const double* aos) = 0;
 	virtual void getState(double* aos) const = 0;
 	virtual void boundary() = 0;
+	double fixedState[6][64] = {};   // per face: the state a 'fixed' boundary writes
 	virtual void constrainU() = 0;
 	virtual double calcDT() = 0;
 	virtual void update() = 0;
@@ -928,6 +929,23 @@ template<class Eqn> struct Solver : SolverBase {
 							else { dst = idx(Sd - g + j); src = idx(Sd - g - 1); }
 							buf[dst] = buf[src];
 							break;
+						case 4: {   // linear extrapolation :782-813: dst = 2 buf[i1] - buf[i2], every state (numStates), ghost by ghost outwards
+							long i1, i2;
+							if (mm == 0) { dst = idx(g - j - 1); i1 = idx(g - j); i2 = idx(g - j + 1); }
+							else { dst = idx(Sd - g + j); i1 = idx(Sd - g + j - 1); i2 = idx(Sd - g + j - 2); }
+							for (int k = 0; k < nS; ++k) buf[dst].ptr[k] = real(2.) * buf[i1].ptr[k] - buf[i2].ptr[k];
+							break; }
+						case 5: {   // quadratic extrapolation :815-846: dst = 3 buf[i1] - 3 buf[i2] + buf[i3]
+							long i1, i2, i3;
+							if (mm == 0) { dst = idx(g - j - 1); i1 = idx(g - j); i2 = idx(g - j + 1); i3 = idx(g - j + 2); }
+							else { dst = idx(Sd - g + j); i1 = idx(Sd - g + j - 1); i2 = idx(Sd - g + j - 2); i3 = idx(Sd - g + j - 3); }
+							for (int k = 0; k < nS; ++k) buf[dst].ptr[k] = real(3.) * buf[i1].ptr[k] - real(3.) * buf[i2].ptr[k] + buf[i3].ptr[k];
+							break; }
+						case 6: {   // fixed (Dirichlet) :746-764: the face's fixedCode writes a state that does not depend on the cell
+							// (init/euler.lua:1859-1879 'square cavity' lid: consFromPrim of constants; eqn/einstein.lua:62-80: flat space)
+							dst = mm == 0 ? idx(j) : idx(Sd - g + j);
+							for (int k = 0; k < nS; ++k) buf[dst].ptr[k] = real(fixedState[2 * side + mm][k]);
+							break; }
 						default: break;   // 'none' :618-621
 						}
 					}
@@ -1512,6 +1530,7 @@ int ho_num_states(void* h) { return static_cast<ho::SolverBase*>(h)->numStates()
 long ho_num_cells(void* h) { return static_cast<ho::SolverBase*>(h)->numCells(); }
 void ho_set_state(void* h, const double* aos) { static_cast<ho::SolverBase*>(h)->setState(aos); }
 void ho_get_state(void* h, double* aos) { static_cast<ho::SolverBase*>(h)->getState(aos); }
+void ho_set_fixed_boundary(void* h, int face, const double* U, int n) { auto* s = static_cast<ho::SolverBase*>(h); for (int k = 0; k < n && k < 64; ++k) s->fixedState[face][k] = U[k]; }
 void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }
 void ho_init_derivs(void* h) { static_cast<ho::SolverBase*>(h)->initDerivs(); }
 void ho_source_test(void* h, const double* U, double* deriv) { static_cast<ho::SolverBase*>(h)->sourceTest(U, deriv); }

@@ -56,6 +56,8 @@ def lib(fma=False):
         L.ho_num_cells.argtypes = [C.c_void_p]
         L.ho_num_cells.restype = C.c_long
         L.ho_set_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.ho_set_fixed_boundary.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
+        L.ho_set_fixed_boundary.restype = None
         L.ho_get_state.argtypes = [C.c_void_p, C.c_void_p]
         L.ho_calc_dt.argtypes = [C.c_void_p]
         L.ho_calc_dt.restype = C.c_double
@@ -149,6 +151,10 @@ class OracleBackend:
 
     def boundary(self):
         self.L.ho_boundary(self.h)
+
+    def set_fixed_boundary(self, face, U):
+        a = (C.c_double * len(U))(*U)
+        self.L.ho_set_fixed_boundary(self.h, int(face), a, len(U))
 
     def constrainU(self):
         self.L.ho_constrainU(self.h)

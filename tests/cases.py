@@ -116,3 +116,22 @@ CASES["slab_march3d_overlap_periodic"] = (dict(eqn="mhd", dim=3, gridSize=[33, 6
                                                              zmin="periodic", zmax="periodic")), 3)
 CASES["slab_march2d_overlap"] = (dict(eqn="euler", dim=2, gridSize=[40, 140], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                                       slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 4)
+
+# the remaining boundary methods of gridsolver.lua:746-846 (linear / quadratic extrapolation, fixed = Dirichlet state).
+# These do not compose to a source-index map, so the GPU runs the reference's x, y, z passes (fill_ghosts_axis).
+CASES["F4_sod_linear_1d"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", fluxLimiter="superbee", integrator="forward Euler", cfl=.3,
+                                  boundary=dict(xmin="linear", xmax="quadratic")), 40)
+CASES["F4_kh_linear_quadratic_2d"] = (dict(eqn="euler", dim=2, gridSize=[56, 40], initCond="Kelvin-Helmholtz", usePLM="plm cons", slopeLimiter="minmod",
+                                           integrator="Runge-Kutta 4", cfl=.15,
+                                           boundary=dict(xmin="linear", xmax="quadratic", ymin="quadratic", ymax="mirror")), 10)
+CASES["F4_cavity_fixed_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 36], initCond="sphere", usePLM="plm cons", slopeLimiter="minmod",
+                                    integrator="Runge-Kutta 3, TVD", cfl=.15,
+                                    boundary=dict(xmin="mirror", xmax="mirror", ymin="mirror",
+                                                  ymax=dict(name="fixed", args=dict(W=dict(rho=1., vx=2., vy=0., vz=0., P=1., ePot=0.))))), 12)
+CASES["F4_sphere_mixed_3d"] = (dict(eqn="euler", dim=3, gridSize=[24, 18, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                    usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1,
+                                    boundary=dict(xmin="linear", xmax="freeflow", ymin="periodic", ymax="periodic", zmin="quadratic",
+                                                  zmax=dict(name="fixed", args=dict(W=dict(rho=.01, vx=0., vy=0., vz=0., P=.01, ePot=0.))))), 5)
+CASES["F4_ot_mhd_linear_2d"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
+                                     integrator="Runge-Kutta 3, TVD", cfl=.15,
+                                     boundary=dict(xmin="linear", xmax="linear", ymin="periodic", ymax="periodic")), 8)
