@@ -23,6 +23,10 @@ class HydroB200Error(RuntimeError):
         self.code = code
 
 
+class hb_op_desc(C.Structure):
+    _fields_ = [("kind", C.c_int), ("max_iters", C.c_int), ("stop_on_epsilon", C.c_int), ("stop_epsilon", C.c_double), ("param", C.c_double)]
+
+
 class hb_fv_desc(C.Structure):
     _fields_ = [
         ("eqn", C.c_int), ("dim", C.c_int), ("n", C.c_int * 3), ("global_n", C.c_int * 3),
@@ -84,6 +88,9 @@ SIGNATURES = {
     "hb_fv_wait_transfers": (C.c_int, [P]),
     "hb_fv_state_devptr": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "hb_fv_boundary": (C.c_int, [P]),
+    "hb_fv_add_op": (C.c_int, [P, C.POINTER(hb_op_desc), C.POINTER(C.c_int)]),
+    "hb_fv_ops_reset": (C.c_int, [P]),
+    "hb_fv_op_info": (C.c_int, [P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "hb_fv_set_fixed_boundary": (C.c_int, [P, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "hb_fv_constrainU": (C.c_int, [P]),
     "hb_fv_init_derivs": (C.c_int, [P]),

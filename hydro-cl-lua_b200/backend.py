@@ -134,6 +134,20 @@ class CudaBackend:
     def boundary(self):
         hb.check(self.L.hb_fv_boundary(self.h))
 
+    def add_op(self, kind, max_iters, stop_on_epsilon, stop_epsilon, param):
+        o = hb.hb_op_desc(kind, max_iters, 1 if stop_on_epsilon else 0, stop_epsilon, param)
+        idx = C.c_int()
+        hb.check(self.L.hb_fv_add_op(self.h, C.byref(o), C.byref(idx)))
+        return idx.value
+
+    def ops_reset(self):
+        hb.check(self.L.hb_fv_ops_reset(self.h))
+
+    def op_info(self, op):
+        it, res = C.c_int(), C.c_double()
+        hb.check(self.L.hb_fv_op_info(self.h, int(op), C.byref(it), C.byref(res)))
+        return it.value, res.value
+
     def set_fixed_boundary(self, face, U):
         a = (C.c_double * len(U))(*U)
         hb.check(self.L.hb_fv_set_fixed_boundary(self.h, int(face), a, len(U)))

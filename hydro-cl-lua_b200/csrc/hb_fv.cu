@@ -167,6 +167,9 @@ struct FvBase {
 	virtual int stateDevPtr(void** p, long long* sy, long long* sz, long long* sv) = 0;
 	virtual int boundary() = 0;
 	virtual int setFixedBoundary(int face, const double* U, int n) = 0;
+	virtual int addOp(const hb_op_desc* op, int* index) = 0;
+	virtual int opsReset() = 0;
+	virtual int opInfo(int op, int* iters, double* residual) = 0;
 	virtual int constrainU() = 0;
 	virtual int calcDT(double* out) = 0;
 	virtual int step(double dt) = 0;
@@ -191,6 +194,13 @@ template<class real> struct Fv : FvBase {
 	const FvOps<real>* ops;
 	GridP<real> grid;
 	BcP bc;
+	// ops (hydro/op): self-gravity, NoDiv over the Jacobi relaxation (hb_ops_kernels.cuh)
+	struct OpState { hb_op_desc d; int pot, vec; OpCtl* ctl; };
+	std::vector<OpState> opsV;
+	real* opWrite = nullptr;               // writeBuf of relaxation.lua:52-57 (one variable)
+	double* opPartial = nullptr;           // per-block partial sums / maxima
+	int opBlocks = 0;
+	bool hasGrav = false, hasNoDiv = false;
 	bool seqBc = false;                    // a linear / quadratic / fixed face: ghost fill = the reference's x, y, z passes (fill_ghosts_axis)
 	double* fixedDev = nullptr;            // [6][HB_FIXED_STRIDE] states of the 'fixed' faces
 	std::vector<real*> upool, lpool;       // element (i=0,j=0,k=0) of variable 0; the allocation starts padX elements earlier
@@ -253,6 +263,9 @@ template<class real> struct Fv : FvBase {
 		for (cudaEvent_t e : {evUpDone, evInFree, evOutReady, evDownDone}) if (e) cudaEventDestroy(e);
 		if (ctl) cudaFree(ctl);
 		if (fixedDev) cudaFree(fixedDev);
+		if (opWrite) cudaFree(opWrite - padX);
+		if (opPartial) cudaFree(opPartial);
+		for (auto& o : opsV) if (o.ctl) cudaFree(o.ctl);
 		if (dtMinBits) cudaFree(dtMinBits);
 		if (comm) Nccl::get().CommDestroy(comm);
 		if (evRim) cudaEventDestroy(evRim);
@@ -522,6 +535,99 @@ template<class real> struct Fv : FvBase {
 		launches++;
 		return exchange(U, nVars);
 	}
+
+	// ---- ops: hydro/op/relaxation.lua, selfgrav.lua, nodiv.lua
+	int addOp(const hb_op_desc* o, int* index) override {
+		if (!o) return setError(HB_ERR_INVALID, "hb_fv_add_op: null argument");
+		if (!ops->opKernel) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are built for euler and mhd");
+		if (comm) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are not built for a decomposed grid");
+		if (o->max_iters < 0) return setError(HB_ERR_INVALID, "hb_fv_add_op: max_iters < 0");
+		OpState s; s.d = *o; s.ctl = nullptr; s.vec = -1;
+		if (o->kind == HB_OP_SELFGRAV) s.pot = nS - 1;                                   // ePot: last variable of euler and mhd
+		else if (o->kind == HB_OP_NODIV && d.eqn == HB_EQN_MHD) { s.pot = 8; s.vec = 5; }   // mhd: B = 5..7, psi = 8
+		else return setError(HB_ERR_INVALID, "hb_fv_add_op: unknown op for this equation (selfgrav: euler, mhd; NoDiv: mhd)");
+		useDevice(ctx);
+		if (!opWrite) {
+			if (int r = allocPadded(&opWrite, sizeof(real) * ((size_t)vstride + (size_t)grid.strideY))) return r;
+			opBlocks = (int)((cells + HB_OP_NT - 1) / HB_OP_NT);
+			HB_CUDA(cudaMalloc(&opPartial, sizeof(double) * (size_t)opBlocks));
+		}
+		HB_CUDA(cudaMalloc(&s.ctl, sizeof(OpCtl)));
+		HB_CUDA(cudaMemset(s.ctl, 0, sizeof(OpCtl)));
+		opsV.push_back(s);
+		if (o->kind == HB_OP_SELFGRAV) { hasGrav = true; useMarch = false; }             // the gravity source lives in the tile kernel
+		else hasNoDiv = true;
+		invalidateGraph();
+		dtValid = false;
+		if (index) *index = (int)opsV.size() - 1;
+		return HB_OK;
+	}
+	OpP<real> opParams(OpState const& s, real* U, int iter = 0) {
+		OpP<real> p;
+		memset(&p, 0, sizeof(p));
+		p.kind = s.d.kind; p.U = U; p.writeBuf = opWrite; p.partial = opPartial; p.ctl = s.ctl; p.pot = s.pot; p.vec = s.vec;
+		p.param = s.d.param; p.stopEpsilon = s.d.stop_epsilon; p.stopOnEpsilon = s.d.stop_on_epsilon; p.iter = iter;
+		double v = 1; for (int k = 0; k < d.dim; ++k) v *= (double)grid.N[k];
+		p.volumeWithoutBorder = v; p.nBlocks = opBlocks;
+		return p;
+	}
+	int opLaunch(int which, OpP<real> const& p) { HB_CUDA(ops->opKernel(which, grid, p, st())); launches++; return HB_OK; }
+	// Relaxation:potentialBoundary (relaxation.lua:135-150,198-200): the solver's boundary methods on the potential alone
+	int potentialBoundary(OpState const& s, real* U) { return fillGhosts(U + (size_t)s.pot * vstride, 1); }
+	// Relaxation:relax (relaxation.lua:165-196); the stop test stays on the device (OpCtl::done)
+	int relax(OpState const& s, real* U) {
+		if (int r = opLaunch(HB_OPK_BEGIN, opParams(s, U))) return r;
+		for (int it = 1; it <= s.d.max_iters; ++it) {
+			OpP<real> const p = opParams(s, U, it);
+			if (int r = opLaunch(HB_OPK_JACOBI, p)) return r;
+			if (int r = opLaunch(HB_OPK_COPY, p)) return r;
+			if (int r = potentialBoundary(s, U)) return r;
+			if (int r = opLaunch(HB_OPK_FINISH, p)) return r;
+		}
+		return HB_OK;
+	}
+	int offsetPotential(OpState const& s, real* U) {       // selfgrav.lua:123-147
+		OpP<real> const p = opParams(s, U);
+		if (int r = opLaunch(HB_OPK_MAX_PARTIAL, p)) return r;
+		if (int r = opLaunch(HB_OPK_MAX_FINISH, p)) return r;
+		return opLaunch(HB_OPK_OFFSET, p);
+	}
+	int opsReset() override {                              // solverbase.lua:2106-2111, relaxation.lua:152-158, selfgrav.lua:93-101
+		useDevice(ctx);
+		for (auto& s : opsV) {
+			if (int r = opLaunch(HB_OPK_INIT, opParams(s, upool[0]))) return r;
+			if (int r = potentialBoundary(s, upool[0])) return r;
+			if (int r = relax(s, upool[0])) return r;
+			if (s.d.kind == HB_OP_SELFGRAV) if (int r = offsetPotential(s, upool[0])) return r;
+			if (int r = fillGhosts(upool[0], nS)) return r;
+		}
+		dtValid = false;
+		return HB_OK;
+	}
+	// op:step of every op after the integrator (solverbase.lua:3230-3237): boundary(), constrainU(), NoDiv:step (nodiv.lua:180-184)
+	int opsStep() {
+		for (auto& s : opsV) {
+			if (s.d.kind != HB_OP_NODIV) continue;
+			if (int r = fillGhosts(upool[0], nS)) return r;
+			HB_CUDA(ops->constrainAll(grid, d.eqn_params, upool[0], st()));
+			launches++;
+			if (int r = fillGhosts(upool[0], nS)) return r;
+			if (int r = relax(s, upool[0])) return r;
+			if (int r = opLaunch(HB_OPK_NODIV, opParams(s, upool[0]))) return r;
+		}
+		return HB_OK;
+	}
+	int opInfo(int op, int* iters, double* residual) override {
+		if (op < 0 || op >= (int)opsV.size()) return setError(HB_ERR_INVALID, "hb_fv_op_info: no such op");
+		useDevice(ctx);
+		OpCtl h;
+		HB_CUDA(cudaMemcpyAsync(&h, opsV[op].ctl, sizeof(h), cudaMemcpyDeviceToHost, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		if (iters) *iters = h.lastIter;
+		if (residual) *residual = h.lastResidual;
+		return HB_OK;
+	}
+
 	int setFixedBoundary(int face, const double* U, int n) override {
 		if (face < 0 || face >= 2 * d.dim || !U || n < 1 || n > nS) return setError(HB_ERR_INVALID, "hb_fv_set_fixed_boundary: bad face or state size");
 		if (d.bc[face] != HB_BC_FIXED) return setError(HB_ERR_INVALID, "hb_fv_set_fixed_boundary: that face's boundary method is not 'fixed'");
@@ -592,7 +698,8 @@ template<class real> struct Fv : FvBase {
 		bool const rk = d.rk_order >= 1;
 		if (rk && !rkZeroed && nS > nI) {
 			// rk.lua:94 clears UBuf (all fields, ghosts too); multAdd restores only the integrated fields (App. C #3)
-			HB_CUDA(cudaMemsetAsync(upool[0] + (size_t)nI * vstride, 0, sizeof(real) * (size_t)(nS - nI) * vstride, st()));
+			// (with ops the potentials of the current state come from op:resetState and are kept for the first relax)
+			if (opsV.empty()) HB_CUDA(cudaMemsetAsync(upool[0] + (size_t)nI * vstride, 0, sizeof(real) * (size_t)(nS - nI) * vstride, st()));
 			for (int k = 1; k < nU; ++k)
 				HB_CUDA(cudaMemsetAsync(upool[k] + (size_t)nI * vstride, 0, sizeof(real) * (size_t)(nS - nI) * vstride, st()));
 			rkZeroed = true;
@@ -607,7 +714,15 @@ template<class real> struct Fv : FvBase {
 		bool const flim = !plm && d.flux_limiter > 0;
 		for (auto& s : plan) {
 			StageP<real> sp;
-			fillStageP(sp, s, s.last);
+			fillStageP(sp, s, s.last && !hasNoDiv);
+			if (hasGrav && s.computeL) {
+				// op:addSource (solverbase.lua:3219-3223) = SelfGrav:addSource (selfgrav.lua:112-121): relax on the stage's input state, the
+				// gravity source joins L inside the stage kernel, offsetPotential afterwards
+				for (auto& o : opsV) if (o.d.kind == HB_OP_SELFGRAV) {
+					if (int r = relax(o, upool[s.uIn])) return r;
+					sp.gravPot = upool[s.uIn] + (size_t)o.pot * vstride;
+				}
+			}
 			cudaEvent_t e0 = nullptr, e1 = nullptr;
 			if (profiling) {
 				if (profUsed == profEvents.size()) {
@@ -638,13 +753,31 @@ template<class real> struct Fv : FvBase {
 			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches += tlsStageLaunches;
+			if (!opsV.empty()) {
+				if (hasGrav && s.computeL) for (auto& o : opsV) if (o.d.kind == HB_OP_SELFGRAV) if (int r = offsetPotential(o, upool[s.uIn])) return r;
+				if (nS > nI && s.uOut != s.uIn) {
+					// the fields the integrator does not touch: rk.lua:94 leaves them 0 in the stage's result, fe.lua keeps them
+					real* dst = upool[s.uOut] + (size_t)nI * vstride;
+					if (rk) HB_CUDA(cudaMemsetAsync(dst, 0, sizeof(real) * (size_t)(nS - nI) * vstride, st()));
+					else HB_CUDA(cudaMemcpyAsync(dst, upool[s.uIn] + (size_t)nI * vstride, sizeof(real) * (size_t)(nS - nI) * vstride, cudaMemcpyDeviceToDevice, st()));
+				}
+			}
 			if (int r = fillGhosts(upool[s.uOut], rk ? nI : nS)) return r;
 		}
-		if (int r = reduceDtMin()) return r;
 		if (plan.back().uOut != 0) {   // order <= 1: ping-pong
 			std::swap(upool[0], upool[plan.back().uOut]);
 			if (useMarch) std::swap(umaps[0], umaps[plan.back().uOut]);
 		}
+		if (hasNoDiv) {
+			// NoDiv changes B after the last stage: the CFL reduction fused into that stage would be stale
+			if (int r = opsStep()) return r;
+			if (int r = fillGhosts(upool[0], nS)) return r;   // SolverBase:update ends with boundary() (solverbase.lua:3186); not redundant after an op:step
+			reset_dtmin<<<1, 1, 0, st()>>>(dtMinBits);
+			HB_CUDA(cudaGetLastError());
+			HB_CUDA(ops->calcDT(grid, d.eqn_params, upool[0], dtMinBits, st()));
+			launches += 2;
+		}
+		if (int r = reduceDtMin()) return r;
 		dtValid = true;
 		return HB_OK;
 	}
@@ -889,6 +1022,9 @@ int hb_fv_get_state_async(hb_fv* fv, double* aos) { HB_FV(fv); return fv->impl->
 int hb_fv_wait_transfers(hb_fv* fv) { HB_FV(fv); return fv->impl->waitTransfers(); }
 int hb_fv_state_devptr(hb_fv* fv, void** p, long long* sy, long long* sz, long long* sv) { HB_FV(fv); return fv->impl->stateDevPtr(p, sy, sz, sv); }
 int hb_fv_boundary(hb_fv* fv) { HB_FV(fv); return fv->impl->boundary(); }
+int hb_fv_add_op(hb_fv* fv, const hb_op_desc* op, int* index) { HB_FV(fv); return fv->impl->addOp(op, index); }
+int hb_fv_ops_reset(hb_fv* fv) { HB_FV(fv); return fv->impl->opsReset(); }
+int hb_fv_op_info(hb_fv* fv, int op, int* it, double* res) { HB_FV(fv); return fv->impl->opInfo(op, it, res); }
 int hb_fv_set_fixed_boundary(hb_fv* fv, int face, const double* cons, int n) { HB_FV(fv); return fv->impl->setFixedBoundary(face, cons, n); }
 int hb_fv_constrainU(hb_fv* fv) { HB_FV(fv); return fv->impl->constrainU(); }
 int hb_fv_init_derivs(hb_fv* fv) { HB_FV(fv); return fv->impl->initDerivs(); }

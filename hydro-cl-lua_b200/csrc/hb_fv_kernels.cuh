@@ -58,6 +58,7 @@ template<class real> struct StageP {
 	real* scratch;         // optional per-solver device scratch (FvOps::scratchElems), e.g. the ADM flux arrays
 	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc (tile kernel; the marching kernel is built for roe)
 	int fluxParam;         // euler-hllc: hllcMethod
+	const real* gravPot;   // optional: the potential (ePot of Uin) of the self-gravity op; the tile kernel adds calcGravityDeriv (selfgrav.cl:53-76) to L
 	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded
 };
 
@@ -268,6 +269,22 @@ fv_stage(GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp,
 		bool const inside = gi < g.S[0] - HB_G && (DIM < 2 || gj < g.S[1] - HB_G) && (DIM < 3 || gk < g.S[2] - HB_G);
 		if (!inside) continue;
 		long long const idx = gi + g.strideY * gj + g.strideZ * gk;
+		if constexpr (Eqn::eqnId <= 1) {
+			// op:addSource of the self-gravity op (solverbase.lua:3219-3223, selfgrav.cl:11-76): accel = central difference of the potential,
+			// deriv.m -= accel rho, deriv.ETotal -= m . accel -- applied to L where the reference applies it to derivBuf
+			if (sp.gravPot && sp.computeL) {
+				real accel[3] = {0, 0, 0};
+				accel[0] = (sp.gravPot[idx + 1] - sp.gravPot[idx - 1]) / (real(2.) * g.dx[0]);
+				if (DIM >= 2) accel[1] = (sp.gravPot[idx + g.strideY] - sp.gravPot[idx - g.strideY]) / (real(2.) * g.dx[1]);
+				if (DIM >= 3) accel[2] = (sp.gravPot[idx + g.strideZ] - sp.gravPot[idx - g.strideZ]) / (real(2.) * g.dx[2]);
+				int const box = boxIdx<DIM, T>(i, j, k);
+				real const rho = Us[box], mx = Us[G::BOX + box], my = Us[2 * G::BOX + box], mz = Us[3 * G::BOX + box];
+				acc[n][1] = acc[n][1] - accel[0] * rho;
+				acc[n][2] = acc[n][2] - accel[1] * rho;
+				acc[n][3] = acc[n][3] - accel[2] * rho;
+				acc[n][4] -= mx * accel[0] + my * accel[1] + mz * accel[2];
+			}
+		}
 		if (sp.Lout) {
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) sp.Lout[idx + q * g.strideV] = acc[n][q];

@@ -7,6 +7,7 @@
 #include "hb_fv_kernels.cuh"
 #include "hb_fv_march.cuh"
 #include "hb_fv_march2d.cuh"
+#include "hb_ops_kernels.cuh"
 
 namespace hb {
 
@@ -36,6 +37,8 @@ template<class real> struct FvOps {
 	// optional (null when unused): device scratch the stage needs (StageP::scratch), in reals; the equation's initDerivs kernel
 	long long (*scratchElems)(GridP<real> const& g);
 	cudaError_t (*initDerivs)(GridP<real> const& g, real* U, cudaStream_t st);
+	// optional (null for equations without ops): the kernels of hydro/op (hb_ops_kernels.cuh), which = HB_OPK_*
+	cudaError_t (*opKernel)(int which, GridP<real> const& g, OpP<real> const& o, cudaStream_t st);
 };
 
 // exported by hb_fv_inst.cu instantiations

@@ -36,10 +36,33 @@ class SolverBase:
         self.backend = self.createBackend(args)
         for face, U in self.fixedBoundaryStates().items():
             self.backend.set_fixed_boundary(face, U)
+        self.createOps(args)
         self.resetState()
 
     def fixedBoundaryStates(self):
         return {}
+
+    def createOps(self, args):
+        """solver.ops (euler.lua:179-188, mhd.lua:110-122).  The reference always inserts SelfGrav and switches it with
+        solver.useGravity (selfgrav.lua:22,113), which an initial condition may set; NoDiv joins mhd in more than one dimension.
+        Here: useGravity=True adds SelfGrav; noDiv='jacobi' adds NoDiv with the Jacobi parent (the default krylov parent is the
+        reference's un-vendored 'solver' library: not built, so NoDiv stays off unless asked for)."""
+        from ..op import NoDiv, SelfGrav
+        opArgs = args.get("opArgs") or {}
+        self.useGravity = bool(args.get("useGravity", False))
+        name = getattr(self.eqn, "name", None)
+        if args.get("noDiv"):
+            if args["noDiv"] != "jacobi":
+                raise NotImplementedError("noDiv=%r: only the Jacobi parent (noDivPoissonSolver=jacobi) is built" % (args["noDiv"],))
+            if name != "mhd" or self.dim < 2:
+                raise ValueError("NoDiv is an op of the mhd equation in more than one dimension (mhd.lua:113-119)")
+            self.ops.append(NoDiv(self, **opArgs))
+        if self.useGravity:
+            if name not in ("euler", "mhd"):
+                raise ValueError("selfgrav is an op of the euler and mhd equations")
+            self.ops.append(SelfGrav(self, **opArgs))
+        for op in self.ops:
+            op.register(self.backend)
 
     # ---- solverbase.lua:511-556 / gridsolver.lua:60-96 (overridden by GridSolver)
     def initMeshVars(self, args):
@@ -111,6 +134,9 @@ class SolverBase:
             self.boundary()
             self.backend.init_derivs()
         self.boundary()
+        if self.ops:
+            # solverbase.lua:2106-2111: op:resetState() then boundary(), for every op
+            self.backend.ops_reset()
         self.constrainU()
 
     def applyInitCond(self):

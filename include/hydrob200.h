@@ -154,6 +154,21 @@ int hb_fv_get_state_async(hb_fv* fv, double* aos_host);
 int hb_fv_wait_transfers(hb_fv* fv);
 int hb_fv_state_devptr(hb_fv* fv, void** soa_dev, long long* stride_y, long long* stride_z, long long* stride_var);
 int hb_fv_set_fixed_boundary(hb_fv* fv, int face, const double* cons, int n);   /* face 0..5 = xmin,xmax,..,zmax; n <= numStates doubles; zeros until set */
+/* ---- ops either side of the step (hydro/op; solver.ops, solverbase.lua:2106-2111, 3219-3237): self-gravity and NoDiv over the Jacobi
+ *      Poisson relaxation (hydro/op/relaxation.lua, poisson.cl, poisson_jacobi.cl).  Once added, hb_fv_step / hb_fv_update run
+ *      op:addSource inside every stage and op:step after the integrator, as SolverBase:step does.  Single GPU. */
+#define HB_OP_SELFGRAV 1      /* hydro/op/selfgrav.lua + selfgrav.cl; euler, mhd; potential = ePot; param = gravitationalConstant / unit_m3_per_kg_s2 */
+#define HB_OP_NODIV 2         /* hydro/op/nodiv.lua with the Jacobi parent (noDivPoissonSolver=jacobi); mhd; potential = psi, vector = B */
+typedef struct hb_op_desc {
+	int kind;                 /* HB_OP_* */
+	int max_iters;            /* Relaxation.maxIters, relaxation.lua:26 (20) */
+	int stop_on_epsilon;      /* relaxation.lua:24 (true) */
+	double stop_epsilon;      /* relaxation.lua:25 (1e-10) */
+	double param;
+} hb_op_desc;
+int hb_fv_add_op(hb_fv* fv, const hb_op_desc* op, int* index_out);
+int hb_fv_ops_reset(hb_fv* fv);                              /* op:resetState() + boundary() of every op (solverbase.lua:2106-2111); call after set_state / boundary */
+int hb_fv_op_info(hb_fv* fv, int op, int* last_iter, double* last_residual);   /* Relaxation.lastIter / lastResidual (blocking) */
 int hb_fv_boundary(hb_fv* fv);                               /* solver:boundary(), gridsolver.lua:1316 */
 int hb_fv_init_derivs(hb_fv* fv);                            /* initDerivsKernelObj(), hydro/init/init.lua:231-235 (adm3d.cl:196-243); no-op for other equations */
 int hb_fv_constrainU(hb_fv* fv);                             /* solver:constrainU() = kernel + boundary(), solverbase.lua:2116-2127 */

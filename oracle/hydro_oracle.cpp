@@ -805,6 +805,9 @@ struct SolverBase {
 	virtual void getState(double* aos) const = 0;
 	virtual void boundary() = 0;
 	double fixedState[6][64] = {};   // per face: the state a 'fixed' boundary writes
+	virtual int addOp(int kind, int maxIters, int stopOnEpsilon, double stopEpsilon, double param) = 0;
+	virtual void opsReset() = 0;
+	virtual void opInfo(int op, int* iters, double* residual) = 0;
 	virtual void constrainU() = 0;
 	virtual double calcDT() = 0;
 	virtual void update() = 0;
@@ -895,7 +898,8 @@ template<class Eqn> struct Solver : SolverBase {
 	}
 
 	// ---- boundary: gridsolver.lua:1070-1213 (kernel generator), :638-780 (methods), :1272-1320 (x, then y, then z)
-	void boundaryOnBuf(std::vector<cons_t>& buf) {
+	// field >= 0: only that state variable (Boundary:assignDstSrc with args.fields, :584-595; no reflectVars: relaxation.lua:135-150)
+	void boundaryOnBuf(std::vector<cons_t>& buf, int field = -1) {
 		for (int side = 0; side < dim; ++side) {
 			int o1 = (side + 1) % 3, o2 = (side + 2) % 3;
 			if (side == 1) { o1 = 0; o2 = 2; }
@@ -916,33 +920,34 @@ template<class Eqn> struct Solver : SolverBase {
 						case 0:   // periodic :638-651
 							if (mm == 0) { dst = idx(j); src = idx(g + (j - g + 2 * N) % N); }
 							else { dst = idx(Sd - 1 - j); src = idx(g + (g - 1 - j) % N); }
-							buf[dst] = buf[src];
+							if (field >= 0) buf[dst].ptr[field] = buf[src].ptr[field]; else buf[dst] = buf[src];
 							break;
 						case 1:   // mirror :654-744
 							if (mm == 0) { dst = idx(j); src = idx(2 * g - 1 - j); }
 							else { dst = idx(Sd - g + j); src = idx(Sd - g - 1 - j); }
-							buf[dst] = buf[src];
-							Eqn::mirrorReflect(buf[dst], side);
+							if (field >= 0) buf[dst].ptr[field] = buf[src].ptr[field];
+							else { buf[dst] = buf[src]; Eqn::mirrorReflect(buf[dst], side); }
 							break;
 						case 2:   // freeflow :766-780
 							if (mm == 0) { dst = idx(j); src = idx(g); }
 							else { dst = idx(Sd - g + j); src = idx(Sd - g - 1); }
-							buf[dst] = buf[src];
+							if (field >= 0) buf[dst].ptr[field] = buf[src].ptr[field]; else buf[dst] = buf[src];
 							break;
 						case 4: {   // linear extrapolation :782-813: dst = 2 buf[i1] - buf[i2], every state (numStates), ghost by ghost outwards
 							long i1, i2;
 							if (mm == 0) { dst = idx(g - j - 1); i1 = idx(g - j); i2 = idx(g - j + 1); }
 							else { dst = idx(Sd - g + j); i1 = idx(Sd - g + j - 1); i2 = idx(Sd - g + j - 2); }
-							for (int k = 0; k < nS; ++k) buf[dst].ptr[k] = real(2.) * buf[i1].ptr[k] - buf[i2].ptr[k];
+							for (int k = 0; k < nS; ++k) if (field < 0 || k == field) buf[dst].ptr[k] = real(2.) * buf[i1].ptr[k] - buf[i2].ptr[k];
 							break; }
 						case 5: {   // quadratic extrapolation :815-846: dst = 3 buf[i1] - 3 buf[i2] + buf[i3]
 							long i1, i2, i3;
 							if (mm == 0) { dst = idx(g - j - 1); i1 = idx(g - j); i2 = idx(g - j + 1); i3 = idx(g - j + 2); }
 							else { dst = idx(Sd - g + j); i1 = idx(Sd - g + j - 1); i2 = idx(Sd - g + j - 2); i3 = idx(Sd - g + j - 3); }
-							for (int k = 0; k < nS; ++k) buf[dst].ptr[k] = real(3.) * buf[i1].ptr[k] - real(3.) * buf[i2].ptr[k] + buf[i3].ptr[k];
+							for (int k = 0; k < nS; ++k) if (field < 0 || k == field) buf[dst].ptr[k] = real(3.) * buf[i1].ptr[k] - real(3.) * buf[i2].ptr[k] + buf[i3].ptr[k];
 							break; }
 						case 6: {   // fixed (Dirichlet) :746-764: the face's fixedCode writes a state that does not depend on the cell
 							// (init/euler.lua:1859-1879 'square cavity' lid: consFromPrim of constants; eqn/einstein.lua:62-80: flat space)
+							if (field >= 0) break;   // a field-restricted pass (the potential of an op) leaves a 'fixed' face as it is
 							dst = mm == 0 ? idx(j) : idx(Sd - g + j);
 							for (int k = 0; k < nS; ++k) buf[dst].ptr[k] = real(fixedState[2 * side + mm][k]);
 							break; }
@@ -1393,6 +1398,150 @@ template<class Eqn> struct Solver : SolverBase {
 		for (long c = 0; c < ncells; ++c) for (int j = 0; j < nS; ++j) aos[c * nS + j] = double(deriv[c].ptr[j]);
 	}
 
+
+	// ---------------------------------------------------------------------------------------------------------------
+	// ops: the Jacobi Poisson relaxation (hydro/op/relaxation.lua:152-196, poisson.cl, poisson_jacobi.cl) and its two
+	// users on this path: self-gravity (hydro/op/selfgrav.lua, selfgrav.cl; euler.lua:179-188, mhd.lua:120-122; potential = ePot) and
+	// NoDiv with the Jacobi solver (hydro/op/nodiv.lua with noDivPoissonSolver=jacobi; mhd.lua:113-119; potential = psi, vector = B).
+	// The default NoDiv parent, poisson_krylov, lives in the un-vendored 'solver' library and is out of scope.
+	struct Op { int kind, maxIters, stopOnEpsilon; double stopEpsilon, param; int pot, vec; double lastResidual; int lastIter; };
+	std::vector<Op> opsList;
+	std::vector<real> writeBuf;
+	int addOp(int kind, int maxIters, int stopOnEpsilon, double stopEpsilon, double param) override {
+		Op o{kind, maxIters, stopOnEpsilon, stopEpsilon, param, nS - 1, -1, 0., 0};
+		if (kind == 1) { if (d.eqn > 1) return -1; o.pot = nS - 1; }                 // ePot is the last state variable of euler and mhd
+		else if (kind == 2) { if (d.eqn != 1) return -1; o.pot = 8; o.vec = 5; }      // mhd: B = ptr[5..7], psi = ptr[8]
+		else return -1;
+		opsList.push_back(o);
+		writeBuf.assign(ncells, real(0));
+		return int(opsList.size()) - 1;
+	}
+	// getPoissonDivCode: selfgrav.lua:43-48 / nodiv.lua:86-118
+	real poissonSource(Op const& o, int i, int j, int k, long index) const {
+		if (o.kind == 1) return real(4. * M_PI * double(UBuf[index].ptr[0]) * o.param / 1.);   // 4 pi rho G / unit_m3_per_kg_s2 (units 1)
+		real source = 0;
+		if (OOB(i, j, k, 1, 1)) return source;
+		for (int s = 0; s < dim; ++s)
+			source = source + (UBuf[index + solver.stepsize[s]].ptr[o.vec + s] - UBuf[index - solver.stepsize[s]].ptr[o.vec + s]) * real(.5 / double(solver.grid_dx.s(s)));
+		return source;
+	}
+	// poisson.cl:36-53 initPotential (SETBOUNDS(numGhost, numGhost)): potential = -source
+	void initPotential(Op const& o) {
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, g, g)) continue;
+			long index = INDEX(i, j, k);
+			UBuf[index].ptr[o.pot] = -poissonSource(o, i, j, k, index);
+		}
+	}
+	// poisson_jacobi.cl:42-167 solveJacobi, cartesian: cell_dx_j = grid_dx_j, cell->volume = prod grid_dx (coord.lua cell_volume), so
+	// volume_intL = volume_intR = .5 (volume + volume)
+	void solveJacobi(Op const& o) {
+		real volume = 1;
+		for (int s = 0; s < dim; ++s) volume = volume * solver.grid_dx.s(s);
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			long index = INDEX(i, j, k);
+			if (OOB(i, j, k, g, g)) { writeBuf[index] = UBuf[index].ptr[o.pot]; reduceBuf[index] = 0; continue; }
+			real const volL = real(.5) * (volume + volume), volR = real(.5) * (volume + volume), volAtX = volume;
+			real skewSum = 0;
+			for (int s = 0; s < dim; ++s) {
+				real const dx = solver.grid_dx.s(s);
+				skewSum = skewSum + (UBuf[index + solver.stepsize[s]].ptr[o.pot] * (volR / (dx * dx)) + UBuf[index - solver.stepsize[s]].ptr[o.pot] * (volL / (dx * dx)));   // real_add3(a,b,c) = a + (b + c), math.cl:221
+			}
+			skewSum = skewSum * (real(1.) / volAtX);
+			real diag = 0;
+			for (int s = 0; s < dim; ++s) { real const dx = solver.grid_dx.s(s); diag = diag - (volR + volL) / (dx * dx); }
+			diag = diag / volAtX;
+			real const source = poissonSource(o, i, j, k, index);
+			real const oldU = UBuf[index].ptr[o.pot];
+			real const newU = (source - skewSum) * (real(1.) / diag);
+			writeBuf[index] = newU;
+			real const residual = (source - skewSum) - diag * oldU;
+			reduceBuf[index] = residual * residual;
+		}
+	}
+	// relaxation.lua:165-196
+	void relax(Op& o) {
+		long volumeWithoutBorder = 1;
+		for (int s = 0; s < dim; ++s) volumeWithoutBorder *= S[s] - 2 * g;
+		for (int it = 1; it <= o.maxIters; ++it) {
+			o.lastIter = it;
+			solveJacobi(o);
+			for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {   // copyWriteToPotentialNoGhost, poisson.cl:55-64
+				if (OOB(i, j, k, g, g)) continue;
+				long index = INDEX(i, j, k);
+				UBuf[index].ptr[o.pot] = writeBuf[index];
+			}
+			boundaryOnBuf(UBuf, o.pot);   // potentialBoundary
+			if (o.stopOnEpsilon) {
+				// reduceSum over all cells (ghost entries are 0); the summation order of lua-opencl's reduce is not pinned: pairwise here
+				std::vector<double> tmp(reduceBuf.begin(), reduceBuf.end());
+				for (size_t n = tmp.size(); n > 1; n = (n + 1) / 2) for (size_t a = 0; a < n / 2; ++a) tmp[a] = tmp[a] + tmp[n - 1 - a];
+				double const residual = std::sqrt(double(real(tmp[0])) / double(volumeWithoutBorder));
+				o.lastResidual = residual;
+				if (std::fabs(residual) <= o.stopEpsilon) break;
+			}
+		}
+	}
+	// selfgrav.lua:123-147 offsetPotential: ePot -= max over all cells (ghost cells included: copyPotentialToReduce is SETBOUNDS(0,0))
+	void offsetPotential(Op const& o) {
+		real mx = UBuf[0].ptr[o.pot];
+		for (long c = 1; c < ncells; ++c) mx = UBuf[c].ptr[o.pot] > mx ? UBuf[c].ptr[o.pot] : mx;
+		for (long c = 0; c < ncells; ++c) UBuf[c].ptr[o.pot] -= mx;
+	}
+	// op:resetState of every op, each followed by boundary() (solverbase.lua:2106-2111; relaxation.lua:152-158; selfgrav.lua:93-101)
+	void opsReset() override {
+		for (auto& o : opsList) {
+			initPotential(o);
+			boundaryOnBuf(UBuf, o.pot);
+			relax(o);
+			if (o.kind == 1) offsetPotential(o);
+			boundary();
+		}
+	}
+	// op:addSource (solverbase.lua:3219-3223): selfgrav.lua:112-121 + selfgrav.cl:53-76 calcGravityDeriv
+	void opsAddSource(std::vector<cons_t>& derivBuf) {
+		for (auto& o : opsList) {
+			if (o.kind != 1) continue;
+			relax(o);
+			#pragma omp parallel for collapse(2)
+			for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+				if (OOB(i, j, k, g, g)) continue;
+				long index = INDEX(i, j, k);
+				real accel[3] = {0, 0, 0};
+				for (int s = 0; s < dim; ++s)
+					accel[s] = (UBuf[index + solver.stepsize[s]].ptr[o.pot] - UBuf[index - solver.stepsize[s]].ptr[o.pot]) / (real(2.) * solver.grid_dx.s(s));
+				cons_t const& U = UBuf[index];
+				cons_t& dv = derivBuf[index];
+				for (int s = 0; s < 3; ++s) dv.ptr[1 + s] = dv.ptr[1 + s] - accel[s] * U.ptr[0];
+				dv.ptr[4] -= U.ptr[1] * accel[0] + U.ptr[2] * accel[1] + U.ptr[3] * accel[2];
+			}
+			offsetPotential(o);
+		}
+	}
+	// op:step (solverbase.lua:3230-3237): boundary(), constrainU(), then nodiv.lua:180-184: relax + noDiv kernel (nodiv.lua:133-157)
+	void opsStep() {
+		for (auto& o : opsList) {
+			if (o.kind != 2) continue;
+			boundary();
+			constrainU();
+			relax(o);
+			std::vector<cons_t> const src = UBuf;   // the kernel reads psi only, which it does not write
+			#pragma omp parallel for collapse(2)
+			for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+				if (OOB(i, j, k, g, g)) continue;
+				long index = INDEX(i, j, k);
+				for (int s = 0; s < dim; ++s) {
+					real const dv = (src[index + solver.stepsize[s]].ptr[o.pot] - src[index - solver.stepsize[s]].ptr[o.pot]) * real(1. / (2. * double(solver.grid_dx.s(s))));
+					UBuf[index].ptr[o.vec + s] = UBuf[index].ptr[o.vec + s] - dv;
+				}
+			}
+		}
+	}
+	void opInfo(int op, int* iters, double* residual) override {
+		if (op >= 0 && op < (int)opsList.size()) { *iters = opsList[op].lastIter; *residual = opsList[op].lastResidual; }
+	}
+
 	// ---- calcDT: eqn.lua:1187-1224 + solverbase.lua:3004-3023 (reduceMin over all cells)
 	double calcDT() override {
 		if (d.use_fixed_dt) return d.fixed_dt;
@@ -1437,10 +1586,11 @@ template<class Eqn> struct Solver : SolverBase {
 		if (d.rk_order == 0) {
 			clearBuffer(feDeriv);
 			calcDeriv(feDeriv, dtArg);
-			addSource(feDeriv);
+			addSource(feDeriv); opsAddSource(feDeriv);
 			multAddInto(UBuf, feDeriv, real(dt_));
 			boundary();
 			constrainU();
+			opsStep();
 			return;
 		}
 		int const order = d.rk_order;
@@ -1452,7 +1602,7 @@ template<class Eqn> struct Solver : SolverBase {
 			if (needed) UBufs[0] = UBuf;
 			needed = false;
 			for (int m = 0; m < order; ++m) needed = needed || beta(m, 0) != 0;
-			if (needed) { clearBuffer(derivBufs[0]); calcDeriv(derivBufs[0], dtArg); addSource(derivBufs[0]); }
+			if (needed) { clearBuffer(derivBufs[0]); calcDeriv(derivBufs[0], dtArg); addSource(derivBufs[0]); opsAddSource(derivBufs[0]); }
 		}
 		for (int i = 1; i <= order; ++i) {   // Lua i = 2..order+1
 			clearBuffer(UBuf);
@@ -1468,9 +1618,10 @@ template<class Eqn> struct Solver : SolverBase {
 				if (needed) UBufs[i] = UBuf;
 				needed = false;
 				for (int m = i; m < order; ++m) needed = needed || beta(m, i) != 0;
-				if (needed) { clearBuffer(derivBufs[i]); calcDeriv(derivBufs[i], dtArg); addSource(derivBufs[i]); }
+				if (needed) { clearBuffer(derivBufs[i]); calcDeriv(derivBufs[i], dtArg); addSource(derivBufs[i]); opsAddSource(derivBufs[i]); }
 			}
 		}
+		opsStep();
 	}
 
 	// ---- SolverBase:update: solverbase.lua:3026-3190 (ops list empty: parity contract)
@@ -1531,6 +1682,9 @@ long ho_num_cells(void* h) { return static_cast<ho::SolverBase*>(h)->numCells();
 void ho_set_state(void* h, const double* aos) { static_cast<ho::SolverBase*>(h)->setState(aos); }
 void ho_get_state(void* h, double* aos) { static_cast<ho::SolverBase*>(h)->getState(aos); }
 void ho_set_fixed_boundary(void* h, int face, const double* U, int n) { auto* s = static_cast<ho::SolverBase*>(h); for (int k = 0; k < n && k < 64; ++k) s->fixedState[face][k] = U[k]; }
+int ho_add_op(void* h, int kind, int maxIters, int stopOnEpsilon, double stopEpsilon, double param) { return static_cast<ho::SolverBase*>(h)->addOp(kind, maxIters, stopOnEpsilon, stopEpsilon, param); }
+void ho_ops_reset(void* h) { static_cast<ho::SolverBase*>(h)->opsReset(); }
+void ho_op_info(void* h, int op, int* iters, double* residual) { static_cast<ho::SolverBase*>(h)->opInfo(op, iters, residual); }
 void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }
 void ho_init_derivs(void* h) { static_cast<ho::SolverBase*>(h)->initDerivs(); }
 void ho_source_test(void* h, const double* U, double* deriv) { static_cast<ho::SolverBase*>(h)->sourceTest(U, deriv); }

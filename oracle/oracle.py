@@ -58,6 +58,11 @@ def lib(fma=False):
         L.ho_set_state.argtypes = [C.c_void_p, C.c_void_p]
         L.ho_set_fixed_boundary.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]
         L.ho_set_fixed_boundary.restype = None
+        L.ho_add_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
+        L.ho_ops_reset.argtypes = [C.c_void_p]
+        L.ho_ops_reset.restype = None
+        L.ho_op_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
+        L.ho_op_info.restype = None
         L.ho_get_state.argtypes = [C.c_void_p, C.c_void_p]
         L.ho_calc_dt.argtypes = [C.c_void_p]
         L.ho_calc_dt.restype = C.c_double
@@ -151,6 +156,20 @@ class OracleBackend:
 
     def boundary(self):
         self.L.ho_boundary(self.h)
+
+    def add_op(self, kind, max_iters, stop_on_epsilon, stop_epsilon, param):
+        r = self.L.ho_add_op(self.h, int(kind), int(max_iters), 1 if stop_on_epsilon else 0, float(stop_epsilon), float(param))
+        if r < 0:
+            raise RuntimeError("oracle: op not available for this equation")
+        return r
+
+    def ops_reset(self):
+        self.L.ho_ops_reset(self.h)
+
+    def op_info(self, op):
+        it, res = C.c_int(), C.c_double()
+        self.L.ho_op_info(self.h, int(op), C.byref(it), C.byref(res))
+        return it.value, res.value
 
     def set_fixed_boundary(self, face, U):
         a = (C.c_double * len(U))(*U)

@@ -135,3 +135,18 @@ CASES["F4_sphere_mixed_3d"] = (dict(eqn="euler", dim=3, gridSize=[24, 18, 12], m
 CASES["F4_ot_mhd_linear_2d"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
                                      integrator="Runge-Kutta 3, TVD", cfl=.15,
                                      boundary=dict(xmin="linear", xmax="linear", ymin="periodic", ymax="periodic")), 8)
+
+# the ops either side of the step -- self-gravity (hydro/op/selfgrav.lua) inside every stage's addSource and NoDiv over the
+# Jacobi relaxation (hydro/op/nodiv.lua, noDivPoissonSolver=jacobi) after the integrator.
+CASES["F3_selfgrav_sphere_fe_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 28], initCond="sphere", fluxLimiter="superbee", integrator="forward Euler",
+                                          cfl=.15, useGravity=True), 8)
+CASES["F3_selfgrav_sphere_rk4_plm_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                               usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1, useGravity=True,
+                                               boundary=dict(xmin="mirror", xmax="mirror", ymin="freeflow", ymax="freeflow",
+                                                             zmin="periodic", zmax="periodic")), 4)
+CASES["F3_selfgrav_sod_rk2_1d"] = (dict(eqn="euler", dim=1, gridSize=[128], initCond="Sod", usePLM="plm cons", slopeLimiter="superbee",
+                                        integrator="Runge-Kutta 2, TVD", cfl=.3, useGravity=True, opArgs=dict(maxIters=7, stopOnEpsilon=False)), 10)
+CASES["F3_nodiv_ot_rk3_2d"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
+                                    integrator="Runge-Kutta 3, TVD", cfl=.15, noDiv="jacobi"), 8)
+CASES["F3_nodiv_selfgrav_ot_fe_3d"] = (dict(eqn="mhd", dim=3, gridSize=[16, 12, 10], initCond="Orszag-Tang", fluxLimiter="minmod",
+                                            integrator="forward Euler", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2], noDiv="jacobi", useGravity=True), 4)
