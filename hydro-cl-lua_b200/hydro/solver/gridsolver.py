@@ -144,6 +144,25 @@ class GridSolver(SolverBase):
         U = self.backend.get_state()
         return U.reshape(self.localGridSize[2], self.localGridSize[1], self.localGridSize[0], self.eqn.numStates)
 
+    # ---- gridsolver.lua:1410-1470: GridSolver:saveBuffer / :save -- FITS dumps in the reference's own layout (hydro/fits.py), and
+    #      the way back, so that a dump written by the reference (saveOnExit / save) can be loaded and compared
+    def saveBuffer(self, U, basefn):
+        from .. import fits
+        real = np.float32 if self.real_bytes == 4 else np.float64
+        fits.write_image(basefn + ".fits", fits.state_to_image(U, real))
+        return basefn + ".fits"
+
+    def save(self, prefix=None):
+        """Writes <prefix>_UBuf.fits (the buffer of this path; the reference's loop also dumps its scratch buffers)."""
+        return self.saveBuffer(self.getState(), (prefix + "_" if prefix else "") + "UBuf")
+
+    def loadBuffer(self, filename):
+        from .. import fits
+        return fits.image_to_state(fits.read_image(filename), self.localGridSize)
+
+    def load(self, prefix=None):
+        self.setState(self.loadBuffer((prefix + "_" if prefix else "") + "UBuf.fits"))
+
     def getGlobalInterior(self):
         """Interior of the whole grid, gathered from every rank's slab (tests of the decomposed path)."""
         Ui = self.interior()

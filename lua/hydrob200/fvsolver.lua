@@ -82,6 +82,31 @@ function B200Solver:refreshSolverProgram()
 	end
 end
 
+-- solver.ops (euler.lua:179-188, mhd.lua:110-122): the ops this library builds are registered with the fused path, which then runs
+-- op:addSource inside every stage and op:step after the integrator (solverbase.lua:3219-3237); call after refreshSolverProgram
+function B200Solver:registerOps()
+	for _, op in ipairs(self.ops) do
+		local d = ffi.new'hb_op_desc'
+		if op.name == 'selfgrav' then
+			if self.useGravity then
+				d.kind = lib.HB_OP_SELFGRAV
+				d.param = self.eqn.guiVars.gravitationalConstant.value      -- / unit_m3_per_kg_s2 = 1 in the default units
+			end
+		elseif op.name == 'NoDiv' then
+			assert(require 'hydro.op.poisson_jacobi':isa(op), "hydrob200: NoDiv needs noDivPoissonSolver=jacobi (the krylov parent is not built)")
+			d.kind = lib.HB_OP_NODIV
+		else
+			error("hydrob200: op not built: "..tostring(op.name))
+		end
+		if d.kind ~= 0 then
+			d.max_iters, d.stop_on_epsilon, d.stop_epsilon = op.maxIters, op.stopOnEpsilon and 1 or 0, op.stopEpsilon
+			check(lib.hb_fv_add_op(self.fv, d, nil), 'hb_fv_add_op')
+		end
+	end
+end
+-- the op:resetState() loop of SolverBase:resetState (solverbase.lua:2106-2111)
+function B200Solver:resetOps() check(lib.hb_fv_ops_reset(self.fv), 'hb_fv_ops_reset') end
+
 function B200Solver:uploadState(aosPtr) check(lib.hb_fv_set_state(self.fv, aosPtr), 'hb_fv_set_state') end
 function B200Solver:downloadState(aosPtr) check(lib.hb_fv_get_state(self.fv, aosPtr), 'hb_fv_get_state') end
 
