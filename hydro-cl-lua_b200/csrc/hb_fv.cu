@@ -549,7 +549,8 @@ template<class real> struct Fv : FvBase {
 		useDevice(ctx);
 		if (!opWrite) {
 			if (int r = allocPadded(&opWrite, sizeof(real) * ((size_t)vstride + (size_t)grid.strideY))) return r;
-			opBlocks = (int)((cells + HB_OP_NT - 1) / HB_OP_NT);
+			long long const rows = (long long)grid.S[1] * grid.S[2];
+			opBlocks = (int)(rows < 148 * 8 ? rows : 148 * 8);          // rows are dealt round-robin to 8 CTAs per SM
 			HB_CUDA(cudaMalloc(&opPartial, sizeof(double) * (size_t)opBlocks));
 		}
 		HB_CUDA(cudaMalloc(&s.ctl, sizeof(OpCtl)));
@@ -569,34 +570,50 @@ template<class real> struct Fv : FvBase {
 		p.param = s.d.param; p.stopEpsilon = s.d.stop_epsilon; p.stopOnEpsilon = s.d.stop_on_epsilon; p.iter = iter;
 		double v = 1; for (int k = 0; k < d.dim; ++k) v *= (double)grid.N[k];
 		p.volumeWithoutBorder = v; p.nBlocks = opBlocks;
+		// sweep 1 reads the potential in U and writes writeBuf, sweep 2 the other way round, ...
+		real* potU = U + (size_t)s.pot * vstride;
+		p.potIn = (iter & 1) ? potU : opWrite;
+		p.potOut = (iter & 1) ? opWrite : potU;
+		// poisson_jacobi.cl:57-117 on a cartesian grid, operation for operation, in `real`
+		real volume = 1;
+		for (int k = 0; k < d.dim; ++k) volume = volume * grid.dx[k];
+		real const volL = real(.5) * (volume + volume), volR = real(.5) * (volume + volume), volAtX = volume;
+		real diag = 0;
+		for (int k = 0; k < d.dim; ++k) {
+			real const dx = grid.dx[k];
+			p.cS[k] = volR / (dx * dx);
+			diag = diag - (volR + volL) / (dx * dx);
+			p.sDiv[k] = real(.5 / double(dx));                 // nodiv.lua:104
+			p.sGrad[k] = real(1. / (2. * double(dx)));         // nodiv.lua:150
+		}
+		p.invVol = real(1.) / volAtX;
+		p.diag = diag / volAtX;
+		p.invDiag = real(1.) / p.diag;
 		return p;
 	}
 	int opLaunch(int which, OpP<real> const& p) { HB_CUDA(ops->opKernel(which, grid, p, st())); launches++; return HB_OK; }
 	// Relaxation:potentialBoundary (relaxation.lua:135-150,198-200): the solver's boundary methods on the potential alone
-	int potentialBoundary(OpState const& s, real* U) { return fillGhosts(U + (size_t)s.pot * vstride, 1); }
-	// Relaxation:relax (relaxation.lua:165-196); the stop test stays on the device (OpCtl::done)
+	int potentialBoundary(real* pot) { return fillGhosts(pot, 1); }
+	// Relaxation:relax (relaxation.lua:165-196); the stop test stays on the device (OpCtl::done), the two copies of the potential alternate
 	int relax(OpState const& s, real* U) {
 		if (int r = opLaunch(HB_OPK_BEGIN, opParams(s, U))) return r;
 		for (int it = 1; it <= s.d.max_iters; ++it) {
 			OpP<real> const p = opParams(s, U, it);
 			if (int r = opLaunch(HB_OPK_JACOBI, p)) return r;
-			if (int r = opLaunch(HB_OPK_COPY, p)) return r;
-			if (int r = potentialBoundary(s, U)) return r;
-			if (int r = opLaunch(HB_OPK_FINISH, p)) return r;
+			if (int r = potentialBoundary(p.potOut)) return r;
 		}
-		return HB_OK;
+		return opLaunch(HB_OPK_FINAL_COPY, opParams(s, U));
 	}
 	int offsetPotential(OpState const& s, real* U) {       // selfgrav.lua:123-147
 		OpP<real> const p = opParams(s, U);
-		if (int r = opLaunch(HB_OPK_MAX_PARTIAL, p)) return r;
-		if (int r = opLaunch(HB_OPK_MAX_FINISH, p)) return r;
+		if (int r = opLaunch(HB_OPK_MAX, p)) return r;
 		return opLaunch(HB_OPK_OFFSET, p);
 	}
 	int opsReset() override {                              // solverbase.lua:2106-2111, relaxation.lua:152-158, selfgrav.lua:93-101
 		useDevice(ctx);
 		for (auto& s : opsV) {
 			if (int r = opLaunch(HB_OPK_INIT, opParams(s, upool[0]))) return r;
-			if (int r = potentialBoundary(s, upool[0])) return r;
+			if (int r = potentialBoundary(upool[0] + (size_t)s.pot * vstride)) return r;
 			if (int r = relax(s, upool[0])) return r;
 			if (s.d.kind == HB_OP_SELFGRAV) if (int r = offsetPotential(s, upool[0])) return r;
 			if (int r = fillGhosts(upool[0], nS)) return r;

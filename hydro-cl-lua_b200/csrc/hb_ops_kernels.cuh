@@ -4,42 +4,51 @@
 //   NoDiv (Jacobi parent)       hydro/op/nodiv.lua (potential = psi, vector = B; mhd.lua:113-119 with noDivPoissonSolver=jacobi)
 //
 // B200 design: the reference reads the residual back to the host after every Jacobi sweep (relaxation.lua:177) to decide
-// whether to stop.  Here the decision stays on the device: op_finish_iter sums the per-block partial residuals in a fixed
+// whether to stop.  Here the decision stays on the device: the sweep kernel sums the per-block partial residuals in a fixed
 // order, writes residual / iteration into OpCtl and raises OpCtl::done; every later sweep of the same relax() returns at
-// once.  A relax() is therefore maxIters x (sweep, copy, ghost fill, finish) launches with no host round trip, and the
-// whole update stays one graph-capturable stream sequence.  The state is SoA, so a sweep reads one variable (7 points)
-// and writes one: 16 B per cell in double, HBM-bound.
+// once.  A relax() is therefore maxIters x (sweep, ghost fill) launches with no host round trip, and the whole update stays
+// one graph-capturable stream sequence.  The residual sum is finished by the sweep's last block (ticket counter, partials
+// combined in index order: deterministic).  The state is SoA, so a sweep reads the potential (7 points, one stream from
+// HBM / L2), the source operand (rho, or the neighbours of B) and writes the potential: 3-4 words per cell, HBM-bound.
 #pragma once
 #include "hb_fv_kernels.cuh"
 
 namespace hb {
 
-struct OpCtl { int done; int lastIter; double lastResidual; double maxVal; };
+struct OpCtl { int done; int lastIter; double lastResidual; double maxVal; unsigned int ticket; };
 
 constexpr int HB_OP_NT = 256;
 
 template<class real> struct OpP {
 	int kind;               // 1 self-gravity, 2 NoDiv
 	real* U;                // variable 0 of the state the op works on
-	real* writeBuf;         // one variable, same strides
+	real* writeBuf;         // one variable, same strides (relaxation.lua:52-57)
+	const real* potIn;      // the sweep reads this copy of the potential ...
+	real* potOut;           // ... and writes that one (U's potential slot and writeBuf alternate, see relax() in hb_fv.cu)
 	double* partial;        // per-block partial sums / maxima
 	OpCtl* ctl;
 	int pot, vec;           // variable index of the potential; first component of the vector field (NoDiv)
 	double param;           // self-gravity: gravitationalConstant / unit_m3_per_kg_s2
 	double stopEpsilon; int stopOnEpsilon;
-	int iter;               // 1-based sweep number (op_finish_iter)
+	int iter;               // 1-based sweep number
 	double volumeWithoutBorder;
-	int nBlocks;            // blocks of the all-cells launches (= entries of `partial`)
+	int nBlocks;            // blocks of the row-strided launches (= entries of `partial`)
+	// grid constants of solveJacobi, formed on the host in `real` with the reference's operations (IEEE division: the same bits as on the device)
+	real cS[3];             // volume_int / (dx_s dx_s)
+	real invVol;            // 1. / volAtX
+	real invDiag;           // 1. / diag
+	real diag;
+	real sDiv[3];           // NoDiv source: .5 / grid_dx_s
+	real sGrad[3];          // noDiv kernel: 1. / (2. grid_dx_s)
 };
 
-// all-cells enumeration (SETBOUNDS(0,0)): i fastest
-template<class real> HB_D bool opCell(GridP<real> const& g, long long w, int& i, int& j, int& k, long long& idx) {
-	long long const S0 = g.S[0], S1 = g.S[1], S2 = g.S[2];
-	if (w >= S0 * S1 * S2) return false;
-	i = int(w % S0); j = int((w / S0) % S1); k = int(w / (S0 * S1));
-	idx = i + g.strideY * j + g.strideZ * k;
-	return true;
-}
+// Rows (j, k) of the ghost-inclusive array are dealt to the blocks round-robin; a block walks its rows along x, so every access is
+// coalesced and the index arithmetic is one integer division per row.
+#define HB_OP_ROWS(g, row, j, k, base) \
+	for (int row = blockIdx.x; row < (g).S[1] * (g).S[2]; row += gridDim.x) \
+		if (int const j = row % (g).S[1], k = row / (g).S[1]; true) \
+			if (long long const base = (g).strideY * j + (g).strideZ * k; true)
+
 template<class real> HB_D bool opOOB(GridP<real> const& g, int i, int j, int k, int l, int r) {
 	return i < l || i >= g.S[0] - r || (g.dim >= 2 && (j < l || j >= g.S[1] - r)) || (g.dim >= 3 && (k < l || k >= g.S[2] - r));
 }
@@ -53,86 +62,86 @@ template<class real> HB_D real opSource(GridP<real> const& g, OpP<real> const& o
 	for (int s = 0; s < g.dim; ++s) {
 		real const* v = o.U + (o.vec + s) * g.strideV;
 		long long const st = opStride(g, s);
-		source = source + (v[idx + st] - v[idx - st]) * real(.5 / double(g.dx[s]));
+		source = source + (v[idx + st] - v[idx - st]) * o.sDiv[s];
 	}
 	return source;
 }
 
 // relax() start: a fresh stop flag
-template<class real> __global__ void op_begin(OpCtl* ctl) { ctl->done = 0; ctl->lastIter = 0; }
+template<class real> __global__ void op_begin(OpCtl* ctl) { ctl->done = 0; ctl->lastIter = 0; ctl->ticket = 0; }
 
 // poisson.cl:36-53 initPotential: potential = -source on the interior
 template<class real> __global__ void op_init_potential(GridP<real> const g, OpP<real> const o) {
-	int i, j, k; long long idx;
-	if (!opCell(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k, idx)) return;
-	if (opOOB(g, i, j, k, HB_G, HB_G)) return;
-	o.U[o.pot * g.strideV + idx] = -opSource(g, o, i, j, k, idx);
+	HB_OP_ROWS(g, row, j, k, base)
+		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) {
+			if (opOOB(g, i, j, k, HB_G, HB_G)) continue;
+			o.U[o.pot * g.strideV + base + i] = -opSource(g, o, i, j, k, base + i);
+		}
 }
 
-template<class real, bool MAX> HB_D void opBlockReduce(double v, double* out) {
+template<bool MAX> HB_D double opCombine(double a, double b) { return MAX ? (b > a ? b : a) : a + b; }
+// block-wide reduction in a fixed order; the result is valid in thread 0
+template<bool MAX> HB_D double opBlockReduce(double v) {
 	__shared__ double red[HB_OP_NT / 32];
 	#pragma unroll
-	for (int m = 16; m > 0; m >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, m); v = MAX ? (u > v ? u : v) : v + u; }
+	for (int m = 16; m > 0; m >>= 1) v = opCombine<MAX>(v, __shfl_xor_sync(0xffffffffu, v, m));
+	__syncthreads();
 	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
 	__syncthreads();
 	if (threadIdx.x < 32) {
 		v = threadIdx.x < HB_OP_NT / 32 ? red[threadIdx.x] : (MAX ? -HUGE_VAL : 0.);
 		#pragma unroll
-		for (int m = 16; m > 0; m >>= 1) { double const u = __shfl_xor_sync(0xffffffffu, v, m); v = MAX ? (u > v ? u : v) : v + u; }
-		if (threadIdx.x == 0) *out = v;
+		for (int m = 16; m > 0; m >>= 1) v = opCombine<MAX>(v, __shfl_xor_sync(0xffffffffu, v, m));
 	}
+	return v;
+}
+// The block that finishes last (ticket counter) combines the per-block partials in index order: deterministic whichever block it is.
+template<bool MAX> HB_D bool opLastBlockReduce(double mine, double* partial, OpCtl* ctl, int nBlocks, double& total) {
+	__shared__ int isLast;
+	if (threadIdx.x == 0) {
+		partial[blockIdx.x] = mine;
+		__threadfence();
+		unsigned int const t = atomicAdd(&ctl->ticket, 1u);
+		isLast = t == (unsigned int)(nBlocks - 1);
+	}
+	__syncthreads();
+	if (!isLast) return false;
+	__threadfence();
+	double v = MAX ? -HUGE_VAL : 0.;
+	for (int n = threadIdx.x; n < nBlocks; n += HB_OP_NT) v = opCombine<MAX>(v, ((volatile double*)partial)[n]);
+	total = opBlockReduce<MAX>(v);
+	if (threadIdx.x == 0) ctl->ticket = 0;
+	return true;
 }
 
-// poisson_jacobi.cl:42-167 solveJacobi on a cartesian grid: cell_dx_j = grid_dx_j and cell->volume = prod grid_dx, so
-// volume_intL = volume_intR = .5 (volume + volume).  Ghost cells copy the potential through; residual^2 goes to the block sum.
-template<class real> __global__ void op_solve_jacobi(GridP<real> const g, OpP<real> const o) {
+// One Jacobi sweep = solveJacobi (poisson_jacobi.cl:42-167, cartesian: cell_dx_j = grid_dx_j, cell->volume = prod grid_dx, so
+// volume_intL = volume_intR = .5 (volume + volume)) + copyWriteToPotentialNoGhost (poisson.cl:55-64) + the residual test of
+// relaxation.lua:176-194.  The reference writes the sweep to writeBuf (ghost cells: the old potential) and copies its interior back;
+// here the two copies of the potential alternate instead (potIn -> potOut; the ghost fill that follows makes potOut what the reference's
+// potential is after its boundary pass), which saves the copy kernel: 3 words per cell and sweep instead of 5.
+template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_solve_jacobi(GridP<real> const g, OpP<real> const o) {
 	if (o.ctl->done) return;
-	int i, j, k; long long idx;
+	real const* __restrict__ pot = o.potIn;
+	real* __restrict__ out = o.potOut;
 	double res2 = 0;
-	if (opCell(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k, idx)) {
-		real const* pot = o.U + o.pot * g.strideV;
-		if (opOOB(g, i, j, k, HB_G, HB_G)) o.writeBuf[idx] = pot[idx];
-		else {
-			real volume = 1;
-			for (int s = 0; s < g.dim; ++s) volume = volume * g.dx[s];
-			real const volL = real(.5) * (volume + volume), volR = real(.5) * (volume + volume), volAtX = volume;
+	HB_OP_ROWS(g, row, j, k, base)
+		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) {
+			long long const idx = base + i;
+			if (opOOB(g, i, j, k, HB_G, HB_G)) { out[idx] = pot[idx]; continue; }
 			real skewSum = 0;
-			for (int s = 0; s < g.dim; ++s) {
-				real const dx = g.dx[s];
-				long long const st = opStride(g, s);
-				skewSum = skewSum + (pot[idx + st] * (volR / (dx * dx)) + pot[idx - st] * (volL / (dx * dx)));   // real_add3 = a + (b + c), math.cl:221
-			}
-			skewSum = skewSum * (real(1.) / volAtX);
-			real diag = 0;
-			for (int s = 0; s < g.dim; ++s) { real const dx = g.dx[s]; diag = diag - (volR + volL) / (dx * dx); }
-			diag = diag / volAtX;
+			skewSum = skewSum + (pot[idx + 1] * o.cS[0] + pot[idx - 1] * o.cS[0]);                                         // real_add3 = a + (b + c), math.cl:221
+			if (g.dim >= 2) skewSum = skewSum + (pot[idx + g.strideY] * o.cS[1] + pot[idx - g.strideY] * o.cS[1]);
+			if (g.dim >= 3) skewSum = skewSum + (pot[idx + g.strideZ] * o.cS[2] + pot[idx - g.strideZ] * o.cS[2]);
+			skewSum = skewSum * o.invVol;
 			real const source = opSource(g, o, i, j, k, idx);
 			real const oldU = pot[idx];
-			o.writeBuf[idx] = (source - skewSum) * (real(1.) / diag);
-			real const residual = (source - skewSum) - diag * oldU;
-			res2 = double(residual * residual);
+			out[idx] = (source - skewSum) * o.invDiag;
+			real const residual = (source - skewSum) - o.diag * oldU;
+			res2 += double(residual * residual);
 		}
-	}
-	if (o.stopOnEpsilon) opBlockReduce<real, false>(res2, o.partial + blockIdx.x);
-}
-
-// poisson.cl:55-64 copyWriteToPotentialNoGhost
-template<class real> __global__ void op_copy_write(GridP<real> const g, OpP<real> const o) {
-	if (o.ctl->done) return;
-	int i, j, k; long long idx;
-	if (!opCell(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k, idx)) return;
-	if (opOOB(g, i, j, k, HB_G, HB_G)) return;
-	o.U[o.pot * g.strideV + idx] = o.writeBuf[idx];
-}
-
-// relaxation.lua:176-194: residual = sqrt(reduceSum / volumeWithoutBorder); stop when |residual| <= stopEpsilon.  One block, fixed order.
-template<class real> __global__ void op_finish_iter(OpP<real> const o) {
-	if (o.ctl->done) return;
-	double v = 0;
-	if (o.stopOnEpsilon) for (int n = threadIdx.x; n < o.nBlocks; n += HB_OP_NT) v += o.partial[n];
-	__shared__ double total;
-	opBlockReduce<real, false>(v, &total);
-	__syncthreads();
+	double const mine = o.stopOnEpsilon ? opBlockReduce<false>(res2) : 0.;
+	double total = 0;
+	if (!opLastBlockReduce<false>(mine, o.partial, o.ctl, o.nBlocks, total)) return;
 	if (threadIdx.x == 0) {
 		o.ctl->lastIter = o.iter;
 		if (o.stopOnEpsilon) {
@@ -143,40 +152,49 @@ template<class real> __global__ void op_finish_iter(OpP<real> const o) {
 	}
 }
 
-// selfgrav.lua:123-147 offsetPotential: the potential minus its maximum over ALL cells (copyPotentialToReduce is SETBOUNDS(0,0))
-template<class real> __global__ void op_max_partial(GridP<real> const g, OpP<real> const o) {
-	int i, j, k; long long idx;
-	double v = -HUGE_VAL;
-	if (opCell(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k, idx)) v = double(o.U[o.pot * g.strideV + idx]);
-	opBlockReduce<real, true>(v, o.partial + blockIdx.x);
+// After the last sweep: an odd number of sweeps leaves the result in writeBuf; bring it home (all cells: its ghost cells are the filled ones)
+template<class real> __global__ void op_final_copy(GridP<real> const g, OpP<real> const o) {
+	if ((o.ctl->lastIter & 1) == 0) return;
+	real* __restrict__ pot = o.U + o.pot * g.strideV;
+	HB_OP_ROWS(g, row, j, k, base)
+		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) pot[base + i] = o.writeBuf[base + i];
 }
-template<class real> __global__ void op_max_finish(OpP<real> const o) {
+
+// selfgrav.lua:123-147 offsetPotential: the potential minus its maximum over ALL cells (copyPotentialToReduce is SETBOUNDS(0,0))
+template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_max(GridP<real> const g, OpP<real> const o) {
+	real const* __restrict__ pot = o.U + o.pot * g.strideV;
 	double v = -HUGE_VAL;
-	for (int n = threadIdx.x; n < o.nBlocks; n += HB_OP_NT) { double const u = o.partial[n]; v = u > v ? u : v; }
-	opBlockReduce<real, true>(v, &o.ctl->maxVal);
+	HB_OP_ROWS(g, row, j, k, base)
+		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) { double const u = double(pot[base + i]); v = u > v ? u : v; }
+	double const mine = opBlockReduce<true>(v);
+	double total = 0;
+	if (!opLastBlockReduce<true>(mine, o.partial, o.ctl, o.nBlocks, total)) return;
+	if (threadIdx.x == 0) o.ctl->maxVal = total;
 }
 template<class real> __global__ void op_offset(GridP<real> const g, OpP<real> const o) {
-	int i, j, k; long long idx;
-	if (!opCell(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k, idx)) return;
-	real* p = o.U + o.pot * g.strideV + idx;
-	*p = *p - real(o.ctl->maxVal);
+	real* __restrict__ pot = o.U + o.pot * g.strideV;
+	real const m = real(o.ctl->maxVal);
+	HB_OP_ROWS(g, row, j, k, base)
+		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) pot[base + i] = pot[base + i] - m;
 }
 
 // nodiv.lua:133-157 noDiv: B -= grad psi (central differences) on the interior
 template<class real> __global__ void op_nodiv(GridP<real> const g, OpP<real> const o) {
-	int i, j, k; long long idx;
-	if (!opCell(g, blockIdx.x * (long long)blockDim.x + threadIdx.x, i, j, k, idx)) return;
-	if (opOOB(g, i, j, k, HB_G, HB_G)) return;
-	real const* pot = o.U + o.pot * g.strideV;
-	for (int s = 0; s < g.dim; ++s) {
-		long long const st = opStride(g, s);
-		real const dv = (pot[idx + st] - pot[idx - st]) * real(1. / (2. * double(g.dx[s])));
-		real* v = o.U + (o.vec + s) * g.strideV + idx;
-		*v = *v - dv;
-	}
+	real const* __restrict__ pot = o.U + o.pot * g.strideV;
+	HB_OP_ROWS(g, row, j, k, base)
+		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) {
+			if (opOOB(g, i, j, k, HB_G, HB_G)) continue;
+			long long const idx = base + i;
+			for (int s = 0; s < g.dim; ++s) {
+				long long const st = opStride(g, s);
+				real const dv = (pot[idx + st] - pot[idx - st]) * o.sGrad[s];
+				real* v = o.U + (o.vec + s) * g.strideV + idx;
+				*v = *v - dv;
+			}
+		}
 }
 
-enum { HB_OPK_BEGIN = 0, HB_OPK_INIT, HB_OPK_JACOBI, HB_OPK_COPY, HB_OPK_FINISH, HB_OPK_MAX_PARTIAL, HB_OPK_MAX_FINISH, HB_OPK_OFFSET, HB_OPK_NODIV };
+enum { HB_OPK_BEGIN = 0, HB_OPK_INIT, HB_OPK_JACOBI, HB_OPK_FINAL_COPY, HB_OPK_MAX, HB_OPK_OFFSET, HB_OPK_NODIV };
 
 template<class real> cudaError_t launchOpKernel(int which, GridP<real> const& g, OpP<real> const& o, cudaStream_t st) {
 	unsigned const nb = (unsigned)o.nBlocks;
@@ -184,10 +202,8 @@ template<class real> cudaError_t launchOpKernel(int which, GridP<real> const& g,
 	case HB_OPK_BEGIN: op_begin<real><<<1, 1, 0, st>>>(o.ctl); break;
 	case HB_OPK_INIT: op_init_potential<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	case HB_OPK_JACOBI: op_solve_jacobi<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_COPY: op_copy_write<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_FINISH: op_finish_iter<real><<<1, HB_OP_NT, 0, st>>>(o); break;
-	case HB_OPK_MAX_PARTIAL: op_max_partial<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_MAX_FINISH: op_max_finish<real><<<1, HB_OP_NT, 0, st>>>(o); break;
+	case HB_OPK_FINAL_COPY: op_final_copy<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_MAX: op_max<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	case HB_OPK_OFFSET: op_offset<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	case HB_OPK_NODIV: op_nodiv<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	default: return cudaErrorInvalidValue;

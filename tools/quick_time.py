@@ -34,6 +34,15 @@ cfgs = {
                      slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15), 10, 512),
     "C3": (dict(eqn="mhd", dim=2, gridSize=[4096, 4096], initCond="Orszag-Tang", usePLM="plm cons",
                 slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15), 5, 512),
+    # the ops -- NoDiv (20 Jacobi sweeps after every step) and self-gravity (20 sweeps inside every stage; tile kernel)
+    "C3_nodiv": (dict(eqn="mhd", dim=2, gridSize=[4096, 4096], initCond="Orszag-Tang", usePLM="plm cons",
+                      slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15, noDiv="jacobi"), 5, 512),
+    "C3_2048_nodiv": (dict(eqn="mhd", dim=2, gridSize=[2048, 2048], initCond="Orszag-Tang", usePLM="plm cons",
+                           slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15, noDiv="jacobi"), 5, 512),
+    "C4_256_grav": (dict(eqn="euler", dim=3, gridSize=[256] * 3, mins=[-2] * 3, maxs=[2] * 3, initCond="sphere", usePLM="plm cons",
+                         slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1, useGravity=True), 3, 640),
+    "C4_256_tile": (dict(eqn="euler", dim=3, gridSize=[256] * 3, mins=[-2] * 3, maxs=[2] * 3, initCond="sphere", usePLM="plm cons",
+                         slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1, stage_kernel=1), 3, 640),
 }
 for w in which:
     cfg, n, balg = cfgs[w]
