@@ -200,6 +200,7 @@ template<class real> struct Fv : FvBase {
 	real* opWrite = nullptr;               // writeBuf of relaxation.lua:52-57 (one variable)
 	double* opPartial = nullptr;           // per-block partial sums / maxima
 	int opBlocks = 0;
+	bool opCtaRows = true;
 	bool hasGrav = false, hasNoDiv = false;
 	bool seqBc = false;                    // a linear / quadratic / fixed face: ghost fill = the reference's x, y, z passes (fill_ghosts_axis)
 	double* fixedDev = nullptr;            // [6][HB_FIXED_STRIDE] states of the 'fixed' faces
@@ -208,7 +209,7 @@ template<class real> struct Fv : FvBase {
 	int padX = 0;                          // leading pad of every row: interior cell i=2 sits on a 128-byte boundary
 	long long vstride = 0;                 // elements between variables (pitchX * S1 * S2)
 	bool useMarch = false;
-	int marchCfg = 0, marchBox[4] = {0, 0, 0, 0}, marchInfoV[6] = {0, 0, 0, 0, 0, 0};
+	int marchCfg = 0, marchBox[4] = {0, 0, 0, 0}, marchInfoV[7] = {0, 0, 0, 0, 0, 0, 0}, marchMaxOps = 0;
 	real* scratchL = nullptr;
 	real* opsScratch = nullptr;            // FvOps::scratchElems (ADM flux arrays)
 	double* stagingAos = nullptr;
@@ -373,11 +374,13 @@ template<class real> struct Fv : FvBase {
 				for (int pass = 0; pass < 2 && !ok; ++pass)
 					for (int cfg = pass == 0 ? cfg0 : 0; !ok && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
 						size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
+						if (marchInfoV[6]) continue;   // configurations with the self-gravity epilogue are taken by hb_fv_add_op only
 						if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
 					}
 			}
 			if (d.stage_kernel == 2 && !ok) return setError(HB_ERR_INVALID, "hb_fv_create: the marching kernel is not built for this configuration");
 			useMarch = ok;
+			marchMaxOps = maxOps;
 			if (useMarch) {
 				umaps.resize(nU);
 				for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &umaps[k])) return r;
@@ -550,13 +553,31 @@ template<class real> struct Fv : FvBase {
 		if (!opWrite) {
 			if (int r = allocPadded(&opWrite, sizeof(real) * ((size_t)vstride + (size_t)grid.strideY))) return r;
 			long long const rows = (long long)grid.S[1] * grid.S[2];
-			opBlocks = (int)(rows < 148 * 8 ? rows : 148 * 8);          // rows are dealt round-robin to 8 CTAs per SM
+			long long const rowBlocks = (rows + HB_OP_WARPS - 1) / HB_OP_WARPS;
+			// many short rows (3-D): a row per warp; few long rows (2-D, 1-D): a row per CTA.  At most 8 CTAs per SM, rows dealt round-robin.
+			opCtaRows = !(grid.S[0] < 1024 && rowBlocks >= 148 * 4);
+			long long const nb = opCtaRows ? rows : rowBlocks;
+			opBlocks = (int)(nb < 148 * 8 ? nb : 148 * 8);
 			HB_CUDA(cudaMalloc(&opPartial, sizeof(double) * (size_t)opBlocks));
 		}
 		HB_CUDA(cudaMalloc(&s.ctl, sizeof(OpCtl)));
 		HB_CUDA(cudaMemset(s.ctl, 0, sizeof(OpCtl)));
 		opsV.push_back(s);
-		if (o->kind == HB_OP_SELFGRAV) { hasGrav = true; useMarch = false; }             // the gravity source lives in the tile kernel
+		if (o->kind == HB_OP_SELFGRAV) {
+			// the gravity source joins L in the stage kernel's epilogue: the marching configuration built with it (same tile geometry, so the
+			// tensor maps stay valid), else the tile kernel
+			hasGrav = true;
+			if (useMarch) {
+				bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
+				int box[4], info[7];
+				bool found = false;
+				for (int cfg = 0; !found && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
+					size_t const smem = (size_t)info[4] + sizeof(real) * (size_t)nI * (size_t)marchMaxOps * (size_t)info[5];
+					if (info[6] && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
+				}
+				useMarch = found;
+			}
+		}
 		else hasNoDiv = true;
 		invalidateGraph();
 		dtValid = false;
@@ -569,7 +590,7 @@ template<class real> struct Fv : FvBase {
 		p.kind = s.d.kind; p.U = U; p.writeBuf = opWrite; p.partial = opPartial; p.ctl = s.ctl; p.pot = s.pot; p.vec = s.vec;
 		p.param = s.d.param; p.stopEpsilon = s.d.stop_epsilon; p.stopOnEpsilon = s.d.stop_on_epsilon; p.iter = iter;
 		double v = 1; for (int k = 0; k < d.dim; ++k) v *= (double)grid.N[k];
-		p.volumeWithoutBorder = v; p.nBlocks = opBlocks;
+		p.volumeWithoutBorder = v; p.nBlocks = opBlocks; p.ctaRows = opCtaRows ? 1 : 0;
 		// sweep 1 reads the potential in U and writes writeBuf, sweep 2 the other way round, ...
 		real* potU = U + (size_t)s.pot * vstride;
 		p.potIn = (iter & 1) ? potU : opWrite;

@@ -71,7 +71,7 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 // memory fits, starting at $HB_MARCH_CFG or 0).  X(index, WX, TY, KM, MINB, VAR)
 #ifdef HB_STRICT
 // the strict build carries fewer configurations (compile time)
-#define HB_MARCH3_LIST(X) X(0, 1, 8, 64, 1, 16) X(1, 1, 8, 32, 1, 0) X(2, 1, 4, 32, 1, 0)
+#define HB_MARCH3_LIST(X) X(0, 1, 8, 64, 1, 16) X(1, 1, 8, 32, 1, 0) X(2, 1, 4, 32, 1, 0) X(3, 1, 8, 64, 1, 48)
 #define HB_MARCH2_LIST(X) X(0, 4, 1, 32, 2, 0) X(1, 3, 1, 32, 2, 0)
 #else
 // Measured on B200, 512 x 512 x 128 Euler double RK4 stage (profiles/r01c_sweep_c4.txt): cfg 0 2.74 ms, cfg 1 2.80, cfg 4 2.74, cfg 5 3.46,
@@ -83,7 +83,8 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(3, 1, 10, 32, 1, 0)   /* 32 x 10 columns, 13 warps (fits with at most two staged RK operands) */ \
 	X(4, 1, 8, 128, 1, 16)  /* 128 planes per CTA */ \
 	X(5, 1, 4, 32, 2, 0)    /* 32 x 4 columns, 7 warps, 2 CTAs / SM */ \
-	X(6, 1, 8, 32, 1, 1)    /* column warps issue their three flux cores as one block (kept for the record: slower) */
+	X(6, 1, 8, 32, 1, 1)    /* column warps issue their three flux cores as one block (kept for the record: slower) */ \
+	X(7, 1, 8, 64, 1, 48)   /* cfg 0 + the self-gravity source in the epilogue (MarchCfg::GRAV; chosen by hb_fv_add_op, never by the auto selection) */
 // 2-D, 2048^2 stage: Euler cfg 0 0.266 ms, cfg 1 0.28; MHD cfg 0 0.730 ms (168 registers, spills), cfg 1 0.706 (254 registers, none)
 #define HB_MARCH2_LIST(X) \
 	X(0, 4, 1, 32, 2, 0)    /* 128 columns, 5 warps, 2 CTAs / SM */ \
@@ -186,19 +187,19 @@ cudaError_t launchMarch2WLim(int lim, const CUtensorMap* tmap, int padX, GridP<r
 	if (lim == 18) return launchMarch2W<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
 	return cudaErrorInvalidValue;
 }
-template<class C> void march2WInfoCfg(int box[4], int info[6]) {
+template<class C> void march2WInfoCfg(int box[4], int info[7]) {
 	typedef March2Geom<C, real> G;
 	box[0] = G::BX; box[1] = 1; box[2] = 1; box[3] = Eqn::nI;
 	info[0] = G::CW * C::NW; info[1] = 1; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
-	info[5] = C::NW * 32;
+	info[5] = C::NW * 32; info[6] = 0;
 }
-template<int DIM, class C> void marchInfoCfg(int box[4], int info[6]) {
+template<int DIM, class C> void marchInfoCfg(int box[4], int info[7]) {
 	typedef MarchGeom<DIM, C, real> G;
 	box[0] = G::BX; box[1] = DIM == 3 ? G::BY : 1; box[2] = 1; box[3] = Eqn::nI;
 	info[0] = G::TX; info[1] = G::TY; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
-	info[5] = G::NREG * 32;
+	info[5] = G::NREG * 32; info[6] = C::GRAV ? 1 : 0;
 }
-bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[6]) {
+bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[7]) {
 	if (!plm || flim || (lim != 8 && lim != 18) || dim < 2 || cfg < 0) return false;
 	cfg = remapCfg(dim, cfg);
 #define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<3, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }

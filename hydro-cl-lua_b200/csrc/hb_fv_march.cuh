@@ -40,6 +40,8 @@ template<int WX_, int TY_, int KM_, int MINB_, int VAR_ = 0> struct MarchCfg {
 	// 2 = marching-axis flux alone, then the x and y fluxes as a pair
 	static constexpr int VAR = VAR_ & 15;
 	static constexpr bool STAGGER = (VAR_ & 16) != 0;   // column warps w, w + 4 run the slope phase at opposite ends of the iteration
+	static constexpr bool GRAV = (VAR_ & 32) != 0;      // the epilogue adds the self-gravity source (StageP::gravPot) to L: a separate configuration, so that
+	                                                    // the default kernel's register allocation is untouched
 };
 
 template<int DIM, class C, class real> struct MarchGeom {
@@ -102,13 +104,32 @@ HB_D void tmaLoad4D(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, in
 // RK combination + constrainU + stores + CFL dt of one finished cell (hydro/int/rk.lua:96-112, solverbase.lua:2116-2127).
 // `own` = the stage input state of this cell (register copy), used for alpha terms that point at the stage input.
 // `ops` = this thread's staged RK operands in shared memory, [operand][q] with stride opStride between entries (see fv_march).
-template<class Eqn>
+template<class Eqn, bool GRAV = false>
 HB_D void stageEpilogue(GridP<typename Eqn::real> const& g, StageP<typename Eqn::real> const& sp, typename Eqn::Params const& ep,
-	long long idx, typename Eqn::real const (&acc)[Eqn::nI], typename Eqn::real const (&own)[Eqn::nI], double dt,
+	long long idx, typename Eqn::real const (&accIn)[Eqn::nI], typename Eqn::real const (&own)[Eqn::nI], double dt,
 	typename Eqn::real& dtCell, typename Eqn::real& rateCell, typename Eqn::real const* ops, int opStride)
 {
 	typedef typename Eqn::real real;
 	constexpr int nI = Eqn::nI;
+	real accG[nI];
+	real const* acc = accIn;
+	if constexpr (GRAV && Eqn::eqnId <= 1) {
+		// op:addSource of the self-gravity op (solverbase.lua:3219-3223, selfgrav.cl:11-76), as in fv_stage: accel = central difference of the
+		// potential, deriv.m -= accel rho, deriv.ETotal -= m . accel
+		#pragma unroll
+		for (int q = 0; q < nI; ++q) accG[q] = accIn[q];
+		if (sp.gravPot && sp.computeL) {
+			real accel[3] = {0, 0, 0};
+			accel[0] = (sp.gravPot[idx + 1] - sp.gravPot[idx - 1]) / (real(2.) * g.dx[0]);
+			if (g.dim >= 2) accel[1] = (sp.gravPot[idx + g.strideY] - sp.gravPot[idx - g.strideY]) / (real(2.) * g.dx[1]);
+			if (g.dim >= 3) accel[2] = (sp.gravPot[idx + g.strideZ] - sp.gravPot[idx - g.strideZ]) / (real(2.) * g.dx[2]);
+			accG[1] = accG[1] - accel[0] * own[0];
+			accG[2] = accG[2] - accel[1] * own[0];
+			accG[3] = accG[3] - accel[2] * own[0];
+			accG[4] -= own[1] * accel[0] + own[2] * accel[1] + own[3] * accel[2];
+		}
+		acc = accG;
+	}
 	if (sp.Lout) {
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) sp.Lout[idx + q * g.strideV] = acc[q];
@@ -364,7 +385,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) acc[q] = g.volOn ? accP[q] - (Fz[q] * aovM - FzP[q] * aovM) : real(0);
 				cpAsyncWaitAll();
-				stageEpilogue<Eqn>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + tid, OPS);
+				stageEpilogue<Eqn, C::GRAV>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + tid, OPS);
 			}
 			if (inside && xy && sp.Uout) {
 				int slot = 0;
@@ -404,7 +425,7 @@ fv_march(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> con
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) acc[q] = g.volOn ? accP[q] - (Fz[q] * aovM - FzP[q] * aovM) : real(0);
 				cpAsyncWaitAll();
-				stageEpilogue<Eqn>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + tid, OPS);
+				stageEpilogue<Eqn, C::GRAV>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + tid, OPS);
 			}
 			if (inside && xy && sp.Uout) {
 				// the RK operands of cell k (alpha terms other than the stage input, beta terms) are consumed one iteration from

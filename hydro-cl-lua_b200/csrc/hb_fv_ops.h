@@ -20,9 +20,9 @@ template<class real> struct FvOps {
 	cudaError_t (*stage)(int dim, bool plm, bool flim, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st);
 	// Plane-marching TMA kernel (hb_fv_march.cuh).  marchInfo: is it built for (dim, plm, flim, slope limiter)?  If so it
 	// returns the TMA box {x, y, z, var} the host must encode into the tensor map of every stage-input buffer and
-	// info = {TX, TY, planes per CTA, threads, dynamic smem bytes without staged RK operands, column threads}.
+	// info = {TX, TY, planes per CTA, threads, dynamic smem bytes without staged RK operands, column threads, epilogue adds the self-gravity source}.
 	// cfg selects a tile configuration (0 = default).
-	bool (*marchInfo)(int dim, bool plm, bool flim, int slopeLimiter, int cfg, int box[4], int info[6]);
+	bool (*marchInfo)(int dim, bool plm, bool flim, int slopeLimiter, int cfg, int box[4], int info[7]);
 	// chunkSel: 0 all chunks along the marching axis, 1 first + last chunk, 2 the chunks in between (overlapped slab exchange)
 	cudaError_t (*march)(int dim, int slopeLimiter, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp,
 		const double* eqnParams, int chunkSel, cudaStream_t st);

@@ -33,6 +33,7 @@ template<class real> struct OpP {
 	int iter;               // 1-based sweep number
 	double volumeWithoutBorder;
 	int nBlocks;            // blocks of the row-strided launches (= entries of `partial`)
+	int ctaRows;            // 1: a row per CTA, 0: a row per warp
 	// grid constants of solveJacobi, formed on the host in `real` with the reference's operations (IEEE division: the same bits as on the device)
 	real cS[3];             // volume_int / (dx_s dx_s)
 	real invVol;            // 1. / volAtX
@@ -42,12 +43,15 @@ template<class real> struct OpP {
 	real sGrad[3];          // noDiv kernel: 1. / (2. grid_dx_s)
 };
 
-// Rows (j, k) of the ghost-inclusive array are dealt to the blocks round-robin; a block walks its rows along x, so every access is
-// coalesced and the index arithmetic is one integer division per row.
+// Rows (j, k) of the ghost-inclusive array are dealt round-robin to WARPS (OpP::ctaRows = 0: many short rows, the 3-D case -- a 260- or
+// 516-cell row wastes at most one 32-cell step instead of most of a CTA-wide one) or to CTAs (ctaRows = 1: few long rows, the 2-D case).
+// Either way every access is a coalesced segment and the index arithmetic is one integer division per row.
+constexpr int HB_OP_WARPS = HB_OP_NT / 32;
 #define HB_OP_ROWS(g, row, j, k, base) \
-	for (int row = blockIdx.x; row < (g).S[1] * (g).S[2]; row += gridDim.x) \
+	for (int row = o.ctaRows ? blockIdx.x : blockIdx.x * HB_OP_WARPS + (threadIdx.x >> 5); row < (g).S[1] * (g).S[2]; row += o.ctaRows ? gridDim.x : gridDim.x * HB_OP_WARPS) \
 		if (int const j = row % (g).S[1], k = row / (g).S[1]; true) \
 			if (long long const base = (g).strideY * j + (g).strideZ * k; true)
+#define HB_OP_LANES(g, i) for (int i = o.ctaRows ? threadIdx.x : (threadIdx.x & 31); i < (g).S[0]; i += o.ctaRows ? HB_OP_NT : 32)
 
 template<class real> HB_D bool opOOB(GridP<real> const& g, int i, int j, int k, int l, int r) {
 	return i < l || i >= g.S[0] - r || (g.dim >= 2 && (j < l || j >= g.S[1] - r)) || (g.dim >= 3 && (k < l || k >= g.S[2] - r));
@@ -73,7 +77,7 @@ template<class real> __global__ void op_begin(OpCtl* ctl) { ctl->done = 0; ctl->
 // poisson.cl:36-53 initPotential: potential = -source on the interior
 template<class real> __global__ void op_init_potential(GridP<real> const g, OpP<real> const o) {
 	HB_OP_ROWS(g, row, j, k, base)
-		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) {
+		HB_OP_LANES(g, i) {
 			if (opOOB(g, i, j, k, HB_G, HB_G)) continue;
 			o.U[o.pot * g.strideV + base + i] = -opSource(g, o, i, j, k, base + i);
 		}
@@ -125,7 +129,7 @@ template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_solve_jacobi
 	real* __restrict__ out = o.potOut;
 	double res2 = 0;
 	HB_OP_ROWS(g, row, j, k, base)
-		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) {
+		HB_OP_LANES(g, i) {
 			long long const idx = base + i;
 			if (opOOB(g, i, j, k, HB_G, HB_G)) { out[idx] = pot[idx]; continue; }
 			real skewSum = 0;
@@ -157,7 +161,7 @@ template<class real> __global__ void op_final_copy(GridP<real> const g, OpP<real
 	if ((o.ctl->lastIter & 1) == 0) return;
 	real* __restrict__ pot = o.U + o.pot * g.strideV;
 	HB_OP_ROWS(g, row, j, k, base)
-		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) pot[base + i] = o.writeBuf[base + i];
+		HB_OP_LANES(g, i) pot[base + i] = o.writeBuf[base + i];
 }
 
 // selfgrav.lua:123-147 offsetPotential: the potential minus its maximum over ALL cells (copyPotentialToReduce is SETBOUNDS(0,0))
@@ -165,7 +169,7 @@ template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_max(GridP<re
 	real const* __restrict__ pot = o.U + o.pot * g.strideV;
 	double v = -HUGE_VAL;
 	HB_OP_ROWS(g, row, j, k, base)
-		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) { double const u = double(pot[base + i]); v = u > v ? u : v; }
+		HB_OP_LANES(g, i) { double const u = double(pot[base + i]); v = u > v ? u : v; }
 	double const mine = opBlockReduce<true>(v);
 	double total = 0;
 	if (!opLastBlockReduce<true>(mine, o.partial, o.ctl, o.nBlocks, total)) return;
@@ -175,14 +179,14 @@ template<class real> __global__ void op_offset(GridP<real> const g, OpP<real> co
 	real* __restrict__ pot = o.U + o.pot * g.strideV;
 	real const m = real(o.ctl->maxVal);
 	HB_OP_ROWS(g, row, j, k, base)
-		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) pot[base + i] = pot[base + i] - m;
+		HB_OP_LANES(g, i) pot[base + i] = pot[base + i] - m;
 }
 
 // nodiv.lua:133-157 noDiv: B -= grad psi (central differences) on the interior
 template<class real> __global__ void op_nodiv(GridP<real> const g, OpP<real> const o) {
 	real const* __restrict__ pot = o.U + o.pot * g.strideV;
 	HB_OP_ROWS(g, row, j, k, base)
-		for (int i = threadIdx.x; i < g.S[0]; i += blockDim.x) {
+		HB_OP_LANES(g, i) {
 			if (opOOB(g, i, j, k, HB_G, HB_G)) continue;
 			long long const idx = base + i;
 			for (int s = 0; s < g.dim; ++s) {
