@@ -72,10 +72,10 @@ template<class real> HB_D real opSource(GridP<real> const& g, OpP<real> const& o
 }
 
 // relax() start: a fresh stop flag
-template<class real> __global__ void op_begin(OpCtl* ctl) { ctl->done = 0; ctl->lastIter = 0; ctl->ticket = 0; }
+template<class real, int MODE> __global__ void op_begin(OpCtl* ctl) { ctl->done = 0; ctl->lastIter = 0; ctl->ticket = 0; }
 
 // poisson.cl:36-53 initPotential: potential = -source on the interior
-template<class real> __global__ void op_init_potential(GridP<real> const g, OpP<real> const o) {
+template<class real, int MODE> __global__ void op_init_potential(GridP<real> const g, OpP<real> const o) {
 	HB_OP_ROWS(g, row, j, k, base)
 		HB_OP_LANES(g, i) {
 			if (opOOB(g, i, j, k, HB_G, HB_G)) continue;
@@ -123,7 +123,7 @@ template<bool MAX> HB_D bool opLastBlockReduce(double mine, double* partial, OpC
 // relaxation.lua:176-194.  The reference writes the sweep to writeBuf (ghost cells: the old potential) and copies its interior back;
 // here the two copies of the potential alternate instead (potIn -> potOut; the ghost fill that follows makes potOut what the reference's
 // potential is after its boundary pass), which saves the copy kernel: 3 words per cell and sweep instead of 5.
-template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_solve_jacobi(GridP<real> const g, OpP<real> const o) {
+template<class real, int MODE> __global__ void __launch_bounds__(HB_OP_NT) op_solve_jacobi(GridP<real> const g, OpP<real> const o) {
 	if (o.ctl->done) return;
 	real const* __restrict__ pot = o.potIn;
 	real* __restrict__ out = o.potOut;
@@ -157,7 +157,7 @@ template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_solve_jacobi
 }
 
 // After the last sweep: an odd number of sweeps leaves the result in writeBuf; bring it home (all cells: its ghost cells are the filled ones)
-template<class real> __global__ void op_final_copy(GridP<real> const g, OpP<real> const o) {
+template<class real, int MODE> __global__ void op_final_copy(GridP<real> const g, OpP<real> const o) {
 	if ((o.ctl->lastIter & 1) == 0) return;
 	real* __restrict__ pot = o.U + o.pot * g.strideV;
 	HB_OP_ROWS(g, row, j, k, base)
@@ -165,7 +165,7 @@ template<class real> __global__ void op_final_copy(GridP<real> const g, OpP<real
 }
 
 // selfgrav.lua:123-147 offsetPotential: the potential minus its maximum over ALL cells (copyPotentialToReduce is SETBOUNDS(0,0))
-template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_max(GridP<real> const g, OpP<real> const o) {
+template<class real, int MODE> __global__ void __launch_bounds__(HB_OP_NT) op_max(GridP<real> const g, OpP<real> const o) {
 	real const* __restrict__ pot = o.U + o.pot * g.strideV;
 	double v = -HUGE_VAL;
 	HB_OP_ROWS(g, row, j, k, base)
@@ -175,7 +175,7 @@ template<class real> __global__ void __launch_bounds__(HB_OP_NT) op_max(GridP<re
 	if (!opLastBlockReduce<true>(mine, o.partial, o.ctl, o.nBlocks, total)) return;
 	if (threadIdx.x == 0) o.ctl->maxVal = total;
 }
-template<class real> __global__ void op_offset(GridP<real> const g, OpP<real> const o) {
+template<class real, int MODE> __global__ void op_offset(GridP<real> const g, OpP<real> const o) {
 	real* __restrict__ pot = o.U + o.pot * g.strideV;
 	real const m = real(o.ctl->maxVal);
 	HB_OP_ROWS(g, row, j, k, base)
@@ -183,7 +183,7 @@ template<class real> __global__ void op_offset(GridP<real> const g, OpP<real> co
 }
 
 // nodiv.lua:133-157 noDiv: B -= grad psi (central differences) on the interior
-template<class real> __global__ void op_nodiv(GridP<real> const g, OpP<real> const o) {
+template<class real, int MODE> __global__ void op_nodiv(GridP<real> const g, OpP<real> const o) {
 	real const* __restrict__ pot = o.U + o.pot * g.strideV;
 	HB_OP_ROWS(g, row, j, k, base)
 		HB_OP_LANES(g, i) {
@@ -200,16 +200,18 @@ template<class real> __global__ void op_nodiv(GridP<real> const g, OpP<real> con
 
 enum { HB_OPK_BEGIN = 0, HB_OPK_INIT, HB_OPK_JACOBI, HB_OPK_FINAL_COPY, HB_OPK_MAX, HB_OPK_OFFSET, HB_OPK_NODIV };
 
-template<class real> cudaError_t launchOpKernel(int which, GridP<real> const& g, OpP<real> const& o, cudaStream_t st) {
+// MODE (0 production, 1 strict = -fmad=false) only makes the kernels of the two builds distinct symbols: without it the linker would
+// merge the equally named instantiations of the two translation units and one build would run the other's code.
+template<class real, int MODE> cudaError_t launchOpKernel(int which, GridP<real> const& g, OpP<real> const& o, cudaStream_t st) {
 	unsigned const nb = (unsigned)o.nBlocks;
 	switch (which) {
-	case HB_OPK_BEGIN: op_begin<real><<<1, 1, 0, st>>>(o.ctl); break;
-	case HB_OPK_INIT: op_init_potential<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_JACOBI: op_solve_jacobi<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_FINAL_COPY: op_final_copy<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_MAX: op_max<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_OFFSET: op_offset<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
-	case HB_OPK_NODIV: op_nodiv<real><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_BEGIN: op_begin<real, MODE><<<1, 1, 0, st>>>(o.ctl); break;
+	case HB_OPK_INIT: op_init_potential<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_JACOBI: op_solve_jacobi<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_FINAL_COPY: op_final_copy<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_MAX: op_max<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_OFFSET: op_offset<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_NODIV: op_nodiv<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();
