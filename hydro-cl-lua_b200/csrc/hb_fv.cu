@@ -79,7 +79,7 @@ struct Nccl {
 		return n;
 	}
 };
-enum { kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclMin = 3 };
+enum { kNcclFloat32 = 7, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2, kNcclMin = 3 };
 #define HB_NCCL(expr) do { int r_ = (expr); if (r_ != 0) return setError(HB_ERR_CUDA, std::string(#expr) + ": " + Nccl::get().GetErrorString(r_)); } while (0)
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (the library links neither libcuda nor libnvrtc)
@@ -543,7 +543,6 @@ template<class real> struct Fv : FvBase {
 	int addOp(const hb_op_desc* o, int* index) override {
 		if (!o) return setError(HB_ERR_INVALID, "hb_fv_add_op: null argument");
 		if (!ops->opKernel) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are built for euler and mhd");
-		if (comm) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are not built for a decomposed grid");
 		if (o->max_iters < 0) return setError(HB_ERR_INVALID, "hb_fv_add_op: max_iters < 0");
 		OpState s; s.d = *o; s.ctl = nullptr; s.vec = -1;
 		if (o->kind == HB_OP_SELFGRAV) s.pot = nS - 1;                                   // ePot: last variable of euler and mhd
@@ -589,7 +588,8 @@ template<class real> struct Fv : FvBase {
 		memset(&p, 0, sizeof(p));
 		p.kind = s.d.kind; p.U = U; p.writeBuf = opWrite; p.partial = opPartial; p.ctl = s.ctl; p.pot = s.pot; p.vec = s.vec;
 		p.param = s.d.param; p.stopEpsilon = s.d.stop_epsilon; p.stopOnEpsilon = s.d.stop_on_epsilon; p.iter = iter;
-		double v = 1; for (int k = 0; k < d.dim; ++k) v *= (double)grid.N[k];
+		double v = 1; for (int k = 0; k < d.dim; ++k) v *= (double)d.global_n[k];     // the whole grid's interior (solver.volumeWithoutBorder)
+		p.deferDecision = comm ? 1 : 0;
 		p.volumeWithoutBorder = v; p.nBlocks = opBlocks; p.ctaRows = opCtaRows ? 1 : 0;
 		// sweep 1 reads the potential in U and writes writeBuf, sweep 2 the other way round, ...
 		real* potU = U + (size_t)s.pot * vstride;
@@ -621,13 +621,23 @@ template<class real> struct Fv : FvBase {
 		for (int it = 1; it <= s.d.max_iters; ++it) {
 			OpP<real> const p = opParams(s, U, it);
 			if (int r = opLaunch(HB_OPK_JACOBI, p)) return r;
-			if (int r = potentialBoundary(p.potOut)) return r;
+			if (int r = potentialBoundary(p.potOut)) return r;    // + the slab exchange of the potential's ghost planes
+			if (comm) {
+				// the residual is a sum over the whole grid: all-reduce the slabs' sums, then finish the iteration on every rank alike
+				double* sum = reinterpret_cast<double*>(reinterpret_cast<char*>(s.ctl) + offsetof(OpCtl, sumLocal));
+				if (s.d.stop_on_epsilon) HB_NCCL(Nccl::get().AllReduce(sum, sum, 1, kNcclFloat64, kNcclSum, comm, st()));
+				if (int r = opLaunch(HB_OPK_DECIDE, p)) return r;
+			}
 		}
 		return opLaunch(HB_OPK_FINAL_COPY, opParams(s, U));
 	}
 	int offsetPotential(OpState const& s, real* U) {       // selfgrav.lua:123-147
 		OpP<real> const p = opParams(s, U);
 		if (int r = opLaunch(HB_OPK_MAX, p)) return r;
+		if (comm) {
+			double* mx = reinterpret_cast<double*>(reinterpret_cast<char*>(s.ctl) + offsetof(OpCtl, maxVal));
+			HB_NCCL(Nccl::get().AllReduce(mx, mx, 1, kNcclFloat64, kNcclMax, comm, st()));
+		}
 		return opLaunch(HB_OPK_OFFSET, p);
 	}
 	int opsReset() override {                              // solverbase.lua:2106-2111, relaxation.lua:152-158, selfgrav.lua:93-101
@@ -771,7 +781,7 @@ template<class real> struct Fv : FvBase {
 				e0 = profEvents[profUsed].first; e1 = profEvents[profUsed].second; profUsed++;
 				HB_CUDA(cudaEventRecord(e0, st()));
 			}
-			if (useMarch && overlap) {
+			if (useMarch && overlap && opsV.empty()) {   // (with ops the exchange stays in-stream)
 				int const nv = rk ? nI : nS;
 				HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 1, st()));
 				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, true, st()));

@@ -15,7 +15,7 @@
 
 namespace hb {
 
-struct OpCtl { int done; int lastIter; double lastResidual; double maxVal; unsigned int ticket; };
+struct OpCtl { int done; int lastIter; double lastResidual; double maxVal; unsigned int ticket; unsigned int pad; double sumLocal; };
 
 constexpr int HB_OP_NT = 256;
 
@@ -34,6 +34,7 @@ template<class real> struct OpP {
 	double volumeWithoutBorder;
 	int nBlocks;            // blocks of the row-strided launches (= entries of `partial`)
 	int ctaRows;            // 1: a row per CTA, 0: a row per warp
+	int deferDecision;      // slab-decomposed grid: the sweep leaves its residual sum in OpCtl::sumLocal; after the all-reduce op_decide finishes the iteration
 	// grid constants of solveJacobi, formed on the host in `real` with the reference's operations (IEEE division: the same bits as on the device)
 	real cS[3];             // volume_int / (dx_s dx_s)
 	real invVol;            // 1. / volAtX
@@ -147,12 +148,25 @@ template<class real, int MODE> __global__ void __launch_bounds__(HB_OP_NT) op_so
 	double total = 0;
 	if (!opLastBlockReduce<false>(mine, o.partial, o.ctl, o.nBlocks, total)) return;
 	if (threadIdx.x == 0) {
+		if (o.deferDecision) { o.ctl->sumLocal = total; return; }
 		o.ctl->lastIter = o.iter;
 		if (o.stopOnEpsilon) {
 			double const residual = sqrt(double(real(total)) / o.volumeWithoutBorder);
 			o.ctl->lastResidual = residual;
 			if (fabs(residual) <= o.stopEpsilon) o.ctl->done = 1;
 		}
+	}
+}
+
+// Slab-decomposed grid: the iteration's bookkeeping after the residual sums of the slabs have been all-reduced into OpCtl::sumLocal.
+// Every rank sees the same sum, so every rank stops at the same sweep.
+template<class real, int MODE> __global__ void op_decide(OpP<real> const o) {
+	if (o.ctl->done) return;
+	o.ctl->lastIter = o.iter;
+	if (o.stopOnEpsilon) {
+		double const residual = sqrt(double(real(o.ctl->sumLocal)) / o.volumeWithoutBorder);
+		o.ctl->lastResidual = residual;
+		if (fabs(residual) <= o.stopEpsilon) o.ctl->done = 1;
 	}
 }
 
@@ -198,7 +212,7 @@ template<class real, int MODE> __global__ void op_nodiv(GridP<real> const g, OpP
 		}
 }
 
-enum { HB_OPK_BEGIN = 0, HB_OPK_INIT, HB_OPK_JACOBI, HB_OPK_FINAL_COPY, HB_OPK_MAX, HB_OPK_OFFSET, HB_OPK_NODIV };
+enum { HB_OPK_BEGIN = 0, HB_OPK_INIT, HB_OPK_JACOBI, HB_OPK_FINAL_COPY, HB_OPK_MAX, HB_OPK_OFFSET, HB_OPK_NODIV, HB_OPK_DECIDE };
 
 // MODE (0 production, 1 strict = -fmad=false) only makes the kernels of the two builds distinct symbols: without it the linker would
 // merge the equally named instantiations of the two translation units and one build would run the other's code.
@@ -212,6 +226,7 @@ template<class real, int MODE> cudaError_t launchOpKernel(int which, GridP<real>
 	case HB_OPK_MAX: op_max<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	case HB_OPK_OFFSET: op_offset<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
 	case HB_OPK_NODIV: op_nodiv<real, MODE><<<nb, HB_OP_NT, 0, st>>>(g, o); break;
+	case HB_OPK_DECIDE: op_decide<real, MODE><<<1, 1, 0, st>>>(o); break;
 	default: return cudaErrorInvalidValue;
 	}
 	return cudaGetLastError();

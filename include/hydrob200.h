@@ -156,7 +156,8 @@ int hb_fv_state_devptr(hb_fv* fv, void** soa_dev, long long* stride_y, long long
 int hb_fv_set_fixed_boundary(hb_fv* fv, int face, const double* cons, int n);   /* face 0..5 = xmin,xmax,..,zmax; n <= numStates doubles; zeros until set */
 /* ---- ops either side of the step (hydro/op; solver.ops, solverbase.lua:2106-2111, 3219-3237): self-gravity and NoDiv over the Jacobi
  *      Poisson relaxation (hydro/op/relaxation.lua, poisson.cl, poisson_jacobi.cl).  Once added, hb_fv_step / hb_fv_update run
- *      op:addSource inside every stage and op:step after the integrator, as SolverBase:step does.  Single GPU. */
+ *      op:addSource inside every stage and op:step after the integrator, as SolverBase:step does.  On a slab-decomposed grid the potential's
+ *      ghost planes travel with every sweep's ghost fill and the residual sum / potential maximum are all-reduced over NCCL. */
 #define HB_OP_SELFGRAV 1      /* hydro/op/selfgrav.lua + selfgrav.cl; euler, mhd; potential = ePot; param = gravitationalConstant / unit_m3_per_kg_s2 */
 #define HB_OP_NODIV 2         /* hydro/op/nodiv.lua with the Jacobi parent (noDivPoissonSolver=jacobi); mhd; potential = psi, vector = B */
 typedef struct hb_op_desc {

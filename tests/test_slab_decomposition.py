@@ -71,7 +71,10 @@ def test_cpu_gloo_two_ranks_equal_single(hydrob200, oracle, tmp_path, case):
                                        ("C4_sphere_rk4_mirror_periodic", "gpu"), ("C5_gauge_wave_slab", "gpu"),
                                        ("C5_warp_bubble_rk4", "gpu_strict"), ("slab_march3d_overlap", "gpu_strict"),
                                        ("slab_march3d_overlap", "gpu"), ("slab_march3d_overlap_periodic", "gpu"),
-                                       ("slab_march2d_overlap", "gpu_strict")])
+                                       ("slab_march2d_overlap", "gpu_strict"),
+                                       # the ops on a decomposed grid: potential ghost planes exchanged per sweep, residual / maximum all-reduced
+                                       ("F3_selfgrav_sphere_rk4_plm_3d", "gpu_strict"), ("F3_nodiv_ot_rk3_2d", "gpu"),
+                                       ("F3_nodiv_selfgrav_ot_fe_3d", "gpu_strict"), ("F3_selfgrav_sphere_fe_2d", "gpu")])
 def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
     import torch
     if torch.cuda.device_count() < 2:
