@@ -37,6 +37,7 @@ class hb_fv_desc(C.Structure):
         ("cfl", C.c_double), ("fixed_dt", C.c_double), ("use_fixed_dt", C.c_int),
         ("eqn_params", C.c_double * 16),
         ("strict_fp", C.c_int), ("use_graph", C.c_int), ("stage_kernel", C.c_int), ("flux", C.c_int), ("flux_param", C.c_int),
+        ("use_ctu", C.c_int),
     ]
 
 

@@ -82,6 +82,7 @@ def desc_from_solver(solver, strict_fp=False, use_graph=True, local_n=None, stag
     d.strict_fp = 1 if strict_fp else 0
     d.use_graph = 1 if use_graph else 0
     d.stage_kernel = stage_kernel
+    d.use_ctu = 1 if getattr(solver, 'useCTU', False) else 0
     return d
 
 

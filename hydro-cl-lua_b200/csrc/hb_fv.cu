@@ -202,6 +202,9 @@ template<class real> struct Fv : FvBase {
 	int opBlocks = 0;
 	bool opCtaRows = true;
 	bool hasGrav = false, hasNoDiv = false;
+	// corner-transport-upwind variant (hb_ctu_kernels.cuh): the reference's ULR and flux buffers
+	bool useCTU = false;
+	real* ctuULR = nullptr; real* ctuFlux = nullptr;
 	bool seqBc = false;                    // a linear / quadratic / fixed face: ghost fill = the reference's x, y, z passes (fill_ghosts_axis)
 	double* fixedDev = nullptr;            // [6][HB_FIXED_STRIDE] states of the 'fixed' faces
 	std::vector<real*> upool, lpool;       // element (i=0,j=0,k=0) of variable 0; the allocation starts padX elements earlier
@@ -264,6 +267,8 @@ template<class real> struct Fv : FvBase {
 		for (cudaEvent_t e : {evUpDone, evInFree, evOutReady, evDownDone}) if (e) cudaEventDestroy(e);
 		if (ctl) cudaFree(ctl);
 		if (fixedDev) cudaFree(fixedDev);
+		if (ctuULR) cudaFree(ctuULR - padX);
+		if (ctuFlux) cudaFree(ctuFlux - padX);
 		if (opWrite) cudaFree(opWrite - padX);
 		if (opPartial) cudaFree(opPartial);
 		for (auto& o : opsV) if (o.ctl) cudaFree(o.ctl);
@@ -385,6 +390,13 @@ template<class real> struct Fv : FvBase {
 				umaps.resize(nU);
 				for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &umaps[k])) return r;
 			}
+		}
+		if (d.use_ctu) {
+			useCTU = true;
+			useMarch = false;
+			size_t const block = (size_t)nI * (size_t)vstride;
+			if (int r = allocPadded(&ctuULR, sizeof(real) * (2 * (size_t)d.dim * block + (size_t)grid.strideY))) return r;
+			if (int r = allocPadded(&ctuFlux, sizeof(real) * ((size_t)d.dim * block + (size_t)grid.strideY))) return r;
 		}
 		if (ops->scratchElems) {
 			if (int r = allocPadded(&opsScratch, sizeof(real) * ((size_t)ops->scratchElems(grid) + (size_t)grid.strideY))) return r;
@@ -543,6 +555,7 @@ template<class real> struct Fv : FvBase {
 	int addOp(const hb_op_desc* o, int* index) override {
 		if (!o) return setError(HB_ERR_INVALID, "hb_fv_add_op: null argument");
 		if (!ops->opKernel) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are built for euler and mhd");
+		if (useCTU && o->kind == HB_OP_SELFGRAV) return setError(HB_ERR_INVALID, "hb_fv_add_op: self-gravity is not built for the CTU variant");
 		if (o->max_iters < 0) return setError(HB_ERR_INVALID, "hb_fv_add_op: max_iters < 0");
 		OpState s; s.d = *o; s.ctl = nullptr; s.vec = -1;
 		if (o->kind == HB_OP_SELFGRAV) s.pot = nS - 1;                                   // ePot: last variable of euler and mhd
@@ -741,6 +754,38 @@ template<class real> struct Fv : FvBase {
 		sp.plmMode = d.use_plm;
 	}
 
+
+	// FiniteVolumeSolver:calcDeriv with useCTU (fvsolver.lua:225-302) + the integrator's combination: calcLR, calcFlux, updateCTU,
+	// boundaryLR, calcFlux, calcDerivFromFlux -- the reference's kernel sequence on its ULR / flux buffers (hb_ctu_kernels.cuh)
+	int ctuStage(StageP<real> const& sp) {
+		CtuP<real> c;
+		memset(&c, 0, sizeof(c));
+		c.ULR = ctuULR; c.flux = ctuFlux; c.blockStride = (long long)nI * vstride;
+		real volume = 1;
+		for (int k = 0; k < d.dim; ++k) volume = volume * grid.dx[k];
+		c.invVolume = real(1.) / volume;
+		for (int k = 0; k < d.dim; ++k) {
+			real const volume_int = real(.5) * (volume + volume);
+			c.areaL[k] = volume_int / grid.dx[k];
+			c.areaR[k] = volume_int / grid.dx[k];
+		}
+		int n = 0;
+		if (sp.computeL) {
+			HB_CUDA(ops->ctuKernel(HB_CTUK_LR, grid, sp, c, d.eqn_params, st())); ++n;
+			HB_CUDA(ops->ctuKernel(HB_CTUK_FLUX, grid, sp, c, d.eqn_params, st())); ++n;
+			HB_CUDA(ops->ctuKernel(HB_CTUK_UPDATE, grid, sp, c, d.eqn_params, st())); ++n;
+			// boundaryLR (gridsolver.lua:463-473,1241-1268): the solver's boundary methods on every L / R record; the reflected variables are the
+			// same per record, so each block is filled like a state of nI variables
+			long long const before = launches;
+			for (int b = 0; b < 2 * d.dim; ++b) if (int r = fillGhosts(ctuULR + (size_t)b * (size_t)c.blockStride, nI)) return r;
+			n += (int)(launches - before); launches = before;
+			HB_CUDA(ops->ctuKernel(HB_CTUK_FLUX, grid, sp, c, d.eqn_params, st())); ++n;
+		}
+		HB_CUDA(ops->ctuKernel(HB_CTUK_FINISH, grid, sp, c, d.eqn_params, st())); ++n;
+		tlsStageLaunches = n;
+		return HB_OK;
+	}
+
 	// integrator:integrate(dt, calcDeriv) + boundary/constrainU after every stage (rk.lua:91-165, fe.lua:33-49)
 	int runStages() {
 		bool const rk = d.rk_order >= 1;
@@ -797,7 +842,8 @@ template<class real> struct Fv : FvBase {
 				continue;
 			}
 			tlsStageLaunches = 1;
-			if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 0, st()));
+			if (useCTU) { if (int r = ctuStage(sp)) return r; }
+			else if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 0, st()));
 			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches += tlsStageLaunches;
@@ -910,7 +956,8 @@ template<class real> struct Fv : FvBase {
 		sp.computeL = 1; sp.dt = ctl + 1;
 		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux; sp.fluxParam = d.flux_param; sp.plmMode = d.use_plm;
 		bool const plm = d.use_plm != 0;
-		if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
+		if (useCTU) { if (int r = ctuStage(sp)) return r; }
+		else if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
 		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
 		launches++;
 		HB_CUDA(cudaMemcpyAsync(ctl + 1, &saved[1], sizeof(double), cudaMemcpyHostToDevice, st()));
@@ -1035,6 +1082,11 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (d->flux == HB_FLUX_EULER_HLLC && (d->flux_param < 0 || d->flux_param > 2)) return setError(HB_ERR_INVALID, "hb_fv_create: hllcMethod must be 0, 1 or 2");
 	if (d->flux != HB_FLUX_ROE && d->flux_limiter != 0) return setError(HB_ERR_INVALID, "hb_fv_create: only the Roe flux uses a flux limiter (hydro/flux/roe.lua:5-19)");
 	if (d->flux != HB_FLUX_ROE && d->eqn == HB_EQN_ADM3D) return setError(HB_ERR_INVALID, "hb_fv_create: hll / rusanov are built for euler and mhd");
+	if (d->use_ctu) {
+		if (d->use_plm != 1 || d->dim < 2) return setError(HB_ERR_INVALID, "hb_fv_create: useCTU is built for 'plm cons' in 2-D and 3-D (the reference switches it off in 1-D, gridsolver.lua:112-115)");
+		if (d->eqn == HB_EQN_ADM3D) return setError(HB_ERR_INVALID, "hb_fv_create: useCTU is built for euler and mhd");
+		if (d->stage_kernel == 2) return setError(HB_ERR_INVALID, "hb_fv_create: useCTU runs the unfused kernel sequence, not the marching kernel");
+	}
 	if (d->eqn == HB_EQN_ADM3D) {
 		if (d->use_plm) return setError(HB_ERR_INVALID, "hb_fv_create: adm3d runs the Roe flux with a flux limiter on cell-centred states; usePLM is not built for it");
 		for (int k = 0; k < 2 * d->dim; ++k) if (d->bc[k] == HB_BC_MIRROR) return setError(HB_ERR_INVALID, "hb_fv_create: mirror boundaries are not built for adm3d");

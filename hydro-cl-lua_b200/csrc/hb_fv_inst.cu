@@ -314,7 +314,7 @@ cudaError_t debugEval(int kind, int side, int n, const double* ep, const double*
 	return cudaGetLastError();
 }
 
-const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval, nullptr, nullptr, launchOpKernel<real, MODE>};
+const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval, nullptr, nullptr, launchOpKernel<real, MODE>, launchCtuKernel<Eqn, MODE>};
 
 }   // namespace
 

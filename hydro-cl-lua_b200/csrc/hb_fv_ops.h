@@ -8,6 +8,7 @@
 #include "hb_fv_march.cuh"
 #include "hb_fv_march2d.cuh"
 #include "hb_ops_kernels.cuh"
+#include "hb_ctu_kernels.cuh"
 
 namespace hb {
 
@@ -39,6 +40,8 @@ template<class real> struct FvOps {
 	cudaError_t (*initDerivs)(GridP<real> const& g, real* U, cudaStream_t st);
 	// optional (null for equations without ops): the kernels of hydro/op (hb_ops_kernels.cuh), which = HB_OPK_*
 	cudaError_t (*opKernel)(int which, GridP<real> const& g, OpP<real> const& o, cudaStream_t st);
+	// optional: the unfused kernels of the corner-transport-upwind variant (hb_ctu_kernels.cuh), which = HB_CTUK_*
+	cudaError_t (*ctuKernel)(int which, GridP<real> const& g, StageP<real> const& sp, CtuP<real> const& c, const double* eqnParams, cudaStream_t st);
 };
 
 // exported by hb_fv_inst.cu instantiations

@@ -63,6 +63,10 @@ class GridSolver(SolverBase):
         if self.usePLM and self.fluxLimiter != 0:
             # gridsolver.lua:119: "are you sure you want to use flux and slope limiters at the same time?"
             raise ValueError("usePLM requires fluxLimiter='donor cell' (gridsolver.lua:119)")
+        # gridsolver.lua:102-115: useCTU, switched off in 1-D
+        self.useCTU = bool(args.get("useCTU", False)) and self.dim > 1
+        if self.useCTU and self.usePLM != "plm cons":
+            raise NotImplementedError("useCTU is built for usePLM='plm cons' (without PLM the reference's kernel rewrites UBuf itself, ctu.cl:77-84)")
         # boundary: cfg.boundary table wins, else what the initCond sets, else freeflow
         self.boundaryMethods = {}
         bargs = args.get("boundary") or {}

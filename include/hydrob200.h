@@ -134,6 +134,8 @@ typedef struct hb_fv_desc {
 	int stage_kernel;         /* 0: auto; 1: tile kernel (fv_stage); 2: plane-marching TMA kernel (fv_march), error if not built for the config */
 	int flux;                 /* HB_FLUX_*: the solver's flux plug-in (hydro/flux/*.lua; solver.flux = 'roe' | 'hll' | 'rusanov' | 'euler-hllc') */
 	int flux_param;           /* euler-hllc: solver.flux.hllcMethod */
+	int use_ctu;              /* solver.useCTU (hydro/solver/gridsolver.lua:102-115, fvsolver.lua:246-272, ctu.cl): corner-transport-upwind correction of the
+	                           * PLM face states between two flux passes; needs use_plm = 1 and dim >= 2 (the reference switches it off in 1-D); euler, mhd */
 } hb_fv_desc;
 
 size_t hb_sizeof_fv_desc(void);                              /* sizeof(hb_fv_desc), for bindings that mirror the struct */

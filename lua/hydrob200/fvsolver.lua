@@ -67,6 +67,7 @@ function B200Solver:refreshSolverProgram()
 	else
 		d.eqn_params[0], d.eqn_params[1] = p.heatCapacityRatio.value, p.mu0.value * p.coulomb.value^2   -- mu0 / unit_kg_m_per_C2
 	end
+	d.use_ctu = self.useCTU and 1 or 0                  -- hydro/solver/gridsolver.lua:102-115
 	d.use_graph = 1
 	local h = ffi.new'hb_fv*[1]'
 	check(lib.hb_fv_create(self.app.env.ctx, d, h), 'hb_fv_create')

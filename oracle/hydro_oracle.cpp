@@ -807,6 +807,7 @@ struct SolverBase {
 	double fixedState[6][64] = {};   // per face: the state a 'fixed' boundary writes
 	virtual int addOp(int kind, int maxIters, int stopOnEpsilon, double stopEpsilon, double param) = 0;
 	virtual void opsReset() = 0;
+	virtual int setCTU(int on) = 0;
 	virtual void opInfo(int op, int* iters, double* residual) = 0;
 	virtual void constrainU() = 0;
 	virtual double calcDT() = 0;
@@ -1356,7 +1357,67 @@ template<class Eqn> struct Solver : SolverBase {
 	void calcDeriv(std::vector<cons_t>& derivBuf, real dt) {
 		if (d.use_plm) calcLR();
 		calcFlux(dt);
+		if (useCTU) {   // fvsolver.lua:246-272: face states advanced half a step by the fluxes of all sides, boundary on the face states, fluxes again
+			updateCTU(dt);
+			boundaryLR();
+			calcFlux(dt);
+		}
 		calcDerivFromFlux(derivBuf);
+	}
+	// ---- updateCTU: hydro/solver/ctu.cl:12-129 with a PLM solver (ULR = consLR_t records), eqn.weightFluxByGridVolume = true (eqn.lua:24),
+	//      cartesian: cell->volume = prod grid_dx for every cell
+	bool useCTU = false;
+	int setCTU(int on) override {
+		if (on && (!d.use_plm || dim < 2)) return -1;   // gridsolver.lua:112-115 switches CTU off in 1-D; without PLM the kernel rewrites UBuf itself (not built)
+		useCTU = on != 0;
+		return 0;
+	}
+	void updateCTU(real dt) {
+		real volume = 1;
+		for (int s = 0; s < dim; ++s) volume = volume * solver.grid_dx.s(s);
+		real const invVolume = real(1.) / volume;
+		real areaL[3], areaR[3];
+		for (int s = 0; s < dim; ++s) {
+			real const volume_int = real(.5) * (volume + volume);
+			areaL[s] = volume_int / solver.grid_dx.s(s);
+			areaR[s] = volume_int / solver.grid_dx.s(s);
+		}
+		#pragma omp parallel for collapse(2)
+		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
+			if (OOB(i, j, k, 1, 1)) continue;
+			long index = INDEX(i, j, k);
+			for (int side = 0; side < dim; ++side) {
+				consLR_t& ULR = ULRBuf[side + dim * index];
+				cons_t fluxCellL, fluxCellR;
+				normal_t n{side};
+				Eqn::fluxFromCons(fluxCellL, solver, ULR.L, n);
+				Eqn::fluxFromCons(fluxCellR, solver, ULR.R, n);
+				for (int q = 0; q < nI; ++q) {
+					for (int side2 = 0; side2 < dim; ++side2) {
+						real fL, fR;
+						if (side2 == side) { fL = fluxCellL.ptr[q]; fR = fluxCellR.ptr[q]; }
+						else {
+							long const indexIntL = side2 + dim * index;
+							fL = fluxBuf[indexIntL].ptr[q];
+							fR = fluxBuf[indexIntL + dim * solver.stepsize[side2]].ptr[q];
+						}
+						real const dF_dx = (fR * areaR[side2] - fL * areaL[side2]) * invVolume;
+						ULR.L.ptr[q] -= real(.5) * dt * dF_dx;
+						ULR.R.ptr[q] -= real(.5) * dt * dF_dx;
+					}
+				}
+			}
+		}
+	}
+	// ---- boundaryLR: gridsolver.lua:463-473,1241-1268: the solver's boundary methods on the consLR_t[dim] records, mirror reflecting
+	//      side[j].L/R of every reflected variable
+	void boundaryLR() {
+		std::vector<cons_t> tmp(ncells);
+		for (int side = 0; side < dim; ++side) for (int lr = 0; lr < 2; ++lr) {
+			for (long c = 0; c < ncells; ++c) tmp[c] = lr ? ULRBuf[side + dim * c].R : ULRBuf[side + dim * c].L;
+			boundaryOnBuf(tmp);   // per-axis passes act on each field of the record independently
+			for (long c = 0; c < ncells; ++c) (lr ? ULRBuf[side + dim * c].R : ULRBuf[side + dim * c].L) = tmp[c];
+		}
 	}
 	// ---- addSource kernel (solverbase.lua:3209-3215; SETBOUNDS_NOGHOST): equations with a source term only
 	void addSource(std::vector<cons_t>& derivBuf) {
@@ -1683,6 +1744,7 @@ void ho_set_state(void* h, const double* aos) { static_cast<ho::SolverBase*>(h)-
 void ho_get_state(void* h, double* aos) { static_cast<ho::SolverBase*>(h)->getState(aos); }
 void ho_set_fixed_boundary(void* h, int face, const double* U, int n) { auto* s = static_cast<ho::SolverBase*>(h); for (int k = 0; k < n && k < 64; ++k) s->fixedState[face][k] = U[k]; }
 int ho_add_op(void* h, int kind, int maxIters, int stopOnEpsilon, double stopEpsilon, double param) { return static_cast<ho::SolverBase*>(h)->addOp(kind, maxIters, stopOnEpsilon, stopEpsilon, param); }
+int ho_set_ctu(void* h, int on) { return static_cast<ho::SolverBase*>(h)->setCTU(on); }
 void ho_ops_reset(void* h) { static_cast<ho::SolverBase*>(h)->opsReset(); }
 void ho_op_info(void* h, int op, int* iters, double* residual) { static_cast<ho::SolverBase*>(h)->opInfo(op, iters, residual); }
 void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }

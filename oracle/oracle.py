@@ -60,6 +60,7 @@ def lib(fma=False):
         L.ho_set_fixed_boundary.restype = None
         L.ho_add_op.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double]
         L.ho_ops_reset.argtypes = [C.c_void_p]
+        L.ho_set_ctu.argtypes = [C.c_void_p, C.c_int]
         L.ho_ops_reset.restype = None
         L.ho_op_info.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]
         L.ho_op_info.restype = None
@@ -135,6 +136,8 @@ class OracleBackend:
             raise RuntimeError("oracle: unsupported configuration")
         self.nS = self.L.ho_num_states(self.h)
         self.ncells = self.L.ho_num_cells(self.h)
+        if getattr(solver, "useCTU", False) and self.L.ho_set_ctu(self.h, 1) != 0:
+            raise RuntimeError("oracle: useCTU needs a PLM solver in more than one dimension")
 
     def __del__(self):
         try:

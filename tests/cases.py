@@ -150,3 +150,16 @@ CASES["F3_nodiv_ot_rk3_2d"] = (dict(eqn="mhd", dim=2, gridSize=[48, 36], initCon
                                     integrator="Runge-Kutta 3, TVD", cfl=.15, noDiv="jacobi"), 8)
 CASES["F3_nodiv_selfgrav_ot_fe_3d"] = (dict(eqn="mhd", dim=3, gridSize=[16, 12, 10], initCond="Orszag-Tang", fluxLimiter="minmod",
                                             integrator="forward Euler", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2], noDiv="jacobi", useGravity=True), 4)
+
+# useCTU (hydro/solver/ctu.cl, fvsolver.lua:246-272): PLM face states advanced half a step by the fluxes of all sides, boundary on
+# the face states, second flux pass -- the reference's unfused kernel sequence on the GPU (hb_ctu_kernels.cuh)
+CASES["F4_ctu_kh_fe_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 40], initCond="Kelvin-Helmholtz", usePLM="plm cons", slopeLimiter="minmod",
+                                 integrator="forward Euler", cfl=.3, useCTU=True), 12)
+CASES["F4_ctu_sphere_rk2_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                      usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 2, TVD", cfl=.2, useCTU=True,
+                                      boundary=dict(xmin="mirror", xmax="freeflow", ymin="periodic", ymax="periodic",
+                                                    zmin="freeflow", zmax="mirror")), 5)
+CASES["F4_ctu_ot_mhd_fe_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
+                                     integrator="forward Euler", cfl=.3, useCTU=True), 8)
+CASES["F4_ctu_hll_kh_rk4_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 28], initCond="Kelvin-Helmholtz", flux="hll", usePLM="plm cons",
+                                      slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.3, useCTU=True), 6)
