@@ -39,7 +39,7 @@ WORKLOADS = {
     "C4": dict(name="3D Euler spherical blast, Roe+PLM(minmod)+RK4, double, freeflow, 512^3 per GPU (z slabs)",
                cfg=dict(eqn="euler", dim=3, gridSize=[512, 512, 512], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
                         usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1),
-               words=16, nI=5, stages=4, cpu_sample=[128, 128, 128]),
+               words=16, nI=5, stages=4, cpu_sample=[192, 192, 192]),
     "C2": dict(name="2D Euler Kelvin-Helmholtz, Roe+PLM(minmod)+RK4-TVD, double, periodic, 2048^2 per GPU (y slabs)",
                cfg=dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                         slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15),
@@ -302,9 +302,9 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle
         cores = oracle.lib().ho_max_threads()
-        rate, sec, cells = cpu_oracle_rate(w, cores, 4)
+        rate, sec, cells = cpu_oracle_rate(w, cores, 8)
         cpu = {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-               "sample": "4 updates of the same workload on a %s interior sample (CPU restatement of the reference kernels, OpenMP, %d threads)" % (
+               "sample": "8 updates of the same workload on a %s interior sample (CPU restatement of the reference kernels, OpenMP, %d threads)" % (
                    "x".join(map(str, w["cpu_sample"])), cores)}
 
     if rank == 0:
