@@ -74,7 +74,9 @@ def test_cpu_gloo_two_ranks_equal_single(hydrob200, oracle, tmp_path, case):
                                        ("slab_march2d_overlap", "gpu_strict"),
                                        # the ops on a decomposed grid: potential ghost planes exchanged per sweep, residual / maximum all-reduced
                                        ("F3_selfgrav_sphere_rk4_plm_3d", "gpu_strict"), ("F3_nodiv_ot_rk3_2d", "gpu"),
-                                       ("F3_nodiv_selfgrav_ot_fe_3d", "gpu_strict"), ("F3_selfgrav_sphere_fe_2d", "gpu")])
+                                       ("F3_nodiv_selfgrav_ot_fe_3d", "gpu_strict"), ("F3_selfgrav_sphere_fe_2d", "gpu"),
+                                       # useCTU on a decomposed grid: the face-state blocks' ghost planes travel with boundaryLR
+                                       ("F4_ctu_sphere_rk2_3d", "gpu_strict"), ("F4_ctu_ot_mhd_fe_2d", "gpu")])
 def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
     import torch
     if torch.cuda.device_count() < 2:
