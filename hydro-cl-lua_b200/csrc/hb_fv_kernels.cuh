@@ -59,7 +59,7 @@ template<class real> struct StageP {
 	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc (tile kernel; the marching kernel is built for roe)
 	int fluxParam;         // euler-hllc: hllcMethod
 	const real* gravPot;   // optional: the potential (ePot of Uin) of the self-gravity op; the tile kernel adds calcGravityDeriv (selfgrav.cl:53-76) to L
-	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded
+	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded, 4 'plm prim'
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {
@@ -131,7 +131,8 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 						real const* u = Us + q * G::BOX + b;
 						UL[q] = u[-step]; U[q] = u[0]; UR[q] = u[step];
 					}
-					plmAthenaFaces<Eqn, SIDE>(L, R, ep, UL, U, UR, sp.plmMode == 3 ? 1 : 0);
+					if (sp.plmMode == 4) plmPrimFaces<Eqn>(L, R, ep, sp.slopeLimiter, UL, U, UR);
+					else plmAthenaFaces<Eqn, SIDE>(L, R, ep, UL, U, UR, sp.plmMode == 3 ? 1 : 0);
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) { SG[q * G::SGN + w] = L[q]; SG[(nI + q) * G::SGN + w] = R[q]; }
 				}

@@ -28,6 +28,31 @@ template<class real> HB_HD real plmHalfSlope(int slopeLimiter, real UL, real U, 
 	return real(.5) * sigma;
 }
 
+// 'plm prim' (plm.cl:191-253): slopes of the primitive variables with the one-sided ratio r = dWL / dWR (no sign branch), face states
+// converted back to conserved variables
+template<class Eqn>
+HB_HD void plmPrimFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R)[Eqn::nI], typename Eqn::Params const& s, int slopeLimiter,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI;
+	real w[nI], wl[nI], wr[nI], nl[nI], nr[nI];
+	Eqn::primArray(w, s, U);
+	Eqn::primArray(wl, s, UL);
+	Eqn::primArray(wr, s, UR);
+	#pragma unroll
+	for (int j = 0; j < nI; ++j) {
+		real const dWR = wr[j] - w[j];
+		real const dWL = w[j] - wl[j];
+		real const r = dWR == 0 ? real(0) : (dWL / dWR);
+		real const sigma = limiter<real>(slopeLimiter, r) * dWR;
+		nl[j] = w[j] - real(.5) * sigma;
+		nr[j] = w[j] + real(.5) * sigma;
+	}
+	Eqn::consFromPrimArray(L, s, nl);
+	Eqn::consFromPrimArray(R, s, nr);
+}
+
 // Roe flux without flux limiter (PLM path, or fluxLimiter == 'donor cell'): roe.cl with useFluxLimiter == false.
 template<class Eqn, int SIDE>
 HB_HD void roeFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,

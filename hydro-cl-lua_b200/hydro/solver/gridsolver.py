@@ -15,7 +15,8 @@ xNames = ("x", "y", "z")
 minmaxs = ("min", "max")
 # 'plm athena': plm.cl:782-879 as the reference tree has it (result->L = cons(Wrv), result->R = cons(Wlv), :877-878);
 # 'plm athena, recorded face order': L = left, R = right face -- reproduces the errors recorded in tests/test-order/schemes.lua
-plmIds = {None: 0, False: 0, "plm cons": 1, "plm athena": 2, "plm athena, recorded face order": 3}
+# 'plm prim': plm.cl:191-253; 'piecewise constant': plm.cl:10-24 (L = R = U: the same fluxes as no PLM with the donor-cell flux limiter)
+plmIds = {None: 0, False: 0, "plm cons": 1, "plm athena": 2, "plm athena, recorded face order": 3, "plm prim": 4, "piecewise constant": 0}
 
 
 class GridSolver(SolverBase):
@@ -57,7 +58,7 @@ class GridSolver(SolverBase):
         self.mindx = min(self.grid_dx)
         self.usePLM = args.get("usePLM") or None
         if self.usePLM not in plmIds:
-            raise NotImplementedError("usePLM=%r: 'plm cons' and 'plm athena' are built" % (self.usePLM,))
+            raise NotImplementedError("usePLM=%r: 'piecewise constant', 'plm cons', 'plm prim' and 'plm athena' are built" % (self.usePLM,))
         self.plmId = plmIds[self.usePLM]
         self.slopeLimiter = hydro_app.limiterIndex(args.get("slopeLimiter", "minmod")) if self.usePLM else 0
         if self.usePLM and self.fluxLimiter != 0:

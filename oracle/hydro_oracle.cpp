@@ -36,7 +36,7 @@ struct ho_desc {
 	int dim;            // 1..3
 	int n[3];           // interior cells per axis (unused axes = 1)
 	int real_bytes;     // 8 = double, 4 = float   (hydro/app.lua:892 'real' selection)
-	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded
+	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded, 4 = 'plm prim' (plm.cl:191-253)
 	int slope_limiter;  // 0-based index into hydro/app.lua:614-635
 	int flux_limiter;   // 0-based index; 0 = 'donor cell' => useFluxLimiter=false (fvsolver.lua:61-63)
 	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none, 4 linear, 5 quadratic, 6 fixed
@@ -1037,6 +1037,33 @@ template<class Eqn> struct Solver : SolverBase {
 	}
 
 	// ---- calcLR: plm.cl:976-997 kernel, 'plm cons' :32-91
+	// 'plm prim' (plm.cl:191-253): slopes of the primitive variables, one-sided ratio r = dWL / dWR (no sign branch), back to conserved
+	void calcCellLR_prim(consLR_t& result, cons_t const& U, cons_t const& UL, cons_t const& UR) const {
+		if constexpr (Eqn::hasEigenForCell) {   // (euler, mhd: the equations with a prim_t)
+			typedef typename Eqn::prim_t prim_t;
+			prim_t W, WL, WR;
+			Eqn::primFromCons(W, solver, U);
+			Eqn::primFromCons(WL, solver, UL);
+			Eqn::primFromCons(WR, solver, UR);
+			prim_t nWL = W, nWR = W;
+			real const* w = reinterpret_cast<real const*>(&W);
+			real const* wl = reinterpret_cast<real const*>(&WL);
+			real const* wr = reinterpret_cast<real const*>(&WR);
+			real* nl = reinterpret_cast<real*>(&nWL);
+			real* nr = reinterpret_cast<real*>(&nWR);
+			for (int j = 0; j < nI; ++j) {
+				real const dWR = wr[j] - w[j];
+				real const dWL = w[j] - wl[j];
+				real const r = dWR == 0 ? real(0) : (dWL / dWR);
+				real const phi = limiter<real>(d.slope_limiter, r);
+				real const sigma = phi * dWR;
+				nl[j] -= real(.5) * sigma;
+				nr[j] += real(.5) * sigma;
+			}
+			Eqn::consFromPrim(result.L, solver, nWL);
+			Eqn::consFromPrim(result.R, solver, nWR);
+		}
+	}
 	void calcLR() {
 		int const sl = d.slope_limiter;
 		#pragma omp parallel for collapse(2)
@@ -1048,6 +1075,7 @@ template<class Eqn> struct Solver : SolverBase {
 				consLR_t& result = ULRBuf[side + dim * index];
 				cons_t const& UL = UBuf[index - solver.stepsize[side]];
 				cons_t const& UR = UBuf[index + solver.stepsize[side]];
+				if (d.use_plm == 4) { calcCellLR_prim(result, U, UL, UR); continue; }
 				if (d.use_plm >= 2) { calcCellLR_athena(result, U, UL, UR, normal_t{side}); continue; }
 				result.L = U; result.R = U;
 				for (int q = 0; q < nI; ++q) {

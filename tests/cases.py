@@ -163,3 +163,15 @@ CASES["F4_ctu_ot_mhd_fe_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCo
                                      integrator="forward Euler", cfl=.3, useCTU=True), 8)
 CASES["F4_ctu_hll_kh_rk4_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 28], initCond="Kelvin-Helmholtz", flux="hll", usePLM="plm cons",
                                       slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.3, useCTU=True), 6)
+
+# more of plm.cl's reconstructions -- 'plm prim' (:191-253, slopes of the primitive variables) and 'piecewise constant' (:10-24)
+CASES["F1_plm_prim_sod_rk2"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm prim", slopeLimiter="superbee",
+                                     integrator="Runge-Kutta 2, TVD", cfl=.3), 30)
+CASES["F1_plm_prim_kh_rk4_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 36], initCond="Kelvin-Helmholtz", usePLM="plm prim", slopeLimiter="minmod",
+                                       integrator="Runge-Kutta 4", cfl=.15), 10)
+CASES["F1_plm_prim_sphere_hll_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere", flux="hll",
+                                           usePLM="plm prim", slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.1), 5)
+CASES["F1_plm_prim_ot_mhd_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCond="Orszag-Tang", usePLM="plm prim", slopeLimiter="minmod",
+                                       integrator="Runge-Kutta 3, TVD", cfl=.15), 8)
+CASES["F1_piecewise_constant_kh_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 28], initCond="Kelvin-Helmholtz", usePLM="piecewise constant",
+                                             integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
