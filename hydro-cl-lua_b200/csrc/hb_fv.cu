@@ -976,7 +976,7 @@ template<class real> struct Fv : FvBase {
 		bool const plm = d.use_plm != 0;
  		ops->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
 		if (useMarch) for (int k = 0; k < 5; ++k) ti[k] = marchInfoV[k];
-		o << "kernel=" << (useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : "fv_march(tma)") : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
+		o << "kernel=" << (useCTU ? "ctu(unfused:calcLR,calcFlux,updateCTU,boundaryLR,calcFlux,finish)" : useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : "fv_march(tma)") : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
 		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
 		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : "")) << "\n";

@@ -51,7 +51,7 @@ def test_gpu_ctu_launch_structure_and_graph(hydrob200):
                integrator="Runge-Kutta 2, TVD", cfl=.4, useCTU=True)
     A = hydrob200.FiniteVolumeSolver(dict(cfg, use_graph=True))
     B = hydrob200.FiniteVolumeSolver(dict(cfg, use_graph=False))
-    assert "fv_stage" in A.backend.describe() or "tile" in A.backend.describe()      # not the marching kernel
+    assert "kernel=ctu(" in A.backend.describe()                                      # the unfused sequence, not a fused stage kernel
     n0 = B.backend.launch_count()
     A.update(4)
     for _ in range(4):
