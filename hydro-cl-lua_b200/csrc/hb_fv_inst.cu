@@ -94,9 +94,10 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 #endif
 // 2-D warp-per-pencil kernel (hb_fv_march2d.cuh): X(index, NW, KM, MINB); these come first in the 2-D cfg numbering
 #ifdef HB_STRICT
-#define HB_MARCH2W_LIST(X) X(0, 4, 32, 1)
+#define HB_MARCH2W_LIST(X) X(0, 4, 32, 1) X(1, 4, 32, 17)
 #else
-#define HB_MARCH2W_LIST(X) X(0, 4, 32, 1) X(1, 2, 32, 1) X(2, 8, 32, 1)
+// MINB + 16: cfg 0 with the self-gravity source in the epilogue (March2Cfg::GRAV; chosen by hb_fv_add_op, never by the auto selection)
+#define HB_MARCH2W_LIST(X) X(0, 4, 32, 1) X(1, 2, 32, 1) X(2, 8, 32, 1) X(3, 4, 32, 17)
 #endif
 constexpr int kMarch2W =
 #define HB_X(i, nw, km, mb) +1
@@ -191,7 +192,7 @@ template<class C> void march2WInfoCfg(int box[4], int info[7]) {
 	typedef March2Geom<C, real> G;
 	box[0] = G::BX; box[1] = 1; box[2] = 1; box[3] = Eqn::nI;
 	info[0] = G::CW * C::NW; info[1] = 1; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
-	info[5] = C::NW * 32; info[6] = 0;
+	info[5] = C::NW * 32; info[6] = C::GRAV ? 1 : 0;
 }
 template<int DIM, class C> void marchInfoCfg(int box[4], int info[7]) {
 	typedef MarchGeom<DIM, C, real> G;

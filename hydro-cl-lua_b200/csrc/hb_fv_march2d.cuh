@@ -24,7 +24,8 @@ namespace hb {
 template<int NW_, int KM_, int MINB_> struct March2Cfg {
 	static constexpr int NW = NW_;       // warps per CTA (independent of each other)
 	static constexpr int KM = KM_;       // nominal rows per warp along the marching axis (the launcher picks the actual count, see rowsPerWarp)
-	static constexpr int MINB = MINB_;
+	static constexpr int MINB = MINB_ & 15;
+	static constexpr bool GRAV = (MINB_ & 16) != 0;   // the epilogue adds the self-gravity source (StageP::gravPot), as MarchCfg::GRAV
 };
 
 template<class C, class real> struct March2Geom {
@@ -135,7 +136,7 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> c
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) acc[q] = g.volOn ? accP[q] - (Fz[q] * aovM - FzP[q] * aovM) : real(0);
 			cpAsyncWaitAll();
-			stageEpilogue<Eqn>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + lane, OPS);
+			stageEpilogue<Eqn, C::GRAV>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + lane, OPS);
 		}
 		if (inside && xy && sp.Uout) {
 			int slot = 0;

@@ -175,3 +175,5 @@ CASES["F1_plm_prim_ot_mhd_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], init
                                        integrator="Runge-Kutta 3, TVD", cfl=.15), 8)
 CASES["F1_piecewise_constant_kh_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 28], initCond="Kelvin-Helmholtz", usePLM="piecewise constant",
                                              integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
+CASES["F3_selfgrav_kh_plm_rk4_2d"] = (dict(eqn="euler", dim=2, gridSize=[64, 40], initCond="Kelvin-Helmholtz", usePLM="plm cons", slopeLimiter="minmod",
+                                           integrator="Runge-Kutta 4", cfl=.15, useGravity=True), 6)     # the 2-D marching kernel's gravity configuration

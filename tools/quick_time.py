@@ -43,6 +43,8 @@ cfgs = {
                          slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1, useGravity=True), 3, 640),
     "C4_256_tile": (dict(eqn="euler", dim=3, gridSize=[256] * 3, mins=[-2] * 3, maxs=[2] * 3, initCond="sphere", usePLM="plm cons",
                          slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1, stage_kernel=1), 3, 640),
+    "C2_grav": (dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                     slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15, useGravity=True), 5, 840),
     # useCTU -- the reference's unfused kernel sequence (hb_ctu_kernels.cuh)
     "C2_ctu": (dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                     slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15, useCTU=True), 5, 840),
