@@ -59,7 +59,7 @@ template<class real> struct StageP {
 	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc (tile kernel; the marching kernel is built for roe)
 	int fluxParam;         // euler-hllc: hllcMethod
 	const real* gravPot;   // optional: the potential (ePot of Uin) of the self-gravity op; the tile kernel adds calcGravityDeriv (selfgrav.cl:53-76) to L
-	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded, 4 'plm prim'
+	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded, 4 'plm prim', 5 'plm cons with flux'
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {
@@ -132,6 +132,7 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 						UL[q] = u[-step]; U[q] = u[0]; UR[q] = u[step];
 					}
 					if (sp.plmMode == 4) plmPrimFaces<Eqn>(L, R, ep, sp.slopeLimiter, UL, U, UR);
+					else if (sp.plmMode == 5) plmConsFluxFaces<Eqn, SIDE>(L, R, ep, sp.slopeLimiter, dtReal / g.dx[SIDE], UL, U, UR);
 					else plmAthenaFaces<Eqn, SIDE>(L, R, ep, UL, U, UR, sp.plmMode == 3 ? 1 : 0);
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) { SG[q * G::SGN + w] = L[q]; SG[(nI + q) * G::SGN + w] = R[q]; }

@@ -53,6 +53,34 @@ HB_HD void plmPrimFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R
 	Eqn::consFromPrimArray(R, s, nr);
 }
 
+// 'plm cons with flux' (plm.cl:95-187, MUSCL-Hancock): conserved slopes with the one-sided ratio, then both face states moved by
+// .5 dt/dx (F(right face state) - F(left face state)) -- added, as the reference has it
+template<class Eqn, int SIDE>
+HB_HD void plmConsFluxFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R)[Eqn::nI], typename Eqn::Params const& s, int slopeLimiter,
+	typename Eqn::real dt_dx, typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI;
+	#pragma unroll
+	for (int j = 0; j < nI; ++j) {
+		real const dUL = U[j] - UL[j];
+		real const dUR = UR[j] - U[j];
+		real const r = dUR == 0 ? real(0) : (dUL / dUR);
+		real const sigma = limiter<real>(slopeLimiter, r) * dUR;
+		L[j] = U[j] - real(.5) * sigma;
+		R[j] = U[j] + real(.5) * sigma;
+	}
+	real FL[nI], FR[nI];
+	Eqn::template fluxFromCons<SIDE>(FL, s, L);
+	Eqn::template fluxFromCons<SIDE>(FR, s, R);
+	#pragma unroll
+	for (int j = 0; j < nI; ++j) {
+		real const dF = FR[j] - FL[j];
+		L[j] += real(.5) * dt_dx * dF;
+		R[j] += real(.5) * dt_dx * dF;
+	}
+}
+
 // Roe flux without flux limiter (PLM path, or fluxLimiter == 'donor cell'): roe.cl with useFluxLimiter == false.
 template<class Eqn, int SIDE>
 HB_HD void roeFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& s,

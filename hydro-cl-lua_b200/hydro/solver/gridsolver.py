@@ -16,7 +16,8 @@ minmaxs = ("min", "max")
 # 'plm athena': plm.cl:782-879 as the reference tree has it (result->L = cons(Wrv), result->R = cons(Wlv), :877-878);
 # 'plm athena, recorded face order': L = left, R = right face -- reproduces the errors recorded in tests/test-order/schemes.lua
 # 'plm prim': plm.cl:191-253; 'piecewise constant': plm.cl:10-24 (L = R = U: the same fluxes as no PLM with the donor-cell flux limiter)
-plmIds = {None: 0, False: 0, "plm cons": 1, "plm athena": 2, "plm athena, recorded face order": 3, "plm prim": 4, "piecewise constant": 0}
+plmIds = {None: 0, False: 0, "plm cons": 1, "plm athena": 2, "plm athena, recorded face order": 3, "plm prim": 4, "plm cons with flux": 5,
+          "piecewise constant": 0}
 
 
 class GridSolver(SolverBase):

@@ -117,7 +117,7 @@ typedef struct hb_fv_desc {
 	int global_n[3];          /* interior cells of the whole grid (== n without decomposition); defines grid_dx */
 	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879; euler, mhd in 1-D / 2-D), 3 = 'plm athena'
 	                           * with the face states assigned L = left, R = right: the order that reproduces the errors the reference
-	                           * recorded for this scheme (its tree has them the other way round at plm.cl:877-878); 4 = 'plm prim' (plm.cl:191-253).
+	                           * recorded for this scheme (its tree has them the other way round at plm.cl:877-878); 4 = 'plm prim' (plm.cl:191-253); 5 = 'plm cons with flux' (plm.cl:95-187).
 	                           * 'piecewise constant' (plm.cl:10-24: L = R = U) is use_plm = 0 with flux_limiter = 0 */
 	int slope_limiter;        /* 0-based index into hydro/app.lua:614-635 */
 	int flux_limiter;         /* 0-based; 0 = 'donor cell' = no flux limiter (hydro/solver/fvsolver.lua:61-63) */

@@ -36,7 +36,7 @@ struct ho_desc {
 	int dim;            // 1..3
 	int n[3];           // interior cells per axis (unused axes = 1)
 	int real_bytes;     // 8 = double, 4 = float   (hydro/app.lua:892 'real' selection)
-	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded, 4 = 'plm prim' (plm.cl:191-253)
+	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded, 4 = 'plm prim' (plm.cl:191-253), 5 = 'plm cons with flux' (plm.cl:95-187)
 	int slope_limiter;  // 0-based index into hydro/app.lua:614-635
 	int flux_limiter;   // 0-based index; 0 = 'donor cell' => useFluxLimiter=false (fvsolver.lua:61-63)
 	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none, 4 linear, 5 quadratic, 6 fixed
@@ -1064,7 +1064,35 @@ template<class Eqn> struct Solver : SolverBase {
 			Eqn::consFromPrim(result.R, solver, nWR);
 		}
 	}
-	void calcLR() {
+	// 'plm cons with flux' (plm.cl:95-187): conserved slopes with the one-sided ratio, then both face states moved by
+	// .5 dt/dx (F(U_R face) - F(U_L face)) -- added, as the reference has it
+	void calcCellLR_consWithFlux(consLR_t& result, cons_t const& U, cons_t const& UL, cons_t const& UR, normal_t n, real dt) const {
+		if constexpr (Eqn::hasEigenForCell) {   // (euler, mhd)
+			cons_t UHalfL = U, UHalfR = U;
+			for (int j = 0; j < nI; ++j) {
+				real const dUL = U.ptr[j] - UL.ptr[j];
+				real const dUR = UR.ptr[j] - U.ptr[j];
+				real const r = dUR == 0 ? real(0) : (dUL / dUR);
+				real const phi = limiter<real>(d.slope_limiter, r);
+				real const sigma = phi * dUR;
+				UHalfL.ptr[j] -= real(.5) * sigma;
+				UHalfR.ptr[j] += real(.5) * sigma;
+			}
+			real const dx = solver.grid_dx.s(n.side);
+			real const dt_dx = dt / dx;
+			cons_t FHalfL, FHalfR;
+			Eqn::fluxFromCons(FHalfL, solver, UHalfL, n);
+			Eqn::fluxFromCons(FHalfR, solver, UHalfR, n);
+			result.L = UHalfL;
+			result.R = UHalfR;
+			for (int j = 0; j < nI; ++j) {
+				real const dF = FHalfR.ptr[j] - FHalfL.ptr[j];
+				result.L.ptr[j] += real(.5) * dt_dx * dF;
+				result.R.ptr[j] += real(.5) * dt_dx * dF;
+			}
+		}
+	}
+	void calcLR(real dtArg = 0) {
 		int const sl = d.slope_limiter;
 		#pragma omp parallel for collapse(2)
 		for (int k = 0; k < S[2]; ++k) for (int j = 0; j < S[1]; ++j) for (int i = 0; i < S[0]; ++i) {
@@ -1076,6 +1104,7 @@ template<class Eqn> struct Solver : SolverBase {
 				cons_t const& UL = UBuf[index - solver.stepsize[side]];
 				cons_t const& UR = UBuf[index + solver.stepsize[side]];
 				if (d.use_plm == 4) { calcCellLR_prim(result, U, UL, UR); continue; }
+				if (d.use_plm == 5) { calcCellLR_consWithFlux(result, U, UL, UR, normal_t{side}, dtArg); continue; }
 				if (d.use_plm >= 2) { calcCellLR_athena(result, U, UL, UR, normal_t{side}); continue; }
 				result.L = U; result.R = U;
 				for (int q = 0; q < nI; ++q) {
@@ -1383,7 +1412,7 @@ template<class Eqn> struct Solver : SolverBase {
 
 	// ---- FiniteVolumeSolver:calcDeriv: fvsolver.lua:225-302 (+ addSource: none for euler / cartesian mhd)
 	void calcDeriv(std::vector<cons_t>& derivBuf, real dt) {
-		if (d.use_plm) calcLR();
+		if (d.use_plm) calcLR(dt);
 		calcFlux(dt);
 		if (useCTU) {   // fvsolver.lua:246-272: face states advanced half a step by the fluxes of all sides, boundary on the face states, fluxes again
 			updateCTU(dt);

@@ -177,3 +177,10 @@ CASES["F1_piecewise_constant_kh_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 2
                                              integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
 CASES["F3_selfgrav_kh_plm_rk4_2d"] = (dict(eqn="euler", dim=2, gridSize=[64, 40], initCond="Kelvin-Helmholtz", usePLM="plm cons", slopeLimiter="minmod",
                                            integrator="Runge-Kutta 4", cfl=.15, useGravity=True), 6)     # the 2-D marching kernel's gravity configuration
+# 'plm cons with flux' (plm.cl:95-187, MUSCL-Hancock half step inside the reconstruction; the stage's dt enters the face states)
+CASES["F1_plm_cons_flux_sod_fe"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm cons with flux", slopeLimiter="minmod",
+                                         integrator="forward Euler", cfl=.3), 40)
+CASES["F1_plm_cons_flux_kh_rk2_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 36], initCond="Kelvin-Helmholtz", usePLM="plm cons with flux",
+                                            slopeLimiter="minmod", integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
+CASES["F1_plm_cons_flux_ot_mhd_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCond="Orszag-Tang", usePLM="plm cons with flux",
+                                            slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 8)
