@@ -541,12 +541,13 @@ template<class real> struct Fv : FvBase {
 		return HB_OK;
 	}
 
-	int fillGhosts(real* U, int nVars) {
+	int fillGhosts(real* U, int nVars, const BcP* methods = nullptr) {
+		BcP const& b = methods ? *methods : bc;
 		if (seqBc) {
-			for (int a = 0; a < d.dim; ++a) { HB_CUDA(ops->ghosts(grid, bc, U, nVars, -2 - a, false, st())); launches++; }
+			for (int a = 0; a < d.dim; ++a) { HB_CUDA(ops->ghosts(grid, b, U, nVars, -2 - a, false, st())); launches++; }
 			return exchange(U, nVars);
 		}
-		HB_CUDA(ops->ghosts(grid, bc, U, nVars, -1, false, st()));
+		HB_CUDA(ops->ghosts(grid, b, U, nVars, -1, false, st()));
 		launches++;
 		return exchange(U, nVars);
 	}
@@ -627,7 +628,12 @@ template<class real> struct Fv : FvBase {
 	}
 	int opLaunch(int which, OpP<real> const& p) { HB_CUDA(ops->opKernel(which, grid, p, st())); launches++; return HB_OK; }
 	// Relaxation:potentialBoundary (relaxation.lua:135-150,198-200): the solver's boundary methods on the potential alone
-	int potentialBoundary(real* pot) { return fillGhosts(pot, 1); }
+	// A 'fixed' face writes whole states (its fixedCode knows nothing of args.fields): the field-restricted pass leaves it alone.
+	int potentialBoundary(real* pot) {
+		BcP b = bc;
+		for (int k = 0; k < 6; ++k) if (b.bc[k] == HB_BC_FIXED) b.bc[k] = HB_BC_NONE;
+		return fillGhosts(pot, 1, &b);
+	}
 	// Relaxation:relax (relaxation.lua:165-196); the stop test stays on the device (OpCtl::done), the two copies of the potential alternate
 	int relax(OpState const& s, real* U) {
 		if (int r = opLaunch(HB_OPK_BEGIN, opParams(s, U))) return r;

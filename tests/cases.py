@@ -184,3 +184,7 @@ CASES["F1_plm_cons_flux_kh_rk2_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 36
                                             slopeLimiter="minmod", integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
 CASES["F1_plm_cons_flux_ot_mhd_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCond="Orszag-Tang", usePLM="plm cons with flux",
                                             slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 8)
+CASES["F3_selfgrav_linear_fixed_bc_2d"] = (dict(eqn="euler", dim=2, gridSize=[36, 28], initCond="sphere", usePLM="plm cons", slopeLimiter="minmod",
+                                                integrator="Runge-Kutta 2, TVD", cfl=.15, useGravity=True,
+                                                boundary=dict(xmin="linear", xmax="quadratic", ymin="mirror",
+                                                              ymax=dict(name="fixed", args=dict(W=dict(rho=.01, vx=0., vy=0., vz=0., P=.01, ePot=0.))))), 6)
