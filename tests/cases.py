@@ -188,3 +188,7 @@ CASES["F3_selfgrav_linear_fixed_bc_2d"] = (dict(eqn="euler", dim=2, gridSize=[36
                                                 integrator="Runge-Kutta 2, TVD", cfl=.15, useGravity=True,
                                                 boundary=dict(xmin="linear", xmax="quadratic", ymin="mirror",
                                                               ymax=dict(name="fixed", args=dict(W=dict(rho=.01, vx=0., vy=0., vz=0., P=.01, ePot=0.))))), 6)
+
+# float builds of the rows either side of the path (strict build bit-identical to the float oracle, production within 1e-5)
+FLOAT_CASES += ["F3_nodiv_ot_rk3_2d", "F3_selfgrav_sphere_rk4_plm_3d", "F4_ctu_kh_fe_2d", "F4_kh_linear_quadratic_2d", "F1_plm_prim_kh_rk4_2d",
+                "F1_plm_cons_flux_kh_rk2_2d"]
