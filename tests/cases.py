@@ -192,3 +192,9 @@ CASES["F3_selfgrav_linear_fixed_bc_2d"] = (dict(eqn="euler", dim=2, gridSize=[36
 # float builds of the rows either side of the path (strict build bit-identical to the float oracle, production within 1e-5)
 FLOAT_CASES += ["F3_nodiv_ot_rk3_2d", "F3_selfgrav_sphere_rk4_plm_3d", "F4_ctu_kh_fe_2d", "F4_kh_linear_quadratic_2d", "F1_plm_prim_kh_rk4_2d",
                 "F1_plm_cons_flux_kh_rk2_2d"]
+
+# ADM with the extrapolating boundary methods (the per-axis ghost passes on 51 variables)
+ADM_CASES["C5_warp_bubble_linear_quadratic_bc"] = (dict(eqn="adm3d", dim=3, gridSize=[12, 10, 8], initCond="Alcubierre warp bubble", fluxLimiter="superbee",
+                                                        integrator="Runge-Kutta 4", cfl=.1,
+                                                        boundary=dict(xmin="linear", xmax="quadratic", ymin="freeflow", ymax="linear",
+                                                                      zmin="quadratic", zmax="freeflow")), 6)
