@@ -89,6 +89,7 @@ SIGNATURES = {
     "hb_fv_wait_transfers": (C.c_int, [P]),
     "hb_fv_state_devptr": (C.c_int, [P, C.POINTER(P), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "hb_fv_boundary": (C.c_int, [P]),
+    "hb_sizeof_op_desc": (C.c_size_t, []),
     "hb_fv_add_op": (C.c_int, [P, C.POINTER(hb_op_desc), C.POINTER(C.c_int)]),
     "hb_fv_ops_reset": (C.c_int, [P]),
     "hb_fv_op_info": (C.c_int, [P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),

@@ -1069,6 +1069,7 @@ using namespace hb;
 extern "C" {
 
 size_t hb_sizeof_fv_desc(void) { return sizeof(hb_fv_desc); }
+size_t hb_sizeof_op_desc(void) { return sizeof(hb_op_desc); }
 int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 	if (!ctx || !d || !out) return setError(HB_ERR_INVALID, "hb_fv_create: null argument");
 	*out = nullptr;

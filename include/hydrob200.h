@@ -170,6 +170,7 @@ typedef struct hb_op_desc {
 	double stop_epsilon;      /* relaxation.lua:25 (1e-10) */
 	double param;
 } hb_op_desc;
+size_t hb_sizeof_op_desc(void);                              /* sizeof(hb_op_desc), for bindings that mirror the struct */
 int hb_fv_add_op(hb_fv* fv, const hb_op_desc* op, int* index_out);
 int hb_fv_ops_reset(hb_fv* fv);                              /* op:resetState() + boundary() of every op (solverbase.lua:2106-2111); call after set_state / boundary */
 int hb_fv_op_info(hb_fv* fv, int op, int* last_iter, double* last_residual);   /* Relaxation.lastIter / lastResidual (blocking) */

@@ -39,6 +39,7 @@ def test_desc_layout_matches_c(hydrob200):
     from importlib import import_module
     hb = import_module("hydro-cl-lua_b200._lib")
     assert hb.lib().hb_sizeof_fv_desc() == C.sizeof(hb.hb_fv_desc)
+    assert hb.lib().hb_sizeof_op_desc() == C.sizeof(hb.hb_op_desc)
 
 
 def test_no_device_means_error_not_fallback(hydrob200):
