@@ -6,9 +6,10 @@ by tests/test-order/run.lua via GridSolver:calcExactError (gridsolver.lua:1337-1
 them through the same procedure: run update() until t >= duration, then the L1 error against the analytic
 solution with the reference's loop bounds.
 
-Rows recorded with the stale 'plm-cons' / Lax-Wendroff-on-Sod schemes are not reproducible on the current
-revision of the reference's kernels (plm.cl was rewritten since; Lax-Wendroff on a shock is oscillatory) and
-are documented as unpinned in DESIGN.md.
+The rows recorded as usePLM='plm-cons' (schemes.lua:81-100) turn out to be the scheme the tree now calls
+'plm cons with flux' (plm.cl:95-187): their Sod column is reproduced below to the recorded digits for every
+limiter that is stable on the shock tube.  Rows recorded with 'plm-prim-alone' / 'plm-cons-alone' / 'plm-eig-prim*'
+are not reproduced by the current tree's variants and stay unpinned.
 """
 import pytest
 
@@ -62,3 +63,36 @@ def test_schemes_lua_kat(hydrob200, oracle, kw, kat_adv, kat_sod, tol_adv, tol_s
     if kat_sod is not None:
         got = run(hydrob200, oracle, "Sod", **kw)
         assert abs(got - kat_sod) <= tol_sod * kat_sod, (got, kat_sod)
+
+
+# The rows the reference recorded as usePLM='plm-cons' with a slope limiter (schemes.lua:81-100; Roe, forward Euler) are the scheme its
+# tree now calls 'plm cons with flux' (plm.cl:95-187, the MUSCL-Hancock variant): the oracle reproduces their Sod column for every
+# limiter that is stable on the shock tube, to the digits recorded.  (The advect-wave column of these rows is reproduced only where the
+# limited scheme is well conditioned on smooth data -- ospre, donor cell; with the compressive limiters the recorded L1 errors are
+# O(1e-2) of an unstable run and depend on rounding.)  This pins plm.cl:95-187 and eleven more of the limiter formulas of
+# hydro/app.lua:614-635 on the reference's own numbers.
+PLM_FLUX_KATS = [
+    # (slopeLimiter, advect-wave KAT or None, Sod KAT, rel tol advect, rel tol Sod)                       schemes.lua line
+    ("minmod", None, 0.0013513761228327, None, 1e-12),                                                  # :100
+    ("ospre", 0.00013263354368475, 0.0016309138954085, 1e-10, 1e-12),                                   # :96
+    ("donor cell", 0.00029551600678436, 0.0025480145819915, 1e-11, 1e-12),                              # :93
+    ("van Albada 1", None, 0.0014345138627451, None, 1e-11),                                            # :98
+    ("UMIST", None, 0.0030517363635154, None, 1e-10),                                                   # :94
+    ("Oshker", None, 0.002464024257206, None, 1e-9),                                                    # :97
+    ("HQUICK", None, 0.0043568816756108, None, 1e-9),                                                   # :91
+    ("Koren", None, 0.0045319629410316, None, 1e-8),                                                    # :90
+    ("HCUS", None, 0.0034376341809745, None, 1e-8),                                                     # :92
+    ("monotized central", None, 0.0048356399731734, None, 1e-8),                                        # :89
+    ("superbee", None, 0.0054859189942998, None, 1e-6),                                                 # :88
+    ("Sweby", None, 0.0025329368985951, None, 1e-6),                                                    # :95
+]
+
+
+@pytest.mark.parametrize("lim,kat_adv,kat_sod,tol_adv,tol_sod", PLM_FLUX_KATS, ids=[k[0] for k in PLM_FLUX_KATS])
+def test_schemes_lua_plm_cons_rows_are_plm_cons_with_flux(hydrob200, oracle, lim, kat_adv, kat_sod, tol_adv, tol_sod):
+    kw = dict(usePLM="plm cons with flux", slopeLimiter=lim, integrator="forward Euler")
+    got = run(hydrob200, oracle, "Sod", **kw)
+    assert abs(got - kat_sod) <= tol_sod * kat_sod, (got, kat_sod)
+    if kat_adv is not None:
+        got = run(hydrob200, oracle, "advect wave", **kw)
+        assert abs(got - kat_adv) <= tol_adv * kat_adv, (got, kat_adv)
