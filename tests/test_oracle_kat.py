@@ -46,6 +46,21 @@ KATS = [
     (dict(flux="euler-hllc", hllcMethod=2, integrator="forward Euler"), 0.00029551600678437, 0.0026034369564245, 1e-11, 1e-12),        # :55
     (dict(flux="euler-hllc", hllcMethod=0, integrator="Runge-Kutta 3, TVD"), 0.00039208124005629, 0.0031547573035925, 1e-10, 1e-12),   # :43
     (dict(flux="euler-hllc", hllcMethod=2, integrator="Runge-Kutta 3, TVD"), 0.00039208124005633, 0.0031547573035925, 1e-10, 1e-12),   # :59
+    # the other flux limiters of hydro/app.lua:614-635 (schemes.lua:61-78): all twenty limiter formulas are pinned
+    (dict(integrator="forward Euler", fluxLimiter="smart"), 1.0911857176237e-06, 0.0006129313415327, 1e-8, 1e-12),   # :61
+    (dict(integrator="forward Euler", fluxLimiter="ospre"), 0.00019705480525943, 0.0020319762206545, 1e-8, 1e-12),   # :62
+    (dict(integrator="forward Euler", fluxLimiter="Fromm"), 1.5346799701183e-07, 0.00062670027933916, 1e-8, 1e-12),   # :63
+    (dict(integrator="forward Euler", fluxLimiter="CHARM"), 1.4822461340873e-06, 0.00060082731534463, 1e-8, 1e-12),   # :64
+    (dict(integrator="forward Euler", fluxLimiter="van Albada 1"), 1.2462029419466e-06, 0.00065025946311501, 1e-8, 1e-12),   # :65
+    (dict(integrator="forward Euler", fluxLimiter="Barth-Jespersen"), 4.808764902909e-07, 0.00045706811880196, 1e-8, 1e-12),   # :66
+    (dict(integrator="forward Euler", fluxLimiter="Beam-Warming"), 1.0595112307524e-06, 0.0013601751183648, 1e-8, 1e-12),   # :67
+    (dict(integrator="forward Euler", fluxLimiter="van Albada 2"), 2.3724738671197e-06, 0.00081184935099592, 1e-8, 1e-12),   # :69
+    (dict(integrator="forward Euler", fluxLimiter="Oshker"), 2.4949277440571e-06, 0.00067671846961815, 1e-8, 1e-12),   # :71
+    (dict(integrator="forward Euler", fluxLimiter="Sweby"), 2.0705889490385e-06, 0.00041546702447137, 1e-8, 1e-12),   # :73
+    (dict(integrator="forward Euler", fluxLimiter="HQUICK"), 1.3626347787182e-06, 0.00059526337064112, 1e-8, 1e-12),   # :74
+    (dict(integrator="forward Euler", fluxLimiter="Koren"), 1.0448963734558e-06, 0.00050202680619077, 1e-8, 1e-12),   # :75
+    (dict(integrator="forward Euler", fluxLimiter="HCUS"), 1.1792669058976e-06, 0.00055928895482656, 1e-8, 1e-12),   # :76
+    (dict(integrator="forward Euler", fluxLimiter="UMIST"), 1.1751903573017e-06, 0.00061938621334895, 1e-8, 1e-12),   # :78
     # SURVEY 8f1 'plm athena'.  The tree assigns the face states the other way round (plm.cl:877-878: L = cons(Wrv), R = cons(Wlv))
     # than the version these rows were recorded with; with L = left, R = right every row is reproduced.
     (dict(usePLM="plm athena, recorded face order", integrator="forward Euler"), 9.7002822784791e-05, 0.00093771140713331, 1e-10, 1e-11),   # :97
