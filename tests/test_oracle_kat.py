@@ -68,6 +68,19 @@ KATS = [
     (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 2"), 1.3132898617302e-06, 0.00067817159415456, 1e-9, 1e-11),     # :112
     (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 3, TVD"), 1.226178781197e-06, 0.00070049425851808, 1e-9, 1e-11),  # :120
     (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 4, TVD"), 1.2279971850421e-06, 0.00069848808747002, 1e-9, 1e-11),  # :119
+    # the remaining integrator rows (schemes.lua:104-125): every Butcher tableau of hydro/int/all.lua is pinned through them
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 2 Ralston"), 1.3128886603164e-06, 0.0007200643702763, 1e-9, 1e-11),       # :118
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 2, TVD"), 1.3118684200161e-06, 0.00072699746948317, 1e-9, 1e-11),         # :119
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 2 Heun"), 1.3118684201669e-06, 0.00072699746948318, 1e-9, 1e-11),         # :120
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 4, non-TVD"), 1.2279744811973e-06, 0.0006978340948199, 1e-8, 1e-11),      # :122
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 4, 3/8ths rule"), 7.2560410495091e-05, 0.00073737230229337, 1e-11, 1e-11),  # :125
+    (dict(usePLM="plm athena, recorded face order", integrator="Runge-Kutta 3"), 0.042519919280547, 0.013615227412304, 1e-11, 1e-11),                 # :116
+    (dict(integrator="Runge-Kutta 2 Heun", fluxLimiter="Lax-Wendroff"), 9.6682087934198e-05, None, 1e-10, None),            # :113
+    (dict(integrator="Runge-Kutta 2 Ralston", fluxLimiter="Lax-Wendroff"), 9.6682087934305e-05, None, 1e-10, None),         # :114
+    (dict(integrator="Runge-Kutta 2", fluxLimiter="Lax-Wendroff"), 9.6682087934377e-05, None, 1e-10, None),                 # :115
+    (dict(integrator="Runge-Kutta 4, 3/8ths rule", fluxLimiter="Lax-Wendroff"), 2.4183176943556e-05, None, 1e-10, None),    # :116
+    (dict(integrator="Runge-Kutta 3", fluxLimiter="Lax-Wendroff"), 0.042514748138836, None, 1e-11, None),                   # :106
+    (dict(integrator="Runge-Kutta 2, non-TVD", fluxLimiter="Lax-Wendroff"), 9.6682087934282e-05, None, 1e-10, None),        # :111
 ]
 
 
