@@ -46,6 +46,7 @@ KATS = [
     (dict(flux="euler-hllc", hllcMethod=2, integrator="forward Euler"), 0.00029551600678437, 0.0026034369564245, 1e-11, 1e-12),        # :55
     (dict(flux="euler-hllc", hllcMethod=0, integrator="Runge-Kutta 3, TVD"), 0.00039208124005629, 0.0031547573035925, 1e-10, 1e-12),   # :43
     (dict(flux="euler-hllc", hllcMethod=2, integrator="Runge-Kutta 3, TVD"), 0.00039208124005633, 0.0031547573035925, 1e-10, 1e-12),   # :59
+    (dict(flux="euler-hllc", hllcMethod=1, integrator="Runge-Kutta 3, TVD"), 0.00039208124005635, 0.0031547573035925, 1e-10, 1e-12),   # :51
     # the other flux limiters of hydro/app.lua:614-635 (schemes.lua:61-78): all twenty limiter formulas are pinned
     (dict(integrator="forward Euler", fluxLimiter="smart"), 1.0911857176237e-06, 0.0006129313415327, 1e-8, 1e-12),   # :61
     (dict(integrator="forward Euler", fluxLimiter="ospre"), 0.00019705480525943, 0.0020319762206545, 1e-8, 1e-12),   # :62
