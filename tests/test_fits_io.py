@@ -51,3 +51,26 @@ def test_solver_save_load_round_trip(hydrob200, oracle, tmp_path):
     A.update()
     B.update()
     assert np.array_equal(A.getState(), B.getState())
+
+
+def test_compare_dump_tool(hydrob200, oracle, tmp_path):
+    """tools/compare_dump.py: a dump of the same configuration compares clean, a perturbed one is reported (SURVEY 8c hook)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("compare_dump", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "compare_dump.py"))
+    tool = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tool)
+    from cases import CASES
+    cfg, _ = CASES["C2_kh_rk4tvd_minmod"]
+    S = hydrob200.FiniteVolumeSolver(dict(cfg, backend=oracle.OracleBackend))
+    for _ in range(3):
+        S.update()
+    fn = S.save(str(tmp_path / "ref"))
+    R = hydrob200.FiniteVolumeSolver(dict(cfg, backend=oracle.OracleBackend))
+    for _ in range(3):
+        R.update()
+    assert tool.compare(R, fn) == 0
+    U = S.getState()
+    U[0, 10, 10, 0] *= 1. + 1e-9
+    S.saveBuffer(U, str(tmp_path / "bad_UBuf"))
+    assert tool.compare(R, str(tmp_path / "bad_UBuf.fits")) == 1
