@@ -26,9 +26,9 @@ template<class real_, bool FAST_ = false> struct Euler {
 	static constexpr int eqnId = 0;
 	static constexpr int nS = 6, nI = 5, nW = 5;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/eqn.lua:46
-	struct Params { real gamma, rhoMin, PMin; real gamma_1, invGamma_1, rhoFloor; };   // the last three: production forms only
+	struct Params { real gamma, rhoMin, PMin; real gamma_1, invGamma_1, rhoFloor, quarterGamma_1; };   // the last four: production forms only
 	static HB_HD Params makeParams(const double* p) {
-		return Params{real(p[0]), real(p[1]), real(p[2]), real(p[0] - 1.), real(1. / (p[0] - 1.)), real(p[1] > 1e-5 ? p[1] : 1e-5)};
+		return Params{real(p[0]), real(p[1]), real(p[2]), real(p[0] - 1.), real(1. / (p[0] - 1.)), real(p[1] > 1e-5 ? p[1] : 1e-5), real(.25) * real(p[0] - 1.)};
 	}
 
 	struct Prim { real rho, v[3], P; };

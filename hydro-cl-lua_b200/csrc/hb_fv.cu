@@ -379,7 +379,7 @@ template<class real> struct Fv : FvBase {
 				for (int pass = 0; pass < 2 && !ok; ++pass)
 					for (int cfg = pass == 0 ? cfg0 : 0; !ok && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
 						size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
-						if (marchInfoV[6]) continue;   // configurations with the self-gravity epilogue are taken by hb_fv_add_op only
+						if (marchInfoV[6] & 1) continue;   // configurations with the self-gravity epilogue are taken by hb_fv_add_op only
 						if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
 					}
 			}
@@ -586,7 +586,7 @@ template<class real> struct Fv : FvBase {
 				bool found = false;
 				for (int cfg = 0; !found && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
 					size_t const smem = (size_t)info[4] + sizeof(real) * (size_t)nI * (size_t)marchMaxOps * (size_t)info[5];
-					if (info[6] && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
+					if ((info[6] & 1) && (info[6] & 2) == (marchInfoV[6] & 2) && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
 				}
 				useMarch = found;
 			}
@@ -748,6 +748,18 @@ template<class real> struct Fv : FvBase {
 		}
 		sp.nB = (int)s.beta.size();
 		for (int k = 0; k < sp.nB; ++k) { sp.bPtr[k] = lpool[s.beta[k].k]; sp.bCoef[k] = s.beta[k].coef; }
+		for (int k = 0; k < sp.nA; ++k) {
+			bool const own = (sp.aOwnMask >> k) & 1;
+			sp.tCoef[sp.nT] = sp.aCoef[k];
+			sp.tSlot[sp.nT++] = own ? -1 : sp.nOps;
+			if (!own) sp.opPtr[sp.nOps++] = sp.aPtr[k];
+		}
+		for (int k = 0; k < sp.nB; ++k) {
+			sp.tCoef[sp.nT] = sp.bCoef[k];
+			sp.tBetaMask |= 1 << sp.nT;
+			sp.tSlot[sp.nT++] = sp.nOps;
+			sp.opPtr[sp.nOps++] = sp.bPtr[k];
+		}
 		sp.betaSelf = s.betaSelf;
 		sp.computeL = s.computeL ? 1 : 0;
 		sp.dt = ctl + 1;
@@ -982,7 +994,7 @@ template<class real> struct Fv : FvBase {
 		bool const plm = d.use_plm != 0;
  		ops->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
 		if (useMarch) for (int k = 0; k < 5; ++k) ti[k] = marchInfoV[k];
-		o << "kernel=" << (useCTU ? "ctu(unfused:calcLR,calcFlux,updateCTU,boundaryLR,calcFlux,finish)" : useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : "fv_march(tma)") : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
+		o << "kernel=" << (useCTU ? "ctu(unfused:calcLR,calcFlux,updateCTU,boundaryLR,calcFlux,finish)" : useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : ((marchInfoV[6] & 2) ? "fv_march3(tma,split-barrier)" : "fv_march(tma)")) : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
 		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
 		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : "")) << "\n";

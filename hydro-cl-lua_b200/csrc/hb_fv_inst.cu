@@ -92,6 +92,30 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(2, 2, 1, 32, 4, 0)    /* 64 columns, 3 warps */ \
 	X(3, 6, 1, 64, 1, 0)    /* 192 columns, 7 warps (TMA boxes are at most 256 elements wide) */
 #endif
+// 3-D second-generation marching kernel (hb_fv_march3.cuh): X(index, TY, KM, VAR); these come first in the 3-D cfg numbering
+#ifdef HB_STRICT
+#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 8, 32, 0) X(3, 6, 64, 0) X(4, 15, 64, 32) X(5, 11, 64, 32) X(6, 8, 32, 32) X(7, 6, 64, 32)
+#else
+#if defined(HB_DEV)
+#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0)
+#else
+#define HB_MARCH3N_LIST(X) \
+	X(0, 15, 64, 0)    /* 32 x 15 columns, 64 planes per CTA, 16 warps at 128 registers (fits with at most two staged RK operands) */ \
+	X(1, 11, 64, 0)    /* 32 x 11 columns, 12 warps at 168 registers (classic RK4's four operands fit) */ \
+	X(2, 8, 64, 0)     /* 32 x 8 columns, 9 warps */ \
+	X(3, 6, 64, 0)     /* 32 x 6 columns, 7 warps: fits 8-variable equations (MHD) with four operands */ \
+	X(4, 15, 128, 0)   /* 128 planes per CTA */ \
+	X(5, 11, 32, 0)    /* 32 planes per CTA */ \
+	X(6, 15, 64, 32)   /* the same with the self-gravity source in the epilogue (chosen by hb_fv_add_op, never by the auto selection) */ \
+	X(7, 11, 64, 32) \
+	X(8, 8, 64, 32) \
+	X(9, 6, 64, 32)
+#endif
+#endif
+constexpr int kMarch3N =
+#define HB_X(i, ty, km, var) +1
+	0 HB_MARCH3N_LIST(HB_X);
+#undef HB_X
 // 2-D warp-per-pencil kernel (hb_fv_march2d.cuh): X(index, NW, KM, MINB); these come first in the 2-D cfg numbering
 #ifdef HB_STRICT
 #define HB_MARCH2W_LIST(X) X(0, 4, 32, 1) X(1, 4, 32, 17)
@@ -141,6 +165,42 @@ cudaError_t launchMarchLim(int lim, const CUtensorMap* tmap, int padX, GridP<rea
 	if (lim == 8) return launchMarch<DIM, 8, C>(tmap, padX, g, sp, ep, chunkSel, st);      // minmod
 	if (lim == 18) return launchMarch<DIM, 18, C>(tmap, padX, g, sp, ep, chunkSel, st);    // superbee
 	return cudaErrorInvalidValue;
+}
+template<int LIM, class C>
+cudaError_t launchMarch3(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
+	typedef March3Geom<C, real> G;
+	auto kern = fv_march3<Eqn, LIM, C, MODE>;
+	int nOps = sp.nB;
+	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
+	size_t const smemMax = G::template smemBytes<Eqn::nI>(2 * HB_MAX_TERMS);
+	static bool attrSet = false;
+	if (!attrSet) {
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemMax < kSmemLimit ? smemMax : kSmemLimit));
+		if (e != cudaSuccess) return e;
+		attrSet = true;
+	}
+	if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+	long long const ntx = (g.N[0] + G::TX - 1) / G::TX;
+	long long const nty = (g.N[1] + G::TY - 1) / G::TY;
+	long long nm = (g.N[2] + C::KM - 1) / C::KM;
+	if (chunkSel == 1) nm = nm < 2 ? nm : 2;
+	else if (chunkSel == 2) nm = nm > 2 ? nm - 2 : 0;
+	if (nm == 0) return cudaSuccess;
+	kern<<<(unsigned)(ntx * nty * nm), G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX, chunkSel);
+	return cudaGetLastError();
+}
+template<class C>
+cudaError_t launchMarch3Lim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
+	if (lim == 8) return launchMarch3<8, C>(tmap, padX, g, sp, ep, chunkSel, st);
+	if (lim == 18) return launchMarch3<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
+	return cudaErrorInvalidValue;
+}
+template<class C> void march3InfoCfg(int box[4], int info[7]) {
+	typedef March3Geom<C, real> G;
+	box[0] = G::BX; box[1] = G::BY; box[2] = 1; box[3] = Eqn::nI;
+	info[0] = G::TX; info[1] = G::TY; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
+	info[5] = G::NCOL * 32; info[6] = (C::GRAV ? 1 : 0) | 2;   // bit 1: fv_march3
 }
 template<int LIM, class C>
 cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
@@ -203,7 +263,10 @@ template<int DIM, class C> void marchInfoCfg(int box[4], int info[7]) {
 bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[7]) {
 	if (!plm || flim || (lim != 8 && lim != 18) || dim < 2 || cfg < 0) return false;
 	cfg = remapCfg(dim, cfg);
-#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) { marchInfoCfg<3, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
+#define HB_X(i, ty, km, var) if (dim == 3 && cfg == i) { march3InfoCfg<March3Cfg<ty, km, var>>(box, info); return true; }
+	HB_MARCH3N_LIST(HB_X)
+#undef HB_X
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == kMarch3N + i) { marchInfoCfg<3, MarchCfg<wx, ty, km, mb, var>>(box, info); return true; }
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) return false; }
 #undef HB_X
 #define HB_X(i, nw, km, mb) if (cfg == i) { march2WInfoCfg<March2Cfg<nw, km, mb>>(box, info); return true; }
@@ -216,7 +279,10 @@ bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int i
 }
 cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
 	cfg = remapCfg(dim, cfg);
-#define HB_X(i, wx, ty, km, mb, var) if (cfg == i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
+#define HB_X(i, ty, km, var) if (dim == 3 && cfg == i) return launchMarch3Lim<March3Cfg<ty, km, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
+	HB_MARCH3N_LIST(HB_X)
+#undef HB_X
+#define HB_X(i, wx, ty, km, mb, var) if (cfg == kMarch3N + i) return launchMarchLim<3, MarchCfg<wx, ty, km, mb, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
 	if (dim == 3) { HB_MARCH3_LIST(HB_X) }
 #undef HB_X
 #define HB_X(i, nw, km, mb) if (cfg == i) return launchMarch2WLim<March2Cfg<nw, km, mb>>(lim, tmap, padX, g, sp, ep, chunkSel, st);

@@ -60,6 +60,12 @@ template<class real> struct StageP {
 	int fluxParam;         // euler-hllc: hllcMethod
 	const real* gravPot;   // optional: the potential (ePot of Uin) of the self-gravity op; the tile kernel adds calcGravityDeriv (selfgrav.cl:53-76) to L
 	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded, 4 'plm prim', 5 'plm cons with flux'
+	// the same RK combination as a compact list in evaluation order (alpha terms, then beta terms; rk.lua:96-112), for kernels that loop
+	// over it (fv_march3): term t adds tCoef[t] (x dt when bit t of tBetaMask is set) times the stage input (tSlot[t] < 0) or staged operand tSlot[t]
+	int nT, tBetaMask, nOps;
+	int tSlot[2 * HB_MAX_TERMS];
+	double tCoef[2 * HB_MAX_TERMS];
+	const real* opPtr[2 * HB_MAX_TERMS];
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {

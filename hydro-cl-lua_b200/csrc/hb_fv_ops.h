@@ -7,6 +7,7 @@
 #include "hb_fv_kernels.cuh"
 #include "hb_fv_march.cuh"
 #include "hb_fv_march2d.cuh"
+#include "hb_fv_march3.cuh"
 #include "hb_ops_kernels.cuh"
 #include "hb_ctu_kernels.cuh"
 

@@ -18,6 +18,7 @@
 #include "hb_roe.cuh"
 #include "hb_eqn_euler.cuh"
 #include "hb_eqn_mhd.cuh"
+#include <cstring>
 
 #if defined(__CUDACC__)
 #define HB_NOINLINE __host__ __device__ __noinline__
@@ -44,6 +45,54 @@ template<class real, int LIM, bool FAST> HB_HD real plmHalfSlopeT(int lim, real 
 		return dL * dR > real(0) ? sg * m : real(0);
 	} else {
 		return plmHalfSlope<real>(lim, UL, U, UR);
+	}
+}
+
+// Both face states of cell b from its neighbours a, c ('plm cons', plm.cl:56-76): lo = U - .5 sigma, hi = U + .5 sigma.
+// Production minmod in double: sigma/2 = h m with m = the difference of smaller magnitude (ONE FP64 compare) and h = .5 when the
+// two differences have the same sign bit, else 0 (integer test on the high words; a zero difference gives m = 0 either way), so a
+// face state is one FMA: 4 FP64 instructions per variable (2 DADD, DSETP, 2 DFMA share) instead of 8.
+HB_HD bool sameSignBit(double a, double b) {
+#if defined(__CUDA_ARCH__)
+	return (__double2hiint(a) ^ __double2hiint(b)) >= 0;
+#else
+	return std::signbit(a) == std::signbit(b);
+#endif
+}
+// x > 0 and the high 32 bits of x above those of the (positive) threshold t: implies x >= t (doubles); plain comparison in float
+HB_HD bool hiWordAbove(double x, double t) {
+#if defined(__CUDA_ARCH__)
+	return __double2hiint(x) > __double2hiint(t);
+#else
+	int64_t a, b; memcpy(&a, &x, 8); memcpy(&b, &t, 8);
+	return int32_t(a >> 32) > int32_t(b >> 32);
+#endif
+}
+HB_HD bool hiWordAbove(float x, float t) { return x >= t; }
+template<class real, int LIM, bool FAST> HB_HD void plmCellFacesT(int lim, real a, real b, real c, real& lo, real& hi) {
+	if constexpr (FAST && LIM == 8 && sizeof(real) == 8) {
+		real const dL = b - a, dR = c - b;
+		real const m = rabs(dL) < rabs(dR) ? dL : dR;
+		lo = b; hi = b;
+		if (sameSignBit(dL, dR)) { lo = fma(real(-.5), m, b); hi = fma(real(.5), m, b); }
+	} else {
+		real const s = plmHalfSlopeT<real, LIM, FAST>(lim, a, b, c);
+		lo = b - s;
+		hi = b + s;
+	}
+}
+// The two face states of the interface between cells b and c from the four-cell stencil a, b, c, d: UL = b + .5 sigma(b), UR = c - .5 sigma(c).
+template<class real, int LIM, bool FAST> HB_HD void plmFacesT(int lim, real a, real b, real c, real d, real& UL, real& UR) {
+	if constexpr (FAST && LIM == 8 && sizeof(real) == 8) {
+		real const d1 = b - a, d2 = c - b, d3 = d - c;
+		real const m1 = rabs(d1) < rabs(d2) ? d1 : d2;
+		real const m2 = rabs(d2) < rabs(d3) ? d2 : d3;
+		UL = b; UR = c;
+		if (sameSignBit(d1, d2)) UL = fma(real(.5), m1, b);
+		if (sameSignBit(d2, d3)) UR = fma(real(-.5), m2, c);
+	} else {
+		UL = b + plmHalfSlopeT<real, LIM, FAST>(lim, a, b, c);
+		UR = c - plmHalfSlopeT<real, LIM, FAST>(lim, b, c, d);
 	}
 }
 
@@ -94,11 +143,13 @@ HB_HD bool eulerRoeFluxCore(typename Eqn::real (&F)[5], typename Eqn::Params con
 	real v[3];
 	#pragma unroll
 	for (int q = 0; q < 3; ++q) v[q] = vL[q] * wL + vR[q] * wR;
-	real const H = (HL * iL) * wL + (HR * iR) * wR;
+	real const H = (HL * yL + HR * yR) * iS;                 // hTotalL wL + hTotalR wR: (1/rho) sqrt(rho) = 1/sqrt(rho)
 	real const eK = real(.5) * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
 	real const h = H - eK;
-	// the reference's special branches (euler.cl:357-426: rhoEpsilon = 1e-5; :442,501: rho < rhoMin)
-	bool const regular = rhoL >= s.rhoFloor && rhoR >= s.rhoFloor && h >= real(1e-5);
+	// the reference's special branches (euler.cl:357-426: rhoEpsilon = 1e-5; :442,501: rho < rhoMin).  The test is conservative and
+	// on the integer pipe: "high word above the threshold's high word" implies x >= threshold for positive x; a state pair within 2^-20
+	// of a threshold, a negative or a zero operand fail it and take the literal code, which is right for every state.
+	bool const regular = hiWordAbove(rhoL, s.rhoFloor) && hiWordAbove(rhoR, s.rhoFloor) && hiWordAbove(h, real(1e-5));
 	real const Cs2 = g1 * h;
 	real Cs, yC;                                             // Cs, 1 / Cs
 	fastRsqrt(Cs2, yC, Cs);
@@ -107,21 +158,23 @@ HB_HD bool eulerRoeFluxCore(typename Eqn::real (&F)[5], typename Eqn::Params con
 	real dm[3];
 	#pragma unroll
 	for (int q = 0; q < 3; ++q) dm[q] = UR[1 + q] - UL[1 + q];
-	real const G = g1 * (eK * drho - (v[0] * dm[0] + v[1] * dm[1] + v[2] * dm[2]) + dE) * iCs2;   // G / Cs^2
-	real const K = (dm[n] - v[n] * drho) * yC;                                                    // K / Cs^2
-	real const b0 = rabs(v[n] - Cs) * (real(.5) * (G - K));
-	real const b4 = rabs(v[n] + Cs) * (real(.5) * (G + K));
-	real const lam = rabs(v[n]);
-	real const b1 = lam * (drho - G);
-	real const b2 = lam * (dm[t1] - v[t1] * drho);
-	real const b3 = lam * (dm[t2] - v[t2] * drho);
-	real const sum = b0 + b1 + b4, dif = (b4 - b0) * Cs;
+	// wave strengths times |lambda|, pre-multiplied by the flux's 1/2: b_j = .5 |lambda_j| alpha_j
+	real const Gq = s.quarterGamma_1 * (eK * drho - (v[0] * dm[0] + v[1] * dm[1] + v[2] * dm[2]) + dE) * iCs2;   // G / (4 Cs^2)
+	real const Kq = (dm[n] - v[n] * drho) * (real(.25) * yC);                                                   // K / (4 Cs^2)
+	real const b0 = rabs(v[n] - Cs) * (Gq - Kq);
+	real const b4 = rabs(v[n] + Cs) * (Gq + Kq);
+	real const lamh = real(.5) * rabs(v[n]);
+	real const b1 = lamh * fma(real(-4.), Gq, drho);
+	real const b2 = lamh * (dm[t1] - v[t1] * drho);
+	real const b3 = lamh * (dm[t2] - v[t2] * drho);
+	real const b04 = b0 + b4;
+	real const sum = b04 + b1, dif = (b4 - b0) * Cs;
 	real const vnL = vL[n], vnR = vR[n];
-	F[0] = real(.5) * ((UL[1 + n] + UR[1 + n]) - sum);
-	F[1 + n] = real(.5) * ((UL[1 + n] * vnL + UR[1 + n] * vnR + (PL + PR)) - (sum * v[n] + dif));
-	F[1 + t1] = real(.5) * ((UL[1 + t1] * vnL + UR[1 + t1] * vnR) - (sum * v[t1] + b2));
-	F[1 + t2] = real(.5) * ((UL[1 + t2] * vnL + UR[1 + t2] * vnR) - (sum * v[t2] + b3));
-	F[4] = real(.5) * ((HL * vnL + HR * vnR) - ((b0 + b4) * H + dif * v[n] + b1 * eK + b2 * v[t1] + b3 * v[t2]));
+	F[0] = fma(real(.5), UL[1 + n] + UR[1 + n], -sum);
+	F[1 + n] = fma(real(.5), (UL[1 + n] * vnL + UR[1 + n] * vnR) + (PL + PR), -fma(sum, v[n], dif));
+	F[1 + t1] = fma(real(.5), UL[1 + t1] * vnL + UR[1 + t1] * vnR, -fma(sum, v[t1], b2));
+	F[1 + t2] = fma(real(.5), UL[1 + t2] * vnL + UR[1 + t2] * vnR, -fma(sum, v[t2], b3));
+	F[4] = fma(real(.5), HL * vnL + HR * vnR, -(b04 * H + dif * v[n] + b1 * eK + b2 * v[t1] + b3 * v[t2]));
 	return regular;
 }
 

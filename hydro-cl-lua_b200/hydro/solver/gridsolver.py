@@ -48,7 +48,9 @@ class GridSolver(SolverBase):
 
     def initObjs(self, args):
         super().initObjs(args)
-        # initCond-supplied domain overrides cfg (solverbase.lua:1546-1560)
+        # initCond-supplied domain (solverbase.lua:1546-1560).  DELIBERATE DEVIATION: the reference lets the initCond
+        # overwrite cfg mins / maxs / boundary unconditionally; here an explicit cfg entry wins, so that a parity case can put any
+        # initial condition on any domain and boundary set.  Without the cfg entry the behaviour is the reference's.
         if self.initCond.mins is not None and "mins" not in args:
             self.mins = [float(v) for v in self.initCond.mins]
         if self.initCond.maxs is not None and "maxs" not in args:
@@ -61,7 +63,8 @@ class GridSolver(SolverBase):
         if self.usePLM not in plmIds:
             raise NotImplementedError("usePLM=%r: 'piecewise constant', 'plm cons', 'plm prim' and 'plm athena' are built" % (self.usePLM,))
         self.plmId = plmIds[self.usePLM]
-        self.slopeLimiter = hydro_app.limiterIndex(args.get("slopeLimiter", "minmod")) if self.usePLM else 0
+        # gridsolver.lua:106: `limiterNames:find(args.slopeLimiter) or 1` -- an omitted slopeLimiter is 'donor cell' (zero slope)
+        self.slopeLimiter = hydro_app.limiterIndex(args.get("slopeLimiter") or "donor cell") if self.usePLM else 0
         if self.usePLM and self.fluxLimiter != 0:
             # gridsolver.lua:119: "are you sure you want to use flux and slope limiters at the same time?"
             raise ValueError("usePLM requires fluxLimiter='donor cell' (gridsolver.lua:119)")
@@ -183,6 +186,9 @@ class GridSolver(SolverBase):
     def calcExactError(self, numStates=None):
         """gridsolver.lua:1337-1366, including its loop bounds (imax = gridSize - 2*ghost - 1 on the ghost-inclusive
         size, i.e. the last two interior cells per axis are skipped) and the division by the full interior volume."""
+        if self.comm is not None:
+            # the reference's loop bounds are on the global grid and the sum is over all cells: gather first
+            raise NotImplementedError("calcExactError on a slab-decomposed solver: gather with getGlobalInterior() and use a single-device solver")
         eqn = self.eqn
         numStates = numStates or eqn.numIntStates
         U = self.getState()

@@ -37,6 +37,10 @@ CASES = {
                                  usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 2),
 }
 
+# gridsolver.lua:106: usePLM without a slopeLimiter key is 'donor cell' (zero slopes: first order), not minmod
+CASES["C2_kh_plm_default_limiter"] = (dict(eqn="euler", dim=2, gridSize=[40, 24], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                                           integrator="Runge-Kutta 2, TVD", cfl=.15), 8)
+
 # the other interface fluxes of the calcFluxForInterface slot (hydro/flux/hll.cl 'Davis direct bounded', rusanov.cl)
 CASES["F2_sod_hll_fe"] = (dict(eqn="euler", dim=1, gridSize=[256], initCond="Sod", flux="hll", integrator="forward Euler", cfl=.3), 60)
 CASES["F2_kh_hll_plm_rk4"] = (dict(eqn="euler", dim=2, gridSize=[64, 40], initCond="Kelvin-Helmholtz", flux="hll", usePLM="plm cons",

@@ -242,7 +242,10 @@ def test_march_kernel_fast_close_to_tile_kernel(hydrob200, name):
 def test_march_is_default_for_plm(hydrob200):
     cfg, _ = CASES["C4_sphere_rk4"]
     S = hydrob200.FiniteVolumeSolver(cfg)
-    assert "fv_march(tma)" in S.backend.describe(), S.backend.describe()
+    assert "fv_march3(tma" in S.backend.describe(), S.backend.describe()      # 3-D: the second-generation marching kernel
+    cfg, _ = CASES["C2_kh_rk4tvd_minmod"]
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    assert "fv_march2d(warp-per-pencil" in S.backend.describe(), S.backend.describe()
     cfg, _ = CASES["C1_sod_fe_superbee"]
     S = hydrob200.FiniteVolumeSolver(cfg)
     assert "fv_stage(tile)" in S.backend.describe()

@@ -13,6 +13,8 @@ hb = import_module("hydro-cl-lua_b200._lib")
 WORK = {
     "C4": (dict(eqn="euler", dim=3, gridSize=[512, 512, 128], mins=[-2] * 3, maxs=[2, 2, -1], initCond="sphere", usePLM="plm cons",
                 slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 640 / 4),
+    "C4r3": (dict(eqn="euler", dim=3, gridSize=[512, 512, 128], mins=[-2] * 3, maxs=[2, 2, -1], initCond="sphere", usePLM="plm cons",
+                  slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.1), 640 / 4),
     "C2": (dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                 slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 840 / 4),
     "C3": (dict(eqn="mhd", dim=2, gridSize=[2048, 2048], initCond="Orszag-Tang", usePLM="plm cons",
