@@ -27,9 +27,11 @@ template<class real_, bool FAST_ = false> struct MHD {
 	static constexpr int eqnId = 1;
 	static constexpr int nS = 10, nI = 8, nW = 7;
 	static constexpr bool roeUseFluxFromCons = true;   // hydro/eqn/mhd.lua:19
-	struct Params { real gamma, mu0; real g2_g1, iMu0, iG1; };   // the last three: production forms only (gamma_2/gamma_1, 1/mu0, 1/gamma_1)
+	// l23s: +1 = the reference's left eigenvector entry l23 = .5 betaZ (mhd.cl:621, the parity contract), -1 = Stone et al. 2008's -.5 betaZ
+	// (eqn_params[2] < 0; with the reference's sign R L != I whenever both transverse field components are non-zero: tests/test_mhd_alfven.py)
+	struct Params { real gamma, mu0; real g2_g1, iMu0, iG1; real l23s; };   // g2_g1, iMu0, iG1: production forms only (gamma_2/gamma_1, 1/mu0, 1/gamma_1)
 	static HB_HD Params makeParams(const double* p) {
-		return Params{real(p[0]), real(p[1]), real((p[0] - 2.) / (p[0] - 1.)), real(1. / p[1]), real(1. / (p[0] - 1.))};
+		return Params{real(p[0]), real(p[1]), real((p[0] - 2.) / (p[0] - 1.)), real(1. / p[1]), real(1. / (p[0] - 1.)), real(p[2] < 0. ? -1. : 1.)};
 	}
 
 	struct Prim { real rho, v[3], P, B[3]; };
@@ -223,7 +225,8 @@ template<class real_, bool FAST_ = false> struct MHD {
 		real const l16 = AHatS * QStarY - alphaF2 * By;
 		real const l17 = AHatS * QStarZ - alphaF2 * Bz;
 		real const l21 = real(.5) * (vy * betaZ - vz * betaY);
-		real const l23 = real(.5) * betaZ;
+		real l23 = real(.5) * betaZ;
+		if (s.l23s < real(0)) l23 = -l23;
 		real const l24 = real(.5) * betaY;
 		real const l26 = real(-.5) * sqrtRho * betaZ * sbx;
 		real const l27 = real(.5) * sqrtRho * betaY * sbx;

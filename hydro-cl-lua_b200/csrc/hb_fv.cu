@@ -106,6 +106,7 @@ struct StagePlan {
 	std::vector<Term> beta;        // k = physical L buffer
 	double betaSelf; bool computeL; bool last;
 	int readsU, readsL;            // words per cell (x nI) for hb_fv_describe
+	int marchCfg = -1;             // marching-kernel configuration of this stage (-1: the solver's): a stage with few RK operands fits a larger tile
 };
 
 // Static plan of one update for a Butcher tableau (hydro/int/rk.lua:17-44 decides the same "needed later" sets).
@@ -209,6 +210,7 @@ template<class real> struct Fv : FvBase {
 	double* fixedDev = nullptr;            // [6][HB_FIXED_STRIDE] states of the 'fixed' faces
 	std::vector<real*> upool, lpool;       // element (i=0,j=0,k=0) of variable 0; the allocation starts padX elements earlier
 	std::vector<CUtensorMap> umaps;        // TMA descriptor of every U buffer (marching kernel)
+	std::map<int, std::vector<CUtensorMap>> umapSets;   // the same for the configurations single stages run with (StagePlan::marchCfg): other box shapes
 	int padX = 0;                          // leading pad of every row: interior cell i=2 sits on a 128-byte boundary
 	long long vstride = 0;                 // elements between variables (pitchX * S1 * S2)
 	bool useMarch = false;
@@ -389,6 +391,31 @@ template<class real> struct Fv : FvBase {
 			if (useMarch) {
 				umaps.resize(nU);
 				for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &umaps[k])) return r;
+				// per-stage configuration: the shared-memory budget is set by the stage's own operand count, so a stage with fewer RK operands
+				// than the largest (classic RK4: 0, 1, 1, 4) takes the first (= preferred) configuration that fits IT.  Same planes per CTA as the
+				// solver's configuration (the overlapped slab exchange selects chunks by that number); $HB_MARCH_PER_STAGE=0 switches it off.
+				const char* ps = getenv("HB_MARCH_PER_STAGE");
+				if (!ps || atoi(ps) != 0) {
+					int const saveBox[4] = {marchBox[0], marchBox[1], marchBox[2], marchBox[3]};
+					for (auto& s : plan) {
+						int n = (int)s.beta.size();
+						for (auto& t : s.alpha) if (t.k != s.uIn) ++n;
+						int box[4], info[7];
+						for (int cfg = cfg0; cfg < marchCfg && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
+							size_t const smem = (size_t)info[4] + sizeof(real) * (size_t)nI * (size_t)n * (size_t)info[5];
+							if ((info[6] & 1) || info[2] != marchInfoV[2] || smem > 232448 - 1024) continue;
+							s.marchCfg = cfg;
+							if (!umapSets.count(cfg)) {
+								memcpy(marchBox, box, sizeof(box));
+								std::vector<CUtensorMap>& v = umapSets[cfg];
+								v.resize(nU);
+								for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &v[k])) return r;
+								memcpy(marchBox, saveBox, sizeof(saveBox));
+							}
+							break;
+						}
+					}
+				}
 			}
 		}
 		if (d.use_ctu) {
@@ -589,6 +616,7 @@ template<class real> struct Fv : FvBase {
 					if ((info[6] & 1) && (info[6] & 2) == (marchInfoV[6] & 2) && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
 				}
 				useMarch = found;
+				for (auto& sPlan : plan) sPlan.marchCfg = -1;   // one configuration (the one with the gravity epilogue) for every stage
 			}
 		}
 		else hasNoDiv = true;
@@ -804,6 +832,9 @@ template<class real> struct Fv : FvBase {
 		return HB_OK;
 	}
 
+	int stageCfg(StagePlan const& s) const { return s.marchCfg >= 0 ? s.marchCfg : marchCfg; }
+	const CUtensorMap* stageMap(StagePlan const& s) { return s.marchCfg >= 0 ? &umapSets[s.marchCfg][s.uIn] : &umaps[s.uIn]; }
+
 	// integrator:integrate(dt, calcDeriv) + boundary/constrainU after every stage (rk.lua:91-165, fe.lua:33-49)
 	int runStages() {
 		bool const rk = d.rk_order >= 1;
@@ -846,13 +877,13 @@ template<class real> struct Fv : FvBase {
 			}
 			if (useMarch && overlap && opsV.empty()) {   // (with ops the exchange stays in-stream)
 				int const nv = rk ? nI : nS;
-				HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 1, st()));
+				HB_CUDA(ops->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 1, st()));
 				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, true, st()));
 				HB_CUDA(cudaEventRecord(evRim, st()));
 				HB_CUDA(cudaStreamWaitEvent(commStream, evRim, 0));
 				if (int r = exchange(upool[s.uOut], nv, commStream)) return r;
 				HB_CUDA(cudaEventRecord(evXchg, commStream));
-				HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 2, st()));
+				HB_CUDA(ops->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 2, st()));
 				if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, false, st()));
 				HB_CUDA(cudaStreamWaitEvent(st(), evXchg, 0));
@@ -861,7 +892,7 @@ template<class real> struct Fv : FvBase {
 			}
 			tlsStageLaunches = 1;
 			if (useCTU) { if (int r = ctuStage(sp)) return r; }
-			else if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[s.uIn], padX, grid, sp, d.eqn_params, 0, st()));
+			else if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 0, st()));
 			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches += tlsStageLaunches;
@@ -878,7 +909,10 @@ template<class real> struct Fv : FvBase {
 		}
 		if (plan.back().uOut != 0) {   // order <= 1: ping-pong
 			std::swap(upool[0], upool[plan.back().uOut]);
-			if (useMarch) std::swap(umaps[0], umaps[plan.back().uOut]);
+			if (useMarch) {
+				std::swap(umaps[0], umaps[plan.back().uOut]);
+				for (auto& kv : umapSets) std::swap(kv.second[0], kv.second[plan.back().uOut]);
+			}
 		}
 		if (hasNoDiv) {
 			// NoDiv changes B after the last stage: the CFL reduction fused into that stage would be stale
@@ -997,7 +1031,9 @@ template<class real> struct Fv : FvBase {
 		o << "kernel=" << (useCTU ? "ctu(unfused:calcLR,calcFlux,updateCTU,boundaryLR,calcFlux,finish)" : useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : ((marchInfoV[6] & 2) ? "fv_march3(tma,split-barrier)" : "fv_march(tma)")) : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
 		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
-		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : "")) << "\n";
+		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : ""));
+		if (useMarch) { o << " stageCfgs="; for (size_t i = 0; i < plan.size(); ++i) o << (i ? "," : "") << stageCfg(plan[i]); }
+		o << "\n";
 		int words = 0;
 		for (size_t i = 0; i < plan.size(); ++i) {
 			auto& s = plan[i];

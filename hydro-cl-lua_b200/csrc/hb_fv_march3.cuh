@@ -54,18 +54,15 @@ template<class C, class real> struct March3Geom {
 HB_D void mbarArrive(uint64_t* bar) {
 	asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" :: "r"(smemAddr(bar)) : "memory");
 }
-// wait with a suspend-time hint: the warp sleeps in the barrier unit instead of re-issuing the test (the hint bounds the sleep, the
-// phase completion ends it)
-HB_D void mbarWaitSleep(uint64_t* bar, uint32_t parity) {
-	asm volatile(
-		"{\n"
-		".reg .pred P1;\n"
-		"LAB_WAIT:\n"
-		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-		"@P1 bra DONE;\n"
-		"bra LAB_WAIT;\n"
-		"DONE:\n"
-		"}" :: "r"(smemAddr(bar)), "r"(parity), "r"(20000u) : "memory");
+// wait of a warp that is not on the critical path (the halo warp waiting for the column warps): back off between tests so that the
+// polling does not take issue slots from the working warps
+HB_D void mbarWaitBackoff(uint64_t* bar, uint32_t parity) {
+	uint32_t done = 0;
+	while (true) {
+		asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}" : "=r"(done) : "r"(smemAddr(bar)), "r"(parity) : "memory");
+		if (done) break;
+		__nanosleep(256);
+	}
 }
 
 // Low-face Roe flux of the cell at ring offset `o` along the axis with ring stride `st` (1: x, BX: y): face states from the
@@ -225,7 +222,7 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 			}
 			__syncwarp();
 			if (lane == 0) mbarArrive(&xbar[it & 1]);
-			mbarWaitSleep(&xbar[it & 1], uint32_t(it >> 1) & 1u);
+			mbarWaitBackoff(&xbar[it & 1], uint32_t(it >> 1) & 1u);
 			// every warp has left plane k-1 (its last reader is the epilogue of iteration k-1): its slot takes plane k+3
 			if (lane == 0 && k + 3 <= ke + 1) {
 				asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -318,7 +315,7 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) Fz[q] = 0;
 			}
-			mbarWaitSleep(&xbar[it & 1], uint32_t(it >> 1) & 1u);
+			mbarWait(&xbar[it & 1], uint32_t(it >> 1) & 1u);
 			// ---- flux differences (fvsolver.cl:97-123) and the epilogue of cell k
 			if (own && inside) {
 				real U0[nI];

@@ -299,7 +299,7 @@ HB_HD void mhdRoeFluxFast(typename Eqn::real (&F)[8], typename Eqn::Params const
 	real const symS = alphaS2 * T + drho * (Css * Cs + afpb) - dB1 * (AHatF * QStarY + alphaS2 * By) - dB2 * (AHatF * QStarZ + alphaS2 * Bz);
 	real const antiF = drho * (Cff * vx - Qs2 * vqstr) - dm0 * Cff + Qs2 * qm;
 	real const antiS = drho * (Css * vx + Qf2 * vqstr) - dm0 * Css - Qf2 * qm;
-	real const A15 = real(.5) * (drho * (vy * betaZ - vz * betaY) + dm1 * betaZ + dm2 * betaY);
+	real const A15 = real(.5) * (drho * (vy * betaZ - vz * betaY) + dm1 * (betaZ * s.l23s) + dm2 * betaY);   // l23s: hb_eqn_mhd.cuh Params
 	real const B15 = real(.5) * sqrtRho * sbx * (dB2 * betaY - dB1 * betaZ);
 	real const r3 = drho * (real(1.) - norm3 * (real(.5) * vSq - g2_g1 * X)) + norm3 * (mv - dE + dB1 * By + dB2 * Bz);
 	// ---- wave strengths a_j = -.5 |lambda_j| dUe_j (roe.cl:91-134 without the limiter term), summed / differenced by pairs

@@ -38,7 +38,10 @@ class MHD(Equation):
         return v["mu0"] / (v["kilogram"] * v["meter"] / (v["coulomb"] * v["coulomb"]))
 
     def eqnParams(self):
-        return [self.vars["heatCapacityRatio"], self.mu0_eff]
+        """{gamma, mu0 / unit_kg_m_per_C2, sign of the left-eigenvector entry l23}.  The reference's eigen_leftTransform has
+        l23 = +.5 betaZ (mhd.cl:621); Stone et al. 2008 -- and R L = I -- need -.5 betaZ.  The reference's sign is the parity contract and
+        the default; eqnArgs = {stone2008_l23 = true} selects the corrected one (tests/test_mhd_alfven.py shows what it changes)."""
+        return [self.vars["heatCapacityRatio"], self.mu0_eff, -1. if self.args.get("stone2008_l23") else 1.]
 
     def consFromPrim(self, W):
         g = self.vars["heatCapacityRatio"]

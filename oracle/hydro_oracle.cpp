@@ -145,6 +145,7 @@ template<class real> struct solver_t {
 	int dim;
 	real heatCapacityRatio, rhoMin, PMin;
 	real mu0_eff;
+	bool l23Negate = false;   // MHD: eqn_params[2] < 0 (see eigen_leftTransform)
 	int f_eqn;                                   // hydro/eqn/einstein.lua:42-48 option index
 	real a_convCoeff, d_convCoeff, V_convCoeff;  // adm3d.lua:218-226
 };
@@ -567,7 +568,10 @@ template<class real_> struct MHD {
 		real const l16 = AHatS * QStarY - alphaF2 * B.y;
 		real const l17 = AHatS * QStarZ - alphaF2 * B.z;
 		real const l21 = real(.5) * (v.y * betaZ - v.z * betaY);
-		real const l23 = real(.5) * betaZ;
+		// mhd.cl:621 has `l23 = .5 * betaZ`; Stone et al. 2008 (and R L = I) need -.5 betaZ: tests/test_mhd_alfven.py.  The reference's sign is
+		// the parity contract and the default; eqn_params[2] < 0 selects the corrected sign.
+		real l23 = real(.5) * betaZ;
+		if (s.l23Negate) l23 = -l23;
 		real const l24 = real(.5) * betaY;
 		real const l26 = real(-.5) * sqrtRho * betaZ * sbx;
 		real const l27 = real(.5) * sqrtRho * betaY * sbx;
@@ -855,6 +859,7 @@ template<class Eqn> struct Solver : SolverBase {
 		solver.stepsize[0] = 1; solver.stepsize[1] = S[0]; solver.stepsize[2] = S[0] * S[1];   // gridsolver.lua:377-380
 		solver.numGhost = g; solver.dim = dim;
 		solver.heatCapacityRatio = d.gamma; solver.rhoMin = d.rhoMin; solver.PMin = d.PMin; solver.mu0_eff = d.mu0_eff;
+		if (d.eqn == 1) solver.l23Negate = d.eqn_params[2] < 0;
 		solver.f_eqn = int(d.eqn_params[0]); solver.a_convCoeff = real(d.eqn_params[1]); solver.d_convCoeff = real(d.eqn_params[2]);
 		solver.V_convCoeff = real(d.eqn_params[3]);
 		// fvsolver.lua:61-63 useFluxLimiter = fluxLimiter > 1 (1-based) and flux.usesFluxLimiter
