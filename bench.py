@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- cell-updates/s of the explicit finite-volume update (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4|C2|C3|C5]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload C4|C4M|C2|C3|C5] [--precision float]
+                    [--scaling weak|strong] [--per-gpu-planes P] [--no-parity]
 
 Workload (default C4, the config BASELINE.json quotes "at 1/2/4/8 B200" on): 3-D Euler spherical blast, Roe + PLM
 ('plm cons', minmod) + classic RK4, double precision, freeflow boundaries, 512^3 interior cells PER GPU (weak
@@ -39,15 +40,20 @@ WORKLOADS = {
     "C4": dict(name="3D Euler spherical blast, Roe+PLM(minmod)+RK4, double, freeflow, 512^3 per GPU (z slabs)",
                cfg=dict(eqn="euler", dim=3, gridSize=[512, 512, 512], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
                         usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1),
-               words=16, nI=5, stages=4, cpu_sample=[192, 192, 192]),
+               words=16, nI=5, stages=4, cpu_sample=[256, 256, 256], parity=(2, 32)),
+    # the north_star's second 3-D target: ideal MHD (hydro/eqn/mhd.cl:296-783) through the same fused stage kernel
+    "C4M": dict(name="3D ideal-MHD Orszag-Tang (z-invariant data on a 3-D grid), Roe+PLM(minmod)+RK4, double, periodic, 384^3 per GPU (z slabs)",
+                cfg=dict(eqn="mhd", dim=3, gridSize=[384, 384, 384], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="Orszag-Tang",
+                         usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1),
+                words=16, nI=8, stages=4, cpu_sample=[128, 128, 128], parity=(2, 16)),
     "C2": dict(name="2D Euler Kelvin-Helmholtz, Roe+PLM(minmod)+RK4-TVD, double, periodic, 2048^2 per GPU (y slabs)",
                cfg=dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                         slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15),
-               words=21, nI=5, stages=4, cpu_sample=[1024, 1024]),
+               words=21, nI=5, stages=4, cpu_sample=[2048, 2048], parity=(4, 256)),
     "C3": dict(name="2D ideal-MHD Orszag-Tang, Roe+PLM(minmod)+RK3-TVD, double, periodic, 4096^2 per GPU (y slabs)",
                cfg=dict(eqn="mhd", dim=2, gridSize=[4096, 4096], initCond="Orszag-Tang", usePLM="plm cons",
                         slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15),
-               words=8, nI=8, stages=3, cpu_sample=[1024, 1024]),
+               words=8, nI=8, stages=3, cpu_sample=[2048, 2048], parity=(4, 256)),
     # 16 words x 37 integrated variables + 4 stages x 14 auxiliary reads = 5184 B per cell-update
     # domain +-1 (two wavelengths): at 256^3 on +-.5 the cell volume is 5.96e-8 and the reference's `volume > 1e-7` guard
     # (fvsolver.cl:97) switches the flux divergence off altogether -- the same reason C4 runs on +-2
@@ -55,7 +61,7 @@ WORKLOADS = {
                cfg=dict(eqn="adm3d", dim=3, gridSize=[256, 256, 256], mins=[-1.] * 3, maxs=[1.] * 3, initCond="testbed - gauge wave",
                         fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1,
                         boundary=dict(xmin="periodic", xmax="periodic", ymin="periodic", ymax="periodic", zmin="periodic", zmax="periodic")),
-               words=16, nI=37, stages=4, extra_bytes=4 * 14 * 8, cpu_sample=[48, 48, 48]),
+               words=16, nI=37, stages=4, extra_bytes=4 * 14 * 8, cpu_sample=[64, 64, 64], parity=None),
 }
 
 
@@ -112,7 +118,8 @@ def cpu_oracle_rate(w, nthreads, steps, warmup=1):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import hydrob200
     import oracle
-    cfg = dict(w["cfg"], gridSize=w["cpu_sample"], backend=oracle.OracleBackendThreads(nthreads))
+    # the -O3 -march=native -ffp-contract=fast build, compiled on this machine (oracle.build_native)
+    cfg = dict(w["cfg"], gridSize=w["cpu_sample"], backend=oracle.OracleBackendThreads(nthreads, native=True))
     S = hydrob200.FiniteVolumeSolver(cfg)
     cells = int(np.prod(w["cpu_sample"]))
     for _ in range(warmup):
@@ -126,20 +133,63 @@ def cpu_oracle_rate(w, nthreads, steps, warmup=1):
     return cells * steps / total, total / steps, cells
 
 
+try:
+    ORIG_AFFINITY = os.sched_getaffinity(0)
+except AttributeError:
+    ORIG_AFFINITY = None
+
+
+def host_threads():
+    """every hardware thread this process may run on (torchrun exports OMP_NUM_THREADS=1: not a property of the machine); the CPU legs
+    run on all of them, whatever NUMA node the e2e leg pinned the process to"""
+    if ORIG_AFFINITY:
+        try:
+            os.sched_setaffinity(0, ORIG_AFFINITY)
+        except OSError:
+            pass
+        return max(1, len(ORIG_AFFINITY))
+    return os.cpu_count() or 1
+
+
+def pin_to_gpu_numa_node(index):
+    """Run this rank (and first-touch its pinned staging buffers) on the CPUs of the NUMA node its GPU hangs off: with eight ranks
+    staging through one node the e2e leg measures that node's memory controller, not PCIe (VERDICT r01 weak #8)."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                             capture_output=True, text=True, timeout=10).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]
+        with open("/sys/bus/pci/devices/%s/numa_node" % bus) as f:
+            node = int(f.read())
+        if node < 0:
+            return "gpu %d: no NUMA affinity reported" % index
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "gpu %d: pinned to NUMA node %d (%d cpus)" % (index, node, len(allowed))
+        return "gpu %d: NUMA node %d has no cpu this process may use" % (index, node)
+    except Exception as e:       # no sysfs / nvidia-smi: leave the affinity alone
+        return "gpu %d: not pinned (%s)" % (index, type(e).__name__)
+
+
 def run_reference(args, w):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
-    cores = oracle.lib().ho_max_threads()
+    cores = host_threads()
     rate, sec, cells = cpu_oracle_rate(w, cores, args.steps, max(1, min(args.warmup, 2)))
-    sample = "one update of the %s workload on a %s interior sample per step (CPU restatement of the reference kernels, OpenMP)" % (
-        args.workload, "x".join(map(str, w["cpu_sample"])))
+    sample = "one update of the %s workload on a %s interior sample per step (CPU restatement of the reference kernels, g++ -O3 -march=native -ffp-contract=fast, OpenMP, %d threads)" % (
+        args.workload, "x".join(map(str, w["cpu_sample"])), cores)
     line = {
         "impl": "reference", "metric": "cell-updates/sec", "value": rate, "unit": "cell-updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "vs_baseline": None, "dtype": "f32" if args.precision == "float" else "f64", "data": "synthetic",
         "config": {"workload": w["name"], "sample": "x".join(map(str, w["cpu_sample"]))},
         "cpu_baseline": {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": "cell-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -157,8 +207,15 @@ def main():
     ap.add_argument("--grid", default=None, help="override the per-GPU interior grid, e.g. 256,256,256")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the in-run parity leg (oracle on a sub-slab of the benchmarked grid)")
+    ap.add_argument("--precision", default="double", choices=["double", "float"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: the per-GPU slab is fixed and the grid grows with N; strong: the workload's grid is split over the N GPUs")
+    ap.add_argument("--per-gpu-planes", type=int, default=0, help="weak scaling with this many planes of the decomposed axis per GPU (SURVEY 8e: 64)")
     args = ap.parse_args()
     w = dict(WORKLOADS[args.workload])
+    if args.precision == "float":
+        w["cfg"] = dict(w["cfg"], precision="float")
     if args.impl == "reference":
         return run_reference(args, w)
     if args.warmup < 3:
@@ -183,12 +240,25 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
         comm = SlabComm(world, rank, dist)
 
+    numa_note = pin_to_gpu_numa_node(local)
     cfg = dict(w["cfg"])
     if args.grid:
         cfg["gridSize"] = [int(x) for x in args.grid.split(",")]
     perGpu = list(cfg["gridSize"])
     ax = cfg["dim"] - 1
-    if world > 1:                     # weak scaling: per-GPU slab fixed, the grid grows along the decomposed axis
+    if args.per_gpu_planes:
+        # same dx as the workload's grid: the domain shrinks with the plane count
+        frac = args.per_gpu_planes / float(perGpu[ax])
+        mins = list(cfg.get("mins", [-1.] * 3)); maxs = list(cfg.get("maxs", [1.] * 3))
+        maxs[ax] = mins[ax] + (maxs[ax] - mins[ax]) * frac
+        cfg["mins"], cfg["maxs"] = mins, maxs
+        perGpu[ax] = args.per_gpu_planes
+        cfg["gridSize"] = list(perGpu)
+    if args.scaling == "strong":
+        if perGpu[ax] % world:
+            raise SystemExit("--scaling strong: %d planes do not split over %d GPUs" % (perGpu[ax], world))
+        perGpu[ax] //= world          # the grid stays, each rank owns 1/N of its planes
+    elif world > 1:                   # weak scaling: per-GPU slab fixed, the grid grows along the decomposed axis
         cfg["gridSize"] = list(perGpu)
         cfg["gridSize"][ax] = perGpu[ax] * world
         span = cfg.get("maxs", [1.] * 3)[ax] - cfg.get("mins", [-1.] * 3)[ax]
@@ -220,6 +290,21 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
+    # ---- parity of THIS run's state against the oracle (N = 1): the first steps of the benchmarked grid, compared on a central
+    # sub-slab with the oracle advancing that slab + its domain of dependence from the same initial state with the same dt sequence
+    # (oracle/subslab.py; the oracle is the checker here, never the thing timed).  The timed updates continue from that state.
+    parity = None
+    tol = 1e-5 if args.precision == "float" else 1e-12
+    if world == 1 and not args.no_parity and w.get("parity"):
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle
+        import subslab
+        nst, planes = w["parity"]
+        r = subslab.subslab_parity(hydrob200, oracle, cfg, nst, planes, G=S, nthreads=host_threads())
+        parity = {k: r[k] for k in ("rel_linf", "per_group", "steps", "planes", "oracle_planes", "finite", "against")}
+        parity["tolerance"] = tol
+        parity["pass"] = bool(r["finite"] and r["rel_linf"] <= tol)
+
     # ---- resident-state throughput: W warm-up updates, then exactly K timed updates (CUDA events on the library's stream)
     hb.check(L.hb_fv_update(B.h, args.warmup))
     n0 = B.launch_count()
@@ -244,7 +329,8 @@ def main():
     hb.check(L.hb_fv_profile_read(B.h, C.byref(sms), C.byref(sn)))
     hb.check(L.hb_fv_profile(B.h, 0))
     stage_ms = sms.value / max(1, sn.value)
-    bytes_per_launch = alg_bytes(w) / w["stages"] * cellsLocal
+    wordScale = .5 if args.precision == "float" else 1.
+    bytes_per_launch = alg_bytes(w) * wordScale / w["stages"] * cellsLocal
     peak, peak_src = peaks()
     achieved = bytes_per_launch / (stage_ms * 1e-3) / 1e9
     traffic = None
@@ -259,7 +345,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": desc.split()[0].replace("kernel=", ""), "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "stage_kernel_ms": stage_ms, "kernel_config": desc,
                 "stage_share_of_step": stage_ms * w["stages"] / (ms / args.steps),
-                "algorithmic_bytes_per_cell_update": alg_bytes(w)}
+                "algorithmic_bytes_per_cell_update": alg_bytes(w) * wordScale}
 
     # ---- end to end through the C-ABI with HOST buffers: upload state (pinned host, AoS doubles) -> update -> download, every step.
     # Blocking calls first (hb_fv_set_state / hb_fv_get_state: what a time-stepping script does), then the non-blocking ones
@@ -291,7 +377,8 @@ def main():
     barrier()
     for h in (hp, hq0, hq1):
         hb.check(L.hb_host_free(h))
-    e2e = {"value": cellsAll * nasync / e2e_s, "unit": "cell-updates/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
+    e2e = {"value": cellsAll * nasync / e2e_s, "unit": "cell-updates/s", "per_gpu": cellsAll * nasync / e2e_s / world,
+           "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes, "host_numa": numa_note,
            "steps": nasync, "ms_per_step": e2e_s / nasync * 1e3,
            "mode": "non-blocking transfers (hb_fv_set_state_async / get_state_async), upload, update and download of consecutive steps overlap",
            "blocking": {"value": cellsAll * args.e2e_steps / e2e_block_s, "steps": args.e2e_steps,
@@ -301,22 +388,22 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle
-        cores = oracle.lib().ho_max_threads()
-        rate, sec, cells = cpu_oracle_rate(w, cores, 8)
+        cores = host_threads()
+        rate, sec, cells = cpu_oracle_rate(w, cores, 4)
         cpu = {"value": rate, "unit": "cell-updates/s", "cores": cores, "kind": "port",
-               "sample": "8 updates of the same workload on a %s interior sample (CPU restatement of the reference kernels, OpenMP, %d threads)" % (
+               "sample": "4 updates of the same workload on a %s interior sample (CPU restatement of the reference kernels, g++ -O3 -march=native -ffp-contract=fast, OpenMP, %d threads)" % (
                    "x".join(map(str, w["cpu_sample"])), cores)}
 
     if rank == 0:
         line = {
             "metric": "cell-updates/sec", "value": value, "unit": "cell-updates/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32" if args.precision == "float" else "f64", "data": "synthetic",
             "config": {"workload": w["name"] if not args.grid else w["name"] + " [grid override %s]" % args.grid,
-                       "per_gpu_grid": perGpu, "global_grid": cfg["gridSize"], "parallelism": "slab-z x%d" % world,
+                       "per_gpu_grid": perGpu, "global_grid": cfg["gridSize"], "parallelism": "slab-%s x%d" % ("xyz"[ax], world),
                        "l2": "state arrays (%.1f GB per buffer) exceed the 126 MB L2; no flush needed" % (B.ncells * nS * 8 / 1e9),
                        "timing": "CUDA events on the library stream, max over ranks", "finite": finite, "t": t_sim, "dt": dt_sim},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
+            "roofline": roofline, "parity": parity, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
         }
         print(json.dumps(line), flush=True)
     if dist is not None:

@@ -1092,7 +1092,9 @@ template<class real> struct Fv : FvBase {
 		// overlap needs chunks that are neither first nor last along the decomposed (= marching) axis; HB_OVERLAP=0 switches it off
 		const char* ov = getenv("HB_OVERLAP");
 		int const km = marchInfoV[2] > 0 ? marchInfoV[2] : 1;
-		overlap = useMarch && !seqBc && (!ov || atoi(ov) != 0) && (grid.N[axis] + km - 1) / km >= 3;
+		// (kernels with the rim / interior split -- marchInfoV[6] bit 2 -- overlap whatever the chunk count: SURVEY 8e's 64 planes per GPU are one chunk)
+		bool const rim = (marchInfoV[6] & 4) != 0;
+		overlap = useMarch && !seqBc && (!ov || atoi(ov) != 0) && (rim ? grid.N[axis] >= 2 * HB_G + 1 : (grid.N[axis] + km - 1) / km >= 3);
 		if (overlap) {
 			HB_CUDA(cudaStreamCreateWithFlags(&commStream, cudaStreamNonBlocking));
 			HB_CUDA(cudaEventCreateWithFlags(&evRim, cudaEventDisableTiming));

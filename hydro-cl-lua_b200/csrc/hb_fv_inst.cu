@@ -184,9 +184,10 @@ cudaError_t launchMarch3(const CUtensorMap* tmap, int padX, GridP<real> const& g
 	long long const ntx = (g.N[0] + G::TX - 1) / G::TX;
 	long long const nty = (g.N[1] + G::TY - 1) / G::TY;
 	long long nm = (g.N[2] + C::KM - 1) / C::KM;
-	if (chunkSel == 1) nm = nm < 2 ? nm : 2;
-	else if (chunkSel == 2) nm = nm > 2 ? nm - 2 : 0;
-	if (nm == 0) return cudaSuccess;
+	if (chunkSel) {                                     // rim / interior split of the overlapped slab exchange (see the kernel)
+		if (g.N[2] < 2 * HB_G + 1) return cudaErrorInvalidConfiguration;
+		nm = chunkSel == 1 ? 2 : (g.N[2] - 2 * HB_G + C::KM - 1) / C::KM;
+	}
 	kern<<<(unsigned)(ntx * nty * nm), G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX, chunkSel);
 	return cudaGetLastError();
 }
@@ -200,7 +201,7 @@ template<class C> void march3InfoCfg(int box[4], int info[7]) {
 	typedef March3Geom<C, real> G;
 	box[0] = G::BX; box[1] = G::BY; box[2] = 1; box[3] = Eqn::nI;
 	info[0] = G::TX; info[1] = G::TY; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
-	info[5] = G::NCOL * 32; info[6] = (C::GRAV ? 1 : 0) | 2;   // bit 1: fv_march3
+	info[5] = G::NCOL * 32; info[6] = (C::GRAV ? 1 : 0) | 2 | 4;   // bit 1: fv_march3; bit 2: chunkSel = rim / interior planes
 }
 template<int LIM, class C>
 cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
@@ -235,9 +236,10 @@ cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& 
 	}
 	int const KM = kmCache;
 	long long nm = (g.N[1] + KM - 1) / KM;
-	if (chunkSel == 1) nm = nm < 2 ? nm : 2;
-	else if (chunkSel == 2) nm = nm > 2 ? nm - 2 : 0;
-	if (nm == 0) return cudaSuccess;
+	if (chunkSel) {                                     // rim / interior split of the overlapped slab exchange (see the kernel)
+		if (g.N[1] < 2 * HB_G + 1) return cudaErrorInvalidConfiguration;
+		nm = chunkSel == 1 ? 2 : (g.N[1] - 2 * HB_G + KM - 1) / KM;
+	}
 	long long const blocks = (nSeg * nm + C::NW - 1) / C::NW;
 	kern<<<(unsigned)blocks, G::NT, smem, st>>>(*tmap, g, sp, Eqn::makeParams(eqnParams), padX, chunkSel, KM);
 	return cudaGetLastError();
@@ -252,7 +254,7 @@ template<class C> void march2WInfoCfg(int box[4], int info[7]) {
 	typedef March2Geom<C, real> G;
 	box[0] = G::BX; box[1] = 1; box[2] = 1; box[3] = Eqn::nI;
 	info[0] = G::CW * C::NW; info[1] = 1; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
-	info[5] = C::NW * 32; info[6] = C::GRAV ? 1 : 0;
+	info[5] = C::NW * 32; info[6] = (C::GRAV ? 1 : 0) | 4;   // bit 2: chunkSel = rim / interior rows
 }
 template<int DIM, class C> void marchInfoCfg(int box[4], int info[7]) {
 	typedef MarchGeom<DIM, C, real> G;

@@ -18,6 +18,7 @@
 //   * the CFL minimum leaves by one atomicMin per warp.
 #pragma once
 #include "hb_fv_march.cuh"
+#include "hb_fv_march3.cuh"
 
 namespace hb {
 
@@ -44,8 +45,8 @@ template<class real> HB_D real shflDown1(real v) { return __shfl_down_sync(0xfff
 
 template<class Eqn, int LIM, class C, int MODE>
 __global__ void __launch_bounds__((March2Geom<C, typename Eqn::real>::NT), C::MINB)
-fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> const g, StageP<typename Eqn::real> const sp,
-	typename Eqn::Params const ep, int const padX, int const chunkSel, int const KM)
+fv_march2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ GridP<typename Eqn::real> g,
+	const __grid_constant__ StageP<typename Eqn::real> sp, const __grid_constant__ typename Eqn::Params ep, int const padX, int const chunkSel, int const KM)
 {
 	typedef typename Eqn::real real;
 	typedef March2Geom<C, real> G;
@@ -55,9 +56,7 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> c
 	constexpr int SLOT = int(G::template slotElems<nI>());
 	extern __shared__ __align__(128) unsigned char march2Smem[];
 	int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-	int nOps = sp.nB;
-	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
-	size_t const wbytes = (G::template warpBytes<nI>(nOps) + 127) / 128 * 128;
+	size_t const wbytes = (G::template warpBytes<nI>(sp.nOps) + 127) / 128 * 128;
 	unsigned char* const base = march2Smem + size_t(w) * wbytes;
 	uint64_t* full = reinterpret_cast<uint64_t*>(base);         // R mbarriers of this warp
 	real* ring = reinterpret_cast<real*>(base + 128);
@@ -66,18 +65,19 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> c
 
 	// ---- this warp's pencil: x segment and chunk of rows
 	int const nSeg = (g.N[0] + G::CW - 1) / G::CW;
-	int nm = (g.N[1] + KM - 1) / KM;
-	int const nmAll = nm;
-	if (chunkSel == 1) nm = nm < 2 ? nm : 2; else if (chunkSel == 2) nm = nm > 2 ? nm - 2 : 0;
+	// chunkSel (overlapped slab exchange, hb_fv.cu): 0 = every row, in chunks of KM; 1 = the RIM: the HB_G lowest (chunk 0) and the HB_G highest
+	// (chunk 1) interior rows, whose values the neighbouring slabs need; 2 = the rows in between, in chunks of KM
+	int const nm = chunkSel == 1 ? 2 : (g.N[1] - (chunkSel == 2 ? 2 * HB_G : 0) + KM - 1) / KM;
 	long long const gw = (long long)blockIdx.x * C::NW + w;
 	if (gw >= (long long)nSeg * nm) return;                     // whole warp leaves: nothing below synchronises across warps
 	int const seg = int(gw % nSeg);
-	int bm = int(gw / nSeg);
-	if (chunkSel == 1) { if (bm != 0) bm = nmAll - 1; } else if (chunkSel == 2) bm += 1;
+	int const bm = int(gw / nSeg);
+	int kb, ke;
+	if (chunkSel == 1) { kb = bm == 0 ? HB_G : g.N[1]; ke = kb + HB_G; }
+	else if (chunkSel == 2) { kb = 2 * HB_G + bm * KM; ke = min(kb + KM, g.N[1]); }
+	else { kb = HB_G + bm * KM; ke = min(kb + KM, HB_G + g.N[1]); }
 	int const c0 = HB_G + seg * G::CW;                          // first cell this warp finishes (lane 1)
 	int const gi = c0 - 1 + lane;                               // this lane's cell
-	int const kb = bm * KM + HB_G;
-	int const ke = min(kb + KM, HB_G + g.N[1]);
 	bool const inside = lane >= 1 && lane <= G::CW && gi < g.S[0] - HB_G;
 	long long const colIdx = gi;
 	long long const strideM = g.strideY;
@@ -125,9 +125,7 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> c
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) {
 			Uk[q] = P[q * BX + ob];
-			real const s = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, Um[q], Uk[q], ring[sN * SLOT + q * BX + ob]);
-			UR[q] = Uk[q] - s;
-			zfN[q] = Uk[q] + s;
+			plmCellFacesT<real, LIM, Eqn::FAST>(lim, Um[q], Uk[q], ring[sN * SLOT + q * BX + ob], UR[q], zfN[q]);
 			Fz[q] = 0;
 		}
 		if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
@@ -136,24 +134,16 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> c
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) acc[q] = g.volOn ? accP[q] - (Fz[q] * aovM - FzP[q] * aovM) : real(0);
 			cpAsyncWaitAll();
-			stageEpilogue<Eqn, C::GRAV>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + lane, OPS);
+			stageEpilogue3<Eqn, C::GRAV>(g, sp, ep, idxK - strideM, acc, Um, dt, dtCell, rateCell, OPB + lane, OPS);
 		}
 		if (inside && xy && sp.Uout) {
-			int slot = 0;
-			#pragma unroll
-			for (int a = 0; a < HB_MAX_TERMS; ++a)
-				if (a < sp.nA && !((sp.aOwnMask >> a) & 1)) {
-					#pragma unroll
-					for (int q = 0; q < nI; ++q) cpAsyncElem<real>(OPB + (slot * nI + q) * OPS + lane, sp.aPtr[a] + idxK + q * g.strideV);
-					++slot;
-				}
-			#pragma unroll
-			for (int b = 0; b < HB_MAX_TERMS; ++b)
-				if (b < sp.nB) {
-					#pragma unroll
-					for (int q = 0; q < nI; ++q) cpAsyncElem<real>(OPB + (slot * nI + q) * OPS + lane, sp.bPtr[b] + idxK + q * g.strideV);
-					++slot;
-				}
+			#pragma unroll 1
+			for (int o = 0; o < sp.nOps; ++o) {
+				real const* src = sp.opPtr[o] + idxK;
+				real* dst = OPB + o * (nI * OPS) + lane;
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) cpAsyncElem<real>(dst + q * OPS, src + q * g.strideV);
+			}
 			cpAsyncCommit();
 		}
 		// ---- x: half slope of the own cell, the left neighbour's right face by shuffle, Roe flux at the own low face, the right
@@ -164,9 +154,8 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, GridP<typename Eqn::real> c
 			real UL[nI], URx[nI], F[nI];
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) {
-				real const sx = plmHalfSlopeT<real, LIM, Eqn::FAST>(lim, P[q * BX + ob - 1], Uk[q], P[q * BX + ob + 1]);
-				real const faceR = Uk[q] + sx;
-				URx[q] = Uk[q] - sx;
+				real faceR;
+				plmCellFacesT<real, LIM, Eqn::FAST>(lim, P[q * BX + ob - 1], Uk[q], P[q * BX + ob + 1], URx[q], faceR);
 				UL[q] = shflUp1<real>(faceR);
 				if (lane == 0) UL[q] = URx[q];                  // lane 0 has no left neighbour in the warp: its flux is never used
 			}

@@ -163,17 +163,19 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 	int const lim = LIM >= 0 ? LIM : sp.slopeLimiter;
 	bool const isCol = w < TY;
 
-	// ---- tile (same numbering and chunk selection as fv_march: hb_fv.cu's overlapped slab exchange relies on it)
+	// ---- tile
 	int const ntx = (g.N[0] + TX - 1) / TX;
 	int const nty = (g.N[1] + TY - 1) / TY;
 	int bid = blockIdx.x;
 	int const bx = bid % ntx; bid /= ntx;
 	int const by = bid % nty; int bm = bid / nty;
-	if (chunkSel == 1) { if (bm != 0) bm = (g.N[2] + C::KM - 1) / C::KM - 1; }
-	else if (chunkSel == 2) bm += 1;
 	int const i0 = bx * TX + HB_G, j0 = by * TY + HB_G;
-	int const kb = bm * C::KM + HB_G;
-	int const ke = min(kb + C::KM, HB_G + g.N[2]);      // exclusive
+	// chunkSel (overlapped slab exchange, hb_fv.cu): 0 = every plane, in chunks of KM; 1 = the RIM: the HB_G lowest (bm = 0) and the HB_G
+	// highest (bm = 1) interior planes, whose values the neighbouring slabs need; 2 = the planes in between, in chunks of KM
+	int kb, ke;
+	if (chunkSel == 1) { kb = bm == 0 ? HB_G : g.N[2]; ke = kb + HB_G; }
+	else if (chunkSel == 2) { kb = 2 * HB_G + bm * C::KM; ke = min(kb + C::KM, g.N[2]); }
+	else { kb = HB_G + bm * C::KM; ke = min(kb + C::KM, HB_G + g.N[2]); }      // ke exclusive
 
 	uint32_t const boxBytes = uint32_t(sizeof(real) * nI * PS);
 	int const tx0 = i0 - G::HL + padX, ty0 = j0 - HB_G;

@@ -124,24 +124,41 @@ class GridSolver(SolverBase):
                 k += 1
         return out
 
-    def cellPositions(self):
+    def cellPositions(self, part=None):
         """coord.lua:1421-1432: x = (i + .5 - g)/N * (max - min) + min on used axes, midpoint otherwise.
-        With a slab decomposition these are the positions of this rank's (ghost-inclusive) slab."""
+        With a slab decomposition these are the positions of this rank's (ghost-inclusive) slab.
+        ``part = (axis, lo, hi)`` restricts one axis to the index range [lo, hi) of the ghost-inclusive local grid."""
         g = self.numGhost
         axes = []
         for j in range(3):
             if j < self.dim:
                 i = np.arange(self.localGridSize[j], dtype=np.float64) + float(self.localOffset[j])
-                axes.append((i + .5 - g) / float(self.sizeWithoutBorder[j]) * (self.maxs[j] - self.mins[j]) + self.mins[j])
+                a = (i + .5 - g) / float(self.sizeWithoutBorder[j]) * (self.maxs[j] - self.mins[j]) + self.mins[j]
+                if part is not None and part[0] == j:
+                    a = a[part[1]:part[2]]
+                axes.append(a)
             else:
                 axes.append(np.array([.5 * (self.maxs[j] + self.mins[j])]))
         z, y, x = np.meshgrid(axes[2], axes[1], axes[0], indexing="ij")
         return x, y, z      # each [Sz, Sy, Sx]
 
     def applyInitCond(self):
-        x, y, z = self.cellPositions()
-        W = self.initCond.prims(x, y, z, self)
-        U = self.eqn.consArray(W)                       # [Sz, Sy, Sx, numStates]
+        """The initial condition is pointwise in the cell position (eqn.lua:622-632: one applyInitCond work-item per cell), so it is
+        evaluated in chunks of planes of the slowest axis: the numpy temporaries of prims + consFromPrim are ~0.9 KB per cell, which at
+        512^3 would be > 100 GB at once."""
+        ax = self.dim - 1
+        n = self.localGridSize[ax]
+        per = self.localNumCells // n
+        step = max(1, int(4e6 // max(per, 1)))
+        S = self.localGridSize
+        U = np.empty((S[2], S[1], S[0], self.eqn.numStates), dtype=np.float64)
+        for lo in range(0, n, step):
+            hi = min(n, lo + step)
+            x, y, z = self.cellPositions((ax, lo, hi))
+            W = self.initCond.prims(x, y, z, self)
+            sl = [slice(None)] * 3
+            sl[2 - ax] = slice(lo, hi)
+            U[sl[0], sl[1], sl[2]] = self.eqn.consArray(W)      # [.., numStates]
         self.setState(U)
 
     def setState(self, U):

@@ -42,11 +42,40 @@ def build(force=False):
 _libs = {}
 
 
+def _cpu_id():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def build_native():
+    """The CPU-baseline build: g++ -O3 -march=native -ffp-contract=fast -fopenmp of the same restatement, compiled ON THE MACHINE THAT
+    RUNS IT (oracle/_native/, git-ignored; rebuilt when the CPU model differs from the one it was built on).  Used by bench.py's
+    cpu_baseline / --impl reference legs only: the parity tests use the two portable builds of oracle/Makefile."""
+    d = os.path.join(_here, "_native")
+    so, stamp = os.path.join(d, "libhydro_oracle_native.so"), os.path.join(d, "built_on.txt")
+    src = os.path.join(_here, "hydro_oracle.cpp")
+    ident = _cpu_id()
+    fresh = os.path.exists(so) and os.path.exists(stamp) and open(stamp).read() == ident and os.path.getmtime(so) >= os.path.getmtime(src)
+    if not fresh:
+        os.makedirs(d, exist_ok=True)
+        subprocess.check_call(["g++", "-std=c++17", "-O3", "-march=native", "-ffp-contract=fast", "-fopenmp", "-shared", "-fPIC", "-w",
+                               "-o", so, src])
+        with open(stamp, "w") as f:
+            f.write(ident)
+    return so
+
+
 def lib(fma=False):
-    key = bool(fma)
+    key = fma if fma == "native" else bool(fma)
     if key not in _libs:
         build()
-        L = C.CDLL(os.path.join(_here, "libhydro_oracle_fma.so" if fma else "libhydro_oracle.so"))
+        L = C.CDLL(build_native() if key == "native" else os.path.join(_here, "libhydro_oracle_fma.so" if fma else "libhydro_oracle.so"))
         L.ho_create.restype = C.c_void_p
         L.ho_create.argtypes = [C.POINTER(ho_desc)]
         for name in ("ho_destroy", "ho_boundary", "ho_constrainU", "ho_init_derivs"):
@@ -226,5 +255,6 @@ class OracleBackendFMA(OracleBackend):
     fma = True
 
 
-def OracleBackendThreads(n):
-    return type("OracleBackendT%d" % n, (OracleBackend,), {"nthreads": n})
+def OracleBackendThreads(n, native=False):
+    """`native`: the -O3 -march=native -ffp-contract=fast build (bench.py's CPU legs)"""
+    return type("OracleBackendT%d" % n, (OracleBackend,), {"nthreads": n, "fma": "native" if native else False})

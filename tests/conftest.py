@@ -11,6 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle")):
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    config.addinivalue_line("markers", "slow: full BASELINE-size cases (minutes of CPU-oracle time); part of -m gpu, deselect with -m 'gpu and not slow'")
 
 
 @pytest.fixture(scope="session")
