@@ -28,6 +28,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")     # (NCCL's version banner goes to stdout: the contract is ONE JSON line there)
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for p in (ROOT,):
     if p not in sys.path:

@@ -76,10 +76,15 @@ SIGNATURES = {
     "hb_kernel_set_arg": (C.c_int, [P, C.c_int, P, C.c_size_t]),
     "hb_kernel_set_arg_buf": (C.c_int, [P, C.c_int, P]),
     "hb_kernel_launch": (C.c_int, [P, size3, size3, C.c_size_t]),
+    "hb_kernel_free": (C.c_int, [P]),
+    "hb_cl_prelude": (C.c_char_p, []),
+    "hb_cl_translate": (C.c_int, [C.c_char_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "hb_module_compile_opencl": (C.c_int, [P, C.c_char_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, C.POINTER(P), C.c_char_p, C.c_size_t]),
     "hb_reduce": (C.c_int, [P, P, C.c_size_t, C.c_int, C.POINTER(C.c_double)]),
     "hb_sizeof_fv_desc": (C.c_size_t, []),
     "hb_fv_create": (C.c_int, [P, C.POINTER(hb_fv_desc), C.POINTER(P)]),
     "hb_fv_destroy": (C.c_int, [P]),
+    "hb_fv_create_from_source": (C.c_int, [P, C.POINTER(hb_fv_desc), C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(P), C.c_char_p, C.c_size_t]),
     "hb_fv_num_states": (C.c_int, [P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "hb_fv_num_cells": (C.c_longlong, [P]),
     "hb_fv_set_state": (C.c_int, [P, P]),

@@ -101,7 +101,18 @@ class CudaBackend:
         self.comm = comm
         self.desc = desc_from_solver(solver, strict, graph, solver.localSizeWithoutBorder, args.get("stage_kernel", 0))
         self.h = hb.P()
-        hb.check(self.L.hb_fv_create(self.ctx.h, C.byref(self.desc), C.byref(self.h)))
+        src = args.get("eqnSource")
+        if src:
+            # the codegen seam: the equation's device functions as source, compiled by NVRTC into the marching kernels (hb_fv_create_from_source).
+            # eqnSource = {name = include name, src = header text, type = class template name}; the host plug-in (args.eqn) supplies sizes / init
+            log = C.create_string_buffer(1 << 16)
+            rc = self.L.hb_fv_create_from_source(self.ctx.h, C.byref(self.desc), src["name"].encode(), src["src"].encode(), src["type"].encode(),
+                                                 C.byref(self.h), log, len(log))
+            self.compile_log = log.value.decode()
+            if rc:
+                raise hb.HydroB200Error(rc, self.L.hb_last_error().decode() + "\n" + self.compile_log)
+        else:
+            hb.check(self.L.hb_fv_create(self.ctx.h, C.byref(self.desc), C.byref(self.h)))
         ns, ni, nw = C.c_int(), C.c_int(), C.c_int()
         hb.check(self.L.hb_fv_num_states(self.h, C.byref(ns), C.byref(ni), C.byref(nw)))
         self.nS, self.nI, self.nW = ns.value, ni.value, nw.value

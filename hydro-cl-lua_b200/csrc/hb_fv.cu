@@ -11,6 +11,7 @@
 // boundary plane pairs are exchanged with ncclSend/ncclRecv and dt is min-allreduced (choppedup.lua:193-233,344-409).
 #include "hb_core.h"
 #include "hb_fv_ops.h"
+#include "hb_jit.h"
 #include <cuda.h>
 #include <dlfcn.h>
 #include <cmath>
@@ -247,7 +248,9 @@ template<class real> struct Fv : FvBase {
 	cudaEvent_t evRim = nullptr, evXchg = nullptr;
 	bool overlap = false;
 
-	Fv(hb_ctx* c, const hb_fv_desc& desc, const FvOps<real>* o) : ctx(c), d(desc), ops(o) {
+	JitProgram* jit = nullptr;             // a run-time compiled equation (hb_fv_create_from_source): its FvOps launch from this program
+	const FvOps<real>* OPS() const { tlsJit = jit; return ops; }
+	Fv(hb_ctx* c, const hb_fv_desc& desc, const FvOps<real>* o, JitProgram* j = nullptr) : ctx(c), d(desc), ops(o), jit(j) {
 		nS = o->nS; nI = o->nI; nW = o->nW;
 		axis = d.dim - 1;
 		ctxRetain(ctx);
@@ -257,6 +260,8 @@ template<class real> struct Fv : FvBase {
 		cudaStreamSynchronize(ctx->stream);
 		if (graphExec) cudaGraphExecDestroy(graphExec);
 		for (auto& e : profEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+		JitProgram* const jitToFree = jit;
+		struct FreeJit { JitProgram* p; ~FreeJit() { if (p) jitFree(p); } } freeJit{jitToFree};
 		for (auto p : upool) cudaFree(p - padX);
 		for (auto p : lpool) cudaFree(p - padX);
 		if (scratchL) cudaFree(scratchL - padX);
@@ -379,13 +384,14 @@ template<class real> struct Fv : FvBase {
 			bool ok = false;
 			if (d.stage_kernel != 1 && d.flux == HB_FLUX_ROE && d.use_plm == 1) {   // the marching kernel is built for Roe + 'plm cons'
 				for (int pass = 0; pass < 2 && !ok; ++pass)
-					for (int cfg = pass == 0 ? cfg0 : 0; !ok && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
+					for (int cfg = pass == 0 ? cfg0 : 0; !ok && OPS()->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, marchBox, marchInfoV); ++cfg) {
 						size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
 						if (marchInfoV[6] & 1) continue;   // configurations with the self-gravity epilogue are taken by hb_fv_add_op only
 						if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
 					}
 			}
 			if (d.stage_kernel == 2 && !ok) return setError(HB_ERR_INVALID, "hb_fv_create: the marching kernel is not built for this configuration");
+			if (jit && !ok) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: a run-time equation runs the marching kernels only (dim 2 or 3, Roe flux, usePLM = 'plm cons', slopeLimiter minmod or superbee, RK operands within shared memory)");
 			useMarch = ok;
 			marchMaxOps = maxOps;
 			if (useMarch) {
@@ -401,7 +407,7 @@ template<class real> struct Fv : FvBase {
 						int n = (int)s.beta.size();
 						for (auto& t : s.alpha) if (t.k != s.uIn) ++n;
 						int box[4], info[7];
-						for (int cfg = cfg0; cfg < marchCfg && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
+						for (int cfg = cfg0; cfg < marchCfg && OPS()->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
 							size_t const smem = (size_t)info[4] + sizeof(real) * (size_t)nI * (size_t)n * (size_t)info[5];
 							if ((info[6] & 1) || info[2] != marchInfoV[2] || smem > 232448 - 1024) continue;
 							s.marchCfg = cfg;
@@ -425,8 +431,8 @@ template<class real> struct Fv : FvBase {
 			if (int r = allocPadded(&ctuULR, sizeof(real) * (2 * (size_t)d.dim * block + (size_t)grid.strideY))) return r;
 			if (int r = allocPadded(&ctuFlux, sizeof(real) * ((size_t)d.dim * block + (size_t)grid.strideY))) return r;
 		}
-		if (ops->scratchElems) {
-			if (int r = allocPadded(&opsScratch, sizeof(real) * ((size_t)ops->scratchElems(grid) + (size_t)grid.strideY))) return r;
+		if (OPS()->scratchElems) {
+			if (int r = allocPadded(&opsScratch, sizeof(real) * ((size_t)OPS()->scratchElems(grid) + (size_t)grid.strideY))) return r;
 		}
 		HB_CUDA(cudaMalloc(&ctl, 4 * sizeof(double)));
 		HB_CUDA(cudaMalloc(&dtMinBits, sizeof(unsigned long long)));
@@ -571,10 +577,10 @@ template<class real> struct Fv : FvBase {
 	int fillGhosts(real* U, int nVars, const BcP* methods = nullptr) {
 		BcP const& b = methods ? *methods : bc;
 		if (seqBc) {
-			for (int a = 0; a < d.dim; ++a) { HB_CUDA(ops->ghosts(grid, b, U, nVars, -2 - a, false, st())); launches++; }
+			for (int a = 0; a < d.dim; ++a) { HB_CUDA(OPS()->ghosts(grid, b, U, nVars, -2 - a, false, st())); launches++; }
 			return exchange(U, nVars);
 		}
-		HB_CUDA(ops->ghosts(grid, b, U, nVars, -1, false, st()));
+		HB_CUDA(OPS()->ghosts(grid, b, U, nVars, -1, false, st()));
 		launches++;
 		return exchange(U, nVars);
 	}
@@ -582,7 +588,7 @@ template<class real> struct Fv : FvBase {
 	// ---- ops: hydro/op/relaxation.lua, selfgrav.lua, nodiv.lua
 	int addOp(const hb_op_desc* o, int* index) override {
 		if (!o) return setError(HB_ERR_INVALID, "hb_fv_add_op: null argument");
-		if (!ops->opKernel) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are built for euler and mhd");
+		if (!OPS()->opKernel) return setError(HB_ERR_INVALID, "hb_fv_add_op: ops are built for euler and mhd");
 		if (useCTU && o->kind == HB_OP_SELFGRAV) return setError(HB_ERR_INVALID, "hb_fv_add_op: self-gravity is not built for the CTU variant");
 		if (o->max_iters < 0) return setError(HB_ERR_INVALID, "hb_fv_add_op: max_iters < 0");
 		OpState s; s.d = *o; s.ctl = nullptr; s.vec = -1;
@@ -611,7 +617,7 @@ template<class real> struct Fv : FvBase {
 				bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
 				int box[4], info[7];
 				bool found = false;
-				for (int cfg = 0; !found && ops->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
+				for (int cfg = 0; !found && OPS()->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
 					size_t const smem = (size_t)info[4] + sizeof(real) * (size_t)nI * (size_t)marchMaxOps * (size_t)info[5];
 					if ((info[6] & 1) && (info[6] & 2) == (marchInfoV[6] & 2) && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
 				}
@@ -654,7 +660,7 @@ template<class real> struct Fv : FvBase {
 		p.invDiag = real(1.) / p.diag;
 		return p;
 	}
-	int opLaunch(int which, OpP<real> const& p) { HB_CUDA(ops->opKernel(which, grid, p, st())); launches++; return HB_OK; }
+	int opLaunch(int which, OpP<real> const& p) { HB_CUDA(OPS()->opKernel(which, grid, p, st())); launches++; return HB_OK; }
 	// Relaxation:potentialBoundary (relaxation.lua:135-150,198-200): the solver's boundary methods on the potential alone
 	// A 'fixed' face writes whole states (its fixedCode knows nothing of args.fields): the field-restricted pass leaves it alone.
 	int potentialBoundary(real* pot) {
@@ -704,7 +710,7 @@ template<class real> struct Fv : FvBase {
 		for (auto& s : opsV) {
 			if (s.d.kind != HB_OP_NODIV) continue;
 			if (int r = fillGhosts(upool[0], nS)) return r;
-			HB_CUDA(ops->constrainAll(grid, d.eqn_params, upool[0], st()));
+			HB_CUDA(OPS()->constrainAll(grid, d.eqn_params, upool[0], st()));
 			launches++;
 			if (int r = fillGhosts(upool[0], nS)) return r;
 			if (int r = relax(s, upool[0])) return r;
@@ -737,7 +743,7 @@ template<class real> struct Fv : FvBase {
 	}
 	int constrainU() override {
 		useDevice(ctx);
-		HB_CUDA(ops->constrainAll(grid, d.eqn_params, upool[0], st()));
+		HB_CUDA(OPS()->constrainAll(grid, d.eqn_params, upool[0], st()));
 		launches++;
 		dtValid = false;
 		return fillGhosts(upool[0], nS);
@@ -745,7 +751,7 @@ template<class real> struct Fv : FvBase {
 	int launchCalcDT() {
 		reset_dtmin<<<1, 1, 0, st()>>>(dtMinBits);
 		HB_CUDA(cudaGetLastError());
-		HB_CUDA(ops->calcDT(grid, d.eqn_params, upool[0], dtMinBits, st()));
+		HB_CUDA(OPS()->calcDT(grid, d.eqn_params, upool[0], dtMinBits, st()));
 		launches += 2;
 		if (int r = reduceDtMin()) return r;
 		dtValid = true;
@@ -817,17 +823,17 @@ template<class real> struct Fv : FvBase {
 		}
 		int n = 0;
 		if (sp.computeL) {
-			HB_CUDA(ops->ctuKernel(HB_CTUK_LR, grid, sp, c, d.eqn_params, st())); ++n;
-			HB_CUDA(ops->ctuKernel(HB_CTUK_FLUX, grid, sp, c, d.eqn_params, st())); ++n;
-			HB_CUDA(ops->ctuKernel(HB_CTUK_UPDATE, grid, sp, c, d.eqn_params, st())); ++n;
+			HB_CUDA(OPS()->ctuKernel(HB_CTUK_LR, grid, sp, c, d.eqn_params, st())); ++n;
+			HB_CUDA(OPS()->ctuKernel(HB_CTUK_FLUX, grid, sp, c, d.eqn_params, st())); ++n;
+			HB_CUDA(OPS()->ctuKernel(HB_CTUK_UPDATE, grid, sp, c, d.eqn_params, st())); ++n;
 			// boundaryLR (gridsolver.lua:463-473,1241-1268): the solver's boundary methods on every L / R record; the reflected variables are the
 			// same per record, so each block is filled like a state of nI variables
 			long long const before = launches;
 			for (int b = 0; b < 2 * d.dim; ++b) if (int r = fillGhosts(ctuULR + (size_t)b * (size_t)c.blockStride, nI)) return r;
 			n += (int)(launches - before); launches = before;
-			HB_CUDA(ops->ctuKernel(HB_CTUK_FLUX, grid, sp, c, d.eqn_params, st())); ++n;
+			HB_CUDA(OPS()->ctuKernel(HB_CTUK_FLUX, grid, sp, c, d.eqn_params, st())); ++n;
 		}
-		HB_CUDA(ops->ctuKernel(HB_CTUK_FINISH, grid, sp, c, d.eqn_params, st())); ++n;
+		HB_CUDA(OPS()->ctuKernel(HB_CTUK_FINISH, grid, sp, c, d.eqn_params, st())); ++n;
 		tlsStageLaunches = n;
 		return HB_OK;
 	}
@@ -877,23 +883,23 @@ template<class real> struct Fv : FvBase {
 			}
 			if (useMarch && overlap && opsV.empty()) {   // (with ops the exchange stays in-stream)
 				int const nv = rk ? nI : nS;
-				HB_CUDA(ops->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 1, st()));
-				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, true, st()));
+				HB_CUDA(OPS()->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 1, st()));
+				HB_CUDA(OPS()->ghosts(grid, bc, upool[s.uOut], nv, axis, true, st()));
 				HB_CUDA(cudaEventRecord(evRim, st()));
 				HB_CUDA(cudaStreamWaitEvent(commStream, evRim, 0));
 				if (int r = exchange(upool[s.uOut], nv, commStream)) return r;
 				HB_CUDA(cudaEventRecord(evXchg, commStream));
-				HB_CUDA(ops->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 2, st()));
+				HB_CUDA(OPS()->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 2, st()));
 				if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
-				HB_CUDA(ops->ghosts(grid, bc, upool[s.uOut], nv, axis, false, st()));
+				HB_CUDA(OPS()->ghosts(grid, bc, upool[s.uOut], nv, axis, false, st()));
 				HB_CUDA(cudaStreamWaitEvent(st(), evXchg, 0));
 				launches += 4;
 				continue;
 			}
 			tlsStageLaunches = 1;
 			if (useCTU) { if (int r = ctuStage(sp)) return r; }
-			else if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 0, st()));
-			else HB_CUDA(ops->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
+			else if (useMarch) HB_CUDA(OPS()->march(d.dim, d.slope_limiter, stageCfg(s), stageMap(s), padX, grid, sp, d.eqn_params, 0, st()));
+			else HB_CUDA(OPS()->stage(d.dim, plm, flim, grid, sp, d.eqn_params, st()));
 			if (profiling) HB_CUDA(cudaEventRecord(e1, st()));
 			launches += tlsStageLaunches;
 			if (!opsV.empty()) {
@@ -920,7 +926,7 @@ template<class real> struct Fv : FvBase {
 			if (int r = fillGhosts(upool[0], nS)) return r;   // SolverBase:update ends with boundary() (solverbase.lua:3186); not redundant after an op:step
 			reset_dtmin<<<1, 1, 0, st()>>>(dtMinBits);
 			HB_CUDA(cudaGetLastError());
-			HB_CUDA(ops->calcDT(grid, d.eqn_params, upool[0], dtMinBits, st()));
+			HB_CUDA(OPS()->calcDT(grid, d.eqn_params, upool[0], dtMinBits, st()));
 			launches += 2;
 		}
 		if (int r = reduceDtMin()) return r;
@@ -1009,8 +1015,8 @@ template<class real> struct Fv : FvBase {
 		sp.slopeLimiter = d.slope_limiter; sp.fluxLimiter = d.flux_limiter; sp.scratch = opsScratch; sp.flux = d.flux; sp.fluxParam = d.flux_param; sp.plmMode = d.use_plm;
 		bool const plm = d.use_plm != 0;
 		if (useCTU) { if (int r = ctuStage(sp)) return r; }
-		else if (useMarch) HB_CUDA(ops->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
-		else HB_CUDA(ops->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
+		else if (useMarch) HB_CUDA(OPS()->march(d.dim, d.slope_limiter, marchCfg, &umaps[0], padX, grid, sp, d.eqn_params, 0, st()));
+		else HB_CUDA(OPS()->stage(d.dim, plm, !plm && d.flux_limiter > 0, grid, sp, d.eqn_params, st()));
 		launches++;
 		HB_CUDA(cudaMemcpyAsync(ctl + 1, &saved[1], sizeof(double), cudaMemcpyHostToDevice, st()));
 		size_t const n = (size_t)nS * (size_t)cells;
@@ -1026,10 +1032,10 @@ template<class real> struct Fv : FvBase {
 		std::ostringstream o;
 		int ti[5];
 		bool const plm = d.use_plm != 0;
- 		ops->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
+ 		OPS()->tileInfo(d.dim, plm, !plm && d.flux_limiter > 0, ti);
 		if (useMarch) for (int k = 0; k < 5; ++k) ti[k] = marchInfoV[k];
-		o << "kernel=" << (useCTU ? "ctu(unfused:calcLR,calcFlux,updateCTU,boundaryLR,calcFlux,finish)" : useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : ((marchInfoV[6] & 2) ? "fv_march3(tma,split-barrier)" : "fv_march(tma)")) : (ops->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
-		o << "eqn=" << ops->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
+		o << "kernel=" << (useCTU ? "ctu(unfused:calcLR,calcFlux,updateCTU,boundaryLR,calcFlux,finish)" : useMarch ? (d.dim == 2 && marchBox[0] <= 40 ? "fv_march2d(warp-per-pencil,tma)" : ((marchInfoV[6] & 2) ? "fv_march3(tma,split-barrier)" : "fv_march(tma)")) : (OPS()->eqnId == HB_EQN_ADM3D ? "adm_flux_xyz+adm_update" : "fv_stage(tile)")) << " cfg=" << marchCfg << " pitchX=" << grid.strideY << " padX=" << padX << " ";
+		o << "eqn=" << OPS()->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
 		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : ""));
 		if (useMarch) { o << " stageCfgs="; for (size_t i = 0; i < plan.size(); ++i) o << (i ? "," : "") << stageCfg(plan[i]); }
@@ -1069,8 +1075,8 @@ template<class real> struct Fv : FvBase {
 	}
 	int initDerivs() override {
 		useDevice(ctx);
-		if (!ops->initDerivs) return HB_OK;      // equations without an initDerivs kernel (hydro/init/init.lua:231-235)
-		HB_CUDA(ops->initDerivs(grid, upool[0], st()));
+		if (!OPS()->initDerivs) return HB_OK;      // equations without an initDerivs kernel (hydro/init/init.lua:231-235)
+		HB_CUDA(OPS()->initDerivs(grid, upool[0], st()));
 		launches++;
 		dtValid = false;
 		return HB_OK;
@@ -1164,6 +1170,35 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 		if (o) impl = new Fv<float>(ctx, *d, o);
 	}
 	if (!impl) return setError(HB_ERR_INVALID, "hb_fv_create: unknown equation id");
+	if (int r = impl->init()) { delete impl; return r; }
+	*out = new hb_fv{impl};
+	return HB_OK;
+}
+// An equation supplied as source (hb_jit.cu): `header_src` defines the class template `eqn_type`<real, FAST> with the plug-in contract of
+// csrc/hb_eqn_euler.cuh; it is registered as the include file `header_name` (naming an embedded header replaces it).  desc->eqn is ignored;
+// desc->eqn_params are handed to the equation's makeParams.  NVRTC compiles the marching / ghost / CFL / constrain kernels over it.
+int hb_fv_create_from_source(hb_ctx* ctx, const hb_fv_desc* d, const char* header_name, const char* header_src, const char* eqn_type,
+	hb_fv** out, char* log, size_t log_cap)
+{
+	if (log && log_cap) log[0] = 0;
+	if (!ctx || !d || !out || !header_name || !header_src || !eqn_type) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: null argument");
+	*out = nullptr;
+	if (d->dim < 2 || d->dim > 3) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: dim must be 2 or 3 (the marching kernels)");
+	for (int k = 0; k < d->dim; ++k) {
+		if (d->n[k] < 1 || d->global_n[k] < d->n[k]) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: bad grid size");
+		for (int m = 0; m < 2; ++m) if (d->bc[2 * k + m] < 0 || d->bc[2 * k + m] > HB_BC_FIXED) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: unknown boundary method");
+	}
+	if (d->rk_order < 0 || d->rk_order > 4) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: rk_order must be 0..4");
+	if (d->use_plm != 1 || d->flux != HB_FLUX_ROE || d->flux_limiter != 0 || d->use_ctu || (d->slope_limiter != 8 && d->slope_limiter != 18))
+		return setError(HB_ERR_INVALID, "hb_fv_create_from_source: a run-time equation runs Roe + usePLM = 'plm cons' with the minmod or superbee slope limiter");
+	std::string err, lg;
+	bool const strict = d->strict_fp != 0;
+	JitProgram* P = ctx->real_bytes == 8
+		? jitCompile<double>(ctx, header_name, header_src, eqn_type, d->dim, d->slope_limiter, strict, d->eqn_params, err, lg)
+		: jitCompile<float>(ctx, header_name, header_src, eqn_type, d->dim, d->slope_limiter, strict, d->eqn_params, err, lg);
+	if (log && log_cap) snprintf(log, log_cap, "%s", lg.c_str());
+	if (!P) return setError(HB_ERR_COMPILE, "hb_fv_create_from_source: " + err);
+	FvBase* impl = ctx->real_bytes == 8 ? (FvBase*)new Fv<double>(ctx, *d, jitOps<double>(P), P) : (FvBase*)new Fv<float>(ctx, *d, jitOps<float>(P), P);
 	if (int r = impl->init()) { delete impl; return r; }
 	*out = new hb_fv{impl};
 	return HB_OK;

@@ -23,8 +23,7 @@
 // Roe flux, acc = ((0 - dFx) - dFy) - dFz, RK combination alpha terms then beta terms, constrainU.  The -fmad=false build of
 // this kernel is therefore bit-identical to the oracle as well (tests/test_gpu_parity.py).
 #pragma once
-#include <cuda.h>
-#include <cstdint>
+#include "hb_rtc_compat.h"
 #include "hb_fv_kernels.cuh"
 #include "hb_roe_fast.cuh"
 

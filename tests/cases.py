@@ -121,6 +121,15 @@ CASES["slab_march3d_overlap_periodic"] = (dict(eqn="mhd", dim=3, gridSize=[33, 6
 CASES["slab_march2d_overlap"] = (dict(eqn="euler", dim=2, gridSize=[40, 140], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                                       slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 4)
 
+# thin slabs: 8 (5) planes per rank on 4 (8) ranks -- one marching chunk; the overlapped exchange splits it into rim and interior planes
+CASES["slab_thin3d"] = (dict(eqn="euler", dim=3, gridSize=[34, 18, 32], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                             usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 3)
+CASES["slab_thin3d8"] = (dict(eqn="euler", dim=3, gridSize=[34, 18, 40], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                              usePLM="plm cons", slopeLimiter="superbee", integrator="Runge-Kutta 3, TVD", cfl=.1,
+                              boundary=dict(xmin="mirror", xmax="mirror", ymin="freeflow", ymax="freeflow", zmin="periodic", zmax="periodic")), 3)
+CASES["slab_thin2d_mhd"] = (dict(eqn="mhd", dim=2, gridSize=[70, 24], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
+                                 integrator="Runge-Kutta 3, TVD", cfl=.15), 3)
+
 # the remaining boundary methods of gridsolver.lua:746-846 (linear / quadratic extrapolation, fixed = Dirichlet state).
 # These do not compose to a source-index map, so the GPU runs the reference's x, y, z passes (fill_ghosts_axis).
 CASES["F4_sod_linear_1d"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", fluxLimiter="superbee", integrator="forward Euler", cfl=.3,

@@ -90,3 +90,29 @@ def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
     ref, tref = single(hydrob200, case, n, strict_fp=(mode == "gpu_strict"), use_graph=False)
     assert np.load(out + ".t.npy")[0] == tref
     assert np.array_equal(got, ref)
+
+
+# ---- more than two ranks: interior ranks have two neighbours; thin slabs (a few planes per rank: the rim / interior split of the overlapped
+# exchange, hb_fv.cu); ADM.  Needs 4 (8) devices: gpurun --gpus 4 (8).
+MANY = [("slab_march3d_overlap", "gpu_strict", 4), ("slab_march3d_overlap", "gpu", 4), ("slab_march3d_overlap_periodic", "gpu", 4),
+        ("slab_march2d_overlap", "gpu_strict", 4), ("slab_thin3d", "gpu_strict", 4), ("slab_thin3d", "gpu", 4), ("slab_thin2d_mhd", "gpu_strict", 4),
+        ("C5_gauge_wave_slab", "gpu_strict", 4), ("C4_sphere_rk4", "gpu_strict", 4), ("F3_selfgrav_sphere_rk4_plm_3d", "gpu_strict", 4),
+        ("slab_march3d_overlap", "gpu_strict", 8), ("slab_march3d_overlap_periodic", "gpu", 8), ("slab_thin3d8", "gpu_strict", 8),
+        ("slab_thin3d8", "gpu", 8)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,mode,world", MANY)
+def test_gpu_many_ranks_equal_single(hydrob200, tmp_path, case, mode, world):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs (run with gpurun --gpus %d)" % (world, world))
+    out = str(tmp_path / "dec")
+    n = 3
+    launch(mode, case, n, out, world=world)
+    got = np.load(out + ".npy")
+    if "overlap" in case or "thin" in case:
+        assert "exchange=overlapped" in open(out + ".describe").read()
+    ref, tref = single(hydrob200, case, n, strict_fp=(mode == "gpu_strict"), use_graph=False)
+    assert np.load(out + ".t.npy")[0] == tref
+    assert np.array_equal(got, ref)
