@@ -346,7 +346,10 @@ template<class real> struct Fv : FvBase {
 		for (int k = 0; k < 6; ++k) bc.bc[k] = d.bc[k];
 		bc.fixedState = nullptr;
 		seqBc = false;
-		for (int k = 0; k < 2 * d.dim; ++k) if (d.bc[k] >= HB_BC_LINEAR) seqBc = true;
+		// (a user-selected 'none' face, gridsolver.lua:618-621: the reference's later per-axis passes still fill the corner / edge ghost cells
+		// next to it from the other axes' methods, which the composed single-pass source map skips -- run the per-axis sequence then.  Faces
+		// owned by a neighbouring slab become 'none' in commInit, on `bc`, and do not count here: the exchange covers them.)
+		for (int k = 0; k < 2 * d.dim; ++k) if (d.bc[k] >= HB_BC_LINEAR || d.bc[k] == HB_BC_NONE) seqBc = true;
 		if (seqBc) {
 			HB_CUDA(cudaMalloc(&fixedDev, sizeof(double) * 6 * HB_FIXED_STRIDE));
 			HB_CUDA(cudaMemset(fixedDev, 0, sizeof(double) * 6 * HB_FIXED_STRIDE));

@@ -8,26 +8,17 @@ hydrob200/env.lua -- the subset of lua-opencl's `cl.obj.env` / `cl.obj.buffer` /
 	hydro/solver/fvsolver.lua:216-221, solverbase.lua:1328-1345  program:kernel(...), k.obj:setArg, k(...) -> Kernel
 	hydro/solver/solverbase.lua:1350-1376            env:reduce{op=...}                          -> reduce closure
 
-Kernel source handed to Program is CUDA C++ (the CUDA-dialect kernel templates); `kernel`, `global`, `constant`
-qualifiers of the reference's OpenCL-C templates are provided as macros by the prelude below, get_global_id() etc. map to
-blockIdx/threadIdx, so the equation-specific device functions emitted by the existing symmath/template codegen compile
-unchanged in most cases.
+Kernel source handed to Program is the OpenCL-C the reference's templates emit.  hb_module_compile_opencl (csrc/hb_cl.cu) rewrites
+the dialect on C tokens -- `kernel` / `global` / `constant` qualifiers, `(real3){.x=..}` compound literals (also inside #define
+bodies, hydro/code/math.cl:47-52) -- prepends hb_cl_prelude() (get_global_id & co., `typedef HB_REAL real`) and compiles with NVRTC
+-default-device for sm_100a, so the per-equation device functions of hydro/eqn/*.cl compile without a hand conversion.  (Round 1 tried
+this with a macro prelude in this file: `#define global` also erases the token inside CUDA's own `__global__`, and no macro turns a
+compound literal into C++.)  tests/test_gpu_fine_grained.py drives exactly this surface from Python on the GPU, including one whole
+unfused RK4 update that is bit-identical to hb_fv_update.
 --]]
 local hb = require 'hydrob200.ffi'
 local ffi, lib, check = hb.ffi, hb.lib, hb.check
 local class = require 'ext.class'
-
-local prelude = [[
-#define kernel extern "C" __global__
-#define global
-#define constant const
-#define local __shared__
-#define get_global_id(i) ((i)==0 ? blockIdx.x*blockDim.x+threadIdx.x : (i)==1 ? blockIdx.y*blockDim.y+threadIdx.y : blockIdx.z*blockDim.z+threadIdx.z)
-#define get_local_id(i) ((i)==0 ? threadIdx.x : (i)==1 ? threadIdx.y : threadIdx.z)
-#define get_group_id(i) ((i)==0 ? blockIdx.x : (i)==1 ? blockIdx.y : blockIdx.z)
-#define barrier(x) __syncthreads()
-#define CLK_LOCAL_MEM_FENCE 0
-]]
 
 local Env = class()
 function Env:init(args)
@@ -37,7 +28,7 @@ function Env:init(args)
 	check(lib.hb_ctx_create(args.device or 0, self.real == 'float' and 4 or 8, p), 'hb_ctx_create')
 	self.ctx = ffi.gc(p[0], lib.hb_ctx_destroy)
 	self.cmds = {self}                                                   -- env.cmds[1]:finish()
-	self.code = prelude
+	self.code = ''                                                       -- (the prelude is added by hb_module_compile_opencl)
 end
 function Env:finish() check(lib.hb_sync(self.ctx), 'hb_sync') end
 function Env:buffer(args) return require'hydrob200.env'.Buffer(self, args) end
@@ -78,7 +69,7 @@ function Kernel:init(program, args)
 	local p = ffi.new'hb_kernel*[1]'
 	check(lib.hb_kernel_get(program.obj, args.name, p), 'hb_kernel_get')
 	self.obj = self                                                     -- k.obj:setArg(i, x)
-	self.h = p[0]
+	self.h = ffi.gc(p[0], lib.hb_kernel_free)
 	self.domain = args.domain
 	if args.setArgs then for i, a in ipairs(args.setArgs) do self:setArg(i-1, a) end end
 end
@@ -101,7 +92,7 @@ function Program:init(env, args) self.env, self.code, self.name = env, args.code
 function Program:compile(args)
 	local p = ffi.new'hb_module*[1]'
 	local log = ffi.new('char[?]', 1 << 16)
-	local rc = lib.hb_module_compile(self.env.ctx, self.env.code..self.code, self.name, nil, 0, p, log, 1 << 16)
+	local rc = lib.hb_module_compile_opencl(self.env.ctx, self.env.code..self.code, self.name, nil, 0, p, log, 1 << 16)
 	self.log = ffi.string(log)
 	if rc ~= 0 then error(self.name..': NVRTC build failed:\n'..self.log) end
 	self.obj = ffi.gc(p[0], lib.hb_module_free)
