@@ -97,7 +97,7 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 #define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 8, 32, 0) X(3, 6, 64, 0) X(4, 15, 64, 32) X(5, 11, 64, 32) X(6, 8, 32, 32) X(7, 6, 64, 32)
 #else
 #if defined(HB_DEV)
-#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0)
+#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 11, 64, 1) X(3, 8, 64, 1)
 #else
 #define HB_MARCH3N_LIST(X) \
 	X(0, 15, 64, 0)    /* 32 x 15 columns, 64 planes per CTA, 16 warps at 128 registers (fits with at most two staged RK operands) */ \
@@ -109,7 +109,9 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(6, 15, 64, 32)   /* the same with the self-gravity source in the epilogue (chosen by hb_fv_add_op, never by the auto selection) */ \
 	X(7, 11, 64, 32) \
 	X(8, 8, 64, 32) \
-	X(9, 6, 64, 32)
+	X(9, 6, 64, 32) \
+	X(10, 11, 64, 1)   /* x and y flux cores of a cell issued as one block (168 registers, 12 warps): measured, see DESIGN 4.1 */ \
+	X(11, 8, 64, 1)
 #endif
 #endif
 constexpr int kMarch3N =

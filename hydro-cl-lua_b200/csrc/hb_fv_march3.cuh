@@ -34,6 +34,7 @@ template<int TY_, int KM_, int VAR_ = 0> struct March3Cfg {
 	static constexpr int TY = TY_;     // rows per CTA = column warps
 	static constexpr int KM = KM_;     // planes per CTA along the marching axis
 	static constexpr bool GRAV = (VAR_ & 32) != 0;      // the epilogue adds the self-gravity source (as MarchCfg::GRAV)
+	static constexpr bool PAIR = (VAR_ & 1) != 0;       // the x and y flux cores of a cell issued as one block (two independent dependent chains)
 };
 
 template<class C, class real> struct March3Geom {
@@ -275,6 +276,22 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 					}
 					cpAsyncCommit();
 				}
+				if constexpr (C::PAIR && FAST) {
+					real ULx[nI], URx[nI], ULy[nI], URy[nI], Fx[nI], Fy[nI];
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) {
+						real const* u = P + q * PS + ob;
+						plmFacesT<real, LIM, FAST>(lim, u[-2], u[-1], u[0], u[1], ULx[q], URx[q]);
+						plmFacesT<real, LIM, FAST>(lim, u[-2 * BX], u[-BX], u[0], u[BX], ULy[q], URy[q]);
+					}
+					roeFluxPairAuto<Eqn, 0, 1>(Fx, Fy, ep, ULx, URx, ULy, URy);
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) {
+						acc[q] = fma(Fy[q], aovY, fma(Fx[q], aovX, zacc[q]));
+						fxx[(q * TY + cj) * (TX + 1) + ci] = Fx[q];
+						fxy[(q * (TY + 1) + cj) * TX + ci] = Fy[q];
+					}
+				} else {
 				real F[nI];
 				lowFaceFlux<Eqn, 0, LIM, PS>(F, ep, lim, P, ob, 1);
 				#pragma unroll
@@ -289,6 +306,7 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 					if constexpr (FAST) acc[q] = fma(F[q], aovY, acc[q]);
 					else if (!g.fluxOn[1]) F[q] = 0;
 					fxy[(q * (TY + 1) + cj) * TX + ci] = F[q];
+				}
 				}
 			}
 			__syncwarp();

@@ -11,10 +11,7 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
         sys.path.insert(0, p)
 
 
-def main():
-    mode, case, nsteps, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
-    import torch.distributed as dist
-    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+def run_case(mode, case, nsteps, out, dist, rank, world):
     import hydrob200
     from importlib import import_module
     SlabComm = import_module("hydro-cl-lua_b200.hydro.solver.choppedup").SlabComm
@@ -22,7 +19,6 @@ def main():
     cfg, _ = dict(CASES, **ADM_CASES)[case]
     if mode == "cpu":
         import oracle
-        dist.init_process_group("gloo", rank=rank, world_size=world)
         comm = SlabComm(world, rank, dist)
         S = hydrob200.FiniteVolumeSolver(dict(cfg, backend=oracle.OracleBackend, comm=comm))
         assert S.rkOrder == 0, "the host-side exchange test drives single-stage (forward Euler) steps"
@@ -35,10 +31,9 @@ def main():
             S.t += dt
             U = comm.exchangeHost(S.getState(), S.dim, periodic)
             S.setState(U)
+        full = S.getGlobalInterior()
     else:
         import torch
-        torch.cuda.set_device(rank % torch.cuda.device_count())
-        dist.init_process_group("nccl", rank=rank, world_size=world)
         comm = SlabComm(world, rank, dist)
         S = hydrob200.FiniteVolumeSolver(dict(cfg, comm=comm, device=rank % torch.cuda.device_count(),
                                               strict_fp=(mode == "gpu_strict"), use_graph=False))
@@ -46,20 +41,37 @@ def main():
         if rank == 0:
             with open(out + ".describe", "w") as f:
                 f.write(S.backend.describe())
-        # the gather below runs on the host through a second, gloo group
-    if mode != "cpu":
-        g = dist.new_group(backend="gloo")
-        import torch
+        # the gather runs on the host through a second, gloo group
         Ui = np.ascontiguousarray(S.interior())
         t = torch.from_numpy(Ui)
         parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t, group=g)
+        dist.all_gather(parts, t, group=run_case.gloo)
         full = np.concatenate([p.numpy() for p in parts], axis=2 - (S.dim - 1))
-    else:
-        full = S.getGlobalInterior()
+        S.backend.close()
     if rank == 0:
         np.save(out, full)
         np.save(out + ".t", np.array([S.t]))
+    dist.barrier()
+
+
+def main():
+    """argv: mode case nsteps out   |   multi "mode:case:nsteps:out,mode:case:nsteps:out,..." (several cases in one process group: one
+    interpreter / torch / NCCL start-up per rank instead of one per case)"""
+    import torch.distributed as dist
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    if sys.argv[1] == "multi":
+        jobs = [j.split(":") for j in sys.argv[2].split(",")]
+    else:
+        jobs = [sys.argv[1:5]]
+    if jobs[0][0] == "cpu":
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        import torch
+        torch.cuda.set_device(rank % torch.cuda.device_count())
+        dist.init_process_group("nccl", rank=rank, world_size=world)
+        run_case.gloo = dist.new_group(backend="gloo")
+    for mode, case, nsteps, out in jobs:
+        run_case(mode, case, int(nsteps), out, dist, rank, world)
     dist.barrier()
     dist.destroy_process_group()
 

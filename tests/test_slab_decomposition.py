@@ -66,26 +66,43 @@ def test_cpu_gloo_two_ranks_equal_single(hydrob200, oracle, tmp_path, case):
     assert np.array_equal(got, ref)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("case,mode", [("C4_sphere_rk4", "gpu_strict"), ("C2_kh_rk4tvd_minmod", "gpu"), ("C3_ot_rk3tvd", "gpu"),
-                                       ("C4_sphere_rk4_mirror_periodic", "gpu"), ("C5_gauge_wave_slab", "gpu"),
-                                       ("C5_warp_bubble_rk4", "gpu_strict"), ("slab_march3d_overlap", "gpu_strict"),
-                                       ("slab_march3d_overlap", "gpu"), ("slab_march3d_overlap_periodic", "gpu"),
-                                       ("slab_march2d_overlap", "gpu_strict"),
-                                       # the ops on a decomposed grid: potential ghost planes exchanged per sweep, residual / maximum all-reduced
-                                       ("F3_selfgrav_sphere_rk4_plm_3d", "gpu_strict"), ("F3_nodiv_ot_rk3_2d", "gpu"),
-                                       ("F3_nodiv_selfgrav_ot_fe_3d", "gpu_strict"), ("F3_selfgrav_sphere_fe_2d", "gpu"),
-                                       # useCTU on a decomposed grid: the face-state blocks' ghost planes travel with boundaryLR
-                                       ("F4_ctu_sphere_rk2_3d", "gpu_strict"), ("F4_ctu_ot_mhd_fe_2d", "gpu")])
-def test_gpu_two_ranks_equal_single(hydrob200, tmp_path, case, mode):
+TWO = [("C4_sphere_rk4", "gpu_strict"), ("C2_kh_rk4tvd_minmod", "gpu"), ("C3_ot_rk3tvd", "gpu"),
+       ("C4_sphere_rk4_mirror_periodic", "gpu"), ("C5_gauge_wave_slab", "gpu"),
+       ("C5_warp_bubble_rk4", "gpu_strict"), ("slab_march3d_overlap", "gpu_strict"),
+       ("slab_march3d_overlap", "gpu"), ("slab_march3d_overlap_periodic", "gpu"),
+       ("slab_march2d_overlap", "gpu_strict"), ("slab_thin3d", "gpu_strict"), ("slab_thin2d_mhd", "gpu"),
+       # the ops on a decomposed grid: potential ghost planes exchanged per sweep, residual / maximum all-reduced
+       ("F3_selfgrav_sphere_rk4_plm_3d", "gpu_strict"), ("F3_nodiv_ot_rk3_2d", "gpu"),
+       ("F3_nodiv_selfgrav_ot_fe_3d", "gpu_strict"), ("F3_selfgrav_sphere_fe_2d", "gpu"),
+       # useCTU on a decomposed grid: the face-state blocks' ghost planes travel with boundaryLR
+       ("F4_ctu_sphere_rk2_3d", "gpu_strict"), ("F4_ctu_ot_mhd_fe_2d", "gpu")]
+
+
+def _steps(case):
+    return 3 if ("overlap" in case or "thin" in case) else 5
+
+
+@pytest.fixture(scope="module")
+def two_rank_runs(tmp_path_factory):
+    """all two-rank cases inside ONE process group (one interpreter / torch / NCCL start-up per rank instead of one per case)"""
     import torch
     if torch.cuda.device_count() < 2:
+        return {}
+    d = tmp_path_factory.mktemp("two")
+    jobs = [(mode, case, _steps(case), str(d / ("%s_%s" % (case, mode)))) for case, mode in TWO]
+    launch_multi(jobs, 2)
+    return {(case, mode): out for mode, case, _, out in jobs}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,mode", TWO)
+def test_gpu_two_ranks_equal_single(hydrob200, two_rank_runs, case, mode):
+    if (case, mode) not in two_rank_runs:
         pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
-    out = str(tmp_path / "dec")
-    n = 3 if "overlap" in case else 5
-    launch(mode, case, n, out)
+    out = two_rank_runs[(case, mode)]
+    n = _steps(case)
     got = np.load(out + ".npy")
-    if "overlap" in case:
+    if "overlap" in case or "thin" in case:
         assert "exchange=overlapped" in open(out + ".describe").read()
     ref, tref = single(hydrob200, case, n, strict_fp=(mode == "gpu_strict"), use_graph=False)
     assert np.load(out + ".t.npy")[0] == tref
@@ -101,15 +118,41 @@ MANY = [("slab_march3d_overlap", "gpu_strict", 4), ("slab_march3d_overlap", "gpu
         ("slab_thin3d8", "gpu", 8)]
 
 
+def launch_multi(jobs, world):
+    port = free_port()
+    procs = []
+    arg = ",".join("%s:%s:%d:%s" % j for j in jobs)
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
+                   OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "slab_worker.py"), "multi", arg], env=env))
+    for p in procs:
+        assert p.wait(timeout=1200) == 0
+
+
+@pytest.fixture(scope="module")
+def many_rank_runs(tmp_path_factory):
+    """every MANY case of one world size runs inside ONE process group (one interpreter / NCCL start-up per rank)"""
+    import torch
+    done = {}
+    for world in sorted(set(w for _, _, w in MANY)):
+        if torch.cuda.device_count() < world:
+            continue
+        d = tmp_path_factory.mktemp("many%d" % world)
+        jobs = [(mode, case, 3, str(d / ("%s_%s" % (case, mode)))) for case, mode, w in MANY if w == world]
+        launch_multi(jobs, world)
+        for mode, case, _, out in jobs:
+            done[(case, mode, world)] = out
+    return done
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case,mode,world", MANY)
-def test_gpu_many_ranks_equal_single(hydrob200, tmp_path, case, mode, world):
-    import torch
-    if torch.cuda.device_count() < world:
+def test_gpu_many_ranks_equal_single(hydrob200, many_rank_runs, case, mode, world):
+    if (case, mode, world) not in many_rank_runs:
         pytest.skip("needs %d GPUs (run with gpurun --gpus %d)" % (world, world))
-    out = str(tmp_path / "dec")
+    out = many_rank_runs[(case, mode, world)]
     n = 3
-    launch(mode, case, n, out, world=world)
     got = np.load(out + ".npy")
     if "overlap" in case or "thin" in case:
         assert "exchange=overlapped" in open(out + ".describe").read()
