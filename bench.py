@@ -47,6 +47,11 @@ WORKLOADS = {
                 cfg=dict(eqn="mhd", dim=3, gridSize=[384, 384, 384], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="Orszag-Tang",
                          usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1),
                 words=16, nI=8, stages=4, cpu_sample=[128, 128, 128], parity=(2, 16)),
+    # the flux-limiter path with the marching structure (fv_march3 GEN; HB_MARCH_GEN=0 keeps it on the tile kernel)
+    "C4FL": dict(name="3D Euler spherical blast, Roe + superbee FLUX limiter (no PLM), RK4, double, freeflow, 256^3 per GPU (z slabs)",
+                 cfg=dict(eqn="euler", dim=3, gridSize=[256, 256, 256], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                          fluxLimiter="superbee", integrator="Runge-Kutta 4", cfl=.1),
+                 words=16, nI=5, stages=4, cpu_sample=[128, 128, 128], parity=(1, 16)),
     "C2": dict(name="2D Euler Kelvin-Helmholtz, Roe+PLM(minmod)+RK4-TVD, double, periodic, 2048^2 per GPU (y slabs)",
                cfg=dict(eqn="euler", dim=2, gridSize=[2048, 2048], initCond="Kelvin-Helmholtz", usePLM="plm cons",
                         slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15),

@@ -122,7 +122,7 @@ cudaError_t initDerivs(GridP<real> const& g, real* U, cudaStream_t st) {
 	return cudaGetLastError();
 }
 
-const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval,
+const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, nullptr, march, ghosts, calcDT, constrainAll, tileInfo, debugEval,
 	scratchElems, initDerivs};
 
 }   // namespace

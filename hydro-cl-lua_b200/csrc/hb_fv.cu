@@ -393,6 +393,15 @@ template<class real> struct Fv : FvBase {
 						if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
 					}
 			}
+			// the general marching configurations (3-D): the other slope limiters, no reconstruction, Roe with a flux limiter, HLL / Rusanov / HLLC
+			// with or without 'plm cons' -- everything else of these rows that round 1 ran through the tile kernel ($HB_MARCH_GEN=0: keep it there)
+			const char* mg = getenv("HB_MARCH_GEN");
+			if (!ok && d.stage_kernel != 1 && d.use_plm <= 1 && !d.use_ctu && OPS()->marchInfoGen && (!mg || atoi(mg) != 0)) {
+				for (int cfg = kMarchGenBase; !ok && OPS()->marchInfoGen(d.dim, cfg, marchBox, marchInfoV); ++cfg) {
+					size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
+					if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
+				}
+			}
 			if (d.stage_kernel == 2 && !ok) return setError(HB_ERR_INVALID, "hb_fv_create: the marching kernel is not built for this configuration");
 			if (jit && !ok) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: a run-time equation runs the marching kernels only (dim 2 or 3, Roe flux, usePLM = 'plm cons', slopeLimiter minmod or superbee, RK operands within shared memory)");
 			useMarch = ok;

@@ -97,7 +97,7 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 #define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 8, 32, 0) X(3, 6, 64, 0) X(4, 15, 64, 32) X(5, 11, 64, 32) X(6, 8, 32, 32) X(7, 6, 64, 32)
 #else
 #if defined(HB_DEV)
-#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 11, 64, 1) X(3, 8, 64, 1)
+#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0)
 #else
 #define HB_MARCH3N_LIST(X) \
 	X(0, 15, 64, 0)    /* 32 x 15 columns, 64 planes per CTA, 16 warps at 128 registers (fits with at most two staged RK operands) */ \
@@ -109,11 +109,13 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(6, 15, 64, 32)   /* the same with the self-gravity source in the epilogue (chosen by hb_fv_add_op, never by the auto selection) */ \
 	X(7, 11, 64, 32) \
 	X(8, 8, 64, 32) \
-	X(9, 6, 64, 32) \
-	X(10, 11, 64, 1)   /* x and y flux cores of a cell issued as one block (168 registers, 12 warps): measured, see DESIGN 4.1 */ \
-	X(11, 8, 64, 1)
+	X(9, 6, 64, 32)
 #endif
 #endif
+// general configurations (March3Cfg::GEN, VAR bit 1): X(index, TY, KM, VAR); cfg = kMarchGenBase + index
+#define HB_MARCH3G_LIST(X) X(0, 8, 64, 2) X(1, 6, 64, 2) X(2, 4, 32, 2)
+// the same for 2-D (March2Cfg::GEN, MINB bit 5): X(index, NW, KM, MINB)
+#define HB_MARCH2G_LIST(X) X(0, 4, 32, 33) X(1, 2, 32, 33)
 constexpr int kMarch3N =
 #define HB_X(i, ty, km, var) +1
 	0 HB_MARCH3N_LIST(HB_X);
@@ -195,9 +197,12 @@ cudaError_t launchMarch3(const CUtensorMap* tmap, int padX, GridP<real> const& g
 }
 template<class C>
 cudaError_t launchMarch3Lim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
-	if (lim == 8) return launchMarch3<8, C>(tmap, padX, g, sp, ep, chunkSel, st);
-	if (lim == 18) return launchMarch3<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
-	return cudaErrorInvalidValue;
+	if constexpr (C::GEN) return launchMarch3<-1, C>(tmap, padX, g, sp, ep, chunkSel, st);      // limiter, reconstruction and flux at run time
+	else {
+		if (lim == 8) return launchMarch3<8, C>(tmap, padX, g, sp, ep, chunkSel, st);
+		if (lim == 18) return launchMarch3<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
+		return cudaErrorInvalidValue;
+	}
 }
 template<class C> void march3InfoCfg(int box[4], int info[7]) {
 	typedef March3Geom<C, real> G;
@@ -248,9 +253,12 @@ cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& 
 }
 template<class C>
 cudaError_t launchMarch2WLim(int lim, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
-	if (lim == 8) return launchMarch2W<8, C>(tmap, padX, g, sp, ep, chunkSel, st);
-	if (lim == 18) return launchMarch2W<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
-	return cudaErrorInvalidValue;
+	if constexpr (C::GEN) return launchMarch2W<-1, C>(tmap, padX, g, sp, ep, chunkSel, st);      // limiter, reconstruction and flux at run time
+	else {
+		if (lim == 8) return launchMarch2W<8, C>(tmap, padX, g, sp, ep, chunkSel, st);
+		if (lim == 18) return launchMarch2W<18, C>(tmap, padX, g, sp, ep, chunkSel, st);
+		return cudaErrorInvalidValue;
+	}
 }
 template<class C> void march2WInfoCfg(int box[4], int info[7]) {
 	typedef March2Geom<C, real> G;
@@ -281,7 +289,23 @@ bool marchInfo(int dim, bool plm, bool flim, int lim, int cfg, int box[4], int i
 #undef HB_X
 	return false;
 }
+bool marchInfoGen(int dim, int cfg, int box[4], int info[7]) {
+#define HB_X(i, nw, km, mb) if (dim == 2 && cfg == kMarchGenBase + i) { march2WInfoCfg<March2Cfg<nw, km, mb>>(box, info); return true; }
+	HB_MARCH2G_LIST(HB_X)
+#undef HB_X
+	if (dim != 3) return false;
+#define HB_X(i, ty, km, var) if (cfg == kMarchGenBase + i) { march3InfoCfg<March3Cfg<ty, km, var>>(box, info); return true; }
+	HB_MARCH3G_LIST(HB_X)
+#undef HB_X
+	return false;
+}
 cudaError_t march(int dim, int lim, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* ep, int chunkSel, cudaStream_t st) {
+#define HB_X(i, ty, km, var) if (dim == 3 && cfg == kMarchGenBase + i) return launchMarch3Lim<March3Cfg<ty, km, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
+	HB_MARCH3G_LIST(HB_X)
+#undef HB_X
+#define HB_X(i, nw, km, mb) if (dim == 2 && cfg == kMarchGenBase + i) return launchMarch2WLim<March2Cfg<nw, km, mb>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
+	HB_MARCH2G_LIST(HB_X)
+#undef HB_X
 	cfg = remapCfg(dim, cfg);
 #define HB_X(i, ty, km, var) if (dim == 3 && cfg == i) return launchMarch3Lim<March3Cfg<ty, km, var>>(lim, tmap, padX, g, sp, ep, chunkSel, st);
 	HB_MARCH3N_LIST(HB_X)
@@ -385,7 +409,7 @@ cudaError_t debugEval(int kind, int side, int n, const double* ep, const double*
 	return cudaGetLastError();
 }
 
-const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, march, ghosts, calcDT, constrainAll, tileInfo, debugEval, nullptr, nullptr, launchOpKernel<real, MODE>, launchCtuKernel<Eqn, MODE>};
+const FvOps<real> theOps = {Eqn::eqnId, Eqn::nS, Eqn::nI, Eqn::nW, stage, marchInfo, marchInfoGen, march, ghosts, calcDT, constrainAll, tileInfo, debugEval, nullptr, nullptr, launchOpKernel<real, MODE>, launchCtuKernel<Eqn, MODE>};
 
 }   // namespace
 

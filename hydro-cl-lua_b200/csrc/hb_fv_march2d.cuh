@@ -27,6 +27,7 @@ template<int NW_, int KM_, int MINB_> struct March2Cfg {
 	static constexpr int KM = KM_;       // nominal rows per warp along the marching axis (the launcher picks the actual count, see rowsPerWarp)
 	static constexpr int MINB = MINB_ & 15;
 	static constexpr bool GRAV = (MINB_ & 16) != 0;   // the epilogue adds the self-gravity source (StageP::gravPot), as MarchCfg::GRAV
+	static constexpr bool GEN = (MINB_ & 32) != 0;    // the general configuration (any slope limiter, no reconstruction, flux limiter, HLL / Rusanov / HLLC): March3Cfg::GEN
 };
 
 template<class C, class real> struct March2Geom {
@@ -100,10 +101,15 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gri
 
 	double const dt = *sp.dt;
 	real const aovX = g.aov[0], aovM = g.aov[MS];
+	constexpr bool GEN = C::GEN;
+	// GEN: 0 no reconstruction, 1 'plm cons', 2 Roe with a flux limiter on cell-centred states (as fv_march3)
+	int const gmode = !GEN ? 1 : (sp.plmMode == 1 ? 1 : (sp.fluxLimiter > 0 ? 2 : 0));
+	real const dtR = GEN ? real(dt) : real(0);
 	real Um[nI], zfP[nI], FzP[nI], accP[nI];
+	real Umm[GEN ? nI : 1];                              // GEN, flux limiter: U[k-2] of the own column
 	mbarWait(&full[0], 0);
 	#pragma unroll
-	for (int q = 0; q < nI; ++q) { Um[q] = ring[q * BX + ob]; zfP[q] = 0; FzP[q] = 0; accP[q] = 0; }
+	for (int q = 0; q < nI; ++q) { Um[q] = ring[q * BX + ob]; zfP[q] = 0; FzP[q] = 0; accP[q] = 0; if constexpr (GEN) Umm[q] = Um[q]; }
 	mbarWait(&full[1], 0);
 
 	real dtCell = inf_of<real>::v(), rateCell = 0;
@@ -122,6 +128,22 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gri
 		}
 		long long const idxK = colIdx + strideM * k;
 		real Uk[nI], Fz[nI], UR[nI], zfN[nI];
+		if constexpr (GEN) {
+			real Un[nI];
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) {
+				Uk[q] = P[q * BX + ob];
+				Un[q] = ring[sN * SLOT + q * BX + ob];
+				real const sK = gmode == 1 ? plmHalfSlope<real>(lim, Um[q], Uk[q], Un[q]) : real(0);
+				UR[q] = gmode == 1 ? Uk[q] - sK : Uk[q];
+				zfN[q] = gmode == 1 ? Uk[q] + sK : Uk[q];
+				Fz[q] = 0;
+			}
+			if (k >= kb && g.fluxOn[MS]) {
+				if (gmode == 2) roeFluxLimited<Eqn, MS>(Fz, ep, sp.fluxLimiter, dtR / g.dx[MS], Umm, Um, Uk, Un);
+				else interfaceFlux<Eqn, MS>(sp.flux, sp.fluxParam, Fz, ep, gmode == 1 ? zfP : Um, UR);
+			}
+		} else {
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) {
 			Uk[q] = P[q * BX + ob];
@@ -129,6 +151,7 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gri
 			Fz[q] = 0;
 		}
 		if (k >= kb && g.fluxOn[MS]) roeFluxAuto<Eqn, MS>(Fz, ep, zfP, UR);
+		}
 		if (k > kb && inside) {
 			real acc[nI];
 			#pragma unroll
@@ -150,7 +173,21 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gri
 		// neighbour's flux by shuffle, flux difference (fvsolver.cl:97-123)
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) accP[q] = 0;
-		if (xy) {                                               // warp-uniform
+		if (GEN && xy) {
+			// the low-face flux straight from the row's four-cell stencil (lane 0 has no cell c0 - 3 in its box: it takes lane 1's stencil, its
+			// flux is never used)
+			real F[nI];
+			if (g.fluxOn[0]) lowFaceFlux<Eqn, 0, LIM, BX, true>(F, ep, lim, P, lane == 0 ? ob + 1 : ob, 1, gmode, sp.flux, sp.fluxParam, sp.fluxLimiter, dtR / g.dx[0]);
+			else {
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) F[q] = 0;
+			}
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) {
+				real const Fhi = shflDown1<real>(F[q]);
+				if (g.volOn) accP[q] = real(0) - (Fhi * aovX - F[q] * aovX);
+			}
+		} else if (xy) {                                        // warp-uniform
 			real UL[nI], URx[nI], F[nI];
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) {
@@ -171,7 +208,7 @@ fv_march2d(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Gri
 			}
 		}
 		#pragma unroll
-		for (int q = 0; q < nI; ++q) { Um[q] = Uk[q]; zfP[q] = zfN[q]; FzP[q] = Fz[q]; }
+		for (int q = 0; q < nI; ++q) { if constexpr (GEN) Umm[q] = Um[q]; Um[q] = Uk[q]; zfP[q] = zfN[q]; FzP[q] = Fz[q]; }
 	}
 	if (sp.dtMinBits) {
 		if (rateCell > real(0)) dtCell = rmin<real>(dtCell, real(1.) / rateCell);

@@ -35,6 +35,10 @@ template<int TY_, int KM_, int VAR_ = 0> struct March3Cfg {
 	static constexpr int KM = KM_;     // planes per CTA along the marching axis
 	static constexpr bool GRAV = (VAR_ & 32) != 0;      // the epilogue adds the self-gravity source (as MarchCfg::GRAV)
 	static constexpr bool PAIR = (VAR_ & 1) != 0;       // the x and y flux cores of a cell issued as one block (two independent dependent chains)
+	// GEN: the general configuration -- any of the 20 slope limiters, no reconstruction, the Roe flux with a flux limiter (4-cell stencil
+	// along every axis; hydro/solver/fvsolver.lua:138-155), and the other fluxes of the calcFluxForInterface slot (HLL, Rusanov, euler-HLLC),
+	// all selected at run time from StageP as in the tile kernel fv_stage, with the literal device functions
+	static constexpr bool GEN = (VAR_ & 2) != 0;
 };
 
 template<class C, class real> struct March3Geom {
@@ -68,19 +72,39 @@ HB_D void mbarWaitBackoff(uint64_t* bar, uint32_t parity) {
 
 // Low-face Roe flux of the cell at ring offset `o` along the axis with ring stride `st` (1: x, BX: y): face states from the
 // four-cell stencil o-2st .. o+st ('plm cons', plm.cl:56-76: UL = U[i-1] + .5 sigma[i-1], UR = U[i] - .5 sigma[i]).
-template<class Eqn, int SIDE, int LIM, int PS>
+// GEN: reconstruction / flux / limiter chosen at run time (see March3Cfg::GEN): mode 0 no reconstruction, 1 'plm cons', 2 flux limiter.
+template<class Eqn, int SIDE, int LIM, int PS, bool GEN = false>
 HB_D void lowFaceFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params const& ep, int lim,
-	typename Eqn::real const* __restrict__ P, int o, int st)
+	typename Eqn::real const* __restrict__ P, int o, int st, int mode = 1, int flux = 0, int fluxParam = 0, int fluxLimiter = 0,
+	typename Eqn::real dt_dx = 0)
 {
 	typedef typename Eqn::real real;
 	constexpr int nI = Eqn::nI;
-	real UL[nI], UR[nI];
-	#pragma unroll
-	for (int q = 0; q < nI; ++q) {
-		real const* u = P + q * PS + o;
-		plmFacesT<real, LIM, Eqn::FAST>(lim, u[-2 * st], u[-st], u[0], u[st], UL[q], UR[q]);
+	if constexpr (GEN) {
+		if (mode == 2) {
+			real U2L[nI], UL[nI], UR[nI], U2R[nI];
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) { real const* u = P + q * PS + o; U2L[q] = u[-2 * st]; UL[q] = u[-st]; UR[q] = u[0]; U2R[q] = u[st]; }
+			roeFluxLimited<Eqn, SIDE>(F, ep, fluxLimiter, dt_dx, U2L, UL, UR, U2R);
+			return;
+		}
+		real UL[nI], UR[nI];
+		#pragma unroll
+		for (int q = 0; q < nI; ++q) {
+			real const* u = P + q * PS + o;
+			if (mode == 1) { UL[q] = u[-st] + plmHalfSlope<real>(lim, u[-2 * st], u[-st], u[0]); UR[q] = u[0] - plmHalfSlope<real>(lim, u[-st], u[0], u[st]); }
+			else { UL[q] = u[-st]; UR[q] = u[0]; }
+		}
+		interfaceFlux<Eqn, SIDE>(flux, fluxParam, F, ep, UL, UR);
+	} else {
+		real UL[nI], UR[nI];
+		#pragma unroll
+		for (int q = 0; q < nI; ++q) {
+			real const* u = P + q * PS + o;
+			plmFacesT<real, LIM, Eqn::FAST>(lim, u[-2 * st], u[-st], u[0], u[st], UL[q], UR[q]);
+		}
+		roeFluxAuto<Eqn, SIDE, true>(F, ep, UL, UR);
 	}
-	roeFluxAuto<Eqn, SIDE, true>(F, ep, UL, UR);
 }
 
 // RK combination + constrainU + stores + CFL dt of one finished cell (hydro/int/rk.lua:96-112, solverbase.lua:2116-2127): the same
@@ -163,6 +187,10 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 	int const tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
 	int const lim = LIM >= 0 ? LIM : sp.slopeLimiter;
 	bool const isCol = w < TY;
+	constexpr bool GEN = C::GEN;
+	// GEN: 0 no reconstruction, 1 'plm cons', 2 Roe with a flux limiter on cell-centred states (gridsolver.lua:119: never both)
+	int const gmode = !GEN ? 1 : (sp.plmMode == 1 ? 1 : (sp.fluxLimiter > 0 ? 2 : 0));
+	real const dtR = GEN ? real(*sp.dt) : real(0);
 
 	// ---- tile
 	int const ntx = (g.N[0] + TX - 1) / TX;
@@ -214,10 +242,10 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 				real* const fxx = FXX + (k & 1) * (nI * G::FXXN);
 				real* const fxy = FXY + (k & 1) * (nI * G::FXYN);
 				real F[nI];
-				lowFaceFlux<Eqn, 1, LIM, PS>(F, ep, lim, P, oY, BX);
+				lowFaceFlux<Eqn, 1, LIM, PS, GEN>(F, ep, lim, P, oY, BX, gmode, sp.flux, sp.fluxParam, sp.fluxLimiter, GEN ? dtR / g.dx[1] : real(0));
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) fxy[(q * (TY + 1) + TY) * TX + lane] = on1 ? F[q] : real(0);
-				lowFaceFlux<Eqn, 0, LIM, PS>(F, ep, lim, P, oX, 1);
+				lowFaceFlux<Eqn, 0, LIM, PS, GEN>(F, ep, lim, P, oX, 1, gmode, sp.flux, sp.fluxParam, sp.fluxLimiter, GEN ? dtR / g.dx[0] : real(0));
 				if (lane < TY) {
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) fxx[(q * TY + lane) * (TX + 1) + TX] = on0 ? F[q] : real(0);
@@ -250,8 +278,13 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 		#pragma unroll
 		for (int q = 0; q < nI; ++q) {
 			real const a = ring[0 * SLOT + q * PS + ob], b = ring[1 * SLOT + q * PS + ob], c = ring[2 * SLOT + q * PS + ob];
-			real lo;
-			plmCellFacesT<real, LIM, FAST>(lim, a, b, c, lo, zf[q]);
+			if constexpr (GEN) {
+				// zf: mode 1 the face state of plane kb-1 towards kb; mode 2 the cell of plane kb-2 (U2L of the first z interface); mode 0 unused
+				zf[q] = gmode == 1 ? b + plmHalfSlope<real>(lim, a, b, c) : a;
+			} else {
+				real lo;
+				plmCellFacesT<real, LIM, FAST>(lim, a, b, c, lo, zf[q]);
+			}
 			zacc[q] = 0;
 		}
 
@@ -293,14 +326,14 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 					}
 				} else {
 				real F[nI];
-				lowFaceFlux<Eqn, 0, LIM, PS>(F, ep, lim, P, ob, 1);
+				lowFaceFlux<Eqn, 0, LIM, PS, GEN>(F, ep, lim, P, ob, 1, gmode, sp.flux, sp.fluxParam, sp.fluxLimiter, GEN ? dtR / g.dx[0] : real(0));
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) {
 					if constexpr (FAST) acc[q] = fma(F[q], aovX, zacc[q]);
 					else if (!g.fluxOn[0]) F[q] = 0;
 					fxx[(q * TY + cj) * (TX + 1) + ci] = F[q];
 				}
-				lowFaceFlux<Eqn, 1, LIM, PS>(F, ep, lim, P, ob, BX);
+				lowFaceFlux<Eqn, 1, LIM, PS, GEN>(F, ep, lim, P, ob, BX, gmode, sp.flux, sp.fluxParam, sp.fluxLimiter, GEN ? dtR / g.dx[1] : real(0));
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) {
 					if constexpr (FAST) acc[q] = fma(F[q], aovY, acc[q]);
@@ -317,12 +350,34 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 			{
 				real const* __restrict__ Q1 = ring + ((k + 1 - (kb - 2)) & 3) * SLOT;
 				real const* __restrict__ Q2 = ring + ((k + 2 - (kb - 2)) & 3) * SLOT;
+				if constexpr (GEN) {
+					real UL[nI], UR[nI], U2R[nI];
+					#pragma unroll
+					for (int q = 0; q < nI; ++q) { UL[q] = P[q * PS + ob]; UR[q] = Q1[q * PS + ob]; U2R[q] = Q2[q * PS + ob]; }
+					if (gmode == 2) {
+						roeFluxLimited<Eqn, 2>(Fz, ep, sp.fluxLimiter, dtR / g.dx[2], zf, UL, UR, U2R);
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) zf[q] = UL[q];
+					} else if (gmode == 1) {
+						real URf[nI];
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) {
+							real const sN = plmHalfSlope<real>(lim, UL[q], UR[q], U2R[q]);
+							URf[q] = UR[q] - sN;
+							U2R[q] = UR[q] + sN;                    // (reused: the face state of plane k+1 towards k+2)
+						}
+						interfaceFlux<Eqn, 2>(sp.flux, sp.fluxParam, Fz, ep, zf, URf);
+						#pragma unroll
+						for (int q = 0; q < nI; ++q) zf[q] = U2R[q];
+					} else interfaceFlux<Eqn, 2>(sp.flux, sp.fluxParam, Fz, ep, UL, UR);
+				} else {
 				real UR[nI], zfN[nI];
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) plmCellFacesT<real, LIM, FAST>(lim, P[q * PS + ob], Q1[q * PS + ob], Q2[q * PS + ob], UR[q], zfN[q]);
 				roeFluxAuto<Eqn, 2, true>(Fz, ep, zf, UR);
 				#pragma unroll
 				for (int q = 0; q < nI; ++q) zf[q] = zfN[q];
+				}
 			}
 			if constexpr (FAST) {
 				#pragma unroll

@@ -17,6 +17,8 @@ namespace hb {
 // for hb_fv_launch_count
 extern thread_local int tlsStageLaunches;
 
+constexpr int kMarchGenBase = 1000;
+
 template<class real> struct FvOps {
 	int eqnId, nS, nI, nW;
 	cudaError_t (*stage)(int dim, bool plm, bool flim, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, cudaStream_t st);
@@ -25,6 +27,9 @@ template<class real> struct FvOps {
 	// info = {TX, TY, planes per CTA, threads, dynamic smem bytes without staged RK operands, column threads, epilogue adds the self-gravity source}.
 	// cfg selects a tile configuration (0 = default).
 	bool (*marchInfo)(int dim, bool plm, bool flim, int slopeLimiter, int cfg, int box[4], int info[7]);
+	// the GENERAL marching configurations (March3Cfg::GEN: any slope limiter, no reconstruction, Roe with a flux limiter, HLL / Rusanov / HLLC;
+	// 3-D): cfg = kMarchGenBase + i, launched through `march` like the others.  Null when not built (ADM, run-time equations).
+	bool (*marchInfoGen)(int dim, int cfg, int box[4], int info[7]);
 	// chunkSel: 0 all chunks along the marching axis, 1 first + last chunk, 2 the chunks in between (overlapped slab exchange)
 	cudaError_t (*march)(int dim, int slopeLimiter, int cfg, const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp,
 		const double* eqnParams, int chunkSel, cudaStream_t st);

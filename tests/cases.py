@@ -137,11 +137,6 @@ CASES["F4_sod_linear_1d"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="
 CASES["F4_kh_linear_quadratic_2d"] = (dict(eqn="euler", dim=2, gridSize=[56, 40], initCond="Kelvin-Helmholtz", usePLM="plm cons", slopeLimiter="minmod",
                                            integrator="Runge-Kutta 4", cfl=.15,
                                            boundary=dict(xmin="linear", xmax="quadratic", ymin="quadratic", ymax="mirror")), 10)
-# a user-selected 'none' face (gridsolver.lua:618-621): its ghost cells keep what they hold, the corner / edge cells next to it are still
-# filled by the other axes' passes (the composed single-pass fill skipped them)
-CASES["F4_sphere_none_face_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 10], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
-                                        usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 2, TVD", cfl=.1,
-                                        boundary=dict(xmin="mirror", xmax="none", ymin="periodic", ymax="periodic", zmin="none", zmax="freeflow")), 5)
 CASES["F4_cavity_fixed_2d"] = (dict(eqn="euler", dim=2, gridSize=[40, 36], initCond="sphere", usePLM="plm cons", slopeLimiter="minmod",
                                     integrator="Runge-Kutta 3, TVD", cfl=.15,
                                     boundary=dict(xmin="mirror", xmax="mirror", ymin="mirror",

@@ -332,3 +332,56 @@ def test_every_limiter_in_both_roles(hydrob200, oracle, role, index):
     got, tgot, _ = run(hydrob200, cfg, n)
     err, per = rel_linf_grouped(got, ref)
     assert err <= TOL_DOUBLE, (name, per)
+
+
+# ---- the GENERAL marching configurations (March3Cfg::GEN): everything of these rows that is not Roe + 'plm cons' + minmod / superbee
+GEN_CASES = {
+    "gen_roe_fluxlimiter_superbee": dict(eqn="euler", dim=3, gridSize=[37, 19, 70], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                         fluxLimiter="superbee", integrator="Runge-Kutta 2, TVD", cfl=.1),
+    "gen_roe_donor_cell_fe": dict(eqn="euler", dim=3, gridSize=[33, 9, 20], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                  integrator="forward Euler", cfl=.1, boundary=dict(xmin="mirror", xmax="mirror", ymin="periodic", ymax="periodic",
+                                                                                   zmin="freeflow", zmax="mirror")),
+    "gen_plm_vanleer_roe": dict(eqn="euler", dim=3, gridSize=[20, 17, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="Sod",
+                                usePLM="plm cons", slopeLimiter="monotized central", integrator="Runge-Kutta 3, TVD", cfl=.1),
+    "gen_plm_hll": dict(eqn="euler", dim=3, gridSize=[34, 10, 66], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere", flux="hll",
+                        usePLM="plm cons", slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1),
+    "gen_hllc_noplm": dict(eqn="euler", dim=3, gridSize=[18, 12, 10], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere", flux="euler-hllc",
+                           hllcMethod=1, integrator="Runge-Kutta 2, TVD", cfl=.1),
+    "gen_mhd_fluxlimiter": dict(eqn="mhd", dim=3, gridSize=[20, 12, 10], initCond="Orszag-Tang", fluxLimiter="minmod", integrator="forward Euler",
+                                cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]),
+    "gen2d_sod_fluxlimiter_mirror": dict(eqn="euler", dim=2, gridSize=[70, 45], initCond="Sod", fluxLimiter="superbee", integrator="Runge-Kutta 2, TVD",
+                                         cfl=.15, boundary=dict(xmin="mirror", xmax="mirror", ymin="mirror", ymax="mirror")),
+    "gen2d_kh_hll_plm_ospre": dict(eqn="euler", dim=2, gridSize=[64, 40], initCond="Kelvin-Helmholtz", flux="hll", usePLM="plm cons",
+                                   slopeLimiter="ospre", integrator="Runge-Kutta 4", cfl=.15),
+    "gen2d_kh_donor_fe": dict(eqn="euler", dim=2, gridSize=[33, 37], initCond="Kelvin-Helmholtz", integrator="forward Euler", cfl=.15),
+    "gen2d_ot_mhd_fluxlimiter": dict(eqn="mhd", dim=2, gridSize=[48, 36], initCond="Orszag-Tang", fluxLimiter="van Albada 1",
+                                     integrator="Runge-Kutta 3, TVD", cfl=.15),
+    "gen_mhd_rusanov_plm": dict(eqn="mhd", dim=3, gridSize=[33, 8, 34], initCond="Orszag-Tang", flux="rusanov", usePLM="plm cons",
+                                slopeLimiter="van Leer", integrator="Runge-Kutta 2, TVD", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]),
+}
+
+
+@pytest.mark.parametrize("name", list(GEN_CASES))
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_general_marching_equals_tile_kernel_strict(hydrob200, name, precision):
+    """3-D: flux-limiter Roe, no reconstruction, the other slope limiters and the other fluxes run the marching structure too (fv_march3 GEN);
+    same literal device functions as the tile kernel: bit-identical in the strict build, ghosts included."""
+    cfg = dict(GEN_CASES[name], precision=precision, strict_fp=True)
+    a, ta, SA = run(hydrob200, cfg, 3, stage_kernel=1)
+    b, tb, SB = run(hydrob200, cfg, 3)
+    assert "fv_stage" in SA.backend.describe()
+    assert ("fv_march3" if cfg["dim"] == 3 else "fv_march2d") in SB.backend.describe() and "cfg=100" in SB.backend.describe(), SB.backend.describe()
+    assert ta == tb
+    both_nan = np.isnan(a) & np.isnan(b)
+    assert ((a == b) | both_nan).all(), "first mismatches (k,j,i,var): %s" % (np.argwhere(~((a == b) | both_nan))[:5].tolist(),)
+
+
+@pytest.mark.parametrize("name", ["gen_roe_fluxlimiter_superbee", "gen_plm_hll", "gen_mhd_fluxlimiter", "gen2d_sod_fluxlimiter_mirror", "gen2d_ot_mhd_fluxlimiter"])
+def test_general_marching_production_within_tolerance(hydrob200, oracle, name):
+    cfg = GEN_CASES[name]
+    ref, tref, _ = run(hydrob200, cfg, 3, backend=oracle.OracleBackend)
+    got, tgot, S = run(hydrob200, cfg, 3)
+    assert "fv_march" in S.backend.describe() and "cfg=100" in S.backend.describe()
+    assert np.isfinite(ref).all()
+    err, per = rel_linf_grouped(got, ref)
+    assert err <= TOL_DOUBLE, per
