@@ -396,7 +396,13 @@ template<class real> struct Fv : FvBase {
 			// the general marching configurations (3-D): the other slope limiters, no reconstruction, Roe with a flux limiter, HLL / Rusanov / HLLC
 			// with or without 'plm cons' -- everything else of these rows that round 1 ran through the tile kernel ($HB_MARCH_GEN=0: keep it there)
 			const char* mg = getenv("HB_MARCH_GEN");
-			if (!ok && d.stage_kernel != 1 && d.use_plm <= 1 && !d.use_ctu && OPS()->marchInfoGen && (!mg || atoi(mg) != 0)) {
+			// Measured (profiles/r02j_bench_C4FL*.json): with the LITERAL flux-limited Roe flux (three eigensystems per interface, fvsolver.lua:138-155)
+			// the marching structure is slower than the tile kernel (0.23 vs 0.43 G cell-updates/s at 256^3: 9 warps at 168 registers against the
+			// tile kernel's occupancy; the arithmetic dominates, not the data movement), so that mode stays on the tile kernel unless
+			// $HB_MARCH_GEN=2 or stage_kernel = 2 asks for it; the reconstruct-or-not + HLL / Rusanov / HLLC / other-limiter modes take the marching kernel.
+			bool const flimMode = d.use_plm == 0 && d.flux_limiter > 0;
+			int const mgv = mg ? atoi(mg) : 1;
+			if (!ok && d.stage_kernel != 1 && d.use_plm <= 1 && !d.use_ctu && OPS()->marchInfoGen && mgv != 0 && (!flimMode || mgv >= 2 || d.stage_kernel == 2)) {
 				for (int cfg = kMarchGenBase; !ok && OPS()->marchInfoGen(d.dim, cfg, marchBox, marchInfoV); ++cfg) {
 					size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
 					if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
@@ -413,7 +419,7 @@ template<class real> struct Fv : FvBase {
 				// than the largest (classic RK4: 0, 1, 1, 4) takes the first (= preferred) configuration that fits IT.  Same planes per CTA as the
 				// solver's configuration (the overlapped slab exchange selects chunks by that number); $HB_MARCH_PER_STAGE=0 switches it off.
 				const char* ps = getenv("HB_MARCH_PER_STAGE");
-				if (!ps || atoi(ps) != 0) {
+				if ((!ps || atoi(ps) != 0) && marchCfg < kMarchGenBase) {      // (the general configurations are not in marchInfo's list)
 					int const saveBox[4] = {marchBox[0], marchBox[1], marchBox[2], marchBox[3]};
 					for (auto& s : plan) {
 						int n = (int)s.beta.size();
@@ -625,6 +631,7 @@ template<class real> struct Fv : FvBase {
 			// the gravity source joins L in the stage kernel's epilogue: the marching configuration built with it (same tile geometry, so the
 			// tensor maps stay valid), else the tile kernel
 			hasGrav = true;
+			if (useMarch && marchCfg >= kMarchGenBase) useMarch = false;      // the general configurations have no gravity epilogue: tile kernel
 			if (useMarch) {
 				bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
 				int box[4], info[7];
