@@ -108,6 +108,7 @@ struct StagePlan {
 	double betaSelf; bool computeL; bool last;
 	int readsU, readsL;            // words per cell (x nI) for hb_fv_describe
 	int marchCfg = -1;             // marching-kernel configuration of this stage (-1: the solver's): a stage with few RK operands fits a larger tile
+	bool opTma = false;            // its configuration stages the RK operands by TMA (StageP::opMaps)
 };
 
 // Static plan of one update for a Butcher tableau (hydro/int/rk.lua:17-44 decides the same "needed later" sets).
@@ -212,6 +213,7 @@ template<class real> struct Fv : FvBase {
 	std::vector<real*> upool, lpool;       // element (i=0,j=0,k=0) of variable 0; the allocation starts padX elements earlier
 	std::vector<CUtensorMap> umaps;        // TMA descriptor of every U buffer (marching kernel)
 	std::map<int, std::vector<CUtensorMap>> umapSets;   // the same for the configurations single stages run with (StagePlan::marchCfg): other box shapes
+	CUtensorMap* opMapsDev = nullptr;                   // [stage][2 * HB_MAX_TERMS] operand tensor maps of the stages whose configuration stages the RK operands by TMA
 	int padX = 0;                          // leading pad of every row: interior cell i=2 sits on a 128-byte boundary
 	long long vstride = 0;                 // elements between variables (pitchX * S1 * S2)
 	bool useMarch = false;
@@ -260,6 +262,7 @@ template<class real> struct Fv : FvBase {
 		cudaStreamSynchronize(ctx->stream);
 		if (graphExec) cudaGraphExecDestroy(graphExec);
 		for (auto& e : profEvents) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+		if (opMapsDev) cudaFree(opMapsDev);
 		JitProgram* const jitToFree = jit;
 		struct FreeJit { JitProgram* p; ~FreeJit() { if (p) jitFree(p); } } freeJit{jitToFree};
 		for (auto p : upool) cudaFree(p - padX);
@@ -297,12 +300,13 @@ template<class real> struct Fv : FvBase {
 		*out = p + padX;
 		return HB_OK;
 	}
-	int encodeMap(real* U, CUtensorMap* map) {
+	int encodeMap(real* U, CUtensorMap* map, const int* boxOverride = nullptr) {
 		EncodeTiled_t enc = encodeTiledFn();
 		if (!enc) return setError(HB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
 		cuuint64_t dims[4] = {(cuuint64_t)grid.strideY, (cuuint64_t)grid.S[1], (cuuint64_t)grid.S[2], (cuuint64_t)nI};
 		cuuint64_t strides[3] = {(cuuint64_t)grid.strideY * sizeof(real), (cuuint64_t)grid.strideZ * sizeof(real), (cuuint64_t)vstride * sizeof(real)};
-		cuuint32_t box[4] = {(cuuint32_t)marchBox[0], (cuuint32_t)marchBox[1], (cuuint32_t)marchBox[2], (cuuint32_t)marchBox[3]};
+		const int* bx = boxOverride ? boxOverride : marchBox;
+		cuuint32_t box[4] = {(cuuint32_t)bx[0], (cuuint32_t)bx[1], (cuuint32_t)bx[2], (cuuint32_t)bx[3]};
 		cuuint32_t es[4] = {1, 1, 1, 1};
 		CUresult r = enc(map, sizeof(real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)(U - padX),
 			dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -396,13 +400,15 @@ template<class real> struct Fv : FvBase {
 			// the general marching configurations (3-D): the other slope limiters, no reconstruction, Roe with a flux limiter, HLL / Rusanov / HLLC
 			// with or without 'plm cons' -- everything else of these rows that round 1 ran through the tile kernel ($HB_MARCH_GEN=0: keep it there)
 			const char* mg = getenv("HB_MARCH_GEN");
-			// Measured (profiles/r02j_bench_C4FL*.json): with the LITERAL flux-limited Roe flux (three eigensystems per interface, fvsolver.lua:138-155)
-			// the marching structure is slower than the tile kernel (0.23 vs 0.43 G cell-updates/s at 256^3: 9 warps at 168 registers against the
-			// tile kernel's occupancy; the arithmetic dominates, not the data movement), so that mode stays on the tile kernel unless
-			// $HB_MARCH_GEN=2 or stage_kernel = 2 asks for it; the reconstruct-or-not + HLL / Rusanov / HLLC / other-limiter modes take the marching kernel.
+			// MEASURED AND NOT THE DEFAULT (profiles/r02k_gen_vs_tile.txt, r02j_bench_C4FL*.json): these modes run the LITERAL device functions
+			// (three eigensystems per interface for the flux limiter, IEEE divisions and square roots behind slow-path branches), and with
+			// that arithmetic the marching structure at 9 warps x 168 registers is 1.3-2.3 x SLOWER than the tile kernel at its higher occupancy
+			// (3-D PLM + HLL 22.0 vs 17.3 ms per 256^3 stage, flux limiter 18.0 vs 9.8, 2-D PLM + HLL 2.9 vs 1.3): what these paths lack is
+			// production-form arithmetic, not data movement.  So they stay on the tile kernel; $HB_MARCH_GEN=1 (2: also the flux-limiter mode)
+			// or stage_kernel = 2 selects the marching kernel (kept as a second implementation: bit-identical in the strict build).
 			bool const flimMode = d.use_plm == 0 && d.flux_limiter > 0;
-			int const mgv = mg ? atoi(mg) : 1;
-			if (!ok && d.stage_kernel != 1 && d.use_plm <= 1 && !d.use_ctu && OPS()->marchInfoGen && mgv != 0 && (!flimMode || mgv >= 2 || d.stage_kernel == 2)) {
+			int const mgv = mg ? atoi(mg) : 0;
+			if (!ok && d.stage_kernel != 1 && d.use_plm <= 1 && !d.use_ctu && OPS()->marchInfoGen && (d.stage_kernel == 2 || (mgv >= 1 && (!flimMode || mgv >= 2)))) {
 				for (int cfg = kMarchGenBase; !ok && OPS()->marchInfoGen(d.dim, cfg, marchBox, marchInfoV); ++cfg) {
 					size_t const smem = (size_t)marchInfoV[4] + sizeof(real) * (size_t)nI * (size_t)maxOps * (size_t)marchInfoV[5];
 					if (smem <= 232448 - 1024) { ok = true; marchCfg = cfg; }
@@ -442,6 +448,7 @@ template<class real> struct Fv : FvBase {
 				}
 			}
 		}
+		if (int r = buildOpMaps()) return r;
 		if (d.use_ctu) {
 			useCTU = true;
 			useMarch = false;
@@ -641,7 +648,7 @@ template<class real> struct Fv : FvBase {
 					if ((info[6] & 1) && (info[6] & 2) == (marchInfoV[6] & 2) && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
 				}
 				useMarch = found;
-				for (auto& sPlan : plan) sPlan.marchCfg = -1;   // one configuration (the one with the gravity epilogue) for every stage
+				for (auto& sPlan : plan) { sPlan.marchCfg = -1; sPlan.opTma = false; }   // one configuration (the one with the gravity epilogue) for every stage
 			}
 		}
 		else hasNoDiv = true;
@@ -823,6 +830,7 @@ template<class real> struct Fv : FvBase {
 		sp.flux = d.flux;
 		sp.fluxParam = d.flux_param;
 		sp.plmMode = d.use_plm;
+		sp.opMaps = s.opTma && opMapsDev ? (const void*)(opMapsDev + (&s - &plan[0]) * 2 * HB_MAX_TERMS) : nullptr;
 	}
 
 
@@ -857,6 +865,31 @@ template<class real> struct Fv : FvBase {
 		return HB_OK;
 	}
 
+	// tensor maps over the RK operand buffers of every stage whose marching configuration fetches them by TMA (box = the tile without halo)
+	int buildOpMaps() {
+		for (auto& s : plan) s.opTma = false;
+		if (!useMarch || marchCfg >= kMarchGenBase) return HB_OK;
+		bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
+		std::vector<CUtensorMap> host(plan.size() * 2 * HB_MAX_TERMS);
+		memset(host.data(), 0, host.size() * sizeof(CUtensorMap));
+		bool any = false;
+		for (size_t i = 0; i < plan.size(); ++i) {
+			auto& s = plan[i];
+			int box[4], info[7];
+			if (!OPS()->marchInfo(d.dim, plm, flim, d.slope_limiter, stageCfg(s), box, info) || !(info[6] & 8)) continue;
+			int const opBox[4] = {info[0], info[1], 1, nI};
+			int n = 0;
+			for (auto& t : s.alpha) if (t.k != s.uIn) { if (int r = encodeMap(upool[t.k], &host[i * 2 * HB_MAX_TERMS + n], opBox)) return r; ++n; }
+			for (auto& t : s.beta) { if (int r = encodeMap(lpool[t.k], &host[i * 2 * HB_MAX_TERMS + n], opBox)) return r; ++n; }
+			s.opTma = true;
+			any = true;
+		}
+		if (!any) return HB_OK;
+		if (!opMapsDev) HB_CUDA(cudaMalloc(&opMapsDev, host.size() * sizeof(CUtensorMap)));
+		HB_CUDA(cudaMemcpyAsync(opMapsDev, host.data(), host.size() * sizeof(CUtensorMap), cudaMemcpyHostToDevice, st()));
+		HB_CUDA(cudaStreamSynchronize(st()));
+		return HB_OK;
+	}
 	int stageCfg(StagePlan const& s) const { return s.marchCfg >= 0 ? s.marchCfg : marchCfg; }
 	const CUtensorMap* stageMap(StagePlan const& s) { return s.marchCfg >= 0 ? &umapSets[s.marchCfg][s.uIn] : &umaps[s.uIn]; }
 

@@ -97,19 +97,24 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 #define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 8, 32, 0) X(3, 6, 64, 0) X(4, 15, 64, 32) X(5, 11, 64, 32) X(6, 8, 32, 32) X(7, 6, 64, 32)
 #else
 #if defined(HB_DEV)
-#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0)
+#define HB_MARCH3N_LIST(X) X(0, 15, 64, 0) X(1, 11, 64, 0) X(2, 15, 64, 16) X(3, 11, 64, 16)
 #else
 #define HB_MARCH3N_LIST(X) \
-	X(0, 15, 64, 0)    /* 32 x 15 columns, 64 planes per CTA, 16 warps at 128 registers (fits with at most two staged RK operands) */ \
-	X(1, 11, 64, 0)    /* 32 x 11 columns, 12 warps at 168 registers (classic RK4's four operands fit) */ \
-	X(2, 8, 64, 0)     /* 32 x 8 columns, 9 warps */ \
-	X(3, 6, 64, 0)     /* 32 x 6 columns, 7 warps: fits 8-variable equations (MHD) with four operands */ \
-	X(4, 15, 128, 0)   /* 128 planes per CTA */ \
-	X(5, 11, 32, 0)    /* 32 planes per CTA */ \
-	X(6, 15, 64, 32)   /* the same with the self-gravity source in the epilogue (chosen by hb_fv_add_op, never by the auto selection) */ \
+	/* VAR 16 (March3Cfg::OPTMA): the RK operands of the epilogue are staged by TMA -- one bulk copy per operand and plane, issued by the halo warp \
+	   a plane ahead behind an 'operand area free' barrier -- instead of per-thread cp.async: measured 2.18 -> 1.99 ms per 512^3 stage (r02m) */ \
+	X(0, 15, 64, 16)   /* 32 x 15 columns, 64 planes per CTA, 16 warps at 128 registers (fits with at most two staged RK operands) */ \
+	X(1, 11, 64, 16)   /* 32 x 11 columns, 12 warps at 168 registers (classic RK4's four operands fit) */ \
+	X(2, 8, 64, 16)    /* 32 x 8 columns, 9 warps */ \
+	X(3, 6, 64, 16)    /* 32 x 6 columns, 7 warps: fits 8-variable equations (MHD) with four operands */ \
+	X(4, 15, 128, 16)  /* 128 planes per CTA */ \
+	X(5, 11, 32, 16)   /* 32 planes per CTA */ \
+	X(6, 15, 64, 32)   /* the self-gravity source in the epilogue, cp.async operands (chosen by hb_fv_add_op, never by the auto selection) */ \
 	X(7, 11, 64, 32) \
 	X(8, 8, 64, 32) \
-	X(9, 6, 64, 32)
+	X(9, 6, 64, 32) \
+	X(10, 15, 64, 0)   /* the round-2 baseline: operands staged by per-thread cp.async ($HB_MARCH_CFG=10 runs 10,10,10,11 for an A/B comparison) */ \
+	X(11, 11, 64, 0) \
+	X(12, 15, 64, 8)   /* operands read from global memory in the epilogue (no staging): measured slower, kept for the record */
 #endif
 #endif
 // general configurations (March3Cfg::GEN, VAR bit 1): X(index, TY, KM, VAR); cfg = kMarchGenBase + index
@@ -176,8 +181,9 @@ cudaError_t launchMarch3(const CUtensorMap* tmap, int padX, GridP<real> const& g
 	auto kern = fv_march3<Eqn, LIM, C, MODE>;
 	int nOps = sp.nB;
 	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	if (C::OPDIRECT) nOps = 0;                          // operands are read from global memory in the epilogue: no staging area
 	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
-	size_t const smemMax = G::template smemBytes<Eqn::nI>(2 * HB_MAX_TERMS);
+	size_t const smemMax = G::template smemBytes<Eqn::nI>(C::OPDIRECT ? 0 : 2 * HB_MAX_TERMS);
 	static bool attrSet = false;
 	if (!attrSet) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemMax < kSmemLimit ? smemMax : kSmemLimit));
@@ -208,7 +214,7 @@ template<class C> void march3InfoCfg(int box[4], int info[7]) {
 	typedef March3Geom<C, real> G;
 	box[0] = G::BX; box[1] = G::BY; box[2] = 1; box[3] = Eqn::nI;
 	info[0] = G::TX; info[1] = G::TY; info[2] = C::KM; info[3] = G::NT; info[4] = (int)G::template smemBytes<Eqn::nI>(0);
-	info[5] = G::NCOL * 32; info[6] = (C::GRAV ? 1 : 0) | 2 | 4;   // bit 1: fv_march3; bit 2: chunkSel = rim / interior planes
+	info[5] = C::OPDIRECT ? 0 : G::NCOL * 32; info[6] = (C::GRAV ? 1 : 0) | 2 | 4 | (C::OPTMA ? 8 : 0);   // bit 3: operands by TMA (StageP::opMaps)   // bit 1: fv_march3; bit 2: chunkSel = rim / interior planes
 }
 template<int LIM, class C>
 cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {

@@ -66,6 +66,10 @@ template<class real> struct StageP {
 	int tSlot[2 * HB_MAX_TERMS];
 	double tCoef[2 * HB_MAX_TERMS];
 	const real* opPtr[2 * HB_MAX_TERMS];
+	// optional (fv_march3 configurations with TMA-staged operands): device array of nOps tensor maps (CUtensorMap, 128 bytes each) over the
+	// operand buffers, box = {32, TY, 1, nI}: the halo warp fetches plane k of every operand with one bulk copy each instead of 5 nOps
+	// per-thread cp.async
+	const void* opMaps;
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {

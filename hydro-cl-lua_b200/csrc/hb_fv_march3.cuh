@@ -39,6 +39,13 @@ template<int TY_, int KM_, int VAR_ = 0> struct March3Cfg {
 	// along every axis; hydro/solver/fvsolver.lua:138-155), and the other fluxes of the calcFluxForInterface slot (HLL, Rusanov, euler-HLLC),
 	// all selected at run time from StageP as in the tile kernel fv_stage, with the literal device functions
 	static constexpr bool GEN = (VAR_ & 2) != 0;
+	// OPDIRECT: the RK operands are read from global memory in the epilogue (plain coalesced loads at the point of use) instead of being
+	// staged per thread through shared memory by cp.async: no operand area in shared memory (every stage fits the tallest tile), no LDGSTS
+	static constexpr bool OPDIRECT = (VAR_ & 8) != 0;
+	// OPTMA: the RK operands of plane k arrive by TMA (one cp.async.bulk.tensor per operand, issued by the halo warp as soon as every warp
+	// has left the operand area, i.e. when the iteration's flux barrier completes) instead of 5 per-thread cp.async per operand: the LSU /
+	// MIO queue carries no LDGSTS (profiles/r02k_fv_march3_c4_full.txt: RK4's four-operand stage stalls on mio_throttle + long_scoreboard)
+	static constexpr bool OPTMA = (VAR_ & 16) != 0;
 };
 
 template<class C, class real> struct March3Geom {
@@ -110,7 +117,7 @@ HB_D void lowFaceFlux(typename Eqn::real (&F)[Eqn::nI], typename Eqn::Params con
 // RK combination + constrainU + stores + CFL dt of one finished cell (hydro/int/rk.lua:96-112, solverbase.lua:2116-2127): the same
 // operations in the same order as stageEpilogue (hb_fv_march.cuh), looping over the stage's compact term list (StageP::nT) instead of
 // testing every slot of the alpha / beta tables.
-template<class Eqn, bool GRAV>
+template<class Eqn, bool GRAV, bool DIRECT = false>
 HB_D void stageEpilogue3(GridP<typename Eqn::real> const& g, StageP<typename Eqn::real> const& sp, typename Eqn::Params const& ep,
 	long long idx, typename Eqn::real (&acc)[Eqn::nI], typename Eqn::real const (&own)[Eqn::nI], double dt,
 	typename Eqn::real& dtCell, typename Eqn::real& rateCell, typename Eqn::real const* ops, int opStride)
@@ -148,9 +155,18 @@ HB_D void stageEpilogue3(GridP<typename Eqn::real> const& g, StageP<typename Eqn
 			#pragma unroll
 			for (int q = 0; q < nI; ++q) U[q] = U[q] + own[q] * c;
 		} else {
-			real const* o = ops + slot * nI * opStride;
-			#pragma unroll
-			for (int q = 0; q < nI; ++q) U[q] = U[q] + o[q * opStride] * c;
+			if constexpr (DIRECT) {
+				real const* o = sp.opPtr[slot] + idx;
+				real v[nI];
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) v[q] = __ldg(o + q * g.strideV);
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) U[q] = U[q] + v[q] * c;
+			} else {
+				real const* o = ops + slot * nI * opStride;
+				#pragma unroll
+				for (int q = 0; q < nI; ++q) U[q] = U[q] + o[q * opStride] * c;
+			}
 		}
 	}
 	if (sp.computeL) {
@@ -177,10 +193,14 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 	extern __shared__ __align__(128) unsigned char march3Smem[];
 	uint64_t* full = reinterpret_cast<uint64_t*>(march3Smem);              // R mbarriers: ring slot filled
 	uint64_t* xbar = full + G::R;                                          // 2 mbarriers: fluxes of plane k published (by iteration parity)
+	uint64_t* opbar = xbar + 2;                                            // OPTMA: the RK operands of plane k have landed
+	uint64_t* opfree = opbar + 1;                                          // OPTMA: every column warp has finished the epilogue of plane k (operand area free)
 	real* ring = reinterpret_cast<real*>(march3Smem + 128);
 	real* FXX = ring + G::R * SLOT;             // x fluxes at the low faces of cells i = 0 .. TX  [parity][q][row][i]
 	real* FXY = FXX + 2 * nI * G::FXXN;         // y fluxes at the low faces of rows j = 0 .. TY   [parity][q][j][i]
-	real* OPB = FXY + 2 * nI * G::FXYN;         // staged RK operands of the column threads        [operand][q][thread]
+	// staged RK operands of the column threads [operand][q][thread], on a 128-byte boundary (a TMA destination when C::OPTMA; the size formula
+	// carries the slack)
+	real* OPB = reinterpret_cast<real*>(march3Smem + ((reinterpret_cast<unsigned char*>(FXY + 2 * nI * G::FXYN) - march3Smem) + 127) / 128 * 128);
 	constexpr int OPS = G::NCOL * 32;
 	__shared__ double redBuf[32];
 
@@ -221,6 +241,8 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 		for (int s = 0; s < G::R; ++s) mbarInit(&full[s], 1);
 		mbarInit(&xbar[0], G::NWARPS);
 		mbarInit(&xbar[1], G::NWARPS);
+		mbarInit(opbar, 1);
+		mbarInit(opfree, G::NCOL);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 		asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 	}
@@ -236,6 +258,19 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 		int const oX = (rowX + HB_G) * BX + TX + G::HL;                    // cell (TX, lane)
 		bool const on0 = FAST || g.fluxOn[0], on1 = FAST || g.fluxOn[1];   // (production: a switched-off side has aov = 0 at the consumer)
 		for (int k = kb - 1, it = 0; k < ke; ++k, ++it) {
+			if constexpr (C::OPTMA) {
+				// the RK operands of plane k, consumed at the END of this iteration: fetched now, a whole iteration ahead, as soon as every column
+				// warp has finished the epilogue of plane k-1 (the operand area's last reader)
+				if (k >= kb && sp.nOps > 0 && sp.Uout) {
+					if (k > kb) mbarWaitBackoff(opfree, uint32_t(k - 1 - kb) & 1u);
+					if (lane == 0) {
+						asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+						mbarExpectTx(opbar, uint32_t(sizeof(real) * nI * OPS) * uint32_t(sp.nOps));
+						for (int o = 0; o < sp.nOps; ++o)
+							tmaLoad4D(OPB + o * (nI * OPS), reinterpret_cast<const CUtensorMap*>(sp.opMaps) + o, opbar, i0 + padX, j0, k, 0);
+					}
+				}
+			}
 			if (k >= kb) {
 				waitPlane(k);
 				real const* __restrict__ P = ring + ((k - (kb - 2)) & 3) * SLOT;
@@ -297,7 +332,7 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 			real acc[nI];
 			// ---- x and y: Roe fluxes at the low faces of the own cell, published for the neighbours towards -x / -y
 			if (own) {
-				if (inside && sp.Uout) {
+				if (!C::OPDIRECT && !C::OPTMA && inside && sp.Uout) {
 					// the RK operands of cell k are consumed at the end of this iteration: start their global -> shared copies now
 					// (per-thread slots: no barrier involved)
 					#pragma unroll 1
@@ -391,6 +426,9 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 				for (int q = 0; q < nI; ++q) Fz[q] = 0;
 			}
 			mbarWait(&xbar[it & 1], uint32_t(it >> 1) & 1u);
+			if constexpr (C::OPTMA) {
+				if (own && sp.nOps > 0 && sp.Uout) mbarWait(opbar, uint32_t(k - kb) & 1u);
+			}
 			// ---- flux differences (fvsolver.cl:97-123) and the epilogue of cell k
 			if (own && inside) {
 				real U0[nI];
@@ -407,8 +445,11 @@ fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ Grid
 					}
 					U0[q] = P[q * PS + ob];
 				}
-				cpAsyncWaitAll();
-				stageEpilogue3<Eqn, C::GRAV>(g, sp, ep, idxK, acc, U0, dt, dtCell, rateCell, OPB + tid, OPS);
+				if constexpr (!C::OPDIRECT && !C::OPTMA) cpAsyncWaitAll();
+				stageEpilogue3<Eqn, C::GRAV, C::OPDIRECT>(g, sp, ep, idxK, acc, U0, dt, dtCell, rateCell, OPB + tid, OPS);
+			}
+			if constexpr (C::OPTMA) {
+				if (own && sp.nOps > 0 && sp.Uout) { __syncwarp(); if (lane == 0) mbarArrive(opfree); }
 			}
 			if constexpr (!FAST) {
 				#pragma unroll
