@@ -109,6 +109,14 @@ struct StagePlan {
 	int readsU, readsL;            // words per cell (x nI) for hb_fv_describe
 	int marchCfg = -1;             // marching-kernel configuration of this stage (-1: the solver's): a stage with few RK operands fits a larger tile
 	bool opTma = false;            // its configuration stages the RK operands by TMA (StageP::opMaps)
+	// folded last stage (foldFinalStage): this stage also writes the running sum of the last stage's combination
+	int accOut = -1, accIn = -1;   // physical U buffers (accIn < 0 with accOut >= 0: the sum starts here, from the stage input)
+	double accCoef = 0, accBetaSelf = 0;
+	int operands() const {         // RK operands a marching kernel stages in shared memory
+		int n = (int)beta.size() + (accIn >= 0 && accOut >= 0 ? 1 : 0);
+		for (auto& t : alpha) if (t.k != uIn) ++n;
+		return n;
+	}
 };
 
 // Static plan of one update for a Butcher tableau (hydro/int/rk.lua:17-44 decides the same "needed later" sets).
@@ -157,6 +165,41 @@ static void buildPlan(int order, const double* A, const double* B, std::vector<S
 			if (!later && lPhys[k] >= 0) liveL.erase(lPhys[k]);
 		}
 	}
+}
+
+// Classic RK4-type tableaux (every stage but the last combines U^0 and its own L only; the last one sums alpha U^0 + dt sum_k beta_k L^k):
+// the reference forms that sum term by term in ascending k (rk.lua:96-112), so its partial sums can be carried from stage to stage --
+// stage k adds (beta_k dt) L^k while L^k is still in registers -- and the last stage reads ONE operand instead of U^0 and every earlier
+// L: no L buffer is written at all, every stage has at most two staged operands (all of them fit the tallest marching tile), and the
+// operations and their order are the reference's, so the result is bit-identical.  Needs a kernel that writes StageP::Aout.
+static bool foldFinalStage(std::vector<StagePlan>& plan, int& nU, int& nL) {
+	int const n = (int)plan.size();
+	if (n < 3) return false;
+	StagePlan const& last = plan[n - 1];
+	if (last.alpha.size() != 1 || last.alpha[0].k != 0 || (int)last.beta.size() != n - 1 || !last.computeL) return false;
+	for (int i = 0; i < n - 1; ++i) {
+		StagePlan const& s = plan[i];
+		if (!s.beta.empty() || s.lOut < 0 || !s.computeL || s.uOut == 0) return false;
+		for (auto& t : s.alpha) if (t.k != 0) return false;
+		if (last.beta[i].k != s.lOut) return false;                 // beta terms in ascending k: term i is L^i
+	}
+	if (plan[0].uIn != 0) return false;
+	int const A = nU++;                                             // the running sum's buffer
+	for (int i = 0; i < n - 1; ++i) {
+		StagePlan& s = plan[i];
+		s.accOut = A;
+		s.accIn = i == 0 ? -1 : A;
+		s.accCoef = i == 0 ? last.alpha[0].coef : 1.;
+		s.accBetaSelf = last.beta[i].coef;
+		s.lOut = -1;
+		if (i > 0) s.readsU++;
+	}
+	StagePlan& l = plan[n - 1];
+	l.alpha.assign(1, Term{A, 1.});
+	l.beta.clear();
+	l.readsU = 2; l.readsL = 0;
+	nL = 0;
+	return true;
 }
 
 struct FvBase {
@@ -218,6 +261,7 @@ template<class real> struct Fv : FvBase {
 	long long vstride = 0;                 // elements between variables (pitchX * S1 * S2)
 	bool useMarch = false;
 	int marchCfg = 0, marchBox[4] = {0, 0, 0, 0}, marchInfoV[7] = {0, 0, 0, 0, 0, 0, 0}, marchMaxOps = 0;
+	bool rkFolded = false;         // the plan carries the last stage's running sum (foldFinalStage)
 	real* scratchL = nullptr;
 	real* opsScratch = nullptr;            // FvOps::scratchElems (ADM flux arrays)
 	double* stagingAos = nullptr;
@@ -364,30 +408,15 @@ template<class real> struct Fv : FvBase {
 			if ((int)s.alpha.size() > HB_MAX_TERMS || (int)s.beta.size() > HB_MAX_TERMS)
 				return setError(HB_ERR_INVALID, "hb_fv_create: tableau row has more than 4 alpha or beta terms");
 		}
-		if (nU < 2 && d.rk_order < 2) nU = 2;
-		for (int k = 0; k < nU; ++k) {
-			real* p = nullptr;
-			if (int r = allocPadded(&p, uBytes())) return r;
-			upool.push_back(p);
-		}
-		for (int k = 0; k < nL; ++k) {
-			real* p = nullptr;
-			if (int r = allocPadded(&p, lBytes())) return r;
-			lpool.push_back(p);
-		}
 		// stage kernel selection: the plane-marching TMA kernel where it is built (dim >= 2, 'plm cons' with minmod / superbee),
 		// else the tile kernel.  d.stage_kernel: 0 auto, 1 tile kernel, 2 marching kernel (error if unavailable).
-		{
-			bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
-			int cfg0 = 0;
-			if (const char* e = getenv("HB_MARCH_CFG")) cfg0 = atoi(e);
+		bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
+		int cfg0 = 0;
+		if (const char* e = getenv("HB_MARCH_CFG")) cfg0 = atoi(e);
+		auto chooseKernel = [&]() -> int {
 			// RK operands staged in shared memory per column thread: the largest count over the stages
 			int maxOps = 0;
-			for (auto& s : plan) {
-				int n = (int)s.beta.size();
-				for (auto& t : s.alpha) if (t.k != s.uIn) ++n;
-				if (n > maxOps) maxOps = n;
-			}
+			for (auto& s : plan) if (s.operands() > maxOps) maxOps = s.operands();
 			bool ok = false;
 			if (d.stage_kernel != 1 && d.flux == HB_FLUX_ROE && d.use_plm == 1) {   // the marching kernel is built for Roe + 'plm cons'
 				for (int pass = 0; pass < 2 && !ok; ++pass)
@@ -418,6 +447,37 @@ template<class real> struct Fv : FvBase {
 			if (jit && !ok) return setError(HB_ERR_INVALID, "hb_fv_create_from_source: a run-time equation runs the marching kernels only (dim 2 or 3, Roe flux, usePLM = 'plm cons', slopeLimiter minmod or superbee, RK operands within shared memory)");
 			useMarch = ok;
 			marchMaxOps = maxOps;
+			return HB_OK;
+		};
+		// the last stage's combination carried from stage to stage (foldFinalStage) where the stage kernel writes the running sum: the
+		// marching kernels with the term-list epilogue (fv_march3, fv_march2d)
+		{
+			std::vector<StagePlan> const planStd = plan;
+			int const nUStd = nU, nLStd = nL;
+			const char* fe = getenv("HB_RK_FOLD");
+			// measured (profiles/r02o_sweep_fold.txt): Euler 512 x 512 x 128 RK4 1.990 -> 1.945 ms per stage (every stage on the 32 x 15 tile); ideal
+			// MHD 1.015 -> 1.044 (eight variables: the extra operand of the middle stages costs more than the last stage gains) -- so the default
+			// folds for equations of up to five integrated variables; $HB_RK_FOLD=1 / 0 forces it on / off
+			bool folded = (fe ? atoi(fe) != 0 : nI <= 5) && OPS()->eqnId != HB_EQN_ADM3D && !d.use_ctu && d.dim >= 2 && foldFinalStage(plan, nU, nL);
+			if (int r = chooseKernel()) return r;
+			if (folded && !(useMarch && ((marchInfoV[6] & 2) || (d.dim == 2 && marchBox[0] <= 40)))) {
+				plan = planStd; nU = nUStd; nL = nLStd; folded = false;
+				if (int r = chooseKernel()) return r;
+			}
+			rkFolded = folded;
+		}
+		if (nU < 2 && d.rk_order < 2) nU = 2;
+		for (int k = 0; k < nU; ++k) {
+			real* p = nullptr;
+			if (int r = allocPadded(&p, uBytes())) return r;
+			upool.push_back(p);
+		}
+		for (int k = 0; k < nL; ++k) {
+			real* p = nullptr;
+			if (int r = allocPadded(&p, lBytes())) return r;
+			lpool.push_back(p);
+		}
+		{
 			if (useMarch) {
 				umaps.resize(nU);
 				for (int k = 0; k < nU; ++k) if (int r = encodeMap(upool[k], &umaps[k])) return r;
@@ -428,8 +488,7 @@ template<class real> struct Fv : FvBase {
 				if ((!ps || atoi(ps) != 0) && marchCfg < kMarchGenBase) {      // (the general configurations are not in marchInfo's list)
 					int const saveBox[4] = {marchBox[0], marchBox[1], marchBox[2], marchBox[3]};
 					for (auto& s : plan) {
-						int n = (int)s.beta.size();
-						for (auto& t : s.alpha) if (t.k != s.uIn) ++n;
+						int const n = s.operands();
 						int box[4], info[7];
 						for (int cfg = cfg0; cfg < marchCfg && OPS()->marchInfo(d.dim, plm, flim, d.slope_limiter, cfg, box, info); ++cfg) {
 							size_t const smem = (size_t)info[4] + sizeof(real) * (size_t)nI * (size_t)n * (size_t)info[5];
@@ -638,7 +697,10 @@ template<class real> struct Fv : FvBase {
 			// the gravity source joins L in the stage kernel's epilogue: the marching configuration built with it (same tile geometry, so the
 			// tensor maps stay valid), else the tile kernel
 			hasGrav = true;
-			if (useMarch && marchCfg >= kMarchGenBase) useMarch = false;      // the general configurations have no gravity epilogue: tile kernel
+			if (useMarch && marchCfg >= kMarchGenBase) {                      // the general configurations have no gravity epilogue: tile kernel
+				if (rkFolded) return setError(HB_ERR_INVALID, "hb_fv_add_op: the general marching configuration has no gravity epilogue; create the solver with $HB_RK_FOLD=0");
+				useMarch = false;
+			}
 			if (useMarch) {
 				bool const plm = d.use_plm != 0, flim = !plm && d.flux_limiter > 0;
 				int box[4], info[7];
@@ -648,6 +710,7 @@ template<class real> struct Fv : FvBase {
 					if ((info[6] & 1) && (info[6] & 2) == (marchInfoV[6] & 2) && !memcmp(box, marchBox, sizeof(box)) && smem <= 232448 - 1024) { found = true; marchCfg = cfg; memcpy(marchInfoV, info, sizeof(info)); }
 				}
 				useMarch = found;
+				if (!useMarch && rkFolded) return setError(HB_ERR_INVALID, "hb_fv_add_op: no marching configuration with the gravity epilogue for this solver; create it with $HB_RK_FOLD=0");
 				for (auto& sPlan : plan) { sPlan.marchCfg = -1; sPlan.opTma = false; }   // one configuration (the one with the gravity epilogue) for every stage
 			}
 		}
@@ -820,6 +883,12 @@ template<class real> struct Fv : FvBase {
 			sp.tSlot[sp.nT++] = sp.nOps;
 			sp.opPtr[sp.nOps++] = sp.bPtr[k];
 		}
+		if (s.accOut >= 0) {
+			sp.Aout = upool[s.accOut];
+			sp.accCoef = s.accCoef; sp.accBetaSelf = s.accBetaSelf;
+			sp.accSlot = -1;
+			if (s.accIn >= 0) { sp.accSlot = sp.nOps; sp.opPtr[sp.nOps++] = upool[s.accIn]; }
+		}
 		sp.betaSelf = s.betaSelf;
 		sp.computeL = s.computeL ? 1 : 0;
 		sp.dt = ctl + 1;
@@ -881,6 +950,7 @@ template<class real> struct Fv : FvBase {
 			int n = 0;
 			for (auto& t : s.alpha) if (t.k != s.uIn) { if (int r = encodeMap(upool[t.k], &host[i * 2 * HB_MAX_TERMS + n], opBox)) return r; ++n; }
 			for (auto& t : s.beta) { if (int r = encodeMap(lpool[t.k], &host[i * 2 * HB_MAX_TERMS + n], opBox)) return r; ++n; }
+			if (s.accOut >= 0 && s.accIn >= 0) { if (int r = encodeMap(upool[s.accIn], &host[i * 2 * HB_MAX_TERMS + n], opBox)) return r; ++n; }   // (fillStageP's operand order)
 			s.opTma = true;
 			any = true;
 		}
@@ -1090,12 +1160,13 @@ template<class real> struct Fv : FvBase {
 		o << "eqn=" << OPS()->eqnId << " real=" << sizeof(real) * 8 << " dim=" << d.dim << " strict_fp=" << d.strict_fp
 		  << " tile=" << ti[0] << "x" << ti[1] << "x" << ti[2] << " threads=" << ti[3] << " smem=" << ti[4]
 		  << " Ubufs=" << nU << " Lbufs=" << nL << (overlap ? " exchange=overlapped" : (comm ? " exchange=in-stream" : ""));
+		if (rkFolded) o << " rkFold=1";
 		if (useMarch) { o << " stageCfgs="; for (size_t i = 0; i < plan.size(); ++i) o << (i ? "," : "") << stageCfg(plan[i]); }
 		o << "\n";
 		int words = 0;
 		for (size_t i = 0; i < plan.size(); ++i) {
 			auto& s = plan[i];
-			int const w = s.readsU + s.readsL + 1 + (s.lOut >= 0 ? 1 : 0);
+			int const w = s.readsU + s.readsL + 1 + (s.lOut >= 0 ? 1 : 0) + (s.accOut >= 0 ? 1 : 0);
 			words += w;
 			o << "stage " << i << ": in=U" << s.uIn << " out=U" << s.uOut << " storeL=" << s.lOut << " alpha=" << s.alpha.size()
 			  << " beta=" << s.beta.size() << " betaSelf=" << s.betaSelf << " words=" << w << "\n";

@@ -115,6 +115,7 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(10, 15, 64, 0)   /* the round-2 baseline: operands staged by per-thread cp.async ($HB_MARCH_CFG=10 runs 10,10,10,11 for an A/B comparison) */ \
 	X(11, 11, 64, 0) \
 	X(12, 15, 64, 8)   /* operands read from global memory in the epilogue (no staging): measured slower, kept for the record */
+	/* two CTAs per SM (March3Cfg::MINB; X(13, 7, 64, 80), X(14, 6, 64, 80)) measured slower: 2.03 / 2.18 against 1.93 ms (profiles/r02n_sweep_minb2.txt) */
 #endif
 #endif
 // general configurations (March3Cfg::GEN, VAR bit 1): X(index, TY, KM, VAR); cfg = kMarchGenBase + index
@@ -149,8 +150,7 @@ template<int DIM, int LIM, class C>
 cudaError_t launchMarch(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
 	typedef MarchGeom<DIM, C, real> G;
 	auto kern = fv_march<Eqn, DIM, LIM, C, MODE>;
-	int nOps = sp.nB;
-	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	int nOps = sp.nOps;                                 // alpha terms on other buffers + beta terms (+ the folded last stage's running sum)
 	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
 	size_t const smemMax = G::template smemBytes<Eqn::nI>(2 * HB_MAX_TERMS);
 	static bool attrSet = false;
@@ -179,8 +179,7 @@ template<int LIM, class C>
 cudaError_t launchMarch3(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
 	typedef March3Geom<C, real> G;
 	auto kern = fv_march3<Eqn, LIM, C, MODE>;
-	int nOps = sp.nB;
-	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	int nOps = sp.nOps;                                 // alpha terms on other buffers + beta terms (+ the folded last stage's running sum)
 	if (C::OPDIRECT) nOps = 0;                          // operands are read from global memory in the epilogue: no staging area
 	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
 	size_t const smemMax = G::template smemBytes<Eqn::nI>(C::OPDIRECT ? 0 : 2 * HB_MAX_TERMS);
@@ -188,6 +187,10 @@ cudaError_t launchMarch3(const CUtensorMap* tmap, int padX, GridP<real> const& g
 	if (!attrSet) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(smemMax < kSmemLimit ? smemMax : kSmemLimit));
 		if (e != cudaSuccess) return e;
+		if (C::MINB > 1) {                                // two CTAs per SM need the whole shared-memory carveout
+			e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+			if (e != cudaSuccess) return e;
+		}
 		attrSet = true;
 	}
 	if (smem > kSmemLimit) return cudaErrorInvalidConfiguration;
@@ -220,8 +223,7 @@ template<int LIM, class C>
 cudaError_t launchMarch2W(const CUtensorMap* tmap, int padX, GridP<real> const& g, StageP<real> const& sp, const double* eqnParams, int chunkSel, cudaStream_t st) {
 	typedef March2Geom<C, real> G;
 	auto kern = fv_march2d<Eqn, LIM, C, MODE>;
-	int nOps = sp.nB;
-	for (int a = 0; a < sp.nA; ++a) if (!((sp.aOwnMask >> a) & 1)) ++nOps;
+	int nOps = sp.nOps;                                 // alpha terms on other buffers + beta terms (+ the folded last stage's running sum)
 	size_t const smem = G::template smemBytes<Eqn::nI>(nOps);
 	size_t const smemMax = G::template smemBytes<Eqn::nI>(2 * HB_MAX_TERMS);
 	static bool attrSet = false;

@@ -70,6 +70,12 @@ template<class real> struct StageP {
 	// operand buffers, box = {32, TY, 1, nI}: the halo warp fetches plane k of every operand with one bulk copy each instead of 5 nOps
 	// per-thread cp.async
 	const void* opMaps;
+	// optional second output (marching kernels; hb_fv.cu foldFinalStage): the running sum of the LAST stage's combination,
+	// Aout = (accSlot == -1 ? 0 + accCoef * stage input : staged operand accSlot) + (accBetaSelf dt) * L -- the partial sums of rk.lua:96-112 in
+	// the reference's order, carried from stage to stage so that the last stage reads one operand instead of every earlier L
+	real* Aout;
+	int accSlot;
+	double accCoef, accBetaSelf;
 };
 
 template<int TX_, int TY_, int TZ_, int NT_> struct Tile {

@@ -46,6 +46,10 @@ template<int TY_, int KM_, int VAR_ = 0> struct March3Cfg {
 	// has left the operand area, i.e. when the iteration's flux barrier completes) instead of 5 per-thread cp.async per operand: the LSU /
 	// MIO queue carries no LDGSTS (profiles/r02k_fv_march3_c4_full.txt: RK4's four-operand stage stalls on mio_throttle + long_scoreboard)
 	static constexpr bool OPTMA = (VAR_ & 16) != 0;
+	// MINB 2 (VAR bit 6): two CTAs per SM (half-height tiles, registers capped for 2 x NT threads).  The warps of one CTA move through the
+	// FP64-dense (flux cores) and FP64-sparse (ring loads, slopes, epilogue) phases of a plane together -- the plane's flux barrier realigns
+	// them -- so the FP64 pipe idles during the sparse phases; a second, unsynchronised CTA fills them
+	static constexpr int MINB = (VAR_ & 64) ? 2 : 1;
 };
 
 template<class C, class real> struct March3Geom {
@@ -142,6 +146,28 @@ HB_D void stageEpilogue3(GridP<typename Eqn::real> const& g, StageP<typename Eqn
 		for (int q = 0; q < nI; ++q) sp.Lout[idx + q * g.strideV] = acc[q];
 	}
 	if (!sp.Uout) return;
+	if (sp.Aout) {
+		// the last stage's running sum (StageP::Aout): partial_s = partial_(s-1) + (beta_s dt) L_s, partial_(-1) = 0 + alpha U^0
+		real const cb = real(sp.accBetaSelf * dt);
+		if (sp.accSlot < 0) {
+			real const ca = real(sp.accCoef);
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) {
+				real a = real(0) + own[q] * ca;
+				a = a + acc[q] * cb;
+				sp.Aout[idx + q * g.strideV] = a;
+			}
+		} else {
+			#pragma unroll
+			for (int q = 0; q < nI; ++q) {
+				real a;
+				if constexpr (DIRECT) a = __ldg(sp.opPtr[sp.accSlot] + idx + q * g.strideV);
+				else a = ops[(sp.accSlot * nI + q) * opStride];
+				a = a + acc[q] * cb;
+				sp.Aout[idx + q * g.strideV] = a;
+			}
+		}
+	}
 	real U[nI];
 	#pragma unroll
 	for (int q = 0; q < nI; ++q) U[q] = 0;
@@ -180,7 +206,7 @@ HB_D void stageEpilogue3(GridP<typename Eqn::real> const& g, StageP<typename Eqn
 }
 
 template<class Eqn, int LIM, class C, int MODE>
-__global__ void __launch_bounds__((March3Geom<C, typename Eqn::real>::NT), 1)
+__global__ void __launch_bounds__((March3Geom<C, typename Eqn::real>::NT), C::MINB)
 fv_march3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ GridP<typename Eqn::real> g,
 	const __grid_constant__ StageP<typename Eqn::real> sp, const __grid_constant__ typename Eqn::Params ep, int const padX, int const chunkSel)
 {

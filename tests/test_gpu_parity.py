@@ -239,6 +239,41 @@ def test_march_kernel_fast_close_to_tile_kernel(hydrob200, name):
     assert err <= 1e-13, per
 
 
+FOLD_CASES = {
+    "march3d_freeflow": MARCH_CASES["march3d_freeflow"],
+    "fold2d_kh_rk4": (dict(eqn="euler", dim=2, gridSize=[300, 100], initCond="Kelvin-Helmholtz", usePLM="plm cons",
+                           slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.15), 4),
+    "fold3d_mhd_rk4": (dict(eqn="mhd", dim=3, gridSize=[36, 12, 35], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
+                            integrator="Runge-Kutta 4", cfl=.1, mins=[-2, -2, -2], maxs=[2, 2, 2]), 2),
+    # with the self-gravity source in the epilogue (the GRAV marching configurations) and the divergence-cleaning op after the update
+    "fold2d_mhd_ops_rk4": (dict(eqn="mhd", dim=2, gridSize=[40, 24], initCond="Orszag-Tang", usePLM="plm cons", slopeLimiter="minmod",
+                                integrator="Runge-Kutta 4", cfl=.15, noDiv="jacobi", useGravity=True), 3),
+    "fold3d_grav_rk4": (dict(eqn="euler", dim=3, gridSize=[34, 12, 20], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere", usePLM="plm cons",
+                             slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1, useGravity=True), 2),
+}
+
+
+@pytest.mark.parametrize("name", list(FOLD_CASES))
+@pytest.mark.parametrize("strict", [True, False])
+def test_rk_fold_is_bitwise_the_unfolded_update(hydrob200, monkeypatch, name, strict):
+    """Classic RK4 on the marching kernels carries the last stage's sum from stage to stage (hb_fv.cu foldFinalStage: one running-sum
+    buffer instead of three L buffers, one operand in the last stage instead of four).  Same operations in the same order as the
+    reference's multAdd sequence (rk.lua:96-112): bit-identical to the unfolded plan in both builds, ghosts included."""
+    cfg, n = FOLD_CASES[name]
+    cfg = dict(cfg, strict_fp=strict)
+    if cfg["eqn"] == "euler":                       # the default for equations of up to five variables (measured: a gain for Euler, a loss for MHD)
+        assert "rkFold=1" in hydrob200.FiniteVolumeSolver(cfg).backend.describe()
+    monkeypatch.setenv("HB_RK_FOLD", "1")
+    a, ta, SA = run(hydrob200, cfg, n)
+    assert "rkFold=1" in SA.backend.describe() and "Lbufs=0" in SA.backend.describe(), SA.backend.describe()
+    monkeypatch.setenv("HB_RK_FOLD", "0")
+    b, tb, SB = run(hydrob200, cfg, n)
+    assert "rkFold" not in SB.backend.describe() and "Lbufs=3" in SB.backend.describe(), SB.backend.describe()
+    assert np.isfinite(a).all() and ta == tb
+    bad = np.argwhere(a != b)
+    assert bad.size == 0, "first mismatches (k,j,i,var): %s  max|diff| %g" % (bad[:5].tolist(), np.abs(a - b).max())
+
+
 def test_march_is_default_for_plm(hydrob200):
     cfg, _ = CASES["C4_sphere_rk4"]
     S = hydrob200.FiniteVolumeSolver(cfg)

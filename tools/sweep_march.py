@@ -19,6 +19,8 @@ WORK = {
                 slopeLimiter="minmod", integrator="Runge-Kutta 4, TVD", cfl=.15), 840 / 4),
     "C3": (dict(eqn="mhd", dim=2, gridSize=[2048, 2048], initCond="Orszag-Tang", usePLM="plm cons",
                 slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.15), 512 / 3),
+    "M3r4": (dict(eqn="mhd", dim=3, gridSize=[256, 256, 64], initCond="Orszag-Tang", usePLM="plm cons", mins=[-2] * 3, maxs=[2] * 3,
+                  slopeLimiter="minmod", integrator="Runge-Kutta 4", cfl=.1), 1024 / 4),
     "M3": (dict(eqn="mhd", dim=3, gridSize=[256, 256, 64], initCond="Orszag-Tang", usePLM="plm cons", mins=[-2] * 3, maxs=[2] * 3,
                 slopeLimiter="minmod", integrator="Runge-Kutta 3, TVD", cfl=.1), 512 / 3),
 }
