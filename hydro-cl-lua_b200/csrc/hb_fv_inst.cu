@@ -104,22 +104,24 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	   a plane ahead behind an 'operand area free' barrier -- instead of per-thread cp.async: measured 2.18 -> 1.99 ms per 512^3 stage (r02m) */ \
 	X(0, 15, 64, 16)   /* 32 x 15 columns, 64 planes per CTA, 16 warps at 128 registers (fits with at most two staged RK operands) */ \
 	X(1, 11, 64, 16)   /* 32 x 11 columns, 12 warps at 168 registers (classic RK4's four operands fit) */ \
-	X(2, 8, 64, 16)    /* 32 x 8 columns, 9 warps */ \
-	X(3, 6, 64, 16)    /* 32 x 6 columns, 7 warps: fits 8-variable equations (MHD) with four operands */ \
+	X(2, 7, 64, 16)    /* 32 x 7 columns, 8 warps = 256 threads: an 8-variable equation (ideal MHD, ~226 registers) keeps all its registers -- 32 x 8 is \
+	                      9 warps, allocated as 384 threads, i.e. capped at 168 registers with spills: measured 28 % slower per row (profiles/r02p_sweep_mhd_ty7.txt) */ \
+	X(3, 6, 64, 16)    /* 32 x 6 columns, 7 warps */ \
 	X(4, 15, 128, 16)  /* 128 planes per CTA */ \
 	X(5, 11, 32, 16)   /* 32 planes per CTA */ \
 	X(6, 15, 64, 32)   /* the self-gravity source in the epilogue, cp.async operands (chosen by hb_fv_add_op, never by the auto selection) */ \
 	X(7, 11, 64, 32) \
-	X(8, 8, 64, 32) \
+	X(8, 7, 64, 32) \
 	X(9, 6, 64, 32) \
 	X(10, 15, 64, 0)   /* the round-2 baseline: operands staged by per-thread cp.async ($HB_MARCH_CFG=10 runs 10,10,10,11 for an A/B comparison) */ \
 	X(11, 11, 64, 0) \
-	X(12, 15, 64, 8)   /* operands read from global memory in the epilogue (no staging): measured slower, kept for the record */
+	X(12, 15, 64, 8)   /* operands read from global memory in the epilogue (no staging): measured slower, kept for the record */ \
+	X(13, 8, 64, 16)   /* 32 x 8 columns, 9 warps (round 2's MHD tile until call p; kept for the comparison) */
 	/* two CTAs per SM (March3Cfg::MINB; X(13, 7, 64, 80), X(14, 6, 64, 80)) measured slower: 2.03 / 2.18 against 1.93 ms (profiles/r02n_sweep_minb2.txt) */
 #endif
 #endif
 // general configurations (March3Cfg::GEN, VAR bit 1): X(index, TY, KM, VAR); cfg = kMarchGenBase + index
-#define HB_MARCH3G_LIST(X) X(0, 8, 64, 2) X(1, 6, 64, 2) X(2, 4, 32, 2)
+#define HB_MARCH3G_LIST(X) X(0, 8, 64, 2) X(1, 6, 64, 2) X(2, 4, 32, 2)   /* (32 x 7 measured slower here: profiles/r02q_gen_vs_tile.txt) */
 // the same for 2-D (March2Cfg::GEN, MINB bit 5): X(index, NW, KM, MINB)
 #define HB_MARCH2G_LIST(X) X(0, 4, 32, 33) X(1, 2, 32, 33)
 constexpr int kMarch3N =

@@ -233,7 +233,7 @@ JitProgram* jitCompile(hb_ctx* ctx, const char* headerName, const char* headerSr
 	       "}\n";
 	std::string const L = std::to_string(lim), M = strict ? "1" : "0";
 	if (dim == 3) {
-		int const tys[4] = {15, 11, 8, 6};
+		int const tys[4] = {15, 11, 7, 6};    // (as HB_MARCH3N_LIST: 8 warps keep a register-hungry equation uncapped)
 		for (int t = 0; t < 4; ++t) {
 			JitMarch m; m.dim = 3; m.ty = tys[t]; m.km = 64; m.nw = 0;
 			m.expr = "hb::fv_march3<HbJitEqn, " + L + ", hb::March3Cfg<" + std::to_string(tys[t]) + ", 64, 0>, " + M + ">";
