@@ -363,6 +363,11 @@ def main():
     for h in (hp, hq0, hq1):
         hb.check(L.hb_host_alloc(nbytes, C.byref(h)))
     hb.check(L.hb_fv_get_state(B.h, hp))
+    # one untimed round trip through each pair of calls: the library allocates its staging buffers on first use
+    hb.check(L.hb_fv_set_state(B.h, hp)); hb.check(L.hb_fv_update(B.h, 1)); hb.check(L.hb_fv_get_state(B.h, hq0))
+    hb.check(L.hb_fv_set_state_async(B.h, hp)); hb.check(L.hb_fv_update(B.h, 1)); hb.check(L.hb_fv_get_state_async(B.h, hq1))
+    hb.check(L.hb_fv_wait_transfers(B.h))
+    hb.check(L.hb_fv_get_state(B.h, hp))
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
