@@ -61,6 +61,25 @@ template<class real_, bool FAST_ = false> struct Euler {
 		Prim W; W.rho = w[0]; W.v[0] = w[1]; W.v[1] = w[2]; W.v[2] = w[3]; W.P = w[4];
 		consFromPrim(U, s, W);
 	}
+	// euler.cl:179-195 apply_dU_dW and :201-222 apply_dW_dU on the (rho, v, P) / (rho, m, ETotal) arrays ('plm eig prim' variants only;
+	// cartesian: coord_lower is the identity)
+	static HB_HD void apply_dU_dW(real (&r)[nI], Params const& s, real const (&WA)[nI], real const (&W)[nI]) {
+		r[0] = W[0];
+		for (int q = 0; q < 3; ++q) r[1 + q] = WA[1 + q] * W[0] + W[1 + q] * WA[0];
+		r[4] = W[0] * real(.5) * (WA[1] * WA[1] + WA[2] * WA[2] + WA[3] * WA[3]) + WA[0] * (W[1] * WA[1] + W[2] * WA[2] + W[3] * WA[3])
+			+ W[4] / (s.gamma - real(1.));
+	}
+	static HB_HD void apply_dW_dU(real (&r)[nI], Params const& s, real const (&WA)[nI], real const (&U)[nI]) {
+		r[0] = U[0];
+		if (U[0] < s.rhoMin) {
+			r[1] = r[2] = r[3] = real(0.);
+			r[4] = real(0.);
+		} else {
+			for (int q = 0; q < 3; ++q) r[1 + q] = U[1 + q] * (real(1.) / WA[0]) - WA[1 + q] * (U[0] / WA[0]);
+			r[4] = (s.gamma - real(1.)) * (real(.5) * (WA[1] * WA[1] + WA[2] * WA[2] + WA[3] * WA[3]) * U[0]
+				- (U[1] * WA[1] + U[2] * WA[2] + U[3] * WA[3]) + U[4]);
+		}
+	}
 	// euler.cl:87-94
 	static HB_HD real calc_Cs(Params const& s, Prim const& W) {
 		if (W.P <= s.PMin) return real(0.);

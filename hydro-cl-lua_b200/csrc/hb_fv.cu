@@ -1258,7 +1258,7 @@ int hb_fv_create(hb_ctx* ctx, const hb_fv_desc* d, hb_fv** out) {
 		for (int m = 0; m < 2; ++m) if (d->bc[2 * k + m] < 0 || d->bc[2 * k + m] > HB_BC_FIXED) return setError(HB_ERR_INVALID, "hb_fv_create: unknown boundary method");
 	}
 	if (d->rk_order < 0 || d->rk_order > 4) return setError(HB_ERR_INVALID, "hb_fv_create: rk_order must be 0..4");
-	if (d->use_plm < 0 || d->use_plm > 5) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM must be none, 'plm cons', 'plm athena', 'plm prim' or 'plm cons with flux'");
+	if (d->use_plm < 0 || d->use_plm > 10) return setError(HB_ERR_INVALID, "hb_fv_create: usePLM must be none, 'plm cons', 'plm athena', 'plm prim', 'plm cons with flux', 'plm eig', 'plm eig prim' or 'plm eig prim ref' ('ppm' is not built)");
 	if (d->use_plm >= 2 && d->eqn == HB_EQN_ADM3D) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' / 'plm prim' are built for euler and mhd");
 	if (d->use_plm >= 2 && d->eqn == HB_EQN_MHD && d->dim == 3) return setError(HB_ERR_INVALID, "hb_fv_create: 'plm athena' / 'plm prim' for mhd are built for 1-D and 2-D grids (the 3-D tile does not hold both face states of 8 variables in shared memory)");
 	if (d->slope_limiter < 0 || d->slope_limiter > 19 || d->flux_limiter < 0 || d->flux_limiter > 19) return setError(HB_ERR_INVALID, "hb_fv_create: limiter index out of range");

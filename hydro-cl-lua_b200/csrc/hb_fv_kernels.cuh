@@ -59,7 +59,7 @@ template<class real> struct StageP {
 	int flux;              // HB_FLUX_*: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc (tile kernel; the marching kernel is built for roe)
 	int fluxParam;         // euler-hllc: hllcMethod
 	const real* gravPot;   // optional: the potential (ePot of Uin) of the self-gravity op; the tile kernel adds calcGravityDeriv (selfgrav.cl:53-76) to L
-	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded, 4 'plm prim', 5 'plm cons with flux'
+	int plmMode;           // hb_fv_desc.use_plm: 0 none, 1 'plm cons', 2 'plm athena' (faces as the reference tree assigns them), 3 'plm athena' with L/R as recorded, 4 'plm prim', 5 'plm cons with flux', 6 'plm eig', 7 'plm eig prim', 8 'plm eig prim ref', 9 / 10 = 7 / 8 with L and R exchanged
 	// the same RK combination as a compact list in evaluation order (alpha terms, then beta terms; rk.lua:96-112), for kernels that loop
 	// over it (fv_march3): term t adds tCoef[t] (x dt when bit t of tBetaMask is set) times the stage input (tSlot[t] < 0) or staged operand tSlot[t]
 	int nT, tBetaMask, nOps;
@@ -149,6 +149,8 @@ HB_D void stageSide(GridP<typename Eqn::real> const& g, StageP<typename Eqn::rea
 					}
 					if (sp.plmMode == 4) plmPrimFaces<Eqn>(L, R, ep, sp.slopeLimiter, UL, U, UR);
 					else if (sp.plmMode == 5) plmConsFluxFaces<Eqn, SIDE>(L, R, ep, sp.slopeLimiter, dtReal / g.dx[SIDE], UL, U, UR);
+					else if (sp.plmMode == 6) plmEigFaces<Eqn, SIDE>(L, R, ep, sp.slopeLimiter, dtReal / g.dx[SIDE], UL, U, UR);
+					else if (sp.plmMode >= 7 && sp.plmMode <= 10) plmEigPrimFaces<Eqn, SIDE>(L, R, ep, sp.plmMode == 8 || sp.plmMode == 10, sp.plmMode >= 9 ? 1 : 0, dtReal / g.dx[SIDE], UL, U, UR);
 					else plmAthenaFaces<Eqn, SIDE>(L, R, ep, UL, U, UR, sp.plmMode == 3 ? 1 : 0);
 					#pragma unroll
 					for (int q = 0; q < nI; ++q) { SG[q * G::SGN + w] = L[q]; SG[(nI + q) * G::SGN + w] = R[q]; }

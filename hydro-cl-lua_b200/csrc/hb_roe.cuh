@@ -172,6 +172,116 @@ HB_HD void plmAthenaFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (
 	else { Eqn::consFromPrimArray(L, s, Wlv); Eqn::consFromPrimArray(R, s, Wrv); }
 }
 
+// 'plm eig' (plm.cl:256-427, the `#if 1` body): conserved differences on the cell's left eigenvectors, the slope limiter on the
+// characteristic ratio dL / dR, each characteristic slope kept only on the side its wave leaves from, back to conserved variables, then
+// the half-step flux difference of 'plm cons with flux'.
+template<class Eqn, int SIDE>
+HB_HD void plmEigFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R)[Eqn::nI], typename Eqn::Params const& s, int slopeLimiter,
+	typename Eqn::real dt_dx, typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI, nW = Eqn::nW;
+	real dUL[nI], dUR[nI];
+	for (int j = 0; j < nI; ++j) {
+		dUL[j] = U[j] - UL[j];
+		dUR[j] = UR[j] - U[j];
+	}
+	typename Eqn::Eig eig;
+	Eqn::eigen_forCell(eig, s, U);
+	real dULEig[nW], dUREig[nW], lam[nW];
+	Eqn::template leftTransform<SIDE>(dULEig, s, eig, dUL);
+	Eqn::template leftTransform<SIDE>(dUREig, s, eig, dUR);
+	Eqn::template waves<SIDE>(lam, s, eig);
+	for (int j = 0; j < nW; ++j) {
+		real const rEig = dUREig[j] == 0 ? real(0) : (dULEig[j] / dUREig[j]);
+		real const sigma = limiter<real>(slopeLimiter, rEig) * dUREig[j];
+		dULEig[j] = sigma;
+		dUREig[j] = sigma;
+		if (lam[j] >= 0) dUREig[j] = 0;
+		if (lam[j] <= 0) dULEig[j] = 0;
+	}
+	real sL[nI], sR[nI];
+	Eqn::template rightTransform<SIDE>(sL, s, eig, dULEig);
+	Eqn::template rightTransform<SIDE>(sR, s, eig, dUREig);
+	for (int j = 0; j < nI; ++j) {
+		L[j] = U[j] - real(.5) * sL[j];
+		R[j] = U[j] + real(.5) * sR[j];
+	}
+	real FL[nI], FR[nI];
+	Eqn::template fluxFromCons<SIDE>(FL, s, L);
+	Eqn::template fluxFromCons<SIDE>(FR, s, R);
+	for (int j = 0; j < nI; ++j) {
+		real const dF = FR[j] - FL[j];
+		L[j] += real(.5) * dt_dx * dF;
+		R[j] += real(.5) * dt_dx * dF;
+	}
+}
+
+// 'plm eig prim' / 'plm eig prim ref' (plm.cl:536-778): primitive differences through dU/dW and the cell's left eigenvectors, the
+// symmetric limiter sign(dC) 2 min(|dL|, |dR|, |dC|) on the characteristic differences (as written: the 2 multiplies the central
+// difference as well), characteristic tracing over dt -- against the reference state of the fastest wave for REF --, back through the
+// right eigenvectors and dW/dU.  faceOrder 0: as the tree assigns them (result->L = the state extrapolated towards +SIDE); 1: exchanged.
+template<class Eqn, int SIDE>
+HB_HD void plmEigPrimFaces(typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R)[Eqn::nI], typename Eqn::Params const& s, bool ref, int faceOrder,
+	typename Eqn::real dt_dx, typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI])
+{
+	typedef typename Eqn::real real;
+	constexpr int nI = Eqn::nI, nW = Eqn::nW;
+	real W[nI], WL[nI], WR[nI];
+	Eqn::primArray(W, s, U); Eqn::primArray(WL, s, UL); Eqn::primArray(WR, s, UR);
+	real dWL[nI], dWR[nI], dWC[nI];
+	for (int j = 0; j < nI; ++j) {
+		dWL[j] = W[j] - WL[j];
+		dWR[j] = WR[j] - W[j];
+		dWC[j] = real(.5) * (WR[j] - WL[j]);
+	}
+	typename Eqn::Eig eig;
+	Eqn::eigen_forCell(eig, s, U);
+	real tmp[nI], dWLEig[nW], dWREig[nW], dWCEig[nW], dWMEig[nW], lam[nW];
+	Eqn::apply_dU_dW(tmp, s, W, dWL); Eqn::template leftTransform<SIDE>(dWLEig, s, eig, tmp);
+	Eqn::apply_dU_dW(tmp, s, W, dWR); Eqn::template leftTransform<SIDE>(dWREig, s, eig, tmp);
+	Eqn::apply_dU_dW(tmp, s, W, dWC); Eqn::template leftTransform<SIDE>(dWCEig, s, eig, tmp);
+	for (int j = 0; j < nW; ++j) {
+		dWMEig[j] = dWLEig[j] * dWREig[j] < real(0.) ? real(0.) : (
+			(dWCEig[j] >= real(0.) ? real(1.) : real(-1.)) * real(2.) * rmin<real>(rmin<real>(rabs(dWLEig[j]), rabs(dWREig[j])), rabs(dWCEig[j])));
+	}
+	Eqn::template waves<SIDE>(lam, s, eig);
+	real aL[nW], aR[nW], sL[nI], sR[nI], W2L[nI], W2R[nI];
+	if (!ref) {
+		for (int j = 0; j < nW; ++j) {
+			aL[j] = lam[j] < 0 ? real(0) : dWMEig[j] * real(.5) * (real(1.) - lam[j] * dt_dx);
+			aR[j] = lam[j] > 0 ? real(0) : dWMEig[j] * real(.5) * (real(1.) + lam[j] * dt_dx);
+		}
+		Eqn::template rightTransform<SIDE>(tmp, s, eig, aL); Eqn::apply_dW_dU(sL, s, W, tmp);
+		Eqn::template rightTransform<SIDE>(tmp, s, eig, aR); Eqn::apply_dW_dU(sR, s, W, tmp);
+		for (int j = 0; j < nI; ++j) {
+			W2L[j] = W[j] + sL[j];
+			W2R[j] = W[j] - sR[j];
+		}
+	} else {
+		real waveMin = rmin<real>(real(0.), lam[0]);          // eigenWaveCodeMinMax: the first and the last wave of the cell's eigensystem
+		real waveMax = rmax<real>(real(0.), lam[nW - 1]);
+		real dWM[nI], WLRef[nI], WRRef[nI];
+		Eqn::template rightTransform<SIDE>(tmp, s, eig, dWMEig); Eqn::apply_dW_dU(dWM, s, W, tmp);
+		for (int j = 0; j < nI; ++j) {
+			WLRef[j] = W[j] + real(.5) * (real(1.) - dt_dx * waveMax) * dWM[j];
+			WRRef[j] = W[j] - real(.5) * (real(1.) + dt_dx * waveMin) * dWM[j];
+		}
+		for (int j = 0; j < nW; ++j) {
+			aL[j] = lam[j] < 0 ? real(0) : (dWMEig[j] * dt_dx * (waveMax - lam[j]));
+			aR[j] = lam[j] > 0 ? real(0) : (dWMEig[j] * dt_dx * (waveMin - lam[j]));
+		}
+		Eqn::template rightTransform<SIDE>(tmp, s, eig, aL); Eqn::apply_dW_dU(sL, s, W, tmp);
+		Eqn::template rightTransform<SIDE>(tmp, s, eig, aR); Eqn::apply_dW_dU(sR, s, W, tmp);
+		for (int j = 0; j < nI; ++j) {
+			W2R[j] = WRRef[j] + real(.5) * sR[j];
+			W2L[j] = WLRef[j] + real(.5) * sL[j];
+		}
+	}
+	if (faceOrder == 0) { Eqn::consFromPrimArray(L, s, W2L); Eqn::consFromPrimArray(R, s, W2R); }
+	else { Eqn::consFromPrimArray(L, s, W2R); Eqn::consFromPrimArray(R, s, W2L); }
+}
+
 // HLL flux, hydro/flux/hll.cl:5-74 with hllCalcWaveMethod = 'Davis direct bounded' (hydro/flux/hll.lua:10):
 //   sL = min(lambdaMin(UL), lambdaMin(interface)), sR = max(lambdaMax(UR), lambdaMax(interface)); interface speeds from the Roe-averaged
 //   eigensystem (eqn.lua:1108-1120), cell speeds from the cons state (eqn.lua:1134-1146).

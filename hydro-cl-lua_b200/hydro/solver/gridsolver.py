@@ -16,8 +16,10 @@ minmaxs = ("min", "max")
 # 'plm athena': plm.cl:782-879 as the reference tree has it (result->L = cons(Wrv), result->R = cons(Wlv), :877-878);
 # 'plm athena, recorded face order': L = left, R = right face -- reproduces the errors recorded in tests/test-order/schemes.lua
 # 'plm prim': plm.cl:191-253; 'piecewise constant': plm.cl:10-24 (L = R = U: the same fluxes as no PLM with the donor-cell flux limiter)
+# 'plm eig': plm.cl:256-427; 'plm eig prim' / 'plm eig prim ref': plm.cl:536-778 (", other face order": L and R exchanged)
 plmIds = {None: 0, False: 0, "plm cons": 1, "plm athena": 2, "plm athena, recorded face order": 3, "plm prim": 4, "plm cons with flux": 5,
-          "piecewise constant": 0}
+          "piecewise constant": 0, "plm eig": 6, "plm eig prim": 7, "plm eig prim ref": 8,
+          "plm eig prim, other face order": 9, "plm eig prim ref, other face order": 10}
 
 
 class GridSolver(SolverBase):
@@ -61,7 +63,7 @@ class GridSolver(SolverBase):
         self.mindx = min(self.grid_dx)
         self.usePLM = args.get("usePLM") or None
         if self.usePLM not in plmIds:
-            raise NotImplementedError("usePLM=%r: 'piecewise constant', 'plm cons', 'plm prim' and 'plm athena' are built" % (self.usePLM,))
+            raise NotImplementedError("usePLM=%r: built are %s ('ppm' is not)" % (self.usePLM, sorted(k for k in plmIds if isinstance(k, str))))
         self.plmId = plmIds[self.usePLM]
         # gridsolver.lua:106: `limiterNames:find(args.slopeLimiter) or 1` -- an omitted slopeLimiter is 'donor cell' (zero slope)
         self.slopeLimiter = hydro_app.limiterIndex(args.get("slopeLimiter") or "donor cell") if self.usePLM else 0

@@ -126,7 +126,9 @@ typedef struct hb_fv_desc {
 	int global_n[3];          /* interior cells of the whole grid (== n without decomposition); defines grid_dx */
 	int use_plm;              /* 0 = none, 1 = 'plm cons' (hydro/solver/plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879; euler, mhd in 1-D / 2-D), 3 = 'plm athena'
 	                           * with the face states assigned L = left, R = right: the order that reproduces the errors the reference
-	                           * recorded for this scheme (its tree has them the other way round at plm.cl:877-878); 4 = 'plm prim' (plm.cl:191-253); 5 = 'plm cons with flux' (plm.cl:95-187).
+	                           * recorded for this scheme (its tree has them the other way round at plm.cl:877-878); 4 = 'plm prim' (plm.cl:191-253); 5 = 'plm cons with flux' (plm.cl:95-187);
+	                           * 6 = 'plm eig' (plm.cl:256-427); 7 = 'plm eig prim', 8 = 'plm eig prim ref' (plm.cl:536-778: result->L is the state extrapolated
+	                           * towards +side, as the tree has it); 9, 10 = 7, 8 with L and R exchanged.  2-10: euler, mhd in 1-D / 2-D; tile kernel.
 	                           * 'piecewise constant' (plm.cl:10-24: L = R = U) is use_plm = 0 with flux_limiter = 0 */
 	int slope_limiter;        /* 0-based index into hydro/app.lua:614-635 */
 	int flux_limiter;         /* 0-based; 0 = 'donor cell' = no flux limiter (hydro/solver/fvsolver.lua:61-63) */

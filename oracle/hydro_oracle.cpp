@@ -36,7 +36,7 @@ struct ho_desc {
 	int dim;            // 1..3
 	int n[3];           // interior cells per axis (unused axes = 1)
 	int real_bytes;     // 8 = double, 4 = float   (hydro/app.lua:892 'real' selection)
-	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded, 4 = 'plm prim' (plm.cl:191-253), 5 = 'plm cons with flux' (plm.cl:95-187)
+	int use_plm;        // 0 = none (cell-centred UL/UR), 1 = 'plm cons' (plm.cl:27-91), 2 = 'plm athena' (plm.cl:782-879), 3 = the same with L/R faces as recorded, 4 = 'plm prim' (plm.cl:191-253), 5 = 'plm cons with flux' (plm.cl:95-187), 6 = 'plm eig' (plm.cl:256-427), 7 = 'plm eig prim', 8 = 'plm eig prim ref' (plm.cl:536-778), 9 / 10 = 7 / 8 with the face states assigned the other way round
 	int slope_limiter;  // 0-based index into hydro/app.lua:614-635
 	int flux_limiter;   // 0-based index; 0 = 'donor cell' => useFluxLimiter=false (fvsolver.lua:61-63)
 	int bc[6];          // xmin,xmax,ymin,ymax,zmin,zmax: 0 periodic, 1 mirror, 2 freeflow, 3 none, 4 linear, 5 quadratic, 6 fixed
@@ -202,6 +202,28 @@ template<class real_> struct Euler {
 		U.ePot = W.ePot;
 	}
 	static real calc_hTotal(real rho, real P, real ETotal) { return (P + ETotal) / rho; }   // euler.cl:17-30
+	// euler.cl:179-195 apply_dU_dW (cartesian: coord_lower is the identity); only used by the 'plm eig prim' variants
+	static void apply_dU_dW(cons_t& r, S const& s, prim_t const& WA, prim_t const& W) {
+		real3 const WA_vL = WA.v;
+		r.rho = W.rho;
+		r.m = real3_add(real3_real_mul(WA.v, W.rho), real3_real_mul(W.v, WA.rho));
+		r.ETotal = W.rho * real(.5) * real3_dot(WA.v, WA_vL) + WA.rho * real3_dot(W.v, WA_vL) + W.P / (s.heatCapacityRatio - real(1.));
+		r.ePot = W.ePot;
+	}
+	// euler.cl:201-222 apply_dW_dU.  Its last line reads `(W)->ePot`: W is not a parameter of the macro but the calling function's cell
+	// state (plm.cl:604), passed here as `Wcell`
+	static void apply_dW_dU(prim_t& r, S const& s, prim_t const& WA, cons_t const& U, prim_t const& Wcell) {
+		real3 const WA_vL = WA.v;
+		r.rho = U.rho;
+		if (U.rho < s.rhoMin) {
+			r.v = real3{0, 0, 0};
+			r.P = 0.;
+		} else {
+			r.v = real3_sub(real3_real_mul(U.m, real(1.) / WA.rho), real3_real_mul(WA.v, U.rho / WA.rho));
+			r.P = (s.heatCapacityRatio - real(1.)) * (real(.5) * real3_dot(WA.v, WA_vL) * U.rho - real3_dot(U.m, WA_vL) + U.ETotal);
+		}
+		r.ePot = Wcell.ePot;
+	}
 	// euler.cl:273-291
 	static void fluxFromCons(cons_t& F, S const& s, cons_t const& U, normal_t n) {
 		prim_t W; primFromCons(W, s, U);
@@ -423,6 +445,27 @@ template<class real_> struct MHD {
 		U.ETotal = EInt + EKin + EMag;
 		U.psi = W.psi;
 		U.ePot = W.ePot;
+	}
+	// mhd.cl:205-223 apply_dU_dW as written: the result's B is the CELL's B (`(result)->B = (WA)->B`, joined to the momentum statement
+	// by a comma operator), not the difference's
+	static void apply_dU_dW(cons_t& r, S const& s, prim_t const& WA, prim_t const& W) {
+		r.rho = W.rho;
+		r.m = real3_add(real3_real_mul(WA.v, W.rho), real3_real_mul(W.v, WA.rho));
+		r.B = WA.B;
+		r.ETotal = W.rho * real(.5) * real3_dot(WA.v, WA.v) + WA.rho * real3_dot(W.v, WA.v) + real3_dot(W.B, WA.B) / s.mu0_eff
+			+ W.P / (s.heatCapacityRatio - real(1.));
+		r.psi = W.psi;
+		r.ePot = W.ePot;
+	}
+	// mhd.cl:227-245 apply_dW_dU
+	static void apply_dW_dU(prim_t& r, S const& s, prim_t const& WA, cons_t const& U, prim_t const&) {
+		r.rho = U.rho;
+		r.v = real3_sub(real3_real_mul(U.m, real(1.) / WA.rho), real3_real_mul(WA.v, U.rho / WA.rho));
+		r.B = U.B;
+		r.P = (s.heatCapacityRatio - real(1.)) * (real(.5) * U.rho * real3_dot(WA.v, WA.v) - real3_dot(U.m, WA.v)
+			- real3_dot(U.B, WA.B) / s.mu0_eff + U.ETotal);
+		r.psi = U.psi;
+		r.ePot = U.ePot;
 	}
 	// mhd.cl:296-340 (note: PMag omits mu0; swapped sqrt(rho) weights on B.y,B.z :335-336)
 	static void calcRoeValues(roe_t& r, S const& s, cons_t const& UL, cons_t const& UR, normal_t n) {
@@ -1097,6 +1140,157 @@ template<class Eqn> struct Solver : SolverBase {
 			}
 		}
 	}
+	// 'plm eig' (plm.cl:256-427, the `#if 1` body): conserved differences projected on the cell's eigenvectors, the slope limiter on the
+	// characteristic ratio dL / dR, each characteristic slope kept on the side its wave leaves from, back to conserved variables, then the
+	// half-step flux difference of 'plm cons with flux'
+	void calcCellLR_eig(consLR_t& result, cons_t const& U, cons_t const& UL, cons_t const& UR, normal_t n, real dt) const {
+		if constexpr (Eqn::hasEigenForCell) {
+			cons_t dUL, dUR, dUC;
+			for (int j = 0; j < nI; ++j) {
+				dUL.ptr[j] = U.ptr[j] - UL.ptr[j];
+				dUR.ptr[j] = UR.ptr[j] - U.ptr[j];
+				dUC.ptr[j] = real(.5) * (UR.ptr[j] - UL.ptr[j]);
+			}
+			for (int j = nI; j < nS; ++j) dUL.ptr[j] = dUR.ptr[j] = dUC.ptr[j] = 0;
+			eigen_t eig;
+			Eqn::eigen_forCell(eig, solver, U, n);
+			waves_t dULEig, dUREig;
+			Eqn::eigen_leftTransform(dULEig, solver, eig, dUL, n);
+			Eqn::eigen_leftTransform(dUREig, solver, eig, dUR, n);
+			// (dUCEig is computed by the reference and not used in this body)
+			real lambda[nW];
+			Eqn::eigenWaves(lambda, solver, eig, n);
+			for (int j = 0; j < nW; ++j) {
+				real const wave_j = lambda[j];
+				real const dULEig_j = dULEig.ptr[j], dUREig_j = dUREig.ptr[j];
+				real const rEig = dUREig_j == 0 ? real(0) : (dULEig_j / dUREig_j);
+				real const phi = limiter<real>(d.slope_limiter, rEig);
+				real const sigma = phi * dUREig_j;
+				dULEig.ptr[j] = sigma;
+				dUREig.ptr[j] = sigma;
+				if (wave_j >= 0) dUREig.ptr[j] = 0;
+				if (wave_j <= 0) dULEig.ptr[j] = 0;
+			}
+			cons_t sL, sR;
+			Eqn::eigen_rightTransform(sL, solver, eig, dULEig, n);
+			Eqn::eigen_rightTransform(sR, solver, eig, dUREig, n);
+			cons_t UHalfL = U, UHalfR = U;
+			for (int j = 0; j < nI; ++j) {
+				UHalfL.ptr[j] -= real(.5) * sL.ptr[j];
+				UHalfR.ptr[j] += real(.5) * sR.ptr[j];
+			}
+			real const dx = solver.grid_dx.s(n.side);
+			real const dt_dx = dt / dx;
+			cons_t FHalfL, FHalfR;
+			Eqn::fluxFromCons(FHalfL, solver, UHalfL, n);
+			Eqn::fluxFromCons(FHalfR, solver, UHalfR, n);
+			result.L = UHalfL;
+			result.R = UHalfR;
+			for (int j = 0; j < nI; ++j) {
+				real const dF = FHalfR.ptr[j] - FHalfL.ptr[j];
+				result.L.ptr[j] += real(.5) * dt_dx * dF;
+				result.R.ptr[j] += real(.5) * dt_dx * dF;
+			}
+		}
+	}
+	// 'plm eig prim' / 'plm eig prim ref' (plm.cl:536-778): primitive differences through dU/dW and the cell's left eigenvectors, the
+	// symmetric MUSCL limiter on the characteristic differences, characteristic tracing over dt (with the reference state of the fastest
+	// wave for `ref`), back through the right eigenvectors and dW/dU.  As in the tree, `result->L` receives the state extrapolated towards
+	// +side (W2L = W + ...) and `result->R` the one towards -side.
+	void calcCellLR_eigPrim(consLR_t& result, cons_t const& U, cons_t const& UL, cons_t const& UR, normal_t n, real dt, bool ref) const {
+		if constexpr (Eqn::hasEigenForCell) {
+			typedef typename Eqn::prim_t prim_t;
+			static_assert(sizeof(prim_t) == sizeof(cons_t), "prim_t is indexed like cons_t (plm.cl:611-618)");
+			prim_t W, WL, WR;
+			Eqn::primFromCons(W, solver, U);
+			Eqn::primFromCons(WL, solver, UL);
+			Eqn::primFromCons(WR, solver, UR);
+			real const* w = reinterpret_cast<real const*>(&W);
+			real const* wl = reinterpret_cast<real const*>(&WL);
+			real const* wr = reinterpret_cast<real const*>(&WR);
+			prim_t dWL, dWR, dWC;
+			real* pl = reinterpret_cast<real*>(&dWL);
+			real* pr = reinterpret_cast<real*>(&dWR);
+			real* pc = reinterpret_cast<real*>(&dWC);
+			for (int j = 0; j < nI; ++j) {
+				pl[j] = w[j] - wl[j];
+				pr[j] = wr[j] - w[j];
+				pc[j] = real(.5) * (wr[j] - wl[j]);
+			}
+			for (int j = nI; j < nS; ++j) pl[j] = pr[j] = pc[j] = 0.;
+			eigen_t eig;
+			Eqn::eigen_forCell(eig, solver, U, n);
+			cons_t tmp;
+			waves_t dWLEig, dWREig, dWCEig;
+			Eqn::apply_dU_dW(tmp, solver, W, dWL); Eqn::eigen_leftTransform(dWLEig, solver, eig, tmp, n);
+			Eqn::apply_dU_dW(tmp, solver, W, dWR); Eqn::eigen_leftTransform(dWREig, solver, eig, tmp, n);
+			Eqn::apply_dU_dW(tmp, solver, W, dWC); Eqn::eigen_leftTransform(dWCEig, solver, eig, tmp, n);
+			waves_t dWMEig;
+			for (int j = 0; j < nW; ++j) {
+				dWMEig.ptr[j] = dWLEig.ptr[j] * dWREig.ptr[j] < real(0.) ? real(0.) : (
+					(dWCEig.ptr[j] >= real(0.) ? real(1.) : real(-1.)) * real(2.)
+					* clmin<real>(clmin<real>(std::fabs(dWLEig.ptr[j]), std::fabs(dWREig.ptr[j])), std::fabs(dWCEig.ptr[j])));
+			}
+			real const dx = solver.grid_dx.s(n.side);
+			real const dt_dx = dt / dx;
+			real lambda[nW];
+			Eqn::eigenWaves(lambda, solver, eig, n);
+			waves_t aL, aR;
+			prim_t sL, sR, W2L, W2R;
+			real* l2 = reinterpret_cast<real*>(&W2L);
+			real* r2 = reinterpret_cast<real*>(&W2R);
+			if (!ref) {
+				for (int j = 0; j < nW; ++j) {
+					real const wave_j = lambda[j];
+					aL.ptr[j] = wave_j < 0 ? real(0) : dWMEig.ptr[j] * real(.5) * (real(1.) - wave_j * dt_dx);
+					aR.ptr[j] = wave_j > 0 ? real(0) : dWMEig.ptr[j] * real(.5) * (real(1.) + wave_j * dt_dx);
+				}
+				Eqn::eigen_rightTransform(tmp, solver, eig, aL, n); Eqn::apply_dW_dU(sL, solver, W, tmp, W);
+				Eqn::eigen_rightTransform(tmp, solver, eig, aR, n); Eqn::apply_dW_dU(sR, solver, W, tmp, W);
+				real const* sl = reinterpret_cast<real const*>(&sL);
+				real const* sr = reinterpret_cast<real const*>(&sR);
+				for (int j = 0; j < nI; ++j) {
+					l2[j] = w[j] + sl[j];
+					r2[j] = w[j] - sr[j];
+				}
+			} else {
+				real waveMin, waveMax;
+				Eqn::eigenWaveMinMax(waveMin, waveMax, solver, eig, n);
+				waveMin = clmin<real>(real(0.), waveMin);
+				waveMax = clmax<real>(real(0.), waveMax);
+				prim_t dWM;
+				Eqn::eigen_rightTransform(tmp, solver, eig, dWMEig, n); Eqn::apply_dW_dU(dWM, solver, W, tmp, W);
+				real const* dm = reinterpret_cast<real const*>(&dWM);
+				real WLRef[nS], WRRef[nS];
+				for (int j = 0; j < nI; ++j) {
+					WLRef[j] = w[j] + real(.5) * (real(1.) - dt_dx * waveMax) * dm[j];
+					WRRef[j] = w[j] - real(.5) * (real(1.) + dt_dx * waveMin) * dm[j];
+				}
+				for (int j = 0; j < nW; ++j) {
+					real const wave_j = lambda[j];
+					aL.ptr[j] = wave_j < 0 ? real(0) : (dWMEig.ptr[j] * dt_dx * (waveMax - wave_j));
+					aR.ptr[j] = wave_j > 0 ? real(0) : (dWMEig.ptr[j] * dt_dx * (waveMin - wave_j));
+				}
+				Eqn::eigen_rightTransform(tmp, solver, eig, aL, n); Eqn::apply_dW_dU(sL, solver, W, tmp, W);
+				Eqn::eigen_rightTransform(tmp, solver, eig, aR, n); Eqn::apply_dW_dU(sR, solver, W, tmp, W);
+				real const* sl = reinterpret_cast<real const*>(&sL);
+				real const* sr = reinterpret_cast<real const*>(&sR);
+				for (int j = 0; j < nI; ++j) {
+					r2[j] = WRRef[j] + real(.5) * sr[j];
+					l2[j] = WLRef[j] + real(.5) * sl[j];
+				}
+			}
+			for (int j = nI; j < nS; ++j) { l2[j] = w[j]; r2[j] = w[j]; }
+			if (d.use_plm >= 9) {
+				// the other face assignment (left face state into L), as for 'plm athena, recorded face order'
+				Eqn::consFromPrim(result.L, solver, W2R);
+				Eqn::consFromPrim(result.R, solver, W2L);
+			} else {
+				Eqn::consFromPrim(result.L, solver, W2L);
+				Eqn::consFromPrim(result.R, solver, W2R);
+			}
+		}
+	}
 	void calcLR(real dtArg = 0) {
 		int const sl = d.slope_limiter;
 		#pragma omp parallel for collapse(2)
@@ -1108,6 +1302,8 @@ template<class Eqn> struct Solver : SolverBase {
 				consLR_t& result = ULRBuf[side + dim * index];
 				cons_t const& UL = UBuf[index - solver.stepsize[side]];
 				cons_t const& UR = UBuf[index + solver.stepsize[side]];
+				if (d.use_plm == 6) { calcCellLR_eig(result, U, UL, UR, normal_t{side}, dtArg); continue; }
+				if (d.use_plm >= 7 && d.use_plm <= 10) { calcCellLR_eigPrim(result, U, UL, UR, normal_t{side}, dtArg, d.use_plm == 8 || d.use_plm == 10); continue; }
 				if (d.use_plm == 4) { calcCellLR_prim(result, U, UL, UR); continue; }
 				if (d.use_plm == 5) { calcCellLR_consWithFlux(result, U, UL, UR, normal_t{side}, dtArg); continue; }
 				if (d.use_plm >= 2) { calcCellLR_athena(result, U, UL, UR, normal_t{side}); continue; }

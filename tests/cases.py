@@ -197,6 +197,24 @@ CASES["F1_plm_cons_flux_kh_rk2_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 36
                                             slopeLimiter="minmod", integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
 CASES["F1_plm_cons_flux_ot_mhd_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCond="Orszag-Tang", usePLM="plm cons with flux",
                                             slopeLimiter="minmod", integrator="forward Euler", cfl=.15), 8)
+# the f1 remainder: 'plm eig' (plm.cl:256-427) and 'plm eig prim' / 'plm eig prim ref' (plm.cl:536-778), literal as the tree has them
+# (", other face order": L and R exchanged -- the orientation in which the extrapolated states face the interface they are used at)
+CASES["F1_plm_eig_sod_fe"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm eig", slopeLimiter="minmod",
+                                   integrator="forward Euler", cfl=.3), 40)
+CASES["F1_plm_eig_kh_rk2_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 36], initCond="Kelvin-Helmholtz", usePLM="plm eig", slopeLimiter="superbee",
+                                      integrator="Runge-Kutta 2, TVD", cfl=.15), 10)
+CASES["F1_plm_eig_prim_sod_rk2"] = (dict(eqn="euler", dim=1, gridSize=[200], initCond="Sod", usePLM="plm eig prim",
+                                         integrator="Runge-Kutta 2, TVD", cfl=.3), 30)
+CASES["F1_plm_eig_prim_ref_kh_2d"] = (dict(eqn="euler", dim=2, gridSize=[48, 36], initCond="Kelvin-Helmholtz", usePLM="plm eig prim ref",
+                                           integrator="forward Euler", cfl=.15), 10)
+CASES["F1_plm_eig_prim_ref_other_sphere_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                                     usePLM="plm eig prim ref, other face order", integrator="Runge-Kutta 3, TVD", cfl=.1), 3)   # (the doubled central slope of plm.cl:640-647 drives the sphere's edge to negative pressure by step 5)
+CASES["F1_plm_eig_prim_ref_sphere_3d"] = (dict(eqn="euler", dim=3, gridSize=[20, 14, 12], mins=[-2, -2, -2], maxs=[2, 2, 2], initCond="sphere",
+                                               usePLM="plm eig prim ref", integrator="Runge-Kutta 3, TVD", cfl=.1), 5)
+CASES["F1_plm_eig_prim_other_ot_mhd_2d"] = (dict(eqn="mhd", dim=2, gridSize=[40, 32], initCond="Orszag-Tang", usePLM="plm eig prim, other face order",
+                                                 integrator="forward Euler", cfl=.15), 8)
+CASES["F1_plm_eig_briowu_mhd"] = (dict(eqn="mhd", dim=1, gridSize=[200], initCond="Brio-Wu", usePLM="plm eig", slopeLimiter="minmod",
+                                       integrator="forward Euler", cfl=.3), 30)
 CASES["F3_selfgrav_linear_fixed_bc_2d"] = (dict(eqn="euler", dim=2, gridSize=[36, 28], initCond="sphere", usePLM="plm cons", slopeLimiter="minmod",
                                                 integrator="Runge-Kutta 2, TVD", cfl=.15, useGravity=True,
                                                 boundary=dict(xmin="linear", xmax="quadratic", ymin="mirror",
