@@ -66,7 +66,7 @@ template<class real_, bool FAST_ = false> struct Euler {
 	static HB_HD void apply_dU_dW(real (&r)[nI], Params const& s, real const (&WA)[nI], real const (&W)[nI]) {
 		r[0] = W[0];
 		for (int q = 0; q < 3; ++q) r[1 + q] = WA[1 + q] * W[0] + W[1 + q] * WA[0];
-		r[4] = W[0] * real(.5) * (WA[1] * WA[1] + WA[2] * WA[2] + WA[3] * WA[3]) + WA[0] * (W[1] * WA[1] + W[2] * WA[2] + W[3] * WA[3])
+		r[4] = W[0] * real(.5) * dot3(WA[1], WA[2], WA[3], WA[1], WA[2], WA[3]) + WA[0] * dot3(W[1], W[2], W[3], WA[1], WA[2], WA[3])
 			+ W[4] / (s.gamma - real(1.));
 	}
 	static HB_HD void apply_dW_dU(real (&r)[nI], Params const& s, real const (&WA)[nI], real const (&U)[nI]) {
@@ -76,8 +76,8 @@ template<class real_, bool FAST_ = false> struct Euler {
 			r[4] = real(0.);
 		} else {
 			for (int q = 0; q < 3; ++q) r[1 + q] = U[1 + q] * (real(1.) / WA[0]) - WA[1 + q] * (U[0] / WA[0]);
-			r[4] = (s.gamma - real(1.)) * (real(.5) * (WA[1] * WA[1] + WA[2] * WA[2] + WA[3] * WA[3]) * U[0]
-				- (U[1] * WA[1] + U[2] * WA[2] + U[3] * WA[3]) + U[4]);
+			r[4] = (s.gamma - real(1.)) * (real(.5) * dot3(WA[1], WA[2], WA[3], WA[1], WA[2], WA[3]) * U[0]
+				- dot3(U[1], U[2], U[3], WA[1], WA[2], WA[3]) + U[4]);
 		}
 	}
 	// euler.cl:87-94

@@ -188,15 +188,15 @@ template<class real_, bool FAST_ = false> struct MHD {
 		r[0] = W[0];
 		for (int q = 0; q < 3; ++q) r[1 + q] = WA[1 + q] * W[0] + W[1 + q] * WA[0];
 		for (int q = 0; q < 3; ++q) r[5 + q] = WA[5 + q];
-		r[4] = W[0] * real(.5) * (WA[1] * WA[1] + WA[2] * WA[2] + WA[3] * WA[3]) + WA[0] * (W[1] * WA[1] + W[2] * WA[2] + W[3] * WA[3])
-			+ (W[5] * WA[5] + W[6] * WA[6] + W[7] * WA[7]) / s.mu0 + W[4] / (s.gamma - real(1.));
+		r[4] = W[0] * real(.5) * dot3(WA[1], WA[2], WA[3], WA[1], WA[2], WA[3]) + WA[0] * dot3(W[1], W[2], W[3], WA[1], WA[2], WA[3])
+			+ dot3(W[5], W[6], W[7], WA[5], WA[6], WA[7]) / s.mu0 + W[4] / (s.gamma - real(1.));
 	}
 	static HB_HD void apply_dW_dU(real (&r)[nI], Params const& s, real const (&WA)[nI], real const (&U)[nI]) {
 		r[0] = U[0];
 		for (int q = 0; q < 3; ++q) r[1 + q] = U[1 + q] * (real(1.) / WA[0]) - WA[1 + q] * (U[0] / WA[0]);
 		for (int q = 0; q < 3; ++q) r[5 + q] = U[5 + q];
-		r[4] = (s.gamma - real(1.)) * (real(.5) * U[0] * (WA[1] * WA[1] + WA[2] * WA[2] + WA[3] * WA[3])
-			- (U[1] * WA[1] + U[2] * WA[2] + U[3] * WA[3]) - (U[5] * WA[5] + U[6] * WA[6] + U[7] * WA[7]) / s.mu0 + U[4]);
+		r[4] = (s.gamma - real(1.)) * (real(.5) * U[0] * dot3(WA[1], WA[2], WA[3], WA[1], WA[2], WA[3])
+			- dot3(U[1], U[2], U[3], WA[1], WA[2], WA[3]) - dot3(U[5], U[6], U[7], WA[5], WA[6], WA[7]) / s.mu0 + U[4]);
 	}
 
 	template<int SIDE> static HB_HD void waves(real (&lam)[nW], Params const&, Eig const& e) {

@@ -848,6 +848,7 @@ struct SolverBase {
 	virtual ~SolverBase() {}
 	virtual void initDerivs() {}
 	virtual void sourceTest(const double*, double*) {}
+	virtual void plmFacesTest(int, double, const double*, const double*, const double*, double*, double*) {}
 	virtual void setState(const double* aos) = 0;
 	virtual void getState(double* aos) const = 0;
 	virtual void boundary() = 0;
@@ -1709,6 +1710,20 @@ template<class Eqn> struct Solver : SolverBase {
 			for (int j = 0; j < nS; ++j) deriv_[j] = double(dv.ptr[j]);
 		}
 	}
+	// unit-test hook: the two face states calcLR writes for one cell (states of nS doubles each; d.use_plm >= 2 variants)
+	void plmFacesTest(int side, double dt_, const double* UL_, const double* U_, const double* UR_, double* L_, double* R_) override {
+		cons_t UL, U, UR;
+		for (int j = 0; j < nS; ++j) { UL.ptr[j] = real(UL_[j]); U.ptr[j] = real(U_[j]); UR.ptr[j] = real(UR_[j]); }
+		consLR_t result;
+		std::memset(&result, 0, sizeof(result));
+		real const dtArg = real(dt_);
+		if (d.use_plm == 6) calcCellLR_eig(result, U, UL, UR, normal_t{side}, dtArg);
+		else if (d.use_plm >= 7 && d.use_plm <= 10) calcCellLR_eigPrim(result, U, UL, UR, normal_t{side}, dtArg, d.use_plm == 8 || d.use_plm == 10);
+		else if (d.use_plm == 4) calcCellLR_prim(result, U, UL, UR);
+		else if (d.use_plm == 5) calcCellLR_consWithFlux(result, U, UL, UR, normal_t{side}, dtArg);
+		else if (d.use_plm >= 2) calcCellLR_athena(result, U, UL, UR, normal_t{side});
+		for (int j = 0; j < nS; ++j) { L_[j] = double(result.L.ptr[j]); R_[j] = double(result.R.ptr[j]); }
+	}
 	void calcDerivOut(double* aos, double dt_) override {
 		std::vector<cons_t> deriv(ncells);
 		std::memset(deriv.data(), 0, sizeof(cons_t) * ncells);
@@ -2008,6 +2023,7 @@ void ho_op_info(void* h, int op, int* iters, double* residual) { static_cast<ho:
 void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }
 void ho_init_derivs(void* h) { static_cast<ho::SolverBase*>(h)->initDerivs(); }
 void ho_source_test(void* h, const double* U, double* deriv) { static_cast<ho::SolverBase*>(h)->sourceTest(U, deriv); }
+void ho_plm_faces_test(void* h, int side, double dt, const double* UL, const double* U, const double* UR, double* L, double* R) { static_cast<ho::SolverBase*>(h)->plmFacesTest(side, dt, UL, U, UR, L, R); }
 void ho_constrainU(void* h) { static_cast<ho::SolverBase*>(h)->constrainU(); }
 double ho_calc_dt(void* h) { return static_cast<ho::SolverBase*>(h)->calcDT(); }
 void ho_update(void* h, int nsteps) { auto* s = static_cast<ho::SolverBase*>(h); for (int i = 0; i < nsteps; ++i) s->update(); }

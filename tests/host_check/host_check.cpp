@@ -44,6 +44,27 @@ template<class Eqn> static double dtCell(const double* params, const double* U_,
 	return double(Eqn::calcDTCell(p, U, dx, dim));
 }
 
+// the two-face-state reconstructions of hb_roe.cuh (sp.plmMode as in hb_fv_kernels.cuh)
+template<class Eqn, int SIDE> static void plmFacesSide(int mode, int lim, typename Eqn::real dt_dx, typename Eqn::Params const& p,
+	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI],
+	typename Eqn::real (&L)[Eqn::nI], typename Eqn::real (&R)[Eqn::nI]) {
+	if (mode == 4) plmPrimFaces<Eqn>(L, R, p, lim, UL, U, UR);
+	else if (mode == 5) plmConsFluxFaces<Eqn, SIDE>(L, R, p, lim, dt_dx, UL, U, UR);
+	else if (mode == 6) plmEigFaces<Eqn, SIDE>(L, R, p, lim, dt_dx, UL, U, UR);
+	else if (mode >= 7 && mode <= 10) plmEigPrimFaces<Eqn, SIDE>(L, R, p, mode == 8 || mode == 10, mode >= 9 ? 1 : 0, dt_dx, UL, U, UR);
+	else plmAthenaFaces<Eqn, SIDE>(L, R, p, UL, U, UR, mode == 3 ? 1 : 0);
+}
+template<class Eqn> static void plmFaces(int side, int mode, int lim, double dt_dx, const double* params, const double* UL_, const double* U_, const double* UR_, double* L_, double* R_) {
+	typedef typename Eqn::real real;
+	typename Eqn::Params p = Eqn::makeParams(params);
+	real UL[Eqn::nI], U[Eqn::nI], UR[Eqn::nI], L[Eqn::nI], R[Eqn::nI];
+	for (int q = 0; q < Eqn::nI; ++q) { UL[q] = real(UL_[q]); U[q] = real(U_[q]); UR[q] = real(UR_[q]); }
+	if (side == 0) plmFacesSide<Eqn, 0>(mode, lim, real(dt_dx), p, UL, U, UR, L, R);
+	else if (side == 1) plmFacesSide<Eqn, 1>(mode, lim, real(dt_dx), p, UL, U, UR, L, R);
+	else plmFacesSide<Eqn, 2>(mode, lim, real(dt_dx), p, UL, U, UR, L, R);
+	for (int q = 0; q < Eqn::nI; ++q) { L_[q] = double(L[q]); R_[q] = double(R[q]); }
+}
+
 #define DISPATCH(call) \
 	if (eqn == 0 && rb == 8) { typedef Euler<double> E; call; } \
 	else if (eqn == 0) { typedef Euler<float> E; call; } \
@@ -51,6 +72,7 @@ template<class Eqn> static double dtCell(const double* params, const double* U_,
 	else { typedef MHD<float> E; call; }
 
 extern "C" {
+void hc_plm_faces(int eqn, int rb, int side, int mode, int lim, double dt_dx, const double* params, const double* UL, const double* U, const double* UR, double* L, double* R) { DISPATCH(plmFaces<E>(side, mode, lim, dt_dx, params, UL, U, UR, L, R)) }
 void hc_roe_flux(int eqn, int rb, int side, const double* params, const double* UL, const double* UR, double* F) { DISPATCH(roe<E>(side, params, UL, UR, F)) }
 void hc_roe_flux_limited(int eqn, int rb, int side, const double* params, int lim, double dt_dx, const double* U4, double* F) { DISPATCH(roeLim<E>(side, params, lim, dt_dx, U4, F)) }
 void hc_constrainU(int eqn, int rb, const double* params, double* U) { DISPATCH(constrain<E>(params, U)) }

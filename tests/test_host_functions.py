@@ -267,3 +267,37 @@ def test_fast_mhd_finish_cell(hc):
             dt_fast = hc.hc_mhd_finish_cell_fast(params.ctypes.data, b.ctypes.data, dx.ctypes.data, dim)
             assert np.allclose(a, b, rtol=1e-14, atol=1e-14 * np.abs(a).max()), (i, a, b)
             assert abs(dt_fast - dt_lit) <= 1e-13 * dt_lit, (i, dt_lit, dt_fast)
+
+
+PLM_MODES = {2: "plm athena", 3: "plm athena, recorded face order", 4: "plm prim", 5: "plm cons with flux", 6: "plm eig", 7: "plm eig prim",
+             8: "plm eig prim ref", 9: "plm eig prim, other face order", 10: "plm eig prim ref, other face order"}
+
+
+@pytest.mark.parametrize("eqn", ["euler", "mhd"])
+@pytest.mark.parametrize("mode", sorted(PLM_MODES))
+def test_two_face_state_reconstructions_match_oracle(hydrob200, oracle, hc, eqn, mode):
+    """Every reconstruction of plm.cl that writes both face states of a cell (hb_roe.cuh: plmAthenaFaces, plmPrimFaces, plmConsFluxFaces,
+    plmEigFaces, plmEigPrimFaces) against the oracle's calcCellLR_* on random neighbouring states, along every axis: bit-identical."""
+    lim = 8
+    S = hydrob200.FiniteVolumeSolver(dict(eqn=eqn, dim=3, gridSize=[4, 4, 4], initCond="Sod" if eqn == "euler" else "Orszag-Tang",
+                                          backend=oracle.OracleBackend, usePLM=PLM_MODES[mode], slopeLimiter="minmod"))
+    Lo = S.backend.L
+    Lo.ho_plm_faces_test.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 5
+    hc.hc_plm_faces.argtypes = [C.c_int] * 5 + [C.c_double] + [C.c_void_p] * 6
+    nI, nS = S.eqn.numIntStates, S.eqn.numStates
+    params = np.array(S.eqn.eqnParams() + [0.] * 8, dtype=np.float64)
+    rng = np.random.default_rng(77 + mode)
+    U = random_states(eqn, 96, rng)
+    # neighbouring cells differ by a fraction of the state (the limiters see both smooth and extremal triples)
+    U[1::3] = U[0::3] + .1 * (U[1::3] - U[0::3])
+    U[2::3] = U[0::3] + .15 * (U[2::3] - U[0::3])
+    dt, dx = .01, float(S.grid_dx[0])
+    for a in range(0, 96, 3):
+        for side in range(3):
+            refL, refR = np.zeros(nS), np.zeros(nS)
+            Lo.ho_plm_faces_test(S.backend.h, side, dt, U[a + 1].ctypes.data, U[a].ctypes.data, U[a + 2].ctypes.data, refL.ctypes.data, refR.ctypes.data)
+            gotL, gotR = np.zeros(nI), np.zeros(nI)
+            ul, u, ur = (np.ascontiguousarray(U[a + k][:nI]) for k in (1, 0, 2))
+            hc.hc_plm_faces(S.eqn.eqnId, 8, side, mode, lim, dt / float(S.grid_dx[side]), params.ctypes.data, ul.ctypes.data, u.ctypes.data, ur.ctypes.data,
+                            gotL.ctypes.data, gotR.ctypes.data)
+            assert np.array_equal(gotL, refL[:nI]) and np.array_equal(gotR, refR[:nI]), (eqn, PLM_MODES[mode], side, gotL - refL[:nI], gotR - refR[:nI])
