@@ -117,6 +117,8 @@ cudaError_t stage(int dim, bool plm, bool flim, GridP<real> const& g, StageP<rea
 	X(11, 11, 64, 0) \
 	X(12, 15, 64, 8)   /* operands read from global memory in the epilogue (no staging): measured slower, kept for the record */ \
 	X(13, 8, 64, 16)   /* 32 x 8 columns, 9 warps (round 2's MHD tile until call p; kept for the comparison) */
+	/* PAIR (VAR bit 0: the x and y cores of a cell as one block) with TMA operands, X(14, 7, 64, 17) X(15, 11, 64, 17) X(16, 15, 64, 17): 2.30 / 2.05 / 2.16 ms
+	   against 2.43 / 2.02 / 1.94 without it -- it pays only where registers are free (8 warps), and 16 warps win (profiles/r02w_sweep_pair.txt) */
 	/* two CTAs per SM (March3Cfg::MINB; X(13, 7, 64, 80), X(14, 6, 64, 80)) measured slower: 2.03 / 2.18 against 1.93 ms (profiles/r02n_sweep_minb2.txt) */
 #endif
 #endif

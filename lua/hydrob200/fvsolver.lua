@@ -41,7 +41,8 @@ function B200Solver:refreshSolverProgram()
 		d.mins[i] = self.mins.s[i]; d.maxs[i] = self.maxs.s[i]
 	end
 	-- 'plm athena' follows plm.cl:782-879 literally (faces as the tree assigns them, :877-878); use_plm = 3 selects L = left, R = right
-	local plmIds = {['piecewise constant'] = 0, ['plm cons'] = 1, ['plm athena'] = 2, ['plm prim'] = 4, ['plm cons with flux'] = 5}
+	local plmIds = {['piecewise constant'] = 0, ['plm cons'] = 1, ['plm athena'] = 2, ['plm prim'] = 4, ['plm cons with flux'] = 5,
+		['plm eig'] = 6, ['plm eig prim'] = 7, ['plm eig prim ref'] = 8}
 	d.use_plm = self.usePLM and assert(plmIds[self.usePLM], "hydrob200: usePLM not built: "..tostring(self.usePLM)) or 0
 	d.slope_limiter = self.slopeLimiter - 1            -- hydro/app.lua:614-635 is 1-based
 	d.flux_limiter = self.fluxLimiter - 1
