@@ -109,6 +109,7 @@ SIGNATURES = {
     "hb_fv_calc_deriv": (C.c_int, [P, C.c_double, P]),
     "hb_fv_launch_count": (C.c_int, [P, C.POINTER(C.c_longlong)]),
     "hb_fv_describe": (C.c_int, [P, C.c_char_p, C.c_size_t]),
+    "hb_rk_plan": (C.c_int, [C.c_int, P, P, C.c_int, C.c_char_p, C.c_size_t]),
     "hb_fv_profile": (C.c_int, [P, C.c_int]),
     "hb_fv_profile_read": (C.c_int, [P, C.POINTER(C.c_double), C.POINTER(C.c_longlong)]),
     "hb_debug_eval": (C.c_int, [P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P, P, P, C.c_size_t, P, C.c_size_t]),

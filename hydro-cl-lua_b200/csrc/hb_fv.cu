@@ -1353,6 +1353,30 @@ int hb_fv_launch_count(hb_fv* fv, long long* n) { HB_FV(fv); if (n) *n = fv->imp
 int hb_fv_describe(hb_fv* fv, char* out, size_t cap) { HB_FV(fv); if (!out || !cap) return setError(HB_ERR_INVALID, "hb_fv_describe: bad buffer"); return fv->impl->describe(out, cap); }
 int hb_fv_profile(hb_fv* fv, int enable) { HB_FV(fv); return fv->impl->profile(enable); }
 int hb_fv_profile_read(hb_fv* fv, double* ms, long long* n) { HB_FV(fv); return fv->impl->profileRead(ms, n); }
+// host-only (no device needed): the static plan of one update for a tableau in the reference's (alpha, beta) form -- which physical buffer
+// every stage reads and writes, its terms in evaluation order, and (fold != 0) the running sum of the last stage -- as text, one line per
+// stage; tests/test_rk_plan.py executes it on scalars against the direct evaluation of rk.lua:91-165
+int hb_rk_plan(int order, const double* alphas, const double* betas, int fold, char* out, size_t cap) {
+	if (!out || !cap || order < 0 || order > 8 || (order >= 1 && (!alphas || !betas))) return setError(HB_ERR_INVALID, "hb_rk_plan: bad argument");
+	std::vector<StagePlan> plan;
+	int nU = 0, nL = 0;
+	buildPlan(order, alphas, betas, plan, nU, nL);
+	bool const folded = fold && foldFinalStage(plan, nU, nL);
+	std::ostringstream o;
+	o.precision(17);
+	o << "nU=" << nU << " nL=" << nL << " folded=" << (folded ? 1 : 0) << "\n";
+	for (size_t i = 0; i < plan.size(); ++i) {
+		StagePlan const& s = plan[i];
+		o << "stage " << i << " in=" << s.uIn << " out=" << s.uOut << " lout=" << s.lOut << " computeL=" << (s.computeL ? 1 : 0) << " betaSelf=" << s.betaSelf
+		  << " operands=" << s.operands() << " alpha=";
+		for (size_t k = 0; k < s.alpha.size(); ++k) o << (k ? "," : "") << s.alpha[k].k << ":" << s.alpha[k].coef;
+		o << " beta=";
+		for (size_t k = 0; k < s.beta.size(); ++k) o << (k ? "," : "") << s.beta[k].k << ":" << s.beta[k].coef;
+		o << " accOut=" << s.accOut << " accIn=" << s.accIn << " accCoef=" << s.accCoef << " accBetaSelf=" << s.accBetaSelf << "\n";
+	}
+	snprintf(out, cap, "%s", o.str().c_str());
+	return HB_OK;
+}
 int hb_ghost_source(int j, int S, int bcMin, int bcMax, int* flip, int* skip) {
 	bool f, s;
 	int const r = ghostSource(j, S, bcMin, bcMax, f, s);

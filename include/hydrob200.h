@@ -205,6 +205,7 @@ int hb_fv_set_time(hb_fv* fv, double t);
 int hb_fv_calc_deriv(hb_fv* fv, double dt, double* aos_host_out);    /* FiniteVolumeSolver:calcDeriv into a zeroed deriv buffer (blocking) */
 int hb_fv_launch_count(hb_fv* fv, long long* kernel_launches);       /* kernels this object has launched so far */
 int hb_fv_describe(hb_fv* fv, char* out, size_t cap);          /* text: kernel, tile shape, smem, per-stage plan (reads / writes per cell) */
+int hb_rk_plan(int order, const double* alphas, const double* betas, int fold, char* out, size_t cap);   /* host-only: the per-stage buffer / term plan hb_fv_update runs for a tableau (hydro/int/rk.lua:17-44,91-165), fold != 0: with the last stage's running sum; text, one line per stage */
 /* per-launch device timing of the fused stage kernel (CUDA events on the context's stream; disables graph replay
  * while enabled): total milliseconds and number of stage launches since hb_fv_profile(fv, 1) */
 int hb_fv_profile(hb_fv* fv, int enable);
