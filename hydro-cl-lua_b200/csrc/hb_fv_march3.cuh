@@ -25,6 +25,9 @@
 //     carried across iterations; the persistent registers are the face state and the flux of the previous z interface only.
 //   * Production arithmetic: minmod by one FP64 compare + an integer sign test (hb_roe_fast.cuh: plmFacesT), fluxes accumulated
 //     into the divergence as they are produced.
+//   * RK operands (the other states / derivatives the stage's combination reads at the finished cell) come by TMA a plane ahead
+//     (March3Cfg::OPTMA), and for classic-RK4-type tableaux the host carries the last stage's sum from stage to stage (StageP::Aout,
+//     hb_fv.cu foldFinalStage), so every stage has at most two operands and runs the tallest tile.
 #pragma once
 #include "hb_fv_march.cuh"
 
@@ -34,7 +37,9 @@ template<int TY_, int KM_, int VAR_ = 0> struct March3Cfg {
 	static constexpr int TY = TY_;     // rows per CTA = column warps
 	static constexpr int KM = KM_;     // planes per CTA along the marching axis
 	static constexpr bool GRAV = (VAR_ & 32) != 0;      // the epilogue adds the self-gravity source (as MarchCfg::GRAV)
-	static constexpr bool PAIR = (VAR_ & 1) != 0;       // the x and y flux cores of a cell issued as one block (two independent dependent chains)
+	// PAIR: the x and y flux cores of a cell issued as one block (two independent dependent chains).  MEASURED AND NOT USED: it spills at
+	// 16 warps x 128 registers, changes nothing at 12 x 168 and gains 6 % at 8 x 208, where the kernel is 20 % slower anyway (r02w)
+	static constexpr bool PAIR = (VAR_ & 1) != 0;
 	// GEN: the general configuration -- any of the 20 slope limiters, no reconstruction, the Roe flux with a flux limiter (4-cell stencil
 	// along every axis; hydro/solver/fvsolver.lua:138-155), and the other fluxes of the calcFluxForInterface slot (HLL, Rusanov, euler-HLLC),
 	// all selected at run time from StageP as in the tile kernel fv_stage, with the literal device functions
@@ -42,13 +47,16 @@ template<int TY_, int KM_, int VAR_ = 0> struct March3Cfg {
 	// OPDIRECT: the RK operands are read from global memory in the epilogue (plain coalesced loads at the point of use) instead of being
 	// staged per thread through shared memory by cp.async: no operand area in shared memory (every stage fits the tallest tile), no LDGSTS
 	static constexpr bool OPDIRECT = (VAR_ & 8) != 0;
-	// OPTMA: the RK operands of plane k arrive by TMA (one cp.async.bulk.tensor per operand, issued by the halo warp as soon as every warp
-	// has left the operand area, i.e. when the iteration's flux barrier completes) instead of 5 per-thread cp.async per operand: the LSU /
-	// MIO queue carries no LDGSTS (profiles/r02k_fv_march3_c4_full.txt: RK4's four-operand stage stalls on mio_throttle + long_scoreboard)
+	// OPTMA (the default configurations): the RK operands of plane k arrive by TMA -- one cp.async.bulk.tensor per operand, issued by the halo
+	// warp at the TOP of iteration k, as soon as the `opfree` mbarrier says every column warp has finished the epilogue of plane k-1; the
+	// column warps wait on `opbar` just before their epilogue -- instead of 5 per-thread cp.async per operand: the LSU / MIO queue carries no
+	// LDGSTS (profiles/r02k_fv_march3_c4_full.txt: RK4's four-operand stage stalled on mio_throttle + long_scoreboard).  2.18 -> 1.99 ms per
+	// 512 x 512 x 128 stage; issuing the copies only when the iteration's flux barrier completes was too late to hide (2.36 ms)
 	static constexpr bool OPTMA = (VAR_ & 16) != 0;
-	// MINB 2 (VAR bit 6): two CTAs per SM (half-height tiles, registers capped for 2 x NT threads).  The warps of one CTA move through the
-	// FP64-dense (flux cores) and FP64-sparse (ring loads, slopes, epilogue) phases of a plane together -- the plane's flux barrier realigns
-	// them -- so the FP64 pipe idles during the sparse phases; a second, unsynchronised CTA fills them
+	// MINB 2 (VAR bit 6): two CTAs per SM (half-height tiles, registers capped for 2 x NT threads).  The idea: the warps of one CTA move
+	// through the FP64-dense (flux cores) and FP64-sparse (ring loads, slopes, epilogue) phases of a plane together, a second, unsynchronised
+	// CTA would fill the sparse phases.  MEASURED AND NOT USED: 2 x 8 warps run 2.03 ms against 1.93 ms for one 16-warp CTA (7 % more halo
+	// work for 2 % better per row: the warps are not phase-locked, there are too few of them; profiles/r02n_sweep_minb2.txt)
 	static constexpr int MINB = (VAR_ & 64) ? 2 : 1;
 };
 
