@@ -275,12 +275,14 @@ PLM_MODES = {2: "plm athena", 3: "plm athena, recorded face order", 4: "plm prim
 
 @pytest.mark.parametrize("eqn", ["euler", "mhd"])
 @pytest.mark.parametrize("mode", sorted(PLM_MODES))
-def test_two_face_state_reconstructions_match_oracle(hydrob200, oracle, hc, eqn, mode):
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_two_face_state_reconstructions_match_oracle(hydrob200, oracle, hc, eqn, mode, precision):
     """Every reconstruction of plm.cl that writes both face states of a cell (hb_roe.cuh: plmAthenaFaces, plmPrimFaces, plmConsFluxFaces,
     plmEigFaces, plmEigPrimFaces) against the oracle's calcCellLR_* on random neighbouring states, along every axis: bit-identical."""
     lim = 8
     S = hydrob200.FiniteVolumeSolver(dict(eqn=eqn, dim=3, gridSize=[4, 4, 4], initCond="Sod" if eqn == "euler" else "Orszag-Tang",
-                                          backend=oracle.OracleBackend, usePLM=PLM_MODES[mode], slopeLimiter="minmod"))
+                                          backend=oracle.OracleBackend, usePLM=PLM_MODES[mode], slopeLimiter="minmod", precision=precision))
+    rb = 8 if precision == "double" else 4
     Lo = S.backend.L
     Lo.ho_plm_faces_test.argtypes = [C.c_void_p, C.c_int, C.c_double] + [C.c_void_p] * 5
     hc.hc_plm_faces.argtypes = [C.c_int] * 5 + [C.c_double] + [C.c_void_p] * 6
@@ -291,6 +293,8 @@ def test_two_face_state_reconstructions_match_oracle(hydrob200, oracle, hc, eqn,
     # neighbouring cells differ by a fraction of the state (the limiters see both smooth and extremal triples)
     U[1::3] = U[0::3] + .1 * (U[1::3] - U[0::3])
     U[2::3] = U[0::3] + .15 * (U[2::3] - U[0::3])
+    if precision == "float":
+        U = U.astype(np.float32).astype(np.float64)
     dt, dx = .01, float(S.grid_dx[0])
     for a in range(0, 96, 3):
         for side in range(3):
@@ -298,6 +302,6 @@ def test_two_face_state_reconstructions_match_oracle(hydrob200, oracle, hc, eqn,
             Lo.ho_plm_faces_test(S.backend.h, side, dt, U[a + 1].ctypes.data, U[a].ctypes.data, U[a + 2].ctypes.data, refL.ctypes.data, refR.ctypes.data)
             gotL, gotR = np.zeros(nI), np.zeros(nI)
             ul, u, ur = (np.ascontiguousarray(U[a + k][:nI]) for k in (1, 0, 2))
-            hc.hc_plm_faces(S.eqn.eqnId, 8, side, mode, lim, dt / float(S.grid_dx[side]), params.ctypes.data, ul.ctypes.data, u.ctypes.data, ur.ctypes.data,
+            hc.hc_plm_faces(S.eqn.eqnId, rb, side, mode, lim, dt / float(S.grid_dx[side]), params.ctypes.data, ul.ctypes.data, u.ctypes.data, ur.ctypes.data,
                             gotL.ctypes.data, gotR.ctypes.data)
             assert np.array_equal(gotL, refL[:nI]) and np.array_equal(gotR, refR[:nI]), (eqn, PLM_MODES[mode], side, gotL - refL[:nI], gotR - refR[:nI])
