@@ -849,6 +849,7 @@ struct SolverBase {
 	virtual void initDerivs() {}
 	virtual void sourceTest(const double*, double*) {}
 	virtual void plmFacesTest(int, double, const double*, const double*, const double*, double*, double*) {}
+	virtual void interfaceFluxTest(int, const double*, const double*, double*) {}
 	virtual void setState(const double* aos) = 0;
 	virtual void getState(double* aos) const = 0;
 	virtual void boundary() = 0;
@@ -1710,6 +1711,19 @@ template<class Eqn> struct Solver : SolverBase {
 			for (int j = 0; j < nS; ++j) deriv_[j] = double(dv.ptr[j]);
 		}
 	}
+	// unit-test hook: the solver's interface flux (d.flux: 0 roe without limiter, 1 hll, 2 rusanov, 3 euler-hllc) of one state pair
+	void interfaceFluxTest(int side, const double* UL_, const double* UR_, double* F_) override {
+		cons_t UL, UR, F;
+		for (int j = 0; j < nS; ++j) { UL.ptr[j] = real(UL_[j]); UR.ptr[j] = real(UR_[j]); F.ptr[j] = 0; }
+		normal_t n{side};
+		if constexpr (Eqn::hasWaveMinMax) {
+			if (d.flux == 1) hllFlux(F, UL, UR, n);
+			else if (d.flux == 2) rusanovFlux(F, UL, UR, n);
+			else if (d.flux == 3) { if constexpr (Eqn::isEuler) hllcFlux(F, UL, UR, n); }
+			else { bool save = useFluxLimiter; useFluxLimiter = false; roeFlux(F, UL, UR, n, 0, nullptr, nullptr, nullptr, nullptr); useFluxLimiter = save; }
+		}
+		for (int j = 0; j < nS; ++j) F_[j] = double(F.ptr[j]);
+	}
 	// unit-test hook: the two face states calcLR writes for one cell (states of nS doubles each; d.use_plm >= 2 variants)
 	void plmFacesTest(int side, double dt_, const double* UL_, const double* U_, const double* UR_, double* L_, double* R_) override {
 		cons_t UL, U, UR;
@@ -2023,6 +2037,7 @@ void ho_op_info(void* h, int op, int* iters, double* residual) { static_cast<ho:
 void ho_boundary(void* h) { static_cast<ho::SolverBase*>(h)->boundary(); }
 void ho_init_derivs(void* h) { static_cast<ho::SolverBase*>(h)->initDerivs(); }
 void ho_source_test(void* h, const double* U, double* deriv) { static_cast<ho::SolverBase*>(h)->sourceTest(U, deriv); }
+void ho_interface_flux_test(void* h, int side, const double* UL, const double* UR, double* F) { static_cast<ho::SolverBase*>(h)->interfaceFluxTest(side, UL, UR, F); }
 void ho_plm_faces_test(void* h, int side, double dt, const double* UL, const double* U, const double* UR, double* L, double* R) { static_cast<ho::SolverBase*>(h)->plmFacesTest(side, dt, UL, U, UR, L, R); }
 void ho_constrainU(void* h) { static_cast<ho::SolverBase*>(h)->constrainU(); }
 double ho_calc_dt(void* h) { return static_cast<ho::SolverBase*>(h)->calcDT(); }

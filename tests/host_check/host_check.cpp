@@ -44,6 +44,17 @@ template<class Eqn> static double dtCell(const double* params, const double* U_,
 	return double(Eqn::calcDTCell(p, U, dx, dim));
 }
 
+// the solver's flux plug-in as the tile kernel selects it (hb_roe.cuh interfaceFlux: 0 roe, 1 hll, 2 rusanov, 3 euler-hllc)
+template<class Eqn> static void ifaceFlux(int side, int flux, int fluxParam, const double* params, const double* UL_, const double* UR_, double* F_) {
+	typedef typename Eqn::real real;
+	typename Eqn::Params p = Eqn::makeParams(params);
+	real UL[Eqn::nI], UR[Eqn::nI], F[Eqn::nI];
+	for (int q = 0; q < Eqn::nI; ++q) { UL[q] = real(UL_[q]); UR[q] = real(UR_[q]); }
+	if (side == 0) interfaceFlux<Eqn, 0>(flux, fluxParam, F, p, UL, UR);
+	else if (side == 1) interfaceFlux<Eqn, 1>(flux, fluxParam, F, p, UL, UR);
+	else interfaceFlux<Eqn, 2>(flux, fluxParam, F, p, UL, UR);
+	for (int q = 0; q < Eqn::nI; ++q) F_[q] = double(F[q]);
+}
 // the two-face-state reconstructions of hb_roe.cuh (sp.plmMode as in hb_fv_kernels.cuh)
 template<class Eqn, int SIDE> static void plmFacesSide(int mode, int lim, typename Eqn::real dt_dx, typename Eqn::Params const& p,
 	typename Eqn::real const (&UL)[Eqn::nI], typename Eqn::real const (&U)[Eqn::nI], typename Eqn::real const (&UR)[Eqn::nI],
@@ -72,6 +83,7 @@ template<class Eqn> static void plmFaces(int side, int mode, int lim, double dt_
 	else { typedef MHD<float> E; call; }
 
 extern "C" {
+void hc_interface_flux(int eqn, int rb, int side, int flux, int fluxParam, const double* params, const double* UL, const double* UR, double* F) { DISPATCH(ifaceFlux<E>(side, flux, fluxParam, params, UL, UR, F)) }
 void hc_plm_faces(int eqn, int rb, int side, int mode, int lim, double dt_dx, const double* params, const double* UL, const double* U, const double* UR, double* L, double* R) { DISPATCH(plmFaces<E>(side, mode, lim, dt_dx, params, UL, U, UR, L, R)) }
 void hc_roe_flux(int eqn, int rb, int side, const double* params, const double* UL, const double* UR, double* F) { DISPATCH(roe<E>(side, params, UL, UR, F)) }
 void hc_roe_flux_limited(int eqn, int rb, int side, const double* params, int lim, double dt_dx, const double* U4, double* F) { DISPATCH(roeLim<E>(side, params, lim, dt_dx, U4, F)) }

@@ -305,3 +305,39 @@ def test_two_face_state_reconstructions_match_oracle(hydrob200, oracle, hc, eqn,
             hc.hc_plm_faces(S.eqn.eqnId, rb, side, mode, lim, dt / float(S.grid_dx[side]), params.ctypes.data, ul.ctypes.data, u.ctypes.data, ur.ctypes.data,
                             gotL.ctypes.data, gotR.ctypes.data)
             assert np.array_equal(gotL, refL[:nI]) and np.array_equal(gotR, refR[:nI]), (eqn, PLM_MODES[mode], side, gotL - refL[:nI], gotR - refR[:nI])
+
+
+FLUXES = [("hll", 0), ("rusanov", 0), ("euler-hllc", 0), ("euler-hllc", 1), ("euler-hllc", 2)]
+
+
+@pytest.mark.parametrize("eqn", ["euler", "mhd"])
+@pytest.mark.parametrize("flux,method", FLUXES, ids=["%s-%d" % f for f in FLUXES])
+@pytest.mark.parametrize("precision", ["double", "float"])
+def test_flux_plugins_match_oracle(hydrob200, oracle, hc, eqn, flux, method, precision):
+    """The other fluxes of the calcFluxForInterface slot (hydro/flux/hll.cl:5-74, rusanov.cl:4-33, euler-hllc.cl:14-243) as the tile kernel
+    runs them (hb_roe.cuh interfaceFlux) against the oracle's hllFlux / rusanovFlux / hllcFlux on random state pairs, every axis."""
+    if flux == "euler-hllc" and eqn != "euler":
+        pytest.skip("euler-hllc is an Euler-only flux (euler-hllc.cl:7-11)")
+    cfg = dict(eqn=eqn, dim=3, gridSize=[4, 4, 4], initCond="Sod" if eqn == "euler" else "Orszag-Tang", backend=oracle.OracleBackend, flux=flux,
+               precision=precision)
+    if flux == "euler-hllc":
+        cfg["hllcMethod"] = method
+    S = hydrob200.FiniteVolumeSolver(cfg)
+    rb = 8 if precision == "double" else 4
+    Lo = S.backend.L
+    Lo.ho_interface_flux_test.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    hc.hc_interface_flux.argtypes = [C.c_int] * 5 + [C.c_void_p] * 4
+    nI, nS = S.eqn.numIntStates, S.eqn.numStates
+    params = np.array(S.eqn.eqnParams() + [0.] * 8, dtype=np.float64)
+    U = random_states(eqn, 64, np.random.default_rng(99))
+    if precision == "float":
+        U = U.astype(np.float32).astype(np.float64)
+    for a in range(0, 64, 2):
+        for side in range(3):
+            ref = np.zeros(nS)
+            Lo.ho_interface_flux_test(S.backend.h, side, U[a].ctypes.data, U[a + 1].ctypes.data, ref.ctypes.data)
+            got = np.zeros(nI)
+            ul, ur = np.ascontiguousarray(U[a][:nI]), np.ascontiguousarray(U[a + 1][:nI])
+            hc.hc_interface_flux(S.eqn.eqnId, rb, side, S.flux.fluxId, getattr(S.flux, "fluxParam", 0), params.ctypes.data, ul.ctypes.data, ur.ctypes.data,
+                                 got.ctypes.data)
+            assert np.array_equal(got, ref[:nI]), (eqn, flux, method, side, got - ref[:nI])
