@@ -1357,7 +1357,7 @@ int hb_fv_profile_read(hb_fv* fv, double* ms, long long* n) { HB_FV(fv); return 
 // every stage reads and writes, its terms in evaluation order, and (fold != 0) the running sum of the last stage -- as text, one line per
 // stage; tests/test_rk_plan.py executes it on scalars against the direct evaluation of rk.lua:91-165
 int hb_rk_plan(int order, const double* alphas, const double* betas, int fold, char* out, size_t cap) {
-	if (!out || !cap || order < 0 || order > 8 || (order >= 1 && (!alphas || !betas))) return setError(HB_ERR_INVALID, "hb_rk_plan: bad argument");
+	if (!out || !cap || order < 0 || order > 4 || (order >= 1 && (!alphas || !betas))) return setError(HB_ERR_INVALID, "hb_rk_plan: bad argument (order 0..4, order x order tables as in hb_fv_desc)");
 	std::vector<StagePlan> plan;
 	int nU = 0, nL = 0;
 	buildPlan(order, alphas, betas, plan, nU, nL);
